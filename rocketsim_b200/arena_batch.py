@@ -1,0 +1,152 @@
+"""``ArenaBatch``: the batched front end of the reference's ``Arena`` interface.
+
+Mirrors the reference surface for the hot path (reference ``src/Sim/Arena/Arena.h``:
+``Create``/``AddCar``/``Step``/``GetMutatorConfig``/``IsBallScored``/``tickCount``;
+``Car::controls``/``GetState``/``SetState`` in ``src/Sim/Car/Car.h:149-152``;
+``Ball::GetState``/``SetState`` in ``src/Sim/Ball/Ball.h:68-69``), with every call applying to
+all arenas of the batch at once.  All compute happens in the CUDA library behind the C ABI
+(``include/rsb_c_api.h``); this class only marshals numpy arrays.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import lib as _lib
+from . import types as T
+
+
+class ArenaBatch:
+    def __init__(self, game_mode: int, n_arenas: int, teams: Sequence[int], car_configs: Optional[np.ndarray] = None,
+                 mutator_config: Optional[np.ndarray] = None, tick_rate: float = 120.0, seed: int = 0, device: int = 0,
+                 lib=None):
+        """``Arena::Create(game_mode, ArenaConfig(), tick_rate)`` x n_arenas, then
+        ``AddCar(team, config)`` for every entry of ``teams`` (car ids 1..n in that order)."""
+        self.L = lib or _lib.load()
+        self.n_arenas = int(n_arenas)
+        self.n_cars = len(teams)
+        self.game_mode = int(game_mode)
+        t = np.asarray(teams, dtype=np.int32)
+        cfg = None if car_configs is None else np.ascontiguousarray(car_configs, dtype=T.CarConfig)
+        if cfg is not None and len(cfg) != self.n_cars:
+            raise ValueError("one CarConfig per car slot expected")
+        mut = None if mutator_config is None else np.array([mutator_config], dtype=T.MutatorConfig)
+        h = C.c_void_p()
+        _lib.check(self.L, self.L.rsb_batch_create(device, game_mode, n_arenas, self.n_cars, _lib.ptr(t) if self.n_cars else None,
+                                                   _lib.ptr(cfg), _lib.ptr(mut), tick_rate, seed, C.byref(h)))
+        self.h = h
+        np_ = C.c_int()
+        _lib.check(self.L, self.L.rsb_batch_info(self.h, None, None, C.byref(np_), None))
+        self.n_pads = np_.value
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.rsb_batch_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- controls / stepping
+    def set_controls(self, controls: np.ndarray):
+        c = np.ascontiguousarray(controls, dtype=T.CarControls).reshape(self.n_arenas, self.n_cars)
+        _lib.check(self.L, self.L.rsb_set_controls(self.h, _lib.ptr(c)))
+
+    def step(self, n_ticks: int = 1):
+        _lib.check(self.L, self.L.rsb_step(self.h, n_ticks))
+
+    def sync(self):
+        _lib.check(self.L, self.L.rsb_sync(self.h))
+
+    def set_stream(self, cuda_stream: int):
+        _lib.check(self.L, self.L.rsb_set_stream(self.h, C.c_void_p(cuda_stream)))
+
+    # ---- state access
+    def _get(self, fn, dtype, shape):
+        out = np.zeros(shape, dtype=dtype)
+        if out.size:
+            _lib.check(self.L, getattr(self.L, fn)(self.h, _lib.ptr(out)))
+        return out
+
+    def get_car_states(self):
+        return self._get("rsb_get_car_states", T.CarState, (self.n_arenas, self.n_cars))
+
+    def get_ball_states(self):
+        return self._get("rsb_get_ball_states", T.BallState, (self.n_arenas,))
+
+    def get_pad_states(self):
+        return self._get("rsb_get_pad_states", T.BoostPadState, (self.n_arenas, self.n_pads))
+
+    def get_car_internals(self):
+        return self._get("rsb_get_car_internals", T.CarInternal, (self.n_arenas, self.n_cars))
+
+    def get_ball_internals(self):
+        return self._get("rsb_get_ball_internals", T.BallInternal, (self.n_arenas,))
+
+    def get_tick_counts(self):
+        return self._get("rsb_get_tick_counts", np.uint64, (self.n_arenas,))
+
+    def get_error_flags(self):
+        return self._get("rsb_get_error_flags", np.uint32, (self.n_arenas,))
+
+    def is_ball_scored(self):
+        return self._get("rsb_is_ball_scored", np.uint8, (self.n_arenas,)).astype(bool)
+
+    def get_observations(self):
+        nf = self.L.rsb_observation_floats(self.h)
+        return self._get("rsb_get_observations", np.float32, (self.n_arenas, nf))
+
+    def get_events(self, cap: int = 65536):
+        out = np.zeros(cap, dtype=T.Event)
+        n = C.c_int()
+        _lib.check(self.L, self.L.rsb_get_events(self.h, _lib.ptr(out), cap, C.byref(n)))
+        return out[: n.value]
+
+    def _idx(self, arena_idx, car_idx=None):
+        ai = np.ascontiguousarray(arena_idx, dtype=np.uint32).ravel()
+        ci = None if car_idx is None else np.ascontiguousarray(car_idx, dtype=np.uint32).ravel()
+        return ai, ci
+
+    def set_car_states(self, arena_idx, car_idx, states):
+        ai, ci = self._idx(arena_idx, car_idx)
+        s = np.ascontiguousarray(states, dtype=T.CarState).ravel()
+        _lib.check(self.L, self.L.rsb_set_car_states(self.h, _lib.ptr(ai), _lib.ptr(ci), len(ai), _lib.ptr(s)))
+
+    def set_car_internals(self, arena_idx, car_idx, internals):
+        ai, ci = self._idx(arena_idx, car_idx)
+        s = np.ascontiguousarray(internals, dtype=T.CarInternal).ravel()
+        _lib.check(self.L, self.L.rsb_set_car_internals(self.h, _lib.ptr(ai), _lib.ptr(ci), len(ai), _lib.ptr(s)))
+
+    def set_ball_states(self, arena_idx, states):
+        ai, _ = self._idx(arena_idx)
+        s = np.ascontiguousarray(states, dtype=T.BallState).ravel()
+        _lib.check(self.L, self.L.rsb_set_ball_states(self.h, _lib.ptr(ai), len(ai), _lib.ptr(s)))
+
+    def set_ball_internals(self, arena_idx, internals):
+        ai, _ = self._idx(arena_idx)
+        s = np.ascontiguousarray(internals, dtype=T.BallInternal).ravel()
+        _lib.check(self.L, self.L.rsb_set_ball_internals(self.h, _lib.ptr(ai), len(ai), _lib.ptr(s)))
+
+    def set_pad_states(self, arena_idx, states):
+        ai, _ = self._idx(arena_idx)
+        s = np.ascontiguousarray(states, dtype=T.BoostPadState).reshape(len(ai), self.n_pads)
+        if self.n_pads:
+            _lib.check(self.L, self.L.rsb_set_pad_states(self.h, _lib.ptr(ai), len(ai), _lib.ptr(s)))
+
+    def seed_rng(self, arena: int, seed: int):
+        _lib.check(self.L, self.L.rsb_seed_rng(self.h, arena, seed))
+
+    def reset_to_random_kickoff(self, seeds, arena_idx=None):
+        s = np.ascontiguousarray(seeds, dtype=np.int32).ravel()
+        if arena_idx is None:
+            if len(s) != self.n_arenas:
+                raise ValueError("one seed per arena expected")
+            _lib.check(self.L, self.L.rsb_reset_to_random_kickoff(self.h, None, self.n_arenas, _lib.ptr(s)))
+        else:
+            ai, _ = self._idx(arena_idx)
+            _lib.check(self.L, self.L.rsb_reset_to_random_kickoff(self.h, _lib.ptr(ai), len(ai), _lib.ptr(s)))

@@ -1,0 +1,971 @@
+// rsb_api.cu -- C ABI (include/rsb_c_api.h), batch management and the CUDA kernels of the
+// batched Arena::Step for sm_100a.
+//
+// One WARP owns one arena: the arena's persistent record (ArenaS) and per-tick scratch
+// (ArenaW) live in HBM/L2 as contiguous per-arena records; the 32 lanes execute the tick as
+// SPMD phases (rsb_tick.h) -- lanes = car x wheel for the suspension rays, lanes = cars for
+// the game logic, lanes = bodies for prediction/integration -- separated by __syncwarp().
+// rsb_step(n) is ONE launch that loops n ticks inside the kernel.
+//
+// Build modes:
+//   nvcc (product):  the only execution path is CUDA; every entry point fails loudly
+//                    when no device is available.  No CPU fallback exists in this build.
+//   g++ -DRSB_HOSTCHECK (tests only, tests/_hostbuild/): the same device functions compiled
+//                    for the host so the CPU-only test tier can diff the kernel arithmetic
+//                    against the oracle.  Never built or loaded by the rocketsim_b200 package.
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/rsb_c_api.h"
+#include "../../include/rsb_bench_inputs.h"
+#include "sim/rsb_tick.h"
+#include "rsb_scene.h"
+
+using namespace rsb;
+
+#ifndef RSB_HOSTCHECK
+#include <cuda_runtime.h>
+#define RSB_GLOBAL __global__
+#else
+#define RSB_GLOBAL
+#endif
+
+static thread_local std::string g_err;
+static int fail(const std::string& s) { g_err = s; return -1; }
+
+// ------------------------------------------------------------------ device memory shim
+#ifndef RSB_HOSTCHECK
+#define CUDA_OK(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) throw std::runtime_error(std::string(#expr) + ": " + cudaGetErrorString(_e)); } while (0)
+static void* dev_alloc(size_t n) { void* p = nullptr; CUDA_OK(cudaMalloc(&p, n ? n : 1)); CUDA_OK(cudaMemset(p, 0, n ? n : 1)); return p; }
+static void dev_free(void* p) { if (p) cudaFree(p); }
+static void h2d(void* d, const void* h, size_t n, cudaStream_t s) { CUDA_OK(cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, s)); }
+static void d2h(void* h, const void* d, size_t n, cudaStream_t s) { CUDA_OK(cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, s)); CUDA_OK(cudaStreamSynchronize(s)); }
+typedef cudaStream_t stream_t;
+#else
+static void* dev_alloc(size_t n) { void* p = calloc(n ? n : 1, 1); if (!p) throw std::runtime_error("alloc"); return p; }
+static void dev_free(void* p) { free(p); }
+typedef int stream_t;
+static void h2d(void* d, const void* h, size_t n, stream_t) { memcpy(d, h, n); }
+static void d2h(void* h, const void* d, size_t n, stream_t) { memcpy(h, d, n); }
+#endif
+
+// ------------------------------------------------------------------ scenes (per game mode)
+struct SceneDev {
+	SceneHost host;
+	Scene* dScene = nullptr;          // device copy of the Scene header
+	std::vector<void*> allocs;
+};
+static std::mutex g_initMutex;
+static bool g_initialized = false;
+static std::map<int, std::vector<std::vector<uint8_t>>> g_meshFiles;
+static std::map<int, SceneHost> g_sceneHost;                 // built at init
+static std::map<std::pair<int, int>, SceneDev*> g_sceneDev;  // (device, mode) -> uploaded scene
+
+static SceneDev* get_scene_dev(int device, int mode) {
+	auto key = std::make_pair(device, mode);
+	auto it = g_sceneDev.find(key);
+	if (it != g_sceneDev.end()) return it->second;
+	auto hs = g_sceneHost.find(mode);
+	if (hs == g_sceneHost.end()) throw std::runtime_error("No arena meshes registered for game mode " + std::to_string(mode) + " (call rsb_init_from_mem first)");
+	SceneDev* sd = new SceneDev();
+	sd->host = hs->second;
+	Scene sc;
+	memset(&sc, 0, sizeof(sc));
+	const SceneHost& h = sd->host;
+	sc.nMeshes = (int)h.meshes.size(); sc.nPlanes = (int)h.planes.size();
+	auto up = [&](const void* src, size_t n) { void* d = dev_alloc(n); if (n) h2d(d, src, n, 0); sd->allocs.push_back(d); return d; };
+	for (int i = 0; i < sc.nMeshes; i++) {
+		const MeshHost& m = h.meshes[i];
+		MeshD& d = sc.meshes[i];
+		d.nodes = (const BvhNode*)up(m.nodes.data(), m.nodes.size() * sizeof(BvhNode)); d.nNodes = (int)m.nodes.size();
+		d.hdrs = (const SubtreeHdr*)up(m.hdrs.data(), m.hdrs.size() * sizeof(SubtreeHdr)); d.nHdrs = (int)m.hdrs.size();
+		d.tris = (const int32_t*)up(m.tris.data(), m.tris.size() * 4);
+		d.verts = (const float*)up(m.verts.data(), m.verts.size() * 4);
+		d.info = (const TriInfo*)up(m.info.data(), m.info.size() * sizeof(TriInfo));
+		d.nTris = m.nTris(); d.nVerts = m.nVerts();
+		d.bvhMin = m.bvhMin; d.bvhMax = m.bvhMax; d.bvhQuant = m.bvhQuant;
+		d.aabbMin = m.aabbMin; d.aabbMax = m.aabbMax; d.group = m.group; d.mask = m.mask;
+	}
+	for (int i = 0; i < sc.nPlanes; i++) sc.planes[i] = h.planes[i];
+	sc.gridMin = h.gridMin; sc.gridMax = h.gridMax; sc.cellSize = h.cellSize;
+	sc.cellsX = h.cellsX; sc.cellsY = h.cellsY; sc.cellsZ = h.cellsZ;
+	sc.cellStart = (const int32_t*)up(h.cellStart.data(), h.cellStart.size() * 4);
+	sc.cellStatics = (const uint8_t*)up(h.cellStatics.data(), h.cellStatics.size());
+	sd->dScene = (Scene*)up(&sc, sizeof(sc));
+#ifndef RSB_HOSTCHECK
+	CUDA_OK(cudaDeviceSynchronize());
+#endif
+	g_sceneDev[key] = sd;
+	return sd;
+}
+
+// ------------------------------------------------------------------ batch
+struct RsbBatch {
+	int device = 0;
+	BatchParams hp;
+	BatchParams* dP = nullptr;
+	ArenaS* dS = nullptr;
+	ArenaW* dW = nullptr;
+	const Scene* dScene = nullptr;
+	EventSink::Ev* dEvents = nullptr;
+	uint32_t* dEventCount = nullptr;
+	uint32_t eventCap = 0;
+	CtrlS* dCtrl = nullptr;        // staging for rsb_set_controls
+	void* dScratch = nullptr;      // staging for get/set
+	size_t scratchBytes = 0;
+	stream_t stream = 0;
+	void ensure_scratch(size_t n) { if (n > scratchBytes) { dev_free(dScratch); dScratch = dev_alloc(n); scratchBytes = n; } }
+};
+
+static void set_device(const RsbBatch* b) {
+#ifndef RSB_HOSTCHECK
+	CUDA_OK(cudaSetDevice(b->device));
+#else
+	(void)b;
+#endif
+}
+
+// ------------------------------------------------------------------ conversions (device code)
+RSB_HD RsbVec to_vec(const V3& v) { RsbVec r; r.x = v.x; r.y = v.y; r.z = v.z; r._w = 0.f; return r; }
+RSB_HD V3 from_vec(const RsbVec& v) { return V3(v.x, v.y, v.z); }
+RSB_HD void basis_to_rotmat(const M3& b, RsbRotMat& r) { r.forward = to_vec(b.col(0)); r.right = to_vec(b.col(1)); r.up = to_vec(b.col(2)); }
+RSB_HD M3 rotmat_to_basis(const RsbRotMat& r) {
+	return M3(V3(r.forward.x, r.right.x, r.up.x), V3(r.forward.y, r.right.y, r.up.y), V3(r.forward.z, r.right.z, r.up.z));
+}
+RSB_HD void ctrl_to_api(const CtrlS& c, RsbCarControls& o) { o.throttle = c.throttle; o.steer = c.steer; o.pitch = c.pitch; o.yaw = c.yaw; o.roll = c.roll; o.jump = c.jump; o.boost = c.boost; o.handbrake = c.handbrake; o._pad = 0; }
+RSB_HD void ctrl_from_api(const RsbCarControls& c, CtrlS& o) { o.throttle = c.throttle; o.steer = c.steer; o.pitch = c.pitch; o.yaw = c.yaw; o.roll = c.roll; o.jump = c.jump != 0; o.boost = c.boost != 0; o.handbrake = c.handbrake != 0; o._pad = 0; }
+
+// Car::GetState (Car.cpp:10-20)
+RSB_HD void car_to_api(const CarS& c, RsbCarState& o) {
+	unsigned char* raw = (unsigned char*)&o;
+	for (size_t i = 0; i < sizeof(RsbCarState); i++) raw[i] = 0;
+	o.pos = to_vec(c.rb.pos * BT_TO_UU);
+	basis_to_rotmat(c.rb.basis, o.rotMat);
+	o.vel = to_vec(c.rb.vel * BT_TO_UU);
+	o.angVel = to_vec(c.rb.angvel);
+	o.tickCountSinceUpdate = c.tickCountSinceUpdate;
+	o.isOnGround = c.isOnGround;
+	for (int i = 0; i < 4; i++) o.wheelsWithContact[i] = c.wheelsWithContact[i];
+	o.hasJumped = c.hasJumped; o.hasDoubleJumped = c.hasDoubleJumped; o.hasFlipped = c.hasFlipped;
+	o.flipRelTorque = to_vec(c.flipRelTorque);
+	o.jumpTime = c.jumpTime; o.flipTime = c.flipTime; o.isFlipping = c.isFlipping; o.isJumping = c.isJumping;
+	o.airTime = c.airTime; o.airTimeSinceJump = c.airTimeSinceJump; o.boost = c.boost; o.timeSinceBoosted = c.timeSinceBoosted;
+	o.isBoosting = c.isBoosting; o.boostingTime = c.boostingTime; o.isSupersonic = c.isSupersonic; o.supersonicTime = c.supersonicTime;
+	o.handbrakeVal = c.handbrakeVal; o.isAutoFlipping = c.isAutoFlipping; o.autoFlipTimer = c.autoFlipTimer; o.autoFlipTorqueScale = c.autoFlipTorqueScale;
+	o.worldContact.hasContact = c.worldContactHas; o.worldContact.contactNormal = to_vec(c.worldContactNormal);
+	o.carContact.otherCarID = c.carContactOtherID; o.carContact.cooldownTimer = c.carContactCooldown;
+	o.isDemoed = c.isDemoed; o.demoRespawnTimer = c.demoRespawnTimer;
+	o.ballHitInfo.isValid = c.bhValid; o.ballHitInfo.relativePosOnBall = to_vec(c.bhRelPos); o.ballHitInfo.ballPos = to_vec(c.bhBallPos);
+	o.ballHitInfo.extraHitVel = to_vec(c.bhExtraVel); o.ballHitInfo.tickCountWhenHit = c.bhTickHit; o.ballHitInfo.tickCountWhenExtraImpulseApplied = c.bhTickExtra;
+	ctrl_to_api(c.lastControls, o.lastControls);
+}
+// Car::SetState (Car.cpp:23-36)
+RSB_HD void car_from_api(const RsbCarState& s, CarS& c) {
+	c.rb.pos = from_vec(s.pos) * UU_TO_BT;
+	c.rb.basis = rotmat_to_basis(s.rotMat);
+	c.rb.vel = from_vec(s.vel) * UU_TO_BT;
+	c.rb.angvel = from_vec(s.angVel);
+	c.velImpulseCache = v3zero();
+	c.tickCountSinceUpdate = 0;
+	c.isOnGround = s.isOnGround != 0;
+	for (int i = 0; i < 4; i++) c.wheelsWithContact[i] = s.wheelsWithContact[i] != 0;
+	c.hasJumped = s.hasJumped != 0; c.hasDoubleJumped = s.hasDoubleJumped != 0; c.hasFlipped = s.hasFlipped != 0;
+	c.flipRelTorque = from_vec(s.flipRelTorque);
+	c.jumpTime = s.jumpTime; c.flipTime = s.flipTime; c.isFlipping = s.isFlipping != 0; c.isJumping = s.isJumping != 0;
+	c.airTime = s.airTime; c.airTimeSinceJump = s.airTimeSinceJump; c.boost = s.boost; c.timeSinceBoosted = s.timeSinceBoosted;
+	c.isBoosting = s.isBoosting != 0; c.boostingTime = s.boostingTime; c.isSupersonic = s.isSupersonic != 0; c.supersonicTime = s.supersonicTime;
+	c.handbrakeVal = s.handbrakeVal; c.isAutoFlipping = s.isAutoFlipping != 0; c.autoFlipTimer = s.autoFlipTimer; c.autoFlipTorqueScale = s.autoFlipTorqueScale;
+	c.worldContactHas = s.worldContact.hasContact != 0; c.worldContactNormal = from_vec(s.worldContact.contactNormal);
+	c.carContactOtherID = s.carContact.otherCarID; c.carContactCooldown = s.carContact.cooldownTimer;
+	c.isDemoed = s.isDemoed != 0; c.demoRespawnTimer = s.demoRespawnTimer;
+	c.bhValid = s.ballHitInfo.isValid != 0; c.bhRelPos = from_vec(s.ballHitInfo.relativePosOnBall); c.bhBallPos = from_vec(s.ballHitInfo.ballPos);
+	c.bhExtraVel = from_vec(s.ballHitInfo.extraHitVel); c.bhTickHit = s.ballHitInfo.tickCountWhenHit; c.bhTickExtra = s.ballHitInfo.tickCountWhenExtraImpulseApplied;
+	ctrl_from_api(s.lastControls, c.lastControls);
+}
+// Ball::GetState / SetState (Ball.cpp:27-51)
+RSB_HD void ball_to_api(const BallS& b, RsbBallState& o) {
+	unsigned char* raw = (unsigned char*)&o;
+	for (size_t i = 0; i < sizeof(RsbBallState); i++) raw[i] = 0;
+	o.pos = to_vec(b.rb.pos * BT_TO_UU);
+	basis_to_rotmat(b.rb.basis, o.rotMat);
+	o.vel = to_vec(b.rb.vel * BT_TO_UU);
+	o.angVel = to_vec(b.rb.angvel);
+	o.tickCountSinceUpdate = b.tickCountSinceUpdate;
+	o.hsInfo.yTargetDir = b.hsYTargetDir; o.hsInfo.curTargetSpeed = b.hsCurTargetSpeed; o.hsInfo.timeSinceHit = b.hsTimeSinceHit;
+	o.dsInfo.chargeLevel = 1;
+}
+RSB_HD void ball_from_api(const RsbBallState& s, BallS& b) {
+	b.rb.pos = from_vec(s.pos) * UU_TO_BT;
+	b.rb.basis = rotmat_to_basis(s.rotMat);
+	b.rb.vel = from_vec(s.vel) * UU_TO_BT;
+	b.rb.angvel = from_vec(s.angVel);
+	b.hsYTargetDir = s.hsInfo.yTargetDir; b.hsCurTargetSpeed = s.hsInfo.curTargetSpeed; b.hsTimeSinceHit = s.hsInfo.timeSinceHit;
+	b.velImpulseCache = v3zero();
+	b.tickCountSinceUpdate = 0;
+}
+
+// ------------------------------------------------------------------ kernels
+#ifndef RSB_HOSTCHECK
+#define KERNEL_1D(i, n) int i = blockIdx.x * blockDim.x + threadIdx.x; if (i >= (n)) return;
+#define LAUNCH_1D(kern, n, b, ...) do { int _ln = (n); if (_ln > 0) { kern<<<(_ln + 127) / 128, 128, 0, (b)->stream>>>(__VA_ARGS__); CUDA_OK(cudaGetLastError()); } } while (0)
+#else
+static thread_local int g_hostIdx = 0;
+#define KERNEL_1D(i, n) int i = g_hostIdx; if (i >= (n)) return;
+#define LAUNCH_1D(kern, n, b, ...) do { int _ln = (n); for (g_hostIdx = 0; g_hostIdx < _ln; g_hostIdx++) kern(__VA_ARGS__); } while (0)
+#endif
+
+constexpr int WARPS_PER_BLOCK = 4;
+
+// The hot kernel: one warp per arena, n_ticks ticks per launch.
+RSB_GLOBAL void
+#ifndef RSB_HOSTCHECK
+__launch_bounds__(WARPS_PER_BLOCK * 32)
+#endif
+arena_step_kernel(ArenaS* S, ArenaW* W, const BatchParams* P, const Scene* sc, EventSink ev, int nArenas, int nTicks, const CtrlS* ctrlSeq, int nCtrl) {
+#ifndef RSB_HOSTCHECK
+	const int arena = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+	if (arena >= nArenas) return;
+	Ctx cx; cx.lane = threadIdx.x & 31; cx.nlanes = 32;
+#else
+	const int arena = g_hostIdx;
+	if (arena >= nArenas) return;
+	Ctx cx; cx.lane = 0; cx.nlanes = 1;
+#endif
+	cx.s = S + arena; cx.w = W + arena; cx.p = P; cx.sc = sc; cx.ev = ev; cx.arena = arena;
+	const int nCars = P->nCars;
+	for (int t = 0; t < nTicks; t++) {
+		if (ctrlSeq) {
+			int ct = t < nCtrl ? t : nCtrl - 1;
+			const CtrlS* src = ctrlSeq + ((size_t)ct * nArenas + arena) * nCars;
+			RSB_FOR_LANES(ci, nCars) cx.s->cars[ci].controls = src[ci];
+			RSB_SYNC();
+		}
+		arena_tick(cx);
+	}
+}
+
+RSB_GLOBAL void set_controls_kernel(ArenaS* S, const RsbCarControls* in, int nArenas, int nCars) {
+	KERNEL_1D(i, nArenas * nCars);
+	ctrl_from_api(in[i], S[i / nCars].cars[i % nCars].controls);
+}
+RSB_GLOBAL void get_car_states_kernel(const ArenaS* S, RsbCarState* out, int nArenas, int nCars) {
+	KERNEL_1D(i, nArenas * nCars);
+	car_to_api(S[i / nCars].cars[i % nCars], out[i]);
+}
+RSB_GLOBAL void set_car_states_kernel(ArenaS* S, const uint32_t* ai, const uint32_t* ci, const RsbCarState* in, int n) {
+	KERNEL_1D(i, n);
+	car_from_api(in[i], S[ai[i]].cars[ci[i]]);
+}
+RSB_GLOBAL void get_ball_states_kernel(const ArenaS* S, RsbBallState* out, int nArenas) {
+	KERNEL_1D(i, nArenas);
+	ball_to_api(S[i].ball, out[i]);
+}
+RSB_GLOBAL void set_ball_states_kernel(ArenaS* S, const uint32_t* ai, const RsbBallState* in, int n) {
+	KERNEL_1D(i, n);
+	ball_from_api(in[i], S[ai[i]].ball);
+}
+RSB_GLOBAL void get_pad_states_kernel(const ArenaS* S, RsbBoostPadState* out, int nArenas, int nPads) {
+	KERNEL_1D(i, nArenas * nPads);
+	const PadS& p = S[i / nPads].pads[i % nPads];
+	RsbBoostPadState o; o.isActive = p.isActive; o._pad[0] = o._pad[1] = o._pad[2] = 0; o.cooldown = p.cooldown; o.prevLockedCarID = p.prevLockedCarID;
+	out[i] = o;
+}
+RSB_GLOBAL void set_pad_states_kernel(ArenaS* S, const uint32_t* ai, const RsbBoostPadState* in, int n, int nPads) {
+	KERNEL_1D(i, n * nPads);
+	PadS& p = S[ai[i / nPads]].pads[i % nPads];
+	p.isActive = in[i].isActive != 0; p.cooldown = in[i].cooldown; p.prevLockedCarID = in[i].prevLockedCarID;
+}
+RSB_GLOBAL void get_misc_kernel(const ArenaS* S, const BatchParams* P, const Scene* sc, uint64_t* ticks, uint8_t* scored, uint32_t* errs, int nArenas) {
+	KERNEL_1D(i, nArenas);
+	if (ticks) ticks[i] = S[i].tickCount;
+	if (errs) errs[i] = S[i].errorFlags;
+	if (scored) { Ctx cx; cx.s = (ArenaS*)&S[i]; cx.w = nullptr; cx.p = P; cx.sc = sc; cx.arena = i; cx.lane = 0; cx.nlanes = 1; cx.ev.buf = nullptr; scored[i] = is_ball_scored(cx) ? 1 : 0; }
+}
+RSB_GLOBAL void get_car_internals_kernel(const ArenaS* S, RsbCarInternal* out, int nArenas, int nCars) {
+	KERNEL_1D(i, nArenas * nCars);
+	const CarS& c = S[i / nCars].cars[i % nCars];
+	RsbCarInternal o;
+	for (int k = 0; k < 4; k++) { o.steerAngle[k] = c.wSteer[k]; o.engineForce[k] = c.wEngine[k]; o.brake[k] = c.wBrake[k]; o.latFriction[k] = c.wLatFriction[k]; o.longFriction[k] = c.wLongFriction[k]; o.extraPushback[k] = c.wExtraPushback[k]; }
+	o.velocityImpulseCache[0] = c.velImpulseCache.x; o.velocityImpulseCache[1] = c.velImpulseCache.y; o.velocityImpulseCache[2] = c.velImpulseCache.z; o.velocityImpulseCache[3] = 0.f;
+	out[i] = o;
+}
+RSB_GLOBAL void set_car_internals_kernel(ArenaS* S, const uint32_t* ai, const uint32_t* ci, const RsbCarInternal* in, int n) {
+	KERNEL_1D(i, n);
+	CarS& c = S[ai[i]].cars[ci[i]];
+	const RsbCarInternal& o = in[i];
+	for (int k = 0; k < 4; k++) { c.wSteer[k] = o.steerAngle[k]; c.wEngine[k] = o.engineForce[k]; c.wBrake[k] = o.brake[k]; c.wLatFriction[k] = o.latFriction[k]; c.wLongFriction[k] = o.longFriction[k]; c.wExtraPushback[k] = o.extraPushback[k]; }
+	c.velImpulseCache = V3(o.velocityImpulseCache[0], o.velocityImpulseCache[1], o.velocityImpulseCache[2]);
+}
+RSB_GLOBAL void get_ball_internals_kernel(const ArenaS* S, RsbBallInternal* out, int nArenas) {
+	KERNEL_1D(i, nArenas);
+	RsbBallInternal o; memset(&o, 0, sizeof(o));
+	o.velocityImpulseCache[0] = S[i].ball.velImpulseCache.x; o.velocityImpulseCache[1] = S[i].ball.velImpulseCache.y; o.velocityImpulseCache[2] = S[i].ball.velImpulseCache.z;
+	o.groundStickApplied = S[i].ball.groundStickApplied;
+	out[i] = o;
+}
+RSB_GLOBAL void set_ball_internals_kernel(ArenaS* S, const uint32_t* ai, const RsbBallInternal* in, int n) {
+	KERNEL_1D(i, n);
+	BallS& b = S[ai[i]].ball;
+	b.velImpulseCache = V3(in[i].velocityImpulseCache[0], in[i].velocityImpulseCache[1], in[i].velocityImpulseCache[2]);
+	b.groundStickApplied = in[i].groundStickApplied != 0;
+}
+RSB_GLOBAL void get_obs_kernel(const ArenaS* S, float* out, int nArenas, int nCars) {
+	KERNEL_1D(i, nArenas);
+	float* o = out + (size_t)i * (9 + 17 * nCars);
+	const BallS& b = S[i].ball;
+	V3 p = b.rb.pos * BT_TO_UU, v = b.rb.vel * BT_TO_UU;
+	o[0] = p.x; o[1] = p.y; o[2] = p.z; o[3] = v.x; o[4] = v.y; o[5] = v.z; o[6] = b.rb.angvel.x; o[7] = b.rb.angvel.y; o[8] = b.rb.angvel.z;
+	for (int c = 0; c < nCars; c++) {
+		const CarS& car = S[i].cars[c];
+		float* q = o + 9 + 17 * c;
+		V3 cp = car.rb.pos * BT_TO_UU, cv = car.rb.vel * BT_TO_UU, f = car.rb.basis.col(0), u = car.rb.basis.col(2);
+		q[0] = cp.x; q[1] = cp.y; q[2] = cp.z; q[3] = f.x; q[4] = f.y; q[5] = f.z; q[6] = u.x; q[7] = u.y; q[8] = u.z;
+		q[9] = cv.x; q[10] = cv.y; q[11] = cv.z; q[12] = car.rb.angvel.x; q[13] = car.rb.angvel.y; q[14] = car.rb.angvel.z; q[15] = car.boost;
+		bool hasFlipOrJump = car.isOnGround || (!car.hasFlipped && !car.hasDoubleJumped && car.airTimeSinceJump < K::DOUBLEJUMP_MAX_DELAY);
+		q[16] = (float)((car.isOnGround ? 1 : 0) | (car.isDemoed ? 2 : 0) | (car.isSupersonic ? 4 : 0) | (hasFlipOrJump ? 8 : 0));
+	}
+}
+RSB_GLOBAL void seed_rng_kernel(ArenaS* S, uint32_t arena, uint32_t seed) {
+	KERNEL_1D(i, 1);
+	S[arena].rng = minstd_seed(seed);
+}
+RSB_GLOBAL void fill_controls_kernel(CtrlS* out, int nArenas, int nCars, int nTicks, uint32_t tick0, uint64_t seed) {
+	KERNEL_1D(i, nArenas * nCars);
+	int arena = i / nCars, car = i % nCars;
+	RsbInputSched s; rsb_inp_init(&s);
+	for (uint32_t t = 0; t < tick0 + (uint32_t)nTicks; t++) {
+		rsb_inp_update(&s, seed, (uint32_t)arena, (uint32_t)car, t);
+		if (t >= tick0) {
+			CtrlS c; c.throttle = s.throttle; c.steer = s.steer; c.pitch = s.pitch; c.yaw = s.yaw; c.roll = s.roll;
+			c.jump = s.jump; c.boost = s.boost; c.handbrake = s.handbrake; c._pad = 0;
+			out[((size_t)(t - tick0) * nArenas + arena) * nCars + car] = c;
+		}
+	}
+}
+
+// Arena::ResetToRandomKickoff (Arena.cpp:113-223) on device, one thread per listed arena.
+struct KickoffTables { K::SpawnPos spawn[5]; K::SpawnPos respawn[4]; int locationAmount; };
+RSB_HD uint32_t minstd_uniform(uint32_t& x, uint32_t range) {
+	// std::uniform_int_distribution<size_t>(0, range-1) on minstd_rand0 (libstdc++ downscaling path)
+	const uint64_t urngrange = 2147483646ull - 1ull;  // max - min
+	const uint64_t scaling = urngrange / range;
+	const uint64_t past = range * scaling;
+	uint64_t ret;
+	do { ret = (uint64_t)minstd_next(x) - 1ull; } while (ret >= past);
+	return (uint32_t)(ret / scaling);
+}
+RSB_GLOBAL void reset_kickoff_kernel(ArenaS* S, const BatchParams* P, const Scene* sc, const uint32_t* ai, const int32_t* seeds, int n, KickoffTables kt) {
+	KERNEL_1D(i, n);
+	const int arena = ai ? (int)ai[i] : i;
+	ArenaS& A = S[arena];
+	const int seed = seeds[i];
+	uint32_t localRng = minstd_seed((uint32_t)seed);
+	uint32_t& rng = (seed == -1) ? A.rng : localRng;
+	int order[5] = {0, 1, 2, 3, 4};
+	const int L = kt.locationAmount;
+	// std::shuffle(first, first+L, g) (libstdc++ bits/stl_algo.h: pairwise draws when range*range fits)
+	{
+		const uint64_t urngrange = 2147483646ull - 1ull;
+		const uint64_t urange = (uint64_t)L;
+		if (urngrange / urange >= urange) {
+			int it = 1;
+			if ((urange % 2) == 0) { uint32_t j = minstd_uniform(rng, 2); int t = order[it]; order[it] = order[j]; order[j] = t; it++; }
+			while (it < L) {
+				const uint32_t swap_range = (uint32_t)it + 1;
+				uint32_t x = minstd_uniform(rng, swap_range * (swap_range + 1));
+				uint32_t p0 = x / (swap_range + 1), p1 = x % (swap_range + 1);
+				int t = order[it]; order[it] = order[p0]; order[p0] = t; it++;
+				t = order[it]; order[it] = order[p1]; order[p1] = t; it++;
+			}
+		} else {
+			for (int it = 1; it < L; it++) { uint32_t j = minstd_uniform(rng, (uint32_t)it + 1); int t = order[it]; order[it] = order[j]; order[j] = t; }
+		}
+	}
+	int nBlue = 0, nOrange = 0;
+	int blue[MAX_CARS], orange[MAX_CARS];
+	for (int c = 0; c < P->nCars; c++) { if (P->team[c] == 0) blue[nBlue++] = c; else orange[nOrange++] = c; }
+	int numAtRespawn[4] = {0, 0, 0, 0};
+	int amount = nBlue > nOrange ? nBlue : nOrange;
+	for (int k = 0; k < amount; k++) {
+		K::SpawnPos sp;
+		if (k < L) {
+			int idx = order[k] < L - 1 ? order[k] : L - 1;
+			sp = kt.spawn[idx];
+		} else {
+			int ridx = (k - L) % L;
+			sp = kt.respawn[ridx];
+			sp.y += 250.f * numAtRespawn[ridx];
+			numAtRespawn[ridx]++;
+		}
+		for (int team = 0; team < 2; team++) {
+			bool isBlue = team == 0;
+			int cnt = isBlue ? nBlue : nOrange;
+			if (k >= cnt) continue;
+			CarS& c = A.cars[isBlue ? blue[k] : orange[k]];
+			car_reset_state(c, P->mut.carSpawnBoostAmount);
+			V3 pos(sp.x, sp.y, K::CAR_SPAWN_REST_Z);
+			float yaw = sp.yaw;
+			if (!isBlue) { pos = pos * V3(-1.f, -1.f, 1.f); yaw = (float)((double)yaw + 3.14159265358979323846); }
+			c.rb.pos = pos * UU_TO_BT;
+			c.rb.basis = basis_from_ypr(yaw, 0.f, 0.f);
+			c.rb.vel = v3zero(); c.rb.angvel = v3zero();
+			c.isOnGround = 1;
+		}
+	}
+	BallS& b = A.ball;
+	b.rb.basis = m3identity(); b.rb.angvel = v3zero();
+	V3 bpos(0.f, 0.f, K::BALL_REST_Z), bvel(0.f, 0.f, 0.f);
+	b.hsYTargetDir = 0.f; b.hsCurTargetSpeed = K::HS_INITIAL_TARGET_SPEED; b.hsTimeSinceHit = 0.f;
+	if (P->mode == HEATSEEKER) {
+		int nextRand = (int)minstd_next(rng);
+		V3 scale(1.f, (nextRand % 2) ? 1.f : -1.f, 1.f);
+		bpos = V3(-1000, -2220, 92.75f) * scale;
+		bvel = V3(0, -65, 650) * scale;
+	} else if (P->mode == SNOWDAY) {
+		bvel.z = kEps;
+	}
+	b.rb.pos = bpos * UU_TO_BT; b.rb.vel = bvel * UU_TO_BT;
+	b.velImpulseCache = v3zero(); b.tickCountSinceUpdate = 0;
+	for (int p = 0; p < P->nPads; p++) { A.pads[p].isActive = 1; A.pads[p].cooldown = 0.f; A.pads[p].prevLockedCarID = 0; }
+	(void)sc;
+}
+
+// ------------------------------------------------------------------ parameter setup (host)
+static void fill_mut(const RsbMutatorConfig& m, MutD& o) {
+	o.gravity = V3(m.gravity.x, m.gravity.y, m.gravity.z);
+	o.carMass = m.carMass; o.carWorldFriction = m.carWorldFriction; o.carWorldRestitution = m.carWorldRestitution;
+	o.ballMass = m.ballMass; o.ballMaxSpeed = m.ballMaxSpeed; o.ballDrag = m.ballDrag; o.ballWorldFriction = m.ballWorldFriction; o.ballWorldRestitution = m.ballWorldRestitution;
+	o.jumpAccel = m.jumpAccel; o.jumpImmediateForce = m.jumpImmediateForce; o.boostAccelGround = m.boostAccelGround; o.boostAccelAir = m.boostAccelAir; o.boostUsedPerSecond = m.boostUsedPerSecond;
+	o.respawnDelay = m.respawnDelay; o.bumpCooldownTime = m.bumpCooldownTime; o.boostPadCooldown_Big = m.boostPadCooldown_Big; o.boostPadCooldown_Small = m.boostPadCooldown_Small; o.carSpawnBoostAmount = m.carSpawnBoostAmount;
+	o.ballHitExtraForceScale = m.ballHitExtraForceScale; o.bumpForceScale = m.bumpForceScale; o.ballRadius = m.ballRadius;
+	o.rechargeBoostPerSecond = m.rechargeBoostPerSecond; o.rechargeBoostDelay = m.rechargeBoostDelay; o.goalBaseThresholdY = m.goalBaseThresholdY;
+	o.unlimitedFlips = m.unlimitedFlips; o.unlimitedDoubleJumps = m.unlimitedDoubleJumps; o.rechargeBoostEnabled = m.rechargeBoostEnabled; o.demoMode = m.demoMode; o.enableTeamDemos = m.enableTeamDemos;
+}
+
+// MutatorConfig(GameMode) (MutatorConfig.cpp:5-40)
+static void default_mutator(int mode, RsbMutatorConfig& m) {
+	memset(&m, 0, sizeof(m));
+	m.gravity.x = 0; m.gravity.y = 0; m.gravity.z = K::GRAVITY_Z;
+	m.carMass = K::CAR_MASS_BT; m.carWorldFriction = 0.3f; m.carWorldRestitution = 0.3f;
+	m.ballMaxSpeed = 6000.f; m.ballDrag = 0.03f;
+	m.jumpAccel = 4375.f / 3.f; m.jumpImmediateForce = 875.f / 3.f;
+	m.boostAccelGround = 2975 / 3.f; m.boostAccelAir = 3175 / 3.f; m.boostUsedPerSecond = K::BOOST_MAX / 3;
+	m.respawnDelay = 3.f; m.bumpCooldownTime = 0.25f; m.boostPadCooldown_Big = 10; m.boostPadCooldown_Small = 4;
+	m.carSpawnBoostAmount = K::BOOST_MAX / 3;
+	m.ballHitExtraForceScale = 1; m.bumpForceScale = 1;
+	m.rechargeBoostPerSecond = 10; m.rechargeBoostDelay = 0.25f;
+	m.demoMode = RSB_DEMO_NORMAL; m.enableTeamDemos = 0; m.goalBaseThresholdY = 5124.25f;
+	switch (mode) {
+	case HOOPS: m.ballRadius = 96.3831f; break;
+	case SNOWDAY: m.ballRadius = K::PUCK_RADIUS; break;
+	default: m.ballRadius = 91.25f;
+	}
+	if (mode == SNOWDAY) { m.ballWorldFriction = 0.1f; m.ballWorldRestitution = 0.3f; m.ballMass = 50; }
+	else { m.ballWorldFriction = 0.35f; m.ballWorldRestitution = 0.6f; m.ballMass = K::BALL_MASS_BT; }
+	if (mode == HEATSEEKER) { m.carSpawnBoostAmount = 100; m.boostUsedPerSecond = 0; }
+	else if (mode == DROPSHOT) { m.carSpawnBoostAmount = 100; m.rechargeBoostEnabled = 1; }
+}
+
+// Car::_BulletSetup (Car.cpp:195-292)
+static void fill_car_cfg(const RsbCarConfig& c, CarCfgD& o) {
+	V3 size(c.hitboxSize.x, c.hitboxSize.y, c.hitboxSize.z);
+	o.hitboxHalf = (size * UU_TO_BT) / 2.f;
+	const float defMargin = 0.04f;
+	o.hitboxImplicit = o.hitboxHalf - V3(defMargin, defMargin, defMargin);
+	float minDim = fminf_(fminf_(o.hitboxHalf.x, o.hitboxHalf.y), o.hitboxHalf.z);
+	// btVector3::minAxis picks the axis; value is the same
+	float safeMargin = 0.1f * minDim;
+	o.hitboxMargin = (safeMargin < defMargin) ? safeMargin : defMargin;
+	o.hitboxOffset = V3(c.hitboxPosOffset.x, c.hitboxPosOffset.y, c.hitboxPosOffset.z) * UU_TO_BT;
+	// btBoxShape::calculateLocalInertia on half extents with margin
+	V3 he = o.hitboxImplicit + V3(o.hitboxMargin, o.hitboxMargin, o.hitboxMargin);
+	float lx = 2.f * he.x, ly = 2.f * he.y, lz = 2.f * he.z;
+	const float mass = K::CAR_MASS_BT;
+	V3 inertia(mass / 12.0f * (ly * ly + lz * lz), mass / 12.0f * (lx * lx + lz * lz), mass / 12.0f * (lx * lx + ly * ly));
+	o.invInertiaLocal = V3(inertia.x != 0.f ? 1.f / inertia.x : 0.f, inertia.y != 0.f ? 1.f / inertia.y : 0.f, inertia.z != 0.f ? 1.f / inertia.z : 0.f);
+	for (int i = 0; i < 4; i++) {
+		bool front = i < 2, left = (i % 2) != 0;
+		const RsbWheelPairConfig& wp = front ? c.frontWheels : c.backWheels;
+		V3 off(wp.connectionPointOffset.x, wp.connectionPointOffset.y, wp.connectionPointOffset.z);
+		if (left) off.y *= -1.f;
+		float rest = wp.suspensionRestLength;
+		rest -= K::MAX_SUSPENSION_TRAVEL;
+		o.wheelConn[i] = off * UU_TO_BT;
+		o.suspRest[i] = rest * UU_TO_BT;
+		o.wheelRadius[i] = wp.wheelRadius * UU_TO_BT;
+		o.forceScale[i] = front ? K::SUSPENSION_FORCE_SCALE_FRONT : K::SUSPENSION_FORCE_SCALE_BACK;
+	}
+	o.dodgeDeadzone = c.dodgeDeadzone;
+	o.threeWheels = c.threeWheels;
+}
+
+static const float LOCS_SMALL_SOCCAR[28][3] = {{0, -4240, 70}, {-1792, -4184, 70}, {1792, -4184, 70}, {-940, -3308, 70}, {940, -3308, 70}, {0, -2816, 70}, {-3584, -2484, 70}, {3584, -2484, 70}, {-1788, -2300, 70}, {1788, -2300, 70}, {-2048, -1036, 70}, {0, -1024, 70}, {2048, -1036, 70}, {-1024, 0, 70}, {1024, 0, 70}, {-2048, 1036, 70}, {0, 1024, 70}, {2048, 1036, 70}, {-1788, 2300, 70}, {1788, 2300, 70}, {-3584, 2484, 70}, {3584, 2484, 70}, {0, 2816, 70}, {-940, 3308, 70}, {940, 3308, 70}, {-1792, 4184, 70}, {1792, 4184, 70}, {0, 4240, 70}};
+static const float LOCS_BIG_SOCCAR[6][3] = {{-3584, 0, 73}, {3584, 0, 73}, {-3072, 4096, 73}, {3072, 4096, 73}, {-3072, -4096, 73}, {3072, -4096, 73}};
+static const float LOCS_SMALL_HOOPS[14][3] = {{1536, -1024, 64}, {-1280, -2304, 64}, {0, -2816, 64}, {-1536, -1024, 64}, {1280, -2304, 64}, {-512, 512, 64}, {-1536, 1024, 64}, {1536, 1024, 64}, {1280, 2304, 64}, {0, 2816, 64}, {512, 512, 64}, {512, -512, 64}, {-512, -512, 64}, {-1280, 2304, 64}};
+static const float LOCS_BIG_HOOPS[6][3] = {{-2176, 2944, 72}, {2176, -2944, 72}, {-2176, -2944, 72}, {-2432, 0, 72}, {2432, 0, 72}, {2175.99f, 2944, 72}};
+
+// Arena ctor pad setup (Arena.cpp:498-534), BoostPad::_Setup (BoostPad.cpp:37-49), BoostPadGrid::Add
+static void fill_pads(int mode, BatchParams& P) {
+	for (int i = 0; i < 80; i++) P.padGrid[i] = -1;
+	P.nPads = 0;
+	if (mode == THE_VOID || mode == DROPSHOT) return;
+	bool hoops = mode == HOOPS;
+	int nSmall = hoops ? 14 : 28;
+	P.nPads = 6 + nSmall;
+	for (int i = 0; i < P.nPads; i++) {
+		bool big = i < 6;
+		const float* p = hoops ? (big ? LOCS_BIG_HOOPS[i] : LOCS_SMALL_HOOPS[i - 6]) : (big ? LOCS_BIG_SOCCAR[i] : LOCS_SMALL_SOCCAR[i - 6]);
+		PadCfgD& d = P.pads[i];
+		V3 posUU(p[0], p[1], p[2]);
+		d.posBT = posUU * UU_TO_BT;
+		d.isBig = big;
+		float boxRad = (big ? K::PAD_BOX_RAD_BIG : K::PAD_BOX_RAD_SMALL) * UU_TO_BT;
+		d.boxMin = d.posBT - V3(boxRad, boxRad, 0.f);
+		d.boxMax = d.posBT + V3(boxRad, boxRad, K::PAD_BOX_HEIGHT * UU_TO_BT);
+		d.cylRadBT = (big ? K::PAD_CYL_RAD_BIG : K::PAD_CYL_RAD_SMALL) * UU_TO_BT;
+		int ix = (int)(posUU.x / 1024 + 4), iy = (int)(posUU.y / 1024 + 5);
+		if (ix < 0 || ix >= 8 || iy < 0 || iy >= 10 || P.padGrid[ix * 10 + iy] != -1) throw std::runtime_error("BoostPadGrid::Add(): pad cell collision");
+		P.padGrid[ix * 10 + iy] = i;
+	}
+}
+
+// Ball::_BulletSetup / MakeBallCollisionShape (Ball.cpp:53-115)
+static void fill_ball(int mode, BatchParams& P) {
+	const MutD& m = P.mut;
+	P.ballInvMass = 1.0f / m.ballMass;
+	P.ballMass = 1.0f / P.ballInvMass;  // btRigidBody::getMass()
+	P.ballIsSphere = mode != SNOWDAY;
+	P.ballNoRot = P.ballIsSphere ? 1 : 0;  // ArenaConfig::noBallRot default true, spheres only
+	P.ballRadiusBT = m.ballRadius * UU_TO_BT;
+	V3 inertia;
+	if (P.ballIsSphere) {
+		float elem = 0.4f * m.ballMass * P.ballRadiusBT * P.ballRadiusBT;
+		inertia = V3(elem, elem, elem);
+		P.puckLocalAabbMin = P.puckLocalAabbMax = v3zero();
+	} else {
+		float angStep = (float)((3.14159265358979323846 * 2) / 20.0);
+		float curAng = 0.f;
+		for (int i = 0; i < 20; i++) {
+			V3 pt(cosf(curAng) * m.ballRadius * UU_TO_BT, sinf(curAng) * m.ballRadius * UU_TO_BT, K::PUCK_HEIGHT / 2 * UU_TO_BT);
+			P.puckPts[2 * i] = pt;
+			pt.z *= -1.f;
+			P.puckPts[2 * i + 1] = pt;
+			curAng += angStep;
+		}
+		// btPolyhedralConvexAabbCachingShape::recalcLocalAabb: support (with margin) along +-axes
+		Convex hull; hull.kind = SH_HULL; hull.margin = 0.04f; hull.pts = P.puckPts; hull.npts = PUCK_POINTS; hull.he = v3zero();
+		const V3 dirs[6] = {V3(1, 0, 0), V3(0, 1, 0), V3(0, 0, 1), V3(-1, 0, 0), V3(0, -1, 0), V3(0, 0, -1)};
+		V3 sup[6];
+		for (int i = 0; i < 6; i++) sup[i] = support_no_margin(hull, dirs[i]);
+		for (int i = 0; i < 3; i++) {
+			P.puckLocalAabbMax.set(i, sup[i][i] + hull.margin);
+			P.puckLocalAabbMin.set(i, sup[i + 3][i] - hull.margin);
+		}
+		// btPolyhedralConvexShape::calculateLocalInertia (AABB box approximation incl. margin)
+		float margin = hull.margin;
+		V3 amin, amax;
+		transform_aabb_mm(P.puckLocalAabbMin, P.puckLocalAabbMax, margin, m3identity(), v3zero(), amin, amax);
+		V3 halfExtents = (amax - amin) * 0.5f;
+		float lx = 2.f * (halfExtents.x + margin), ly = 2.f * (halfExtents.y + margin), lz = 2.f * (halfExtents.z + margin);
+		float x2 = lx * lx, y2 = ly * ly, z2 = lz * lz;
+		float scaledmass = m.ballMass * 0.08333333f;
+		inertia = scaledmass * V3(y2 + z2, x2 + z2, x2 + y2);
+	}
+	P.ballInvInertiaLocal = V3(inertia.x != 0.f ? 1.f / inertia.x : 0.f, inertia.y != 0.f ? 1.f / inertia.y : 0.f, inertia.z != 0.f ? 1.f / inertia.z : 0.f);
+}
+
+static const RsbCarConfig& preset_octane() {
+	static RsbCarConfig c;
+	static bool init = false;
+	if (!init) {
+		memset(&c, 0, sizeof(c));
+		c.hitboxSize = RsbVec{120.507f, 86.6994f, 38.6591f, 0}; c.hitboxPosOffset = RsbVec{13.8757f, 0, 20.755f, 0};
+		c.frontWheels.wheelRadius = 12.50f; c.frontWheels.suspensionRestLength = 38.755f; c.frontWheels.connectionPointOffset = RsbVec{51.25f, 25.90f, 20.755f, 0};
+		c.backWheels.wheelRadius = 15.00f; c.backWheels.suspensionRestLength = 37.055f; c.backWheels.connectionPointOffset = RsbVec{-33.75f, 29.50f, 20.755f, 0};
+		c.threeWheels = 0; c.dodgeDeadzone = 0.5f;
+		init = true;
+	}
+	return c;
+}
+
+// scratch layout for the indexed setters: [arena idx | car idx | payload]
+template <class T>
+static void stage_set(RsbBatch* b, const uint32_t* ai, const uint32_t* ci, int n, const T* payload, size_t payloadCount, uint32_t** dai, uint32_t** dci, T** dpl) {
+	size_t idxBytes = ((size_t)n * 4 + 15) & ~(size_t)15;
+	size_t total = 2 * idxBytes + payloadCount * sizeof(T);
+	b->ensure_scratch(total);
+	char* base = (char*)b->dScratch;
+	*dai = (uint32_t*)base; *dci = (uint32_t*)(base + idxBytes); *dpl = (T*)(base + 2 * idxBytes);
+	h2d(*dai, ai, (size_t)n * 4, b->stream);
+	if (ci) h2d(*dci, ci, (size_t)n * 4, b->stream);
+	h2d(*dpl, payload, payloadCount * sizeof(T), b->stream);
+}
+static void check_idx(RsbBatch* b, const uint32_t* ai, const uint32_t* ci, int n) {
+	for (int i = 0; i < n; i++) {
+		if (ai[i] >= (uint32_t)b->hp.nArenas) throw std::runtime_error("arena index out of range");
+		if (ci && ci[i] >= (uint32_t)b->hp.nCars) throw std::runtime_error("car index out of range");
+	}
+}
+
+// ------------------------------------------------------------------ C ABI
+#define API_BEGIN try {
+#define API_END } catch (const std::exception& e) { return fail(e.what()); } return 0;
+
+extern "C" {
+
+const char* rsb_last_error(void) { return g_err.c_str(); }
+
+int rsb_sizeof(const char* n) {
+	std::string s(n);
+	if (s == "RsbVec") return sizeof(RsbVec); if (s == "RsbRotMat") return sizeof(RsbRotMat);
+	if (s == "RsbCarControls") return sizeof(RsbCarControls); if (s == "RsbBallHitInfo") return sizeof(RsbBallHitInfo);
+	if (s == "RsbCarState") return sizeof(RsbCarState); if (s == "RsbBallState") return sizeof(RsbBallState);
+	if (s == "RsbMutatorConfig") return sizeof(RsbMutatorConfig); if (s == "RsbCarConfig") return sizeof(RsbCarConfig);
+	if (s == "RsbBoostPadState") return sizeof(RsbBoostPadState); if (s == "RsbCarInternal") return sizeof(RsbCarInternal);
+	if (s == "RsbBallInternal") return sizeof(RsbBallInternal); if (s == "RsbEvent") return sizeof(RsbEvent);
+	if (s == "ArenaS") return sizeof(ArenaS); if (s == "ArenaW") return sizeof(ArenaW);
+	return -1;
+}
+
+int rsb_init_from_mem(int n_meshes, const int* mesh_modes, const uint8_t* const* mesh_ptrs, const size_t* mesh_sizes) {
+	API_BEGIN
+	std::lock_guard<std::mutex> lk(g_initMutex);
+	if (g_initialized) return 0;  // idempotent like RocketSim::InitFromMem (RocketSim.cpp:98-106)
+	std::map<int, std::vector<MeshHost>> meshes;
+	for (int i = 0; i < n_meshes; i++) meshes[mesh_modes[i]].push_back(build_mesh(mesh_ptrs[i], mesh_sizes[i]));
+	for (auto& kv : meshes) g_sceneHost[kv.first] = build_scene(kv.first, std::move(kv.second));
+	g_sceneHost[THE_VOID] = build_scene(THE_VOID, {});
+	g_initialized = true;
+	API_END
+}
+
+int rsb_batch_create(int device, int game_mode, int n_arenas, int n_cars, const int* teams, const RsbCarConfig* car_configs,
+                     const RsbMutatorConfig* mutator, float tick_rate, uint32_t seed, RsbBatch** out) {
+	API_BEGIN
+	if (!out) throw std::runtime_error("out is NULL");
+	*out = nullptr;
+	if (n_arenas <= 0) throw std::runtime_error("n_arenas must be positive");
+	if (n_cars < 0 || n_cars > MAX_CARS) throw std::runtime_error("n_cars must be in [0, " + std::to_string(MAX_CARS) + "]");
+	if (!(tick_rate >= 15 && tick_rate <= 120)) throw std::runtime_error("Tickrate must be from 15 to 120tps");  // Arena.cpp:419
+	if (game_mode == DROPSHOT) throw std::runtime_error("Dropshot is out of scope of the batched path");
+	{
+		std::lock_guard<std::mutex> lk(g_initMutex);
+		if (!g_initialized) throw std::runtime_error("Cannot create Arena, RocketSim has not been initialized, call rsb_init_from_mem() first");
+		if (g_sceneHost.find(game_mode) == g_sceneHost.end() || (game_mode != THE_VOID && g_sceneHost[game_mode].meshes.empty()))
+			throw std::runtime_error("No arena meshes found for gamemode " + std::to_string(game_mode));  // Arena.cpp:997-1002
+	}
+#ifndef RSB_HOSTCHECK
+	int ndev = 0;
+	if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) throw std::runtime_error("no CUDA device: rocketsim_b200 has no CPU path");
+	if (device < 0 || device >= ndev) throw std::runtime_error("bad CUDA device index");
+	CUDA_OK(cudaSetDevice(device));
+#endif
+	RsbBatch* b = new RsbBatch();
+	b->device = device;
+	BatchParams& P = b->hp;
+	memset(&P, 0, sizeof(P));
+	P.mode = game_mode; P.nCars = n_cars; P.nArenas = n_arenas;
+	P.dt = 1 / tick_rate;
+	RsbMutatorConfig mc;
+	if (mutator) mc = *mutator; else default_mutator(game_mode, mc);
+	fill_mut(mc, P.mut);
+	P.gravityBT = P.mut.gravity * UU_TO_BT;
+	fill_ball(game_mode, P);
+	for (int i = 0; i < n_cars; i++) {
+		fill_car_cfg(car_configs ? car_configs[i] : preset_octane(), P.carCfg[i]);
+		P.team[i] = teams ? teams[i] : (i < (n_cars + 1) / 2 ? 0 : 1);
+	}
+	fill_pads(game_mode, P);
+	b->dScene = get_scene_dev(device, game_mode)->dScene;
+	const SceneHost& sh = get_scene_dev(device, game_mode)->host;
+	b->dP = (BatchParams*)dev_alloc(sizeof(BatchParams));
+	h2d(b->dP, &P, sizeof(P), 0);
+	b->dS = (ArenaS*)dev_alloc(sizeof(ArenaS) * (size_t)n_arenas);
+	b->dW = (ArenaW*)dev_alloc(sizeof(ArenaW) * (size_t)n_arenas);
+	b->eventCap = (uint32_t)std::max(4096, n_arenas * 4);
+	b->dEvents = (EventSink::Ev*)dev_alloc(sizeof(EventSink::Ev) * b->eventCap);
+	b->dEventCount = (uint32_t*)dev_alloc(sizeof(uint32_t));
+	b->dCtrl = (CtrlS*)dev_alloc(sizeof(CtrlS) * (size_t)n_arenas * std::max(1, n_cars));
+
+	// initial arena record: Arena ctor + AddCar/Respawn (Arena.cpp:50-62, 416-540)
+	std::vector<ArenaS> init((size_t)n_arenas);
+	ArenaW tmpW; memset(&tmpW, 0, sizeof(tmpW));
+	Scene hsc; memset(&hsc, 0, sizeof(hsc));
+	hsc.gridMin = sh.gridMin; hsc.gridMax = sh.gridMax; hsc.cellSize = sh.cellSize; hsc.cellsX = sh.cellsX; hsc.cellsY = sh.cellsY; hsc.cellsZ = sh.cellsZ;
+	for (int a = 0; a < n_arenas; a++) {
+		ArenaS& A = init[a];
+		memset(&A, 0, sizeof(A));
+		A.rng = minstd_seed(seed + (uint32_t)a);
+		A.ball.rb.pos = V3(0, 0, K::BALL_REST_Z) * UU_TO_BT;  // ball->SetState(BallState())
+		A.ball.rb.basis = m3identity();
+		A.ball.hsCurTargetSpeed = K::HS_INITIAL_TARGET_SPEED;
+		for (int p = 0; p < P.nPads; p++) { A.pads[p].isActive = 1; }
+		Ctx cx; cx.s = &A; cx.w = &tmpW; cx.p = &P; cx.sc = &hsc; cx.arena = a; cx.lane = 0; cx.nlanes = 1; cx.ev.buf = nullptr;
+		for (int c = 0; c < n_cars; c++) {
+			tmpW.body[c + 1].invInertiaLocal = P.carCfg[c].invInertiaLocal;
+			car_respawn(cx, c);  // AddCar -> Respawn(gameMode, -1, carSpawnBoostAmount)
+		}
+		// broadphase proxies are created from the body transforms at construction time:
+		// ball at (0,0,radius), cars at the origin (Ball.cpp:92-93, Car.cpp:211-215)
+		for (int bidx = 0; bidx <= n_cars; bidx++) {
+			V3 mn, mx;
+			V3 org = (bidx == 0) ? V3(0, 0, P.mut.ballRadius * UU_TO_BT) : v3zero();
+			body_shape_aabb(cx, bidx, m3identity(), org, mn, mx);
+			int i, j, k;
+			A.cellIdx[bidx] = grid_cell_of(hsc, mn, i, j, k);
+			A.cellStamp[bidx] = (uint32_t)bidx + 1;
+		}
+		A.stampCounter = (uint32_t)n_cars + 2;
+	}
+	h2d(b->dS, init.data(), sizeof(ArenaS) * (size_t)n_arenas, 0);
+#ifndef RSB_HOSTCHECK
+	CUDA_OK(cudaDeviceSynchronize());
+#endif
+	*out = b;
+	API_END
+}
+
+int rsb_batch_destroy(RsbBatch* b) {
+	API_BEGIN
+	if (!b) return 0;
+	set_device(b);
+#ifndef RSB_HOSTCHECK
+	cudaDeviceSynchronize();
+#endif
+	dev_free(b->dP); dev_free(b->dS); dev_free(b->dW); dev_free(b->dEvents); dev_free(b->dEventCount); dev_free(b->dCtrl); dev_free(b->dScratch);
+	delete b;
+	API_END
+}
+
+int rsb_batch_info(RsbBatch* b, int* na, int* nc, int* np, int* mode) {
+	if (!b) return fail("null batch");
+	if (na) *na = b->hp.nArenas; if (nc) *nc = b->hp.nCars; if (np) *np = b->hp.nPads; if (mode) *mode = b->hp.mode;
+	return 0;
+}
+
+int rsb_set_stream(RsbBatch* b, void* s) {
+	if (!b) return fail("null batch");
+#ifndef RSB_HOSTCHECK
+	b->stream = (cudaStream_t)s;
+#else
+	(void)s;
+#endif
+	return 0;
+}
+
+static EventSink sink_of(RsbBatch* b) { EventSink e; e.buf = b->dEvents; e.count = b->dEventCount; e.cap = b->eventCap; return e; }
+
+static void launch_step(RsbBatch* b, int n_ticks, const CtrlS* seq, int nCtrl) {
+	const BatchParams& P = b->hp;
+#ifndef RSB_HOSTCHECK
+	int blocks = (P.nArenas + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
+	arena_step_kernel<<<blocks, WARPS_PER_BLOCK * 32, 0, b->stream>>>(b->dS, b->dW, b->dP, b->dScene, sink_of(b), P.nArenas, n_ticks, seq, nCtrl);
+	CUDA_OK(cudaGetLastError());
+#else
+	for (g_hostIdx = 0; g_hostIdx < P.nArenas; g_hostIdx++) arena_step_kernel(b->dS, b->dW, b->dP, b->dScene, sink_of(b), P.nArenas, n_ticks, seq, nCtrl);
+#endif
+}
+
+int rsb_set_controls(RsbBatch* b, const RsbCarControls* controls) {
+	API_BEGIN
+	set_device(b);
+	size_t n = (size_t)b->hp.nArenas * b->hp.nCars;
+	if (n == 0) return 0;
+	b->ensure_scratch(n * sizeof(RsbCarControls));
+	h2d(b->dScratch, controls, n * sizeof(RsbCarControls), b->stream);
+	LAUNCH_1D(set_controls_kernel, (int)n, b, b->dS, (const RsbCarControls*)b->dScratch, b->hp.nArenas, b->hp.nCars);
+	API_END
+}
+int rsb_set_controls_device(RsbBatch* b, const void* d) {
+	API_BEGIN
+	set_device(b);
+	size_t n = (size_t)b->hp.nArenas * b->hp.nCars;
+	LAUNCH_1D(set_controls_kernel, (int)n, b, b->dS, (const RsbCarControls*)d, b->hp.nArenas, b->hp.nCars);
+	API_END
+}
+int rsb_step(RsbBatch* b, int n_ticks) {
+	API_BEGIN
+	set_device(b);
+	if (n_ticks > 0) launch_step(b, n_ticks, nullptr, 0);
+	API_END
+}
+int rsb_step_with_controls_device(RsbBatch* b, const void* d_seq, int n_ticks) {
+	API_BEGIN
+	set_device(b);
+	if (n_ticks > 0) launch_step(b, n_ticks, (const CtrlS*)d_seq, n_ticks);
+	API_END
+}
+int rsb_sync(RsbBatch* b) {
+	API_BEGIN
+	set_device(b);
+#ifndef RSB_HOSTCHECK
+	CUDA_OK(cudaStreamSynchronize(b->stream));
+#endif
+	API_END
+}
+
+#define GET_IMPL(kern, T, count, ...) \
+	API_BEGIN set_device(b); size_t _n = (count); if (_n == 0) return 0; b->ensure_scratch(_n * sizeof(T)); \
+	LAUNCH_1D(kern, (int)_n, b, __VA_ARGS__); d2h(out, b->dScratch, _n * sizeof(T), b->stream); API_END
+
+int rsb_get_car_states(RsbBatch* b, RsbCarState* out) { GET_IMPL(get_car_states_kernel, RsbCarState, (size_t)b->hp.nArenas * b->hp.nCars, b->dS, (RsbCarState*)b->dScratch, b->hp.nArenas, b->hp.nCars) }
+int rsb_get_ball_states(RsbBatch* b, RsbBallState* out) { GET_IMPL(get_ball_states_kernel, RsbBallState, (size_t)b->hp.nArenas, b->dS, (RsbBallState*)b->dScratch, b->hp.nArenas) }
+int rsb_get_pad_states(RsbBatch* b, RsbBoostPadState* out) { GET_IMPL(get_pad_states_kernel, RsbBoostPadState, (size_t)b->hp.nArenas * b->hp.nPads, b->dS, (RsbBoostPadState*)b->dScratch, b->hp.nArenas, b->hp.nPads) }
+int rsb_get_car_internals(RsbBatch* b, RsbCarInternal* out) { GET_IMPL(get_car_internals_kernel, RsbCarInternal, (size_t)b->hp.nArenas * b->hp.nCars, b->dS, (RsbCarInternal*)b->dScratch, b->hp.nArenas, b->hp.nCars) }
+int rsb_get_ball_internals(RsbBatch* b, RsbBallInternal* out) { GET_IMPL(get_ball_internals_kernel, RsbBallInternal, (size_t)b->hp.nArenas, b->dS, (RsbBallInternal*)b->dScratch, b->hp.nArenas) }
+int rsb_observation_floats(RsbBatch* b) { return 9 + 17 * b->hp.nCars; }
+int rsb_get_observations(RsbBatch* b, float* out) {
+	API_BEGIN set_device(b);
+	size_t n = (size_t)b->hp.nArenas * (9 + 17 * b->hp.nCars);
+	b->ensure_scratch(n * 4);
+	LAUNCH_1D(get_obs_kernel, b->hp.nArenas, b, b->dS, (float*)b->dScratch, b->hp.nArenas, b->hp.nCars);
+	d2h(out, b->dScratch, n * 4, b->stream);
+	API_END
+}
+
+static void misc_get(RsbBatch* b, uint64_t* ticks, uint8_t* scored, uint32_t* errs) {
+	set_device(b);
+	int n = b->hp.nArenas;
+	b->ensure_scratch((size_t)n * 16);
+	uint64_t* dt = (uint64_t*)b->dScratch; uint32_t* de = (uint32_t*)((char*)b->dScratch + (size_t)n * 8); uint8_t* ds = (uint8_t*)((char*)b->dScratch + (size_t)n * 12);
+	LAUNCH_1D(get_misc_kernel, n, b, b->dS, b->dP, b->dScene, ticks ? dt : nullptr, scored ? ds : nullptr, errs ? de : nullptr, n);
+	if (ticks) d2h(ticks, dt, (size_t)n * 8, b->stream);
+	if (errs) d2h(errs, de, (size_t)n * 4, b->stream);
+	if (scored) d2h(scored, ds, (size_t)n, b->stream);
+}
+int rsb_get_tick_counts(RsbBatch* b, uint64_t* out) { API_BEGIN misc_get(b, out, nullptr, nullptr); API_END }
+int rsb_is_ball_scored(RsbBatch* b, uint8_t* out) { API_BEGIN misc_get(b, nullptr, out, nullptr); API_END }
+int rsb_get_error_flags(RsbBatch* b, uint32_t* out) { API_BEGIN misc_get(b, nullptr, nullptr, out); API_END }
+
+int rsb_set_car_states(RsbBatch* b, const uint32_t* ai, const uint32_t* ci, int n, const RsbCarState* st) {
+	API_BEGIN set_device(b); if (n <= 0) return 0; check_idx(b, ai, ci, n);
+	uint32_t *dai, *dci; RsbCarState* dp;
+	stage_set(b, ai, ci, n, st, (size_t)n, &dai, &dci, &dp);
+	LAUNCH_1D(set_car_states_kernel, n, b, b->dS, dai, dci, dp, n);
+	API_END
+}
+int rsb_set_ball_states(RsbBatch* b, const uint32_t* ai, int n, const RsbBallState* st) {
+	API_BEGIN set_device(b); if (n <= 0) return 0; check_idx(b, ai, nullptr, n);
+	uint32_t *dai, *dci; RsbBallState* dp;
+	stage_set(b, ai, (const uint32_t*)nullptr, n, st, (size_t)n, &dai, &dci, &dp);
+	LAUNCH_1D(set_ball_states_kernel, n, b, b->dS, dai, dp, n);
+	API_END
+}
+int rsb_set_pad_states(RsbBatch* b, const uint32_t* ai, int n, const RsbBoostPadState* st) {
+	API_BEGIN set_device(b); if (n <= 0 || b->hp.nPads == 0) return 0; check_idx(b, ai, nullptr, n);
+	uint32_t *dai, *dci; RsbBoostPadState* dp;
+	stage_set(b, ai, (const uint32_t*)nullptr, n, st, (size_t)n * b->hp.nPads, &dai, &dci, &dp);
+	LAUNCH_1D(set_pad_states_kernel, n * b->hp.nPads, b, b->dS, dai, dp, n, b->hp.nPads);
+	API_END
+}
+int rsb_set_car_internals(RsbBatch* b, const uint32_t* ai, const uint32_t* ci, int n, const RsbCarInternal* in) {
+	API_BEGIN set_device(b); if (n <= 0) return 0; check_idx(b, ai, ci, n);
+	uint32_t *dai, *dci; RsbCarInternal* dp;
+	stage_set(b, ai, ci, n, in, (size_t)n, &dai, &dci, &dp);
+	LAUNCH_1D(set_car_internals_kernel, n, b, b->dS, dai, dci, dp, n);
+	API_END
+}
+int rsb_set_ball_internals(RsbBatch* b, const uint32_t* ai, int n, const RsbBallInternal* in) {
+	API_BEGIN set_device(b); if (n <= 0) return 0; check_idx(b, ai, nullptr, n);
+	uint32_t *dai, *dci; RsbBallInternal* dp;
+	stage_set(b, ai, (const uint32_t*)nullptr, n, in, (size_t)n, &dai, &dci, &dp);
+	LAUNCH_1D(set_ball_internals_kernel, n, b, b->dS, dai, dp, n);
+	API_END
+}
+int rsb_seed_rng(RsbBatch* b, uint32_t arena, uint32_t seed) {
+	API_BEGIN set_device(b);
+	if (arena >= (uint32_t)b->hp.nArenas) throw std::runtime_error("arena index out of range");
+	LAUNCH_1D(seed_rng_kernel, 1, b, b->dS, arena, seed);
+	API_END
+}
+
+int rsb_get_events(RsbBatch* b, RsbEvent* out, int cap, int* n_out) {
+	API_BEGIN set_device(b);
+	uint32_t cnt = 0;
+	d2h(&cnt, b->dEventCount, 4, b->stream);
+	uint32_t n = std::min(cnt, b->eventCap);
+	std::vector<EventSink::Ev> ev(n);
+	if (n) d2h(ev.data(), b->dEvents, n * sizeof(EventSink::Ev), b->stream);
+	uint32_t zero = 0;
+	h2d(b->dEventCount, &zero, 4, b->stream);
+	std::stable_sort(ev.begin(), ev.end(), [](const EventSink::Ev& x, const EventSink::Ev& y) { return x.arena != y.arena ? x.arena < y.arena : x.tick < y.tick; });
+	int m = (int)std::min<uint32_t>(n, (uint32_t)std::max(cap, 0));
+	for (int i = 0; i < m; i++) { out[i].arena = ev[i].arena; out[i].type = ev[i].type; out[i].a = ev[i].a; out[i].b = ev[i].b; out[i].tick = ev[i].tick; }
+	if (n_out) *n_out = m;
+	API_END
+}
+
+int rsb_reset_to_random_kickoff(RsbBatch* b, const uint32_t* ai, int n, const int32_t* seeds) {
+	API_BEGIN set_device(b);
+	if (!ai) n = b->hp.nArenas; else check_idx(b, ai, nullptr, n);
+	if (n <= 0) return 0;
+	const float P4 = (float)(3.14159265358979323846 / 4), P2 = (float)(3.14159265358979323846 / 2);
+	KickoffTables kt;
+	const int mode = b->hp.mode;
+	const K::SpawnPos soccar[5] = {{-2048, -2560, P4 * 1}, {2048, -2560, P4 * 3}, {-256, -3840, P4 * 2}, {256, -3840, P4 * 2}, {0, -4608, P4 * 2}};
+	const K::SpawnPos hoops[5] = {{-1536, -3072, P4 * 2}, {1536, -3072, P4 * 2}, {-256, -2816, P4 * 2}, {256, -2816, P4 * 2}, {0, -3200, P4 * 2}};
+	const K::SpawnPos heat[5] = {{-1000, -4620, P2}, {1000, -4620, P2}, {-2000, -4620, P2}, {2000, -4620, P2}, {0, 0, 0}};
+	const K::SpawnPos* sp = mode == HOOPS ? hoops : (mode == HEATSEEKER ? heat : soccar);
+	for (int i = 0; i < 5; i++) kt.spawn[i] = sp[i];
+	for (int i = 0; i < 4; i++) kt.respawn[i] = respawn_slot(mode == HOOPS, i);
+	kt.locationAmount = mode == HEATSEEKER ? 4 : 5;
+	size_t idxBytes = ((size_t)n * 4 + 15) & ~(size_t)15;
+	b->ensure_scratch(2 * idxBytes);
+	uint32_t* dai = (uint32_t*)b->dScratch; int32_t* dseed = (int32_t*)((char*)b->dScratch + idxBytes);
+	if (ai) h2d(dai, ai, (size_t)n * 4, b->stream);
+	h2d(dseed, seeds, (size_t)n * 4, b->stream);
+	LAUNCH_1D(reset_kickoff_kernel, n, b, b->dS, b->dP, b->dScene, ai ? dai : nullptr, dseed, n, kt);
+	API_END
+}
+
+int rsb_bench_fill_controls_device(RsbBatch* b, void* d_seq, int n_ticks, uint32_t tick0, uint64_t seed) {
+	API_BEGIN set_device(b);
+	LAUNCH_1D(fill_controls_kernel, b->hp.nArenas * b->hp.nCars, b, (CtrlS*)d_seq, b->hp.nArenas, b->hp.nCars, n_ticks, tick0, seed);
+	API_END
+}
+
+// ---- scene introspection ----
+int rsb_scene_num_meshes(int mode) { auto it = g_sceneHost.find(mode); return it == g_sceneHost.end() ? 0 : (int)it->second.meshes.size(); }
+int rsb_scene_counts(int mode, int mesh, int* c) {
+	auto it = g_sceneHost.find(mode);
+	if (it == g_sceneHost.end() || mesh < 0 || mesh >= (int)it->second.meshes.size()) return fail("no such mesh");
+	const MeshHost& m = it->second.meshes[mesh];
+	c[0] = (int)m.nodes.size(); c[1] = (int)m.hdrs.size(); c[2] = m.nTris(); c[3] = m.nVerts();
+	int ni = 0; for (const TriInfo& t : m.info) if (t.flags >= 0) ni++;
+	c[4] = ni;
+	return 0;
+}
+int rsb_scene_dump(int mode, int mesh, void* nodes, void* headers, float* quant9, void* triinfo) {
+	auto it = g_sceneHost.find(mode);
+	if (it == g_sceneHost.end() || mesh < 0 || mesh >= (int)it->second.meshes.size()) return fail("no such mesh");
+	const MeshHost& m = it->second.meshes[mesh];
+	memcpy(nodes, m.nodes.data(), m.nodes.size() * 16);
+	for (size_t i = 0; i < m.hdrs.size(); i++) {
+		char* p = (char*)headers + 20 * i;
+		memcpy(p, m.hdrs[i].qmin, 6); memcpy(p + 6, m.hdrs[i].qmax, 6); memcpy(p + 12, &m.hdrs[i].root, 4); memcpy(p + 16, &m.hdrs[i].size, 4);
+	}
+	uint16_t q0[3] = {0, 0, 0}, q1[3] = {1, 1, 1};
+	V3 mn = scene_detail::unquantize(m, q0), one = scene_detail::unquantize(m, q1);
+	quant9[0] = mn.x; quant9[1] = mn.y; quant9[2] = mn.z; quant9[3] = quant9[4] = quant9[5] = 0.f;
+	quant9[6] = one.x - mn.x; quant9[7] = one.y - mn.y; quant9[8] = one.z - mn.z;
+	memcpy(triinfo, m.info.data(), m.info.size() * 16);
+	return 0;
+}
+int rsb_scene_cells(int mode, int32_t* cell_start, int cap_start, uint8_t* statics, int cap_statics, int* n_cells, int* n_entries) {
+	auto it = g_sceneHost.find(mode);
+	if (it == g_sceneHost.end()) return fail("no such scene");
+	const SceneHost& s = it->second;
+	if (n_cells) *n_cells = (int)s.cellStart.size() - 1;
+	if (n_entries) *n_entries = (int)s.cellStatics.size();
+	if (cell_start && cap_start >= (int)s.cellStart.size()) memcpy(cell_start, s.cellStart.data(), s.cellStart.size() * 4);
+	if (statics && cap_statics >= (int)s.cellStatics.size()) memcpy(statics, s.cellStatics.data(), s.cellStatics.size());
+	return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,461 @@
+// rsb_scene.h -- HOST-side, load-time half of the hot path: turns the .cmf collision meshes of a
+// game mode into the flattened static scene the kernels traverse:
+//   .cmf parse                          reference src/CollisionMeshFile/CollisionMeshFile.cpp:11-61
+//   quantised BVH (node order exact)    bt/BulletCollision/CollisionShapes/btOptimizedBvh.cpp:28-180,
+//                                       bt/BulletCollision/BroadphaseCollision/btQuantizedBvh.cpp:76-305
+//   internal-edge (triangle info) map   bt/BulletCollision/CollisionDispatch/btInternalEdgeUtility.cpp:47-353
+//   arena planes                        reference src/Sim/Arena/Arena.cpp:1030-1068
+//   broadphase static cell lists        bt/BulletCollision/BroadphaseCollision/btRSBroadphase.cpp:43-182
+// The reference rebuilds the cell lists for every Arena (18k brute-force mesh scans each);
+// here they are built once per game mode and shared by every arena of every batch.
+#pragma once
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "sim/rsb_state.h"
+#include "sim/rsb_ray.h"
+
+namespace rsb {
+
+struct MeshHost {
+	std::vector<int32_t> tris;     // 3 per triangle
+	std::vector<float> verts;      // 4 per vertex
+	std::vector<BvhNode> nodes;
+	std::vector<SubtreeHdr> hdrs;
+	std::vector<TriInfo> info;
+	V3 bvhMin, bvhMax, bvhQuant;
+	V3 aabbMin, aabbMax;
+	int group = 0, mask = 0;
+	int nTris() const { return (int)tris.size() / 3; }
+	int nVerts() const { return (int)verts.size() / 4; }
+};
+
+struct SceneHost {
+	int mode = THE_VOID;
+	std::vector<MeshHost> meshes;
+	std::vector<PlaneD> planes;
+	V3 gridMin, gridMax;
+	float cellSize = 0.f;
+	int cellsX = 0, cellsY = 0, cellsZ = 0;
+	std::vector<int32_t> cellStart;
+	std::vector<uint8_t> cellStatics;
+};
+
+namespace scene_detail {
+
+inline void quantize(const MeshHost& m, const V3& p, int isMax, uint16_t out[3]) {
+	V3 v = (p - m.bvhMin) * m.bvhQuant;
+	if (isMax) {
+		out[0] = (uint16_t)(((uint16_t)(v.x + 1.f)) | 1);
+		out[1] = (uint16_t)(((uint16_t)(v.y + 1.f)) | 1);
+		out[2] = (uint16_t)(((uint16_t)(v.z + 1.f)) | 1);
+	} else {
+		out[0] = (uint16_t)(((uint16_t)(v.x)) & 0xfffe);
+		out[1] = (uint16_t)(((uint16_t)(v.y)) & 0xfffe);
+		out[2] = (uint16_t)(((uint16_t)(v.z)) & 0xfffe);
+	}
+}
+inline V3 unquantize(const MeshHost& m, const uint16_t q[3]) {
+	return V3((float)q[0] / m.bvhQuant.x, (float)q[1] / m.bvhQuant.y, (float)q[2] / m.bvhQuant.z) + m.bvhMin;
+}
+inline V3 vdivv(const V3& a, const V3& b) { return V3(a.x / b.x, a.y / b.y, a.z / b.z); }
+
+// btQuantizedBvh::setQuantizationValues (three-pass refinement)
+inline void set_quantization(MeshHost& m, const V3& aabbMin, const V3& aabbMax) {
+	const V3 clampValue(1.f, 1.f, 1.f);
+	const V3 k(65533.0f, 65533.0f, 65533.0f);
+	m.bvhMin = aabbMin - clampValue;
+	m.bvhMax = aabbMax + clampValue;
+	V3 aabbSize = m.bvhMax - m.bvhMin;
+	m.bvhQuant = vdivv(k, aabbSize);
+	uint16_t q[3];
+	quantize(m, m.bvhMin, 0, q);
+	V3 v = unquantize(m, q);
+	m.bvhMin = vmin(m.bvhMin, v - clampValue);
+	aabbSize = m.bvhMax - m.bvhMin;
+	m.bvhQuant = vdivv(k, aabbSize);
+	quantize(m, m.bvhMax, 1, q);
+	v = unquantize(m, q);
+	m.bvhMax = vmax(m.bvhMax, v + clampValue);
+	aabbSize = m.bvhMax - m.bvhMin;
+	m.bvhQuant = vdivv(k, aabbSize);
+}
+
+inline void tri_verts(const MeshHost& m, int t, V3 out[3]) {
+	for (int j = 0; j < 3; j++) {
+		const float* p = &m.verts[4 * m.tris[3 * t + j]];
+		out[j] = V3(p[0], p[1], p[2]);
+	}
+}
+
+struct Builder {
+	MeshHost& m;
+	std::vector<BvhNode> leaves;
+	int cur = 0;
+	explicit Builder(MeshHost& mm) : m(mm) {}
+
+	V3 leaf_min(int i) const { return unquantize(m, leaves[i].qmin); }
+	V3 leaf_max(int i) const { return unquantize(m, leaves[i].qmax); }
+
+	int calc_splitting_axis(int start, int end) {
+		V3 means(0, 0, 0), variance(0, 0, 0);
+		int n = end - start;
+		for (int i = start; i < end; i++) means += 0.5f * (leaf_max(i) + leaf_min(i));
+		means *= (1.f / (float)n);
+		for (int i = start; i < end; i++) {
+			V3 center = 0.5f * (leaf_max(i) + leaf_min(i));
+			V3 d = center - means;
+			d = d * d;
+			variance += d;
+		}
+		variance *= (1.f / ((float)n - 1));
+		// btVector3::maxAxis
+		return variance.x < variance.y ? (variance.y < variance.z ? 2 : 1) : (variance.x < variance.z ? 2 : 0);
+	}
+	int sort_and_calc_splitting_index(int start, int end, int axis) {
+		int splitIndex = start;
+		int n = end - start;
+		V3 means(0, 0, 0);
+		for (int i = start; i < end; i++) means += 0.5f * (leaf_max(i) + leaf_min(i));
+		means *= (1.f / (float)n);
+		float splitValue = means[axis];
+		for (int i = start; i < end; i++) {
+			V3 center = 0.5f * (leaf_max(i) + leaf_min(i));
+			if (center[axis] > splitValue) {
+				BvhNode t = leaves[i]; leaves[i] = leaves[splitIndex]; leaves[splitIndex] = t;
+				splitIndex++;
+			}
+		}
+		int rangeBalanced = n / 3;
+		bool unbalanced = ((splitIndex <= (start + rangeBalanced)) || (splitIndex >= (end - 1 - rangeBalanced)));
+		if (unbalanced) splitIndex = start + (n >> 1);
+		return splitIndex;
+	}
+	void update_subtree_headers(int left, int right) {
+		const BvhNode& l = m.nodes[left];
+		int lsz = l.idx >= 0 ? 1 : -l.idx;
+		const BvhNode& r = m.nodes[right];
+		int rsz = r.idx >= 0 ? 1 : -r.idx;
+		if (lsz * 16 <= 2048) { SubtreeHdr h; memcpy(h.qmin, l.qmin, 6); memcpy(h.qmax, l.qmax, 6); h.root = left; h.size = lsz; m.hdrs.push_back(h); }
+		if (rsz * 16 <= 2048) { SubtreeHdr h; memcpy(h.qmin, r.qmin, 6); memcpy(h.qmax, r.qmax, 6); h.root = right; h.size = rsz; m.hdrs.push_back(h); }
+	}
+	void build_tree(int start, int end) {
+		int n = end - start;
+		int curIndex = cur;
+		if (n == 1) { m.nodes[cur] = leaves[start]; cur++; return; }
+		int axis = calc_splitting_axis(start, end);
+		int split = sort_and_calc_splitting_index(start, end, axis);
+		int internal = cur;
+		quantize(m, m.bvhMax, 0, m.nodes[cur].qmin);
+		quantize(m, m.bvhMin, 1, m.nodes[cur].qmax);
+		for (int i = start; i < end; i++) {
+			uint16_t qmn[3], qmx[3];
+			quantize(m, leaf_min(i), 0, qmn);
+			quantize(m, leaf_max(i), 1, qmx);
+			for (int k = 0; k < 3; k++) {
+				if (m.nodes[cur].qmin[k] > qmn[k]) m.nodes[cur].qmin[k] = qmn[k];
+				if (m.nodes[cur].qmax[k] < qmx[k]) m.nodes[cur].qmax[k] = qmx[k];
+			}
+		}
+		cur++;
+		int left = cur;
+		build_tree(start, split);
+		int right = cur;
+		build_tree(split, end);
+		int escape = cur - curIndex;
+		if (escape * 16 > 2048) update_subtree_headers(left, right);
+		m.nodes[internal].idx = -escape;
+	}
+};
+
+// AABB query in report order (subtree headers, stackless walk): calls f(triIndex)
+template <class F>
+inline void bvh_query(const MeshHost& m, const V3& aabbMin, const V3& aabbMax, F&& f) {
+	uint16_t qmin[3], qmax[3];
+	V3 cmin = vmin(vmax(aabbMin, m.bvhMin), m.bvhMax), cmax = vmin(vmax(aabbMax, m.bvhMin), m.bvhMax);
+	quantize(m, cmin, 0, qmin);
+	quantize(m, cmax, 1, qmax);
+	for (const SubtreeHdr& hd : m.hdrs) {
+		if (!quant_overlap(qmin, qmax, hd.qmin, hd.qmax)) continue;
+		int cur = hd.root, end = hd.root + hd.size;
+		while (cur < end) {
+			const BvhNode& nd = m.nodes[cur];
+			bool ov = quant_overlap(qmin, qmax, nd.qmin, nd.qmax);
+			bool leaf = nd.idx >= 0;
+			if (leaf && ov) f(nd.idx & 0x1fffff);
+			if (ov || leaf) cur++; else cur += -nd.idx;
+		}
+	}
+}
+
+inline V3 calc_normal(const V3 t[3]) { return normalized(cross(t[1] - t[0], t[2] - t[0])); }
+inline V3 quat_rotate_h(const Q4& q, const V3& v) {
+	Q4 t = q4(q.w * v.x + q.y * v.z - q.z * v.y, q.w * v.y + q.z * v.x - q.x * v.z, q.w * v.z + q.x * v.y - q.y * v.x, -q.x * v.x - q.y * v.y - q.z * v.z);
+	Q4 qi = q4(-q.x, -q.y, -q.z, q.w);
+	Q4 r = qmul(t, qi);
+	return V3(r.x, r.y, r.z);
+}
+
+// btConnectivityProcessor::processTriangle for (A = triA, B = triB)
+inline void connect(MeshHost& m, int triA, const V3 A[3], int triB) {
+	if (triA == triB) return;
+	V3 B[3];
+	tri_verts(m, triB, B);
+	const float equalVertexThreshold = 0.0001f * 0.0001f;
+	const float planarEpsilon = 0.0001f;
+	int numshared = 0;
+	int sharedA[3] = {-1, -1, -1}, sharedB[3] = {-1, -1, -1};
+	float crossBSqr = len2(cross(B[1] - B[0], B[2] - B[0]));
+	if (crossBSqr < equalVertexThreshold) return;
+	float crossASqr = len2(cross(A[1] - A[0], A[2] - A[0]));
+	if (crossASqr < equalVertexThreshold) return;
+	for (int i = 0; i < 3; i++) {
+		for (int j = 0; j < 3; j++) {
+			if (len2(A[i] - B[j]) < equalVertexThreshold) {
+				sharedA[numshared] = i; sharedB[numshared] = j; numshared++;
+				if (numshared >= 3) return;
+			}
+		}
+		if (numshared >= 3) return;
+	}
+	if (numshared != 2) return;
+	if (sharedA[0] == 0 && sharedA[1] == 2) {
+		sharedA[0] = 2; sharedA[1] = 0;
+		int tmp = sharedB[1]; sharedB[1] = sharedB[0]; sharedB[0] = tmp;
+	}
+	TriInfo& info = m.info[triA];
+	if (info.flags < 0) { info.flags = 0; info.a01 = info.a12 = info.a20 = k2Pi; }
+	int sumvertsA = sharedA[0] + sharedA[1];
+	int otherIndexA = 3 - sumvertsA;
+	V3 edge = A[sharedA[1]] - A[sharedA[0]];
+	int otherIndexB = 3 - (sharedB[0] + sharedB[1]);
+	V3 tB[3] = {B[sharedB[1]], B[sharedB[0]], B[otherIndexB]};
+	V3 normalA = calc_normal(A);
+	V3 normalB = calc_normal(tB);
+	edge = normalized(edge);
+	V3 edgeCrossA = normalized(cross(edge, normalA));
+	{
+		V3 tmp = A[otherIndexA] - A[sharedA[0]];
+		if (dot(edgeCrossA, tmp) < 0.f) edgeCrossA *= -1.f;
+	}
+	V3 edgeCrossB = normalized(cross(edge, normalB));
+	{
+		V3 tmp = B[otherIndexB] - B[sharedB[0]];
+		if (dot(edgeCrossB, tmp) < 0.f) edgeCrossB *= -1.f;
+	}
+	float angle2 = 0.f, ang4 = 0.f;
+	V3 calculatedEdge = cross(edgeCrossA, edgeCrossB);
+	float l2 = len2(calculatedEdge);
+	float correctedAngle = 0.f;
+	bool isConvex = false;
+	if (l2 < planarEpsilon) {
+		angle2 = 0.f; ang4 = 0.f;
+	} else {
+		calculatedEdge = normalized(calculatedEdge);
+		V3 calculatedNormalA = normalized(cross(calculatedEdge, edgeCrossA));
+		angle2 = get_angle(calculatedNormalA, edgeCrossA, edgeCrossB);
+		ang4 = kPi - angle2;
+		float dotA = dot(normalA, edgeCrossB);
+		isConvex = (dotA < 0.f);
+		correctedAngle = isConvex ? ang4 : -ang4;
+	}
+	(void)angle2;
+	switch (sumvertsA) {
+	case 1: {
+		V3 e = A[0] - A[1];
+		V3 computedNormalB = quat_rotate_h(q_axis_angle(e, -correctedAngle), normalA);
+		if (dot(computedNormalB, normalB) < 0.f) info.flags |= 8;
+		info.a01 = -correctedAngle;
+		if (isConvex) info.flags |= 1;
+		break;
+	}
+	case 2: {
+		V3 e = A[2] - A[0];
+		V3 computedNormalB = quat_rotate_h(q_axis_angle(e, -correctedAngle), normalA);
+		if (dot(computedNormalB, normalB) < 0.f) info.flags |= 32;
+		info.a20 = -correctedAngle;
+		if (isConvex) info.flags |= 4;
+		break;
+	}
+	case 3: {
+		V3 e = A[1] - A[2];
+		V3 computedNormalB = quat_rotate_h(q_axis_angle(e, -correctedAngle), normalA);
+		if (dot(computedNormalB, normalB) < 0.f) info.flags |= 16;
+		info.a12 = -correctedAngle;
+		if (isConvex) info.flags |= 2;
+		break;
+	}
+	}
+}
+
+}  // namespace scene_detail
+
+inline MeshHost build_mesh(const uint8_t* data, size_t size) {
+	using namespace scene_detail;
+	if (size < 8) throw std::runtime_error("collision mesh file too small");
+	int32_t nt, nv;
+	memcpy(&nt, data, 4); memcpy(&nv, data + 4, 4);
+	const int MAXC = 1000 * 1000;
+	if (nt <= 0 || nv <= 0 || nt > MAXC || nv > MAXC)
+		throw std::runtime_error("Invalid collision mesh file (bad triangle/vertex count: [" + std::to_string(nt) + ", " + std::to_string(nv) + "])");
+	if (size < 8 + (size_t)nt * 12 + (size_t)nv * 12) throw std::runtime_error("Invalid collision mesh file (input data overflown)");
+	MeshHost m;
+	m.tris.resize((size_t)nt * 3);
+	memcpy(m.tris.data(), data + 8, (size_t)nt * 12);
+	for (int32_t ix : m.tris) if (ix < 0 || ix >= nv) throw std::runtime_error("Invalid collision mesh file (bad triangle vertex index)");
+	m.verts.assign((size_t)nv * 4, 0.f);
+	const uint8_t* vp = data + 8 + (size_t)nt * 12;
+	for (int i = 0; i < nv; i++) memcpy(&m.verts[4 * i], vp + 12 * (size_t)i, 12);
+
+	// local AABB = extremes over triangle vertices (mesh margin 0)
+	V3 mn(kLargeFloat, kLargeFloat, kLargeFloat), mx(-kLargeFloat, -kLargeFloat, -kLargeFloat);
+	// btTriangleMeshShape::recalcLocalAabb: per axis support vertex with maxDot starting at -BT_LARGE_FLOAT
+	for (int t = 0; t < nt; t++) { V3 v[3]; tri_verts(m, t, v); for (int j = 0; j < 3; j++) { mn = vmin(mn, v[j]); mx = vmax(mx, v[j]); } }
+	m.aabbMin = mn; m.aabbMax = mx;
+
+	set_quantization(m, mn, mx);
+	Builder b(m);
+	b.leaves.resize(nt);
+	for (int t = 0; t < nt; t++) {
+		V3 v[3]; tri_verts(m, t, v);
+		V3 amin(kLargeFloat, kLargeFloat, kLargeFloat), amax(-kLargeFloat, -kLargeFloat, -kLargeFloat);
+		for (int j = 0; j < 3; j++) { amin = vmin(amin, v[j]); amax = vmax(amax, v[j]); }
+		const float MIN_DIM = 0.002f, MIN_HALF = 0.001f;
+		if (amax.x - amin.x < MIN_DIM) { amax.x = amax.x + MIN_HALF; amin.x = amin.x - MIN_HALF; }
+		if (amax.y - amin.y < MIN_DIM) { amax.y = amax.y + MIN_HALF; amin.y = amin.y - MIN_HALF; }
+		if (amax.z - amin.z < MIN_DIM) { amax.z = amax.z + MIN_HALF; amin.z = amin.z - MIN_HALF; }
+		quantize(m, amin, 0, b.leaves[t].qmin);
+		quantize(m, amax, 1, b.leaves[t].qmax);
+		b.leaves[t].idx = t;  // partId 0
+	}
+	m.nodes.resize((size_t)2 * nt);
+	memset(m.nodes.data(), 0, m.nodes.size() * sizeof(BvhNode));
+	b.build_tree(0, nt);
+	m.nodes.resize(b.cur);
+	if (m.hdrs.empty()) {
+		SubtreeHdr h; memcpy(h.qmin, m.nodes[0].qmin, 6); memcpy(h.qmax, m.nodes[0].qmax, 6);
+		h.root = 0; h.size = m.nodes[0].idx >= 0 ? 1 : -m.nodes[0].idx;
+		m.hdrs.push_back(h);
+	}
+	// btGenerateInternalEdgeInfo
+	m.info.assign(nt, TriInfo{-1, k2Pi, k2Pi, k2Pi});
+	for (int t = 0; t < nt; t++) {
+		V3 A[3]; tri_verts(m, t, A);
+		V3 amin(kLargeFloat, kLargeFloat, kLargeFloat), amax(-kLargeFloat, -kLargeFloat, -kLargeFloat);
+		for (int j = 0; j < 3; j++) { amin = vmin(amin, A[j]); amax = vmax(amax, A[j]); }
+		bvh_query(m, amin, amax, [&](int tb) { connect(m, t, A, tb); });
+	}
+	return m;
+}
+
+inline PlaneD make_plane(const V3& posUU, const V3& n) {
+	PlaneD p;
+	p.n = n; p.pos = posUU * UU_TO_BT;
+	p.d = dot(n, p.pos);
+	// btStaticPlaneShape::getAabb (single-axis slab, half-infinite behind the plane)
+	p.aabbMin = V3(-kLargeFloat, -kLargeFloat, -kLargeFloat);
+	p.aabbMax = V3(kLargeFloat, kLargeFloat, kLargeFloat);
+	const float OFF = 0.2f;
+	int axis = (n.x != 0.f) ? 0 : ((n.y != 0.f) ? 1 : 2);
+	bool backwards = n[axis] < 0.f;
+	float o = p.pos[axis];
+	p.aabbMin.set(axis, o + (0.f - OFF));
+	p.aabbMax.set(axis, o + (0.f + OFF));
+	if (backwards) p.aabbMax.set(axis, kLargeFloat); else p.aabbMin.set(axis, -kLargeFloat);
+	return p;
+}
+
+inline void grid_indices(const SceneHost& s, const V3& pos, int& i, int& j, int& k) {
+	V3 f = (pos - s.gridMin) / s.cellSize;
+	i = (int)f.x; j = (int)f.y; k = (int)f.z;
+	i = i < 0 ? 0 : (i > s.cellsX - 1 ? s.cellsX - 1 : i);
+	j = j < 0 ? 0 : (j > s.cellsY - 1 ? s.cellsY - 1 : j);
+	k = k < 0 ? 0 : (k > s.cellsZ - 1 ? s.cellsZ - 1 : k);
+}
+
+inline SceneHost build_scene(int mode, std::vector<MeshHost> meshes) {
+	using namespace scene_detail;
+	SceneHost s;
+	s.mode = mode;
+	s.meshes = std::move(meshes);
+	const bool isHoops = mode == HOOPS;
+	if ((int)s.meshes.size() > MAX_MESHES) throw std::runtime_error("too many collision meshes for one game mode");
+	for (MeshHost& m : s.meshes) {
+		bool net = isHoops && m.nVerts() == 505;  // Arena.cpp:1016-1019
+		m.group = net ? FILT_HOOPS_NET : FILT_STATIC;
+		m.mask = net ? FILT_HOOPS_NET : (FILT_ALL ^ FILT_STATIC);
+	}
+	if (mode != THE_VOID) {
+		float extentX = isHoops ? K::ARENA_EXTENT_X_HOOPS : K::ARENA_EXTENT_X;
+		float extentY = isHoops ? K::ARENA_EXTENT_Y_HOOPS : K::ARENA_EXTENT_Y;
+		float height = isHoops ? K::ARENA_HEIGHT_HOOPS : K::ARENA_HEIGHT;
+		s.planes.push_back(make_plane(V3(0, 0, 0), V3(0, 0, 1)));
+		s.planes.push_back(make_plane(V3(0, 0, height), V3(0, 0, -1)));
+		s.planes.push_back(make_plane(V3(-extentX, 0, height / 2), V3(1, 0, 0)));
+		s.planes.push_back(make_plane(V3(extentX, 0, height / 2), V3(-1, 0, 0)));
+		if (isHoops) {
+			s.planes.push_back(make_plane(V3(0, -extentY, height / 2), V3(0, 1, 0)));
+			s.planes.push_back(make_plane(V3(0, extentY, height / 2), V3(0, -1, 0)));
+		}
+	}
+	// btRSBroadphase grid from the default ArenaConfig (ArenaConfig.h:23-41, Arena.cpp:446-458)
+	s.gridMin = V3(-5600, -6000, 0) * UU_TO_BT;
+	s.gridMax = V3(5600, 6000, 2200) * UU_TO_BT;
+	s.cellSize = 370 * UU_TO_BT * 1.f;
+	V3 range = s.gridMax - s.gridMin;
+	auto cl = [](float v) { int c = (int)ceilf(v); return c < 1 ? 1 : c; };
+	s.cellsX = cl(range.x / s.cellSize); s.cellsY = cl(range.y / s.cellSize); s.cellsZ = cl(range.z / s.cellSize);
+	const int total = s.cellsX * s.cellsY * s.cellsZ;
+	std::vector<std::vector<uint8_t>> cells(total);
+	const int nStatics = (int)s.meshes.size() + (int)s.planes.size();
+	const V3 ct(0.02f, 0.02f, 0.02f);
+	for (int o = 0; o < nStatics; o++) {
+		const bool isMesh = o < (int)s.meshes.size();
+		V3 amin, amax;
+		if (isMesh) { amin = s.meshes[o].aabbMin - ct; amax = s.meshes[o].aabbMax + ct; }
+		else { amin = s.planes[o - s.meshes.size()].aabbMin - ct; amax = s.planes[o - s.meshes.size()].aabbMax + ct; }
+		V3 cmax = vmin(amax, s.gridMax);
+		int iMin, jMin, kMin, iMax, jMax, kMax;
+		grid_indices(s, amin, iMin, jMin, kMin);
+		grid_indices(s, cmax, iMax, jMax, kMax);
+		for (int i = iMin; i <= iMax; i++) for (int j = jMin; j <= jMax; j++) for (int k = kMin; k <= kMax; k++) {
+			if (isMesh) {
+				const MeshHost& m = s.meshes[o];
+				V3 cellMin = s.gridMin + V3((float)i, (float)j, (float)k) * s.cellSize;
+				V3 cellMax = cellMin + V3(s.cellSize, s.cellSize, s.cellSize);
+				bool hit = false;
+				for (int t = 0; t < m.nTris() && !hit; t++) {
+					V3 tv[3]; tri_verts(m, t, tv);
+					bool ok = true;
+					const int order[3] = {2, 0, 1};
+					for (int q = 0; q < 3 && ok; q++) {
+						int a = order[q];
+						if (fminf_(fminf_(tv[0][a], tv[1][a]), tv[2][a]) > cellMax[a]) ok = false;
+						else if (fmaxf_(fmaxf_(tv[0][a], tv[1][a]), tv[2][a]) < cellMin[a]) ok = false;
+					}
+					if (ok) hit = true;
+				}
+				if (!hit) continue;
+			}
+			for (int i1 = -1; i1 <= 1; i1++) for (int j1 = -1; j1 <= 1; j1++) for (int k1 = -1; k1 <= 1; k1++) {
+				int ci = i + i1, cj = j + j1, ck = k + k1;
+				if (ci < 0 || cj < 0 || ck < 0 || ci >= s.cellsX || cj >= s.cellsY || ck >= s.cellsZ) continue;
+				auto& cell = cells[ci * s.cellsY * s.cellsZ + cj * s.cellsZ + ck];
+				bool exists = false;
+				for (uint8_t e : cell) if (e == (uint8_t)o) { exists = true; break; }
+				if (!exists) cell.push_back((uint8_t)o);
+			}
+		}
+	}
+	s.cellStart.resize(total + 1);
+	s.cellStart[0] = 0;
+	for (int c = 0; c < total; c++) {
+		s.cellStatics.insert(s.cellStatics.end(), cells[c].begin(), cells[c].end());
+		s.cellStart[c + 1] = (int32_t)s.cellStatics.size();
+	}
+	return s;
+}
+
+}  // namespace rsb

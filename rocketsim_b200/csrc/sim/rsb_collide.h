@@ -1,0 +1,727 @@
+// rsb_collide.h -- per-tick collision detection of one arena: swept AABBs, grid broadphase
+// pairs, narrowphase per pair and the game's contact hooks.  Restates
+//   btCollisionWorld::updateAabbs / updateSingleAabb      bt/BulletCollision/CollisionDispatch/btCollisionWorld.cpp:143-193
+//   btRSBroadphase::setAabb / calculateOverlappingPairs   bt/BulletCollision/BroadphaseCollision/btRSBroadphase.cpp:286-323, 392-468
+//   algorithm table                                       bt/BulletCollision/CollisionDispatch/btDefaultCollisionConfiguration.cpp:265-342
+//   compound / convex-concave / convex-plane / sphere-triangle algorithms (files cited at each function)
+//   btManifoldResult::addContactPoint                     bt/BulletCollision/CollisionDispatch/btManifoldResult.cpp:109-207
+//   btPersistentManifold (4-point cache)                  bt/BulletCollision/NarrowPhaseCollision/btPersistentManifold.cpp:110-329
+//   Arena::_BulletContactAddedCallback and hooks          src/Sim/Arena/Arena.cpp:244-414
+//   btAdjustInternalEdgeContacts                          bt/BulletCollision/CollisionDispatch/btInternalEdgeUtility.cpp:357-798
+#pragma once
+#include "rsb_work.h"
+#include "rsb_ray.h"
+#include "rsb_ball.h"
+#include "rsb_gjk.h"
+
+namespace rsb {
+
+constexpr float kContactBreaking = 0.02f;  // gContactBreakingThreshold
+
+RSB_HD V3 static_origin(const Ctx& cx, int obj) {
+	int k = obj - STATIC_BASE;
+	if (k < cx.sc->nMeshes) return v3zero();
+	return cx.sc->planes[k - cx.sc->nMeshes].pos;
+}
+RSB_HD void static_aabb(const Ctx& cx, int obj, V3& mn, V3& mx) {
+	int k = obj - STATIC_BASE;
+	if (k < cx.sc->nMeshes) { mn = cx.sc->meshes[k].aabbMin; mx = cx.sc->meshes[k].aabbMax; }
+	else { mn = cx.sc->planes[k - cx.sc->nMeshes].aabbMin; mx = cx.sc->planes[k - cx.sc->nMeshes].aabbMax; }
+}
+// broadphase proxy AABB of a static = shape AABB +- gContactBreakingThreshold (updateSingleAabb)
+RSB_HD void static_proxy_aabb(const Ctx& cx, int obj, V3& mn, V3& mx) {
+	static_aabb(cx, obj, mn, mx);
+	const V3 ct(0.02f, 0.02f, 0.02f);
+	mn -= ct; mx += ct;
+}
+
+RSB_HD M3 m3abs(const M3& m) { return M3(vabs(m.r[0]), vabs(m.r[1]), vabs(m.r[2])); }
+
+// btTransformAabb(halfExtents, margin, t) (btAabbUtil2.h:172-180) -- box / hull child AABB
+RSB_HD void transform_aabb_he(const V3& he, float margin, const M3& basis, const V3& origin, V3& mn, V3& mx) {
+	V3 h = he + V3(margin, margin, margin);
+	M3 ab = m3abs(basis);
+	V3 extent(dot(h, ab.r[0]), dot(h, ab.r[1]), dot(h, ab.r[2]));
+	mn = origin - extent; mx = origin + extent;
+}
+// btTransformAabb(localMin, localMax, margin, t) (btAabbUtil2.h:182-196) / btCompoundShape::getAabb
+RSB_HD void transform_aabb_mm(const V3& lmin, const V3& lmax, float margin, const M3& basis, const V3& origin, V3& mn, V3& mx) {
+	V3 lh = 0.5f * (lmax - lmin);
+	lh += V3(margin, margin, margin);
+	V3 lc = 0.5f * (lmax + lmin);
+	M3 ab = m3abs(basis);
+	V3 center = basis * lc + origin;
+	V3 extent(dot(lh, ab.r[0]), dot(lh, ab.r[1]), dot(lh, ab.r[2]));
+	mn = center - extent; mx = center + extent;
+}
+
+// local AABB of the compound = AABB of its single box child at the child offset
+// (btCompoundShape::addChildShape, btCompoundShape.cpp:59-105)
+RSB_HD void compound_local_aabb(const CarCfgD& cfg, V3& lmin, V3& lmax) {
+	transform_aabb_he(cfg.hitboxImplicit, cfg.hitboxMargin, m3identity(), cfg.hitboxOffset, lmin, lmax);
+}
+RSB_HD void compound_aabb(const CarCfgD& cfg, const M3& basis, const V3& origin, V3& mn, V3& mx) {
+	V3 lmin, lmax;
+	compound_local_aabb(cfg, lmin, lmax);
+	transform_aabb_mm(lmin, lmax, 0.f, basis, origin, mn, mx);
+}
+
+RSB_HD void body_shape_aabb(const Ctx& cx, int b, const M3& basis, const V3& origin, V3& mn, V3& mx) {
+	const BatchParams& P = *cx.p;
+	if (b == 0) {
+		if (P.ballIsSphere) {
+			float margin = P.ballRadiusBT + 0.08f;  // btSphereShape::getAabb (btSphereShape.cpp:52-59)
+			V3 e(margin, margin, margin);
+			mn = origin - e; mx = origin + e;
+		} else {
+			transform_aabb_mm(P.puckLocalAabbMin, P.puckLocalAabbMax, 0.04f, basis, origin, mn, mx);
+		}
+	} else {
+		compound_aabb(P.carCfg[b - 1], basis, origin, mn, mx);
+	}
+}
+
+RSB_HD bool aabb_overlap(const V3& min1, const V3& max1, const V3& min2, const V3& max2) {
+	bool overlap = true;
+	overlap = (min1.x > max2.x || max1.x < min2.x) ? false : overlap;
+	overlap = (min1.z > max2.z || max1.z < min2.z) ? false : overlap;
+	overlap = (min1.y > max2.y || max1.y < min2.y) ? false : overlap;
+	return overlap;
+}
+
+// updateSingleAabb for the dynamic bodies + btRSBroadphase::setAabb cell bookkeeping
+RSB_HD void update_aabbs(const Ctx& cx) {
+	const int nb = n_bodies(cx);
+	const V3 ct(kContactBreaking, kContactBreaking, kContactBreaking);
+	for (int b = 0; b < nb; b++) {
+		BodyW& bw = cx.w->body[b];
+		const RigidS& rb = rigid_of(cx, b);
+		V3 mn, mx, mn2, mx2;
+		body_shape_aabb(cx, b, rb.basis, rb.pos, mn, mx);
+		mn -= ct; mx += ct;
+		body_shape_aabb(cx, b, bw.interp.basis, bw.interp.origin, mn2, mx2);
+		mn2 -= ct; mx2 += ct;
+		mn = vmin(mn, mn2); mx = vmax(mx, mx2);
+		bool changed = !(mn.x == bw.aabbMin.x && mn.y == bw.aabbMin.y && mn.z == bw.aabbMin.z && mx.x == bw.aabbMax.x && mx.y == bw.aabbMax.y && mx.z == bw.aabbMax.z);
+		bw.aabbMin = mn; bw.aabbMax = mx;
+		(void)changed;
+		int i, j, k;
+		int newIdx = grid_cell_of(*cx.sc, mn, i, j, k);
+		if (newIdx != cx.s->cellIdx[b]) {
+			cx.s->cellIdx[b] = newIdx;
+			if (nb > 1) cx.s->cellStamp[b] = ++cx.s->stampCounter;
+		}
+	}
+}
+
+RSB_HD void body_filter(const Ctx& cx, int obj, int& group, int& mask) {
+	if (obj >= STATIC_BASE) {
+		int k = obj - STATIC_BASE;
+		if (k < cx.sc->nMeshes) { group = cx.sc->meshes[k].group; mask = cx.sc->meshes[k].mask; }
+		else { group = FILT_STATIC; mask = FILT_ALL ^ FILT_STATIC; }
+	} else if (obj == 0) { group = FILT_DEFAULT | FILT_HOOPS_NET | FILT_DROPSHOT_TILE; mask = FILT_ALL; }
+	else { group = FILT_DEFAULT | FILT_DROPSHOT_FLOOR; mask = FILT_ALL; }
+}
+
+RSB_HD void add_pair(const Ctx& cx, int a, int b) {
+	ArenaW& w = *cx.w;
+	int ga, ma, gb, mb;
+	body_filter(cx, a, ga, ma); body_filter(cx, b, gb, mb);
+	if (!((ga & mb) && (gb & ma))) return;  // needsBroadphaseCollision
+	if (w.nPairs >= MAX_MANIFOLDS) { cx.s->errorFlags |= ERR_MANIFOLD_OVERFLOW; return; }
+	w.pairA[w.nPairs] = a; w.pairB[w.nPairs] = b; w.nPairs++;
+}
+
+// calculateOverlappingPairs: pair list in creation order; (proxy0, proxy1) sorted by handle id
+// (statics first; ball before cars; lower car index first).
+RSB_HD void compute_pairs(const Ctx& cx) {
+	ArenaW& w = *cx.w;
+	const Scene& sc = *cx.sc;
+	const int nb = n_bodies(cx);
+	w.nPairs = 0;
+	for (int b = 0; b < nb; b++) {
+		const BodyW& bw = w.body[b];
+		int cell = cx.s->cellIdx[b];
+		for (int s = sc.cellStart[cell]; s < sc.cellStart[cell + 1]; s++) {
+			int obj = STATIC_BASE + sc.cellStatics[s];
+			V3 mn, mx; static_proxy_aabb(cx, obj, mn, mx);
+			if (aabb_overlap(bw.aabbMin, bw.aabbMax, mn, mx)) add_pair(cx, obj, b);
+		}
+		if (nb > 1) {
+			const int cY = sc.cellsY, cZ = sc.cellsZ;
+			int ci = cell / (cY * cZ), cj = (cell / cZ) % cY, ck = cell % cZ;
+			uint32_t lastStamp = 0; bool first = true;
+			for (int iter = 0; iter < nb; iter++) {
+				int best = -1; uint32_t bestStamp = 0xffffffffu;
+				for (int o = 0; o < nb; o++) {
+					uint32_t st = cx.s->cellStamp[o];
+					if (!first && st <= lastStamp) continue;
+					if (st < bestStamp) { bestStamp = st; best = o; }
+				}
+				if (best < 0) break;
+				first = false; lastStamp = bestStamp;
+				int o = best;
+				if (o == b) continue;
+				int idx = cx.s->cellIdx[o];
+				int oi = idx / (cY * cZ), oj = (idx / cZ) % cY, ok = idx % cZ;
+				if (abs(oi - ci) > 1 || abs(oj - cj) > 1 || abs(ok - ck) > 1) continue;
+				const BodyW& ow = w.body[o];
+				if (!aabb_overlap(bw.aabbMin, bw.aabbMax, ow.aabbMin, ow.aabbMax)) continue;
+				int lo = b < o ? b : o, hi = b < o ? o : b;
+				bool exists = false;
+				for (int k = 0; k < w.nPairs; k++) if (w.pairA[k] == lo && w.pairB[k] == hi) { exists = true; break; }
+				if (!exists) add_pair(cx, lo, hi);
+			}
+		}
+	}
+}
+
+// ------------------------------------------------------------------ manifolds + contact hooks
+RSB_HD float body_angular_motion_disc(const Ctx& cx, int obj) {
+	// btCollisionShape::getAngularMotionDisc (btCollisionShape.cpp:126-158)
+	if (obj >= STATIC_BASE) return kLargeFloat;
+	const BatchParams& P = *cx.p;
+	if (obj == 0 && P.ballIsSphere) return (P.ballRadiusBT + 0.08f) + 0.f;
+	V3 mn, mx;
+	body_shape_aabb(cx, obj, m3identity(), v3zero(), mn, mx);
+	float radius = len(mx - mn) * 0.5f;
+	V3 center = (mn + mx) * 0.5f;
+	return radius + len(center);
+}
+
+RSB_HD int new_manifold(const Ctx& cx, int body0, int body1) {
+	ArenaW& w = *cx.w;
+	if (w.nManifolds >= MAX_MANIFOLDS) { cx.s->errorFlags |= ERR_MANIFOLD_OVERFLOW; return -1; }
+	Manifold& m = w.manifolds[w.nManifolds];
+	m.body0 = body0; m.body1 = body1; m.nPts = 0;
+	float t0 = body_angular_motion_disc(cx, body0) * kContactBreaking;
+	float t1 = body_angular_motion_disc(cx, body1) * kContactBreaking;
+	m.breakingThresh = t0 < t1 ? t0 : t1;
+	m.processingThresh = kLargeFloat;
+	return w.nManifolds++;
+}
+
+RSB_HD Xform obj_xform(const Ctx& cx, int obj) {
+	Xform t;
+	if (obj >= STATIC_BASE) { t.basis = m3identity(); t.origin = static_origin(cx, obj); }
+	else { const RigidS& rb = rigid_of(cx, obj); t.basis = rb.basis; t.origin = rb.pos; }
+	return t;
+}
+
+// sortCachedPoints (btPersistentManifold.cpp:110-189), gContactCalcArea3Points = true
+RSB_HD int sort_cached_points(const Manifold& m, const ContactPt& pt) {
+	int maxPenetrationIndex = -1;
+	float maxPenetration = pt.dist;
+	for (int i = 0; i < 4; i++) if (m.pts[i].dist < maxPenetration) { maxPenetrationIndex = i; maxPenetration = m.pts[i].dist; }
+	float res0 = 0.f, res1 = 0.f, res2 = 0.f, res3 = 0.f;
+	if (maxPenetrationIndex != 0) { V3 a0 = pt.localA - m.pts[1].localA; V3 b0 = m.pts[3].localA - m.pts[2].localA; res0 = len2(cross(a0, b0)); }
+	if (maxPenetrationIndex != 1) { V3 a1 = pt.localA - m.pts[0].localA; V3 b1 = m.pts[3].localA - m.pts[2].localA; res1 = len2(cross(a1, b1)); }
+	if (maxPenetrationIndex != 2) { V3 a2 = pt.localA - m.pts[0].localA; V3 b2 = m.pts[3].localA - m.pts[1].localA; res2 = len2(cross(a2, b2)); }
+	if (maxPenetrationIndex != 3) { V3 a3 = pt.localA - m.pts[0].localA; V3 b3 = m.pts[2].localA - m.pts[1].localA; res3 = len2(cross(a3, b3)); }
+	// btVector4::closestAxis4 = absolute4().maxAxis4(): first index of the maximum
+	float v[4] = {fabsf(res0), fabsf(res1), fabsf(res2), fabsf(res3)};
+	int maxIndex = -1; float maxVal = -kLargeFloat;
+	for (int i = 0; i < 4; i++) if (v[i] > maxVal) { maxIndex = i; maxVal = v[i]; }
+	return maxIndex;
+}
+
+RSB_HD float get_angle(const V3& edgeA, const V3& normalA, const V3& normalB) { return atan2f(dot(normalB, edgeA), dot(normalB, normalA)); }
+RSB_HD V3 quat_rotate(const Q4& q, const V3& v) {  // quatRotate (btQuaternion.h): q * v * q^-1
+	// q * v (quaternion times vector)
+	Q4 t = q4(q.w * v.x + q.y * v.z - q.z * v.y, q.w * v.y + q.z * v.x - q.x * v.z, q.w * v.z + q.x * v.y - q.y * v.x, -q.x * v.x - q.y * v.y - q.z * v.z);
+	Q4 qi = q4(-q.x, -q.y, -q.z, q.w);
+	Q4 r = qmul(t, qi);
+	return V3(r.x, r.y, r.z);
+}
+RSB_HD V3 nearest_point_in_segment(const V3& point, const V3& line0, const V3& line1) {
+	V3 lineDelta = line1 - line0;
+	if (fuzzy_zero(lineDelta)) return line0;
+	float delta = dot(point - line0, lineDelta) / dot(lineDelta, lineDelta);
+	if (delta < 0.f) delta = 0.f; else if (delta > 1.f) delta = 1.f;
+	return line0 + lineDelta * delta;
+}
+RSB_HD bool clamp_normal(const V3& edge, const V3& tri_normal, const V3& localContactNormalOnB, float correctedEdgeAngle, V3& clamped) {
+	V3 edgeCross = normalized(cross(edge, tri_normal));
+	float curAngle = get_angle(edgeCross, tri_normal, localContactNormalOnB);
+	if (correctedEdgeAngle < 0.f) {
+		if (curAngle < correctedEdgeAngle) {
+			float diffAngle = correctedEdgeAngle - curAngle;
+			clamped = m3_from_quat(q_axis_angle(edge, diffAngle)) * localContactNormalOnB;
+			return true;
+		}
+	}
+	if (correctedEdgeAngle >= 0.f) {
+		if (curAngle > correctedEdgeAngle) {
+			float diffAngle = correctedEdgeAngle - curAngle;
+			clamped = m3_from_quat(q_axis_angle(edge, diffAngle)) * localContactNormalOnB;
+			return true;
+		}
+	}
+	return false;
+}
+
+// btAdjustInternalEdgeContacts with normalAdjustFlags = 0; the triangle's mesh sits at the
+// world origin with identity basis, so "local" == world for B.
+RSB_HD void adjust_internal_edge(const Ctx& cx, ContactPt& cp, const MeshD& mesh, int triIndex) {
+	const TriInfo info = mesh.info[triIndex];
+	if (info.flags < 0) return;  // no entry in the triangle info map
+	V3 v0, v1, v2;
+	mesh_triangle(mesh, triIndex, v0, v1, v2);
+	V3 tri_normal = normalized(cross(v1 - v0, v2 - v0));
+	V3 nearest = nearest_point_in_segment(cp.localB, v0, v1);
+	const V3 contact = cp.localB;
+	bool isNearEdge = false;
+	int numConcaveEdgeHits = 0, numConvexEdgeHits = 0;
+	V3 localContactNormalOnB = normalized(transpose(m3identity()) * cp.normalB);
+	const float maxEdgeAngle = k2Pi, edgeDistThresh = 0.1f, convexEps = 0.f;
+	int bestedge = -1;
+	float disttobestedge = kLargeFloat;
+	if (fabsf(info.a01) < maxEdgeAngle) { V3 n = nearest_point_in_segment(cp.localB, v0, v1); float l = len(contact - n); if (l < disttobestedge) { bestedge = 0; disttobestedge = l; } }
+	if (fabsf(info.a12) < maxEdgeAngle) { V3 n = nearest_point_in_segment(cp.localB, v1, v2); float l = len(contact - n); if (l < disttobestedge) { bestedge = 1; disttobestedge = l; } }
+	if (fabsf(info.a20) < maxEdgeAngle) { V3 n = nearest_point_in_segment(cp.localB, v2, v0); float l = len(contact - n); if (l < disttobestedge) { bestedge = 2; disttobestedge = l; } }
+
+	for (int e = 0; e < 3; e++) {
+		float angle = e == 0 ? info.a01 : (e == 1 ? info.a12 : info.a20);
+		V3 ea = e == 0 ? v0 : (e == 1 ? v1 : v2);
+		V3 eb = e == 0 ? v1 : (e == 1 ? v2 : v0);
+		if (e > 0) nearest = nearest_point_in_segment(contact, ea, eb);
+		if (!(fabsf(angle) < maxEdgeAngle)) continue;
+		float l = len(contact - nearest);
+		if (!(l < edgeDistThresh)) continue;
+		if (bestedge != e) continue;
+		V3 edge = ea - eb;
+		isNearEdge = true;
+		if (angle == 0.f) { numConcaveEdgeHits++; continue; }
+		bool isEdgeConvex = (info.flags & (1 << e)) != 0;          // TRI_INFO_VxVy_CONVEX = 1,2,4
+		float swapFactor = isEdgeConvex ? 1.f : -1.f;
+		V3 nA = swapFactor * tri_normal;
+		Q4 orn = q_axis_angle(edge, angle);
+		V3 computedNormalB = quat_rotate(orn, tri_normal);
+		if (info.flags & (8 << e)) computedNormalB *= -1.f;        // TRI_INFO_VxVy_SWAP_NORMALB = 8,16,32
+		V3 nB = swapFactor * computedNormalB;
+		float NdotA = dot(localContactNormalOnB, nA);
+		float NdotB = dot(localContactNormalOnB, nB);
+		bool backFacingNormal = (NdotA < convexEps) && (NdotB < convexEps);
+		if (backFacingNormal) { numConcaveEdgeHits++; continue; }
+		numConvexEdgeHits++;
+		// edges 1 and 2 re-derive the local normal WITHOUT normalising it (shadowed variable in the reference)
+		V3 lcn = (e == 0) ? localContactNormalOnB : (transpose(m3identity()) * cp.normalB);
+		V3 clamped;
+		bool isClamped = clamp_normal(edge, swapFactor * tri_normal, lcn, angle, clamped);
+		if (isClamped) {
+			if (dot(clamped, 1.f * tri_normal) > 0.f) {
+				V3 newNormal = m3identity() * clamped;
+				cp.normalB = newNormal;
+				cp.posB = cp.posA - cp.normalB * cp.dist;
+				cp.localB = vmul(cp.posB - v3zero(), m3identity());
+			}
+		}
+	}
+	(void)numConvexEdgeHits;
+	if (isNearEdge) {
+		if (numConcaveEdgeHits > 0) {
+			V3 newNormal = tri_normal * 1.f;
+			float d = dot(newNormal, localContactNormalOnB);
+			if (d < 0.f) return;
+			cp.normalB = m3identity() * newNormal;
+			cp.posB = cp.posA - cp.normalB * cp.dist;
+			cp.localB = vmul(cp.posB - v3zero(), m3identity());
+		}
+	}
+}
+
+// Car::Demolish + bump logic: Arena::_BtCallback_OnCarCarCollision (Arena.cpp:323-405)
+RSB_HD void on_car_car_collision(const Ctx& cx, int c1, int c2, ContactPt& cp) {
+	cp.friction = K::CARCAR_COLLISION_FRICTION;
+	cp.restitution = K::CARCAR_COLLISION_RESTITUTION;
+	const MutD& mut = cx.p->mut;
+	for (int i = 0; i < 2; i++) {
+		bool isSwapped = (i == 1);
+		if (isSwapped) { int t = c1; c1 = c2; c2 = t; }
+		CarS& car1 = cx.s->cars[c1];
+		CarS& car2 = cx.s->cars[c2];
+		if (car1.isDemoed || car2.isDemoed) return;
+		if ((car1.carContactOtherID == (uint32_t)(c2 + 1)) && (car1.carContactCooldown > 0.f)) continue;
+		V3 pos1 = car1.rb.pos * BT_TO_UU, vel1 = car1.rb.vel * BT_TO_UU;
+		V3 pos2 = car2.rb.pos * BT_TO_UU, vel2 = car2.rb.vel * BT_TO_UU;
+		V3 deltaPos = pos2 - pos1;
+		if (dot(vel1, deltaPos) > 0.f) {
+			V3 velDir = rs_normalized(vel1);
+			V3 dirToOtherCar = rs_normalized(deltaPos);
+			float speedTowardsOtherCar = dot(vel1, dirToOtherCar);
+			float otherCarAwaySpeed = dot(vel2, velDir);
+			if (speedTowardsOtherCar > otherCarAwaySpeed) {
+				V3 localPoint = isSwapped ? cp.localB : cp.localA;
+				bool hitWithBumper = (localPoint.x * BT_TO_UU) > K::BUMP_MIN_FORWARD_DIST;
+				if (hitWithBumper) {
+					bool isDemo;
+					switch (mut.demoMode) {
+					case 1: isDemo = true; break;
+					case 2: isDemo = false; break;
+					default: isDemo = car1.isSupersonic != 0;
+					}
+					if (isDemo && !mut.enableTeamDemos) isDemo = cx.p->team[c1] != cx.p->team[c2];
+					if (isDemo) {
+						car2.isDemoed = 1;
+						car2.demoRespawnTimer = mut.respawnDelay;
+					} else {
+						bool groundHit = car2.isOnGround != 0;
+						float baseScale = groundHit ? curve_bump_vel_ground(speedTowardsOtherCar) : curve_bump_vel_air(speedTowardsOtherCar);
+						V3 hitUpDir = car2.isOnGround ? car2.rb.basis.col(2) : V3(0.f, 0.f, 1.f);
+						V3 bumpImpulse = velDir * baseScale + hitUpDir * curve_bump_upward(speedTowardsOtherCar) * mut.bumpForceScale;
+						car2.velImpulseCache += bumpImpulse * UU_TO_BT;
+					}
+					car1.carContactOtherID = (uint32_t)(c2 + 1);
+					car1.carContactCooldown = mut.bumpCooldownTime;
+					push_event(cx, isDemo ? 3u : 2u, (uint32_t)(c1 + 1), (uint32_t)(c2 + 1));
+				}
+			}
+		}
+	}
+}
+
+// btManifoldResult::addContactPoint + gContactAddedCallback.  body0/body1 of the manifold
+// are "A"/"B"; (normalOnB, pointOnB, depth) as reported by the detector.  triMesh/triIndex
+// identify the triangle when B is an arena mesh (else triMesh < 0).
+RSB_HD void add_contact_point(const Ctx& cx, int mi, const V3& normalOnB, const V3& pointInWorld, float depth, int triMesh, int triIndex) {
+	ArenaW& w = *cx.w;
+	Manifold& m = w.manifolds[mi];
+	if (depth > m.breakingThresh) return;
+	ContactPt pt;
+	V3 pointA = pointInWorld + normalOnB * depth;
+	Xform t0 = obj_xform(cx, m.body0), t1 = obj_xform(cx, m.body1);
+	pt.localA = xf_inv_apply(t0, pointA);
+	pt.localB = xf_inv_apply(t1, pointInWorld);
+	pt.normalB = normalOnB; pt.dist = depth;
+	pt.posA = pointA; pt.posB = pointInWorld;
+	pt.isSpecial = 0;
+	pt.partId0 = -1; pt.index0 = (m.body0 < STATIC_BASE && m.body0 > 0) ? 0 : -1;
+	pt.partId1 = triMesh >= 0 ? 0 : -1; pt.index1 = triMesh >= 0 ? triIndex : -1;
+	// combined friction / restitution (btManifoldResult.cpp:56-77)
+	{
+		bool s0 = m.body0 >= STATIC_BASE, s1 = m.body1 >= STATIC_BASE;
+		float fa = s0 ? K::ARENA_COLLISION_BASE_FRICTION : w.body[m.body0].friction;
+		float fb = s1 ? K::ARENA_COLLISION_BASE_FRICTION : w.body[m.body1].friction;
+		float ra = s0 ? K::ARENA_COLLISION_BASE_RESTITUTION : w.body[m.body0].restitution;
+		float rb = s1 ? K::ARENA_COLLISION_BASE_RESTITUTION : w.body[m.body1].restitution;
+		if (s0 || s1) { pt.friction = (fa < fb) ? fa : fb; pt.restitution = (ra > rb) ? ra : rb; }
+		else { pt.friction = fa * fb; pt.restitution = ra * rb; }
+	}
+	int insertIndex = m.nPts;
+	if (insertIndex == 4) insertIndex = sort_cached_points(m, pt);
+	else m.nPts++;
+	if (insertIndex < 0) insertIndex = 0;
+	m.pts[insertIndex] = pt;
+	ContactPt& cp = m.pts[insertIndex];
+
+	// ---- Arena::_BulletContactAddedCallback ----
+	const bool d0 = m.body0 < STATIC_BASE, d1 = m.body1 < STATIC_BASE;
+	if ((d0 && w.body[m.body0].noResponse) || (d1 && w.body[m.body1].noResponse)) return;
+	// manifold orders used here: (car, ball) (carHi, carLo) (car, world) (ball, world)
+	if (d0 && m.body0 > 0) {
+		int car = m.body0 - 1;
+		if (d1 && m.body1 == 0) {
+			V3 relBallPos = cp.localB * BT_TO_UU;
+			cp.friction = K::CARBALL_COLLISION_FRICTION;
+			cp.restitution = K::CARBALL_COLLISION_RESTITUTION;
+			ball_on_hit(cx, car, relBallPos);
+		} else if (d1) {
+			on_car_car_collision(cx, car, m.body1 - 1, cp);
+		} else {
+			cx.s->cars[car].worldContactHas = 1;
+			cx.s->cars[car].worldContactNormal = cp.normalB;
+			cp.friction = cx.p->mut.carWorldFriction;
+			cp.restitution = cx.p->mut.carWorldRestitution;
+		}
+	} else if (d0 && m.body0 == 0 && !d1) {
+		ball_on_world_collision(cx, cp.normalB);
+		if (cx.p->mode != SNOWDAY) cp.isSpecial = 1;
+	}
+	if (triMesh >= 0) adjust_internal_edge(cx, cp, cx.sc->meshes[triMesh], triIndex);
+}
+
+// btPersistentManifold::refreshContactPoints (btPersistentManifold.cpp:263-329)
+RSB_HD void refresh_contact_points(const Ctx& cx, int mi) {
+	Manifold& m = cx.w->manifolds[mi];
+	Xform tA = obj_xform(cx, m.body0), tB = obj_xform(cx, m.body1);
+	for (int i = m.nPts - 1; i >= 0; i--) {
+		ContactPt& p = m.pts[i];
+		p.posA = xf_apply(tA, p.localA);
+		p.posB = xf_apply(tB, p.localB);
+		p.dist = dot(p.posA - p.posB, p.normalB);
+	}
+	for (int i = m.nPts - 1; i >= 0; i--) {
+		ContactPt& p = m.pts[i];
+		bool remove = false;
+		if (!(p.dist <= m.breakingThresh)) remove = true;
+		else {
+			V3 projectedPoint = p.posA - p.normalB * p.dist;
+			V3 projectedDifference = p.posB - projectedPoint;
+			float distance2d = dot(projectedDifference, projectedDifference);
+			if (distance2d > m.breakingThresh * m.breakingThresh) remove = true;
+		}
+		if (remove) {
+			int last = m.nPts - 1;
+			if (i != last) m.pts[i] = m.pts[last];
+			m.nPts--;
+		}
+	}
+}
+
+// ------------------------------------------------------------------ narrowphase algorithms
+// SphereTriangleDetector::collide (SphereTriangleDetector.cpp:139-243)
+RSB_HD bool sphere_triangle(const V3& sphereCenter, float radius, const V3 v[3], float contactBreakingThreshold, V3& point, V3& resultNormal, float& depth) {
+	float radiusWithThreshold = radius + contactBreakingThreshold;
+	V3 normal = cross(v[1] - v[0], v[2] - v[0]);
+	float l2 = len2(normal);
+	bool hasContact = false;
+	V3 contactPoint = v3zero();
+	if (l2 >= kEps * kEps) {
+		normal = normal / sqrtf(l2);
+		V3 p1ToCentre = sphereCenter - v[0];
+		float distanceFromPlane = dot(p1ToCentre, normal);
+		if (distanceFromPlane < 0.f) { distanceFromPlane *= -1.f; normal *= -1.f; }
+		bool isInsideContactPlane = distanceFromPlane < radiusWithThreshold;
+		if (isInsideContactPlane) {
+			// pointInTriangle (barycentric variant, :274-296)
+			V3 u = v[1] - v[0], vv = v[2] - v[0];
+			V3 n = cross(u, vv);
+			float nLenSq = dot(n, n);
+			V3 wv = sphereCenter - v[0];
+			float gamma = dot(cross(u, wv), n) / nLenSq;
+			float beta = dot(cross(wv, vv), n) / nLenSq;
+			float alpha = 1 - gamma - beta;
+			bool inside = ((0 <= alpha) && (alpha <= 1) && (0 <= beta) && (beta <= 1) && (0 <= gamma) && (gamma <= 1));
+			if (inside) {
+				hasContact = true;
+				contactPoint = sphereCenter - normal * distanceFromPlane;
+			} else {
+				float contactCapsuleRadiusSqr = radiusWithThreshold * radiusWithThreshold;
+				// closestPointTriangle (:88-131)
+				const V3 a = v[0], b = v[1], c = v[2], p = sphereCenter;
+				const V3 ab = b - a, ac = c - a, ap = p - a;
+				V3 q;
+				const float d1 = dot(ab, ap), d2 = dot(ac, ap);
+				bool done = false;
+				if (d1 <= 0.f && d2 <= 0.f) { q = a; done = true; }
+				float d3 = 0, d4 = 0, d5 = 0, d6 = 0;
+				if (!done) { const V3 bp = p - b; d3 = dot(ab, bp); d4 = dot(ac, bp); if (d3 >= 0.f && d4 <= d3) { q = b; done = true; } }
+				if (!done) { const V3 cp = p - c; d5 = dot(ab, cp); d6 = dot(ac, cp); if (d6 >= 0.f && d5 <= d6) { q = c; done = true; } }
+				if (!done) { const float vc = d1 * d4 - d3 * d2; if (vc <= 0.f && d1 >= 0.f && d3 <= 0.f) { const float t = d1 / (d1 - d3); q = a + t * ab; done = true; }
+					if (!done) { const float vb = d5 * d2 - d1 * d6; if (vb <= 0.f && d2 >= 0.f && d6 <= 0.f) { const float t = d2 / (d2 - d6); q = a + t * ac; done = true; }
+						if (!done) { const float va = d3 * d6 - d5 * d4; if (va <= 0.f && (d4 - d3) >= 0.f && (d5 - d6) >= 0.f) { const float t = (d4 - d3) / ((d4 - d3) + (d5 - d6)); q = b + t * (c - b); done = true; }
+							if (!done) { const float denom = 1.f / (va + vb + vc); const float t = vb * denom; const float s = vc * denom; q = a + t * ab + s * ac; } } } }
+				float distanceSqr = len2(q - sphereCenter);
+				if (distanceSqr < contactCapsuleRadiusSqr) { hasContact = true; contactPoint = q; }
+			}
+		}
+	}
+	if (hasContact) {
+		V3 contactToCentre = sphereCenter - contactPoint;
+		float distanceSqr = len2(contactToCentre);
+		if (distanceSqr < radiusWithThreshold * radiusWithThreshold) {
+			if (distanceSqr > kEps) {
+				float distance = sqrtf(distanceSqr);
+				resultNormal = normalized(contactToCentre);
+				point = contactPoint;
+				depth = -(radius - distance);
+			} else {
+				resultNormal = normal;
+				point = contactPoint;
+				depth = -radius;
+			}
+			return true;
+		}
+	}
+	return false;
+}
+
+RSB_HD bool triangle_vs_aabb(const V3 t[3], const V3& mn, const V3& mx) {  // TestTriangleAgainstAabb2 (Z, X, Y)
+	const int order[3] = {2, 0, 1};
+	for (int k = 0; k < 3; k++) {
+		int i = order[k];
+		if (fminf_(fminf_(t[0][i], t[1][i]), t[2][i]) > mx[i]) return false;
+		if (fmaxf_(fmaxf_(t[0][i], t[1][i]), t[2][i]) < mn[i]) return false;
+	}
+	return true;
+}
+
+// Convex (ball sphere / puck hull / car box) vs an arena mesh:
+// btConvexConcaveCollisionAlgorithm::processCollision + btConvexTriangleCallback::processTriangle
+// (btConvexConcaveCollisionAlgorithm.cpp:71-250) over the BVH's AABB query
+// (btQuantizedBvh.cpp:655-729: subtree headers in order, stackless walk inside each).
+RSB_HD void convex_vs_mesh(const Ctx& cx, int mi, int body, const Convex& shape, const Xform& xf, int meshIdx) {
+	const MeshD& mesh = cx.sc->meshes[meshIdx];
+	Manifold& mf = cx.w->manifolds[mi];
+	// convex AABB in triangle space (mesh at origin, identity): shape->getAabb(convexInTriangleSpace)
+	V3 amin, amax;
+	if (shape.kind == SH_SPHERE) { float mg = shape.margin + 0.08f; V3 e(mg, mg, mg); amin = xf.origin - e; amax = xf.origin + e; }
+	else if (shape.kind == SH_BOX) transform_aabb_he(shape.he, shape.margin, xf.basis, xf.origin, amin, amax);
+	else transform_aabb_mm(cx.p->puckLocalAabbMin, cx.p->puckLocalAabbMax, shape.margin, xf.basis, xf.origin, amin, amax);
+	// extraMargin = mesh margin (0) + closestPointDistanceThreshold (0)
+	uint16_t qmin[3], qmax[3];
+	bvh_quantize_clamped(mesh, amin, 0, qmin);
+	bvh_quantize_clamped(mesh, amax, 1, qmax);
+	for (int h = 0; h < mesh.nHdrs; h++) {
+		const SubtreeHdr hd = mesh.hdrs[h];
+		if (!quant_overlap(qmin, qmax, hd.qmin, hd.qmax)) continue;
+		int cur = hd.root;
+		const int end = hd.root + hd.size;
+		while (cur < end) {
+			const BvhNode nd = mesh.nodes[cur];
+			bool ov = quant_overlap(qmin, qmax, nd.qmin, nd.qmax);
+			bool isLeaf = nd.idx >= 0;
+			if (isLeaf && ov) {
+				int tri = nd.idx & 0x1fffff;
+				V3 t[3];
+				mesh_triangle(mesh, tri, t[0], t[1], t[2]);
+				if (triangle_vs_aabb(t, amin, amax)) {
+					// early out on the triangle's supporting plane, both sides (:102-138)
+					bool skip = false;
+					{
+						V3 tn = normalized(cross(t[1] - t[0], t[2] - t[0]));
+						M3 invB = inverse(xf.basis);
+						for (int side = 0; side < 2 && !skip; side++) {
+							V3 localPt = support_with_margin(shape, invB * tn);
+							V3 worldPt = xf_apply(xf, localPt);
+							float proj_distPt = dot(tn, worldPt);
+							float proj_distTr = dot(tn, t[0]);
+							float dist = proj_distTr - proj_distPt;
+							if (dist > mf.breakingThresh) skip = true;
+							tn *= -1.f;
+						}
+					}
+					if (!skip) {
+						if (shape.kind == SH_SPHERE) {
+							V3 point, normal; float depth;
+							// sphereInTr origin = (center - 0) * I
+							V3 c = vmul(xf.origin - v3zero(), m3identity());
+							if (sphere_triangle(c, shape.margin, t, mf.breakingThresh, point, normal, depth))
+								add_contact_point(cx, mi, m3identity() * normal, m3identity() * point + v3zero(), depth, meshIdx, tri);
+						} else {
+							Convex triShape; triShape.kind = SH_TRI; triShape.margin = 0.f; triShape.he = v3zero();
+							triShape.tri[0] = t[0]; triShape.tri[1] = t[1]; triShape.tri[2] = t[2]; triShape.pts = nullptr; triShape.npts = 0;
+							Xform xfT; xfT.basis = m3identity(); xfT.origin = v3zero();
+							convex_convex(cx, mi, shape, xf, triShape, xfT, meshIdx, tri);
+						}
+					}
+				}
+			}
+			if (ov || isLeaf) cur++;
+			else cur += -nd.idx;
+		}
+	}
+	refresh_contact_points(cx, mi);
+	(void)body;
+}
+
+// btConvexPlaneCollisionAlgorithm::processCollision (btConvexPlaneCollisionAlgorithm.cpp:92-161)
+RSB_HD void convex_vs_plane(const Ctx& cx, int mi, const Convex& shape, const Xform& xf, const PlaneD& pl) {
+	Manifold& mf = cx.w->manifolds[mi];
+	const V3 planeNormal = pl.n;
+	M3 planeInConvexBasis = transpose(xf.basis) * m3identity();
+	V3 convexInPlaneOrigin = (m3identity() * xf.origin) + (m3identity() * (-pl.pos));
+	M3 convexInPlaneBasis = m3identity() * xf.basis;
+	V3 vtx = support_with_margin(shape, planeInConvexBasis * (-planeNormal));
+	V3 vtxInPlane = convexInPlaneBasis * vtx + convexInPlaneOrigin;
+	float distance = dot(planeNormal, vtxInPlane) - 0.f;
+	bool hasCollision = distance < mf.breakingThresh;
+	if (hasCollision) {
+		V3 vtxInPlaneProjected = vtxInPlane - distance * planeNormal;
+		V3 vtxInPlaneWorld = m3identity() * vtxInPlaneProjected + pl.pos;
+		V3 normalOnSurfaceB = m3identity() * planeNormal;
+		add_contact_point(cx, mi, normalOnSurfaceB, vtxInPlaneWorld, distance, -1, -1);
+	}
+	if (mf.nPts) refresh_contact_points(cx, mi);
+}
+
+RSB_HD Convex car_box(const CarCfgD& cfg) {
+	Convex c; c.kind = SH_BOX; c.margin = cfg.hitboxMargin; c.he = cfg.hitboxImplicit; c.pts = nullptr; c.npts = 0;
+	return c;
+}
+RSB_HD Xform car_child_xform(const RigidS& rb, const CarCfgD& cfg) {
+	Xform t; t.basis = rb.basis * m3identity(); t.origin = rb.basis * cfg.hitboxOffset + rb.pos;
+	return t;
+}
+RSB_HD void convex_world_aabb(const Ctx& cx, const Convex& s, const Xform& t, V3& mn, V3& mx) {
+	if (s.kind == SH_SPHERE) { float mg = s.margin + 0.08f; V3 e(mg, mg, mg); mn = t.origin - e; mx = t.origin + e; }
+	else if (s.kind == SH_BOX) transform_aabb_he(s.he, s.margin, t.basis, t.origin, mn, mx);
+	else transform_aabb_mm(cx.p->puckLocalAabbMin, cx.p->puckLocalAabbMax, s.margin, t.basis, t.origin, mn, mx);
+}
+
+// performDiscreteCollisionDetection for one arena
+RSB_HD void collide_world(const Ctx& cx) {
+	ArenaW& w = *cx.w;
+	const BatchParams& P = *cx.p;
+	const Scene& sc = *cx.sc;
+	w.nManifolds = 0;
+	update_aabbs(cx);
+	compute_pairs(cx);
+	for (int k = 0; k < w.nPairs; k++) {
+		const int a = w.pairA[k], b = w.pairB[k];
+		const bool sa = a >= STATIC_BASE;
+		// btCollisionDispatcher::needsCollision: skip when both are inactive (statics are inactive)
+		bool actA = sa ? false : body_active(w.body[a]);
+		bool actB = body_active(w.body[b]);
+		if (!actA && !actB) continue;
+		if (sa) {
+			const int sk = a - STATIC_BASE;
+			const bool isMesh = sk < sc.nMeshes;
+			const RigidS& rb = rigid_of(cx, b);
+			if (b == 0) {
+				Convex shape = ball_convex(P);
+				Xform xf; xf.basis = rb.basis; xf.origin = rb.pos;
+				int mi = new_manifold(cx, 0, a);
+				if (mi < 0) continue;
+				if (isMesh) convex_vs_mesh(cx, mi, 0, shape, xf, sk);
+				else convex_vs_plane(cx, mi, shape, xf, sc.planes[sk - sc.nMeshes]);
+			} else {
+				const CarCfgD& cfg = P.carCfg[b - 1];
+				Convex shape = car_box(cfg);
+				Xform xf = car_child_xform(rb, cfg);
+				// btCompoundLeafCallback::ProcessChildShape: child AABB vs the other shape's AABB
+				V3 cmn, cmx, omn, omx;
+				convex_world_aabb(cx, shape, xf, cmn, cmx);
+				static_aabb(cx, a, omn, omx);
+				if (!aabb_overlap(cmn, cmx, omn, omx)) continue;
+				int mi = new_manifold(cx, b, a);
+				if (mi < 0) continue;
+				if (isMesh) convex_vs_mesh(cx, mi, b, shape, xf, sk);
+				else convex_vs_plane(cx, mi, shape, xf, sc.planes[sk - sc.nMeshes]);
+			}
+		} else if (a == 0) {
+			// (ball, car): swapped compound -> convex-convex(box of the car, ball shape); manifold (car, ball)
+			const CarCfgD& cfg = P.carCfg[b - 1];
+			const RigidS& rc = rigid_of(cx, b);
+			const RigidS& rball = rigid_of(cx, 0);
+			Convex box = car_box(cfg); Xform xfc = car_child_xform(rc, cfg);
+			Convex ball = ball_convex(P); Xform xfb; xfb.basis = rball.basis; xfb.origin = rball.pos;
+			V3 cmn, cmx, omn, omx;
+			convex_world_aabb(cx, box, xfc, cmn, cmx);
+			convex_world_aabb(cx, ball, xfb, omn, omx);
+			if (!aabb_overlap(cmn, cmx, omn, omx)) continue;
+			int mi = new_manifold(cx, b, 0);
+			if (mi < 0) continue;
+			convex_convex(cx, mi, box, xfc, ball, xfb, -1, -1);
+			refresh_contact_points(cx, mi);
+		} else {
+			// (carLo=a, carHi=b): compound-compound -> ... -> box-box(body0 = box of b, body1 = box of a); manifold (b, a)
+			const CarCfgD& cfgA = P.carCfg[a - 1]; const CarCfgD& cfgB = P.carCfg[b - 1];
+			const RigidS& ra = rigid_of(cx, a); const RigidS& rbb = rigid_of(cx, b);
+			Convex boxA = car_box(cfgA), boxB = car_box(cfgB);
+			Xform xfA = car_child_xform(ra, cfgA), xfB = car_child_xform(rbb, cfgB);
+			V3 amn, amx, bmn, bmx, cmn, cmx;
+			convex_world_aabb(cx, boxA, xfA, amn, amx);   // child of A
+			compound_aabb(cfgB, rbb.basis, rbb.pos, cmn, cmx);  // whole compound B
+			if (!aabb_overlap(amn, amx, cmn, cmx)) continue;
+			convex_world_aabb(cx, boxB, xfB, bmn, bmx);   // child of B vs box A
+			if (!aabb_overlap(bmn, bmx, amn, amx)) continue;
+			int mi = new_manifold(cx, b, a);
+			if (mi < 0) continue;
+			box_box(cx, mi, boxB, xfB, boxA, xfA);
+			refresh_contact_points(cx, mi);
+		}
+	}
+}
+
+}  // namespace rsb

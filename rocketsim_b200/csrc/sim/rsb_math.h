@@ -1,0 +1,257 @@
+// rsb_math.h -- fp32 vector / matrix / quaternion primitives for the batched arena tick.
+//
+// Semantics follow the math the reference path runs on (vendored Bullet LinearMath, SSE
+// build: /root/reference/libsrc/bullet3-3.24/LinearMath/btVector3.h:229-249 dot =
+// (x*x'+y*y')+z*z'; btMatrix3x3.h:216-288 setRotation, :421-499 getRotation (SIMD
+// variant), :1093-1104 inverse; btQuaternion.h:108-115; btTransformUtil.h:32-87), but the
+// types are our own plain structs usable from CUDA device code and from a host compile
+// (tests only).  Compile with -fmad=false / -ffp-contract=off: the reference build has no
+// FMA contraction.
+#pragma once
+
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define RSB_HD __host__ __device__ __forceinline__
+#define RSB_HD_NOINLINE __host__ __device__ __noinline__
+#else
+#define RSB_HD inline
+#define RSB_HD_NOINLINE
+#endif
+
+namespace rsb {
+
+constexpr float kEps = 1.1920928955078125e-7f;  // FLT_EPSILON (SIMD_EPSILON)
+constexpr float kPi = 3.1415926535897932384626433832795029f;
+constexpr float k2Pi = 2.0f * kPi;
+constexpr float kHalfPi = kPi * 0.5f;
+constexpr float kSqrt12 = 0.7071067811865475244008443621048490f;
+constexpr float UU_TO_BT = 1.f / 50.f;
+constexpr float BT_TO_UU = 50.f;
+
+RSB_HD float fminf_(float a, float b) { return a < b ? a : b; }
+RSB_HD float fmaxf_(float a, float b) { return a > b ? a : b; }
+// RS_CLAMP(val,min,max) = RS_MIN(RS_MAX(val,min),max) with (a>b)?a:b macros (Framework.h:47-50)
+RSB_HD float rs_clamp(float v, float lo, float hi) {
+	float t = (v > lo) ? v : lo;
+	return (t < hi) ? t : hi;
+}
+RSB_HD int rs_sgn(float v) { return (v > 0) - (v < 0); }
+
+struct V3 {
+	float x, y, z;
+	RSB_HD V3() {}
+	RSB_HD V3(float x_, float y_, float z_) : x(x_), y(y_), z(z_) {}
+	RSB_HD float operator[](int i) const { return i == 0 ? x : (i == 1 ? y : z); }
+	RSB_HD void set(int i, float v) { if (i == 0) x = v; else if (i == 1) y = v; else z = v; }
+};
+
+RSB_HD V3 v3(float x, float y, float z) { return V3(x, y, z); }
+RSB_HD V3 v3zero() { return V3(0.f, 0.f, 0.f); }
+RSB_HD V3 operator+(const V3& a, const V3& b) { return V3(a.x + b.x, a.y + b.y, a.z + b.z); }
+RSB_HD V3 operator-(const V3& a, const V3& b) { return V3(a.x - b.x, a.y - b.y, a.z - b.z); }
+RSB_HD V3 operator-(const V3& a) { return V3(-a.x, -a.y, -a.z); }
+RSB_HD V3 operator*(const V3& a, float s) { return V3(a.x * s, a.y * s, a.z * s); }
+RSB_HD V3 operator*(float s, const V3& a) { return V3(a.x * s, a.y * s, a.z * s); }
+RSB_HD V3 operator*(const V3& a, const V3& b) { return V3(a.x * b.x, a.y * b.y, a.z * b.z); }
+RSB_HD V3 operator/(const V3& a, float s) { float r = 1.0f / s; return V3(a.x * r, a.y * r, a.z * r); }  // btVector3 /= : multiply by reciprocal
+RSB_HD V3 vdiv(const V3& a, float s) { return V3(a.x / s, a.y / s, a.z / s); }                             // RocketSim::Vec / float : true division
+RSB_HD V3& operator+=(V3& a, const V3& b) { a = a + b; return a; }
+RSB_HD V3& operator-=(V3& a, const V3& b) { a = a - b; return a; }
+RSB_HD V3& operator*=(V3& a, float s) { a = a * s; return a; }
+RSB_HD float dot(const V3& a, const V3& b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
+RSB_HD V3 cross(const V3& a, const V3& b) {
+	return V3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+}
+RSB_HD float len2(const V3& a) { return dot(a, a); }
+RSB_HD float len(const V3& a) { return sqrtf(dot(a, a)); }
+RSB_HD bool is_zero(const V3& a) { return a.x == 0.f && a.y == 0.f && a.z == 0.f; }
+RSB_HD bool fuzzy_zero(const V3& a) { return len2(a) < kEps * kEps; }
+RSB_HD V3 normalized(const V3& a) { return a * (1.0f / sqrtf(len2(a))); }  // btVector3::normalize
+// btVector3::safeNormalize (btVector3.h:292-305)
+RSB_HD V3 safe_normalized(const V3& a) {
+	float l2 = len2(a);
+	if (l2 >= kEps * kEps) return a * (1.0f / sqrtf(l2));
+	return V3(1.f, 0.f, 0.f);
+}
+// RocketSim::Vec::Normalized (MathTypes.h:96-103): length via sqrt, true division, zero if tiny
+RSB_HD V3 rs_normalized(const V3& a) {
+	float l2 = len2(a);
+	float l = (l2 > 0.f) ? sqrtf(l2) : 0.f;
+	if (l > kEps * kEps) return vdiv(a, l);
+	return v3zero();
+}
+RSB_HD V3 vmin(const V3& a, const V3& b) { return V3(fminf_(a.x, b.x), fminf_(a.y, b.y), fminf_(a.z, b.z)); }
+RSB_HD V3 vmax(const V3& a, const V3& b) { return V3(fmaxf_(a.x, b.x), fmaxf_(a.y, b.y), fmaxf_(a.z, b.z)); }
+RSB_HD V3 vabs(const V3& a) { return V3(fabsf(a.x), fabsf(a.y), fabsf(a.z)); }
+RSB_HD V3 lerp(const V3& a, const V3& b, float t) {  // btVector3::setInterpolate3: s*v0 + rt*v1, s = 1-rt
+	float s = 1.0f - t;
+	return V3(s * a.x + t * b.x, s * a.y + t * b.y, s * a.z + t * b.z);
+}
+
+// btPlaneSpace1 (btVector3.h:1266-1294)
+RSB_HD void plane_space1(const V3& n, V3& p, V3& q) {
+	if (fabsf(n.z) > kSqrt12) {
+		float a = n.y * n.y + n.z * n.z;
+		float k = 1.0f / sqrtf(a);
+		p = V3(0.f, -n.z * k, n.y * k);
+		q = V3(a * k, -n.x * p.z, n.x * p.y);
+	} else {
+		float a = n.x * n.x + n.y * n.y;
+		float k = 1.0f / sqrtf(a);
+		p = V3(-n.y * k, n.x * k, 0.f);
+		q = V3(-n.z * p.y, n.z * p.x, a * k);
+	}
+}
+
+// Row-major 3x3 (btMatrix3x3 layout: r[i] = row i).  RocketSim's RotMat columns
+// forward/right/up are the COLUMNS of this matrix (MathTypes.h:178-186).
+struct M3 {
+	V3 r[3];
+	RSB_HD M3() {}
+	RSB_HD M3(const V3& a, const V3& b, const V3& c) { r[0] = a; r[1] = b; r[2] = c; }
+	RSB_HD V3 col(int j) const { return V3(r[0][j], r[1][j], r[2][j]); }
+};
+
+RSB_HD M3 m3identity() { return M3(V3(1, 0, 0), V3(0, 1, 0), V3(0, 0, 1)); }
+RSB_HD V3 operator*(const M3& m, const V3& v) { return V3(dot(m.r[0], v), dot(m.r[1], v), dot(m.r[2], v)); }
+// row-vector * matrix (btMatrix3x3.h:1225-1262)
+RSB_HD V3 vmul(const V3& v, const M3& m) {
+	return V3((v.x * m.r[0].x + v.y * m.r[1].x) + v.z * m.r[2].x,
+	          (v.x * m.r[0].y + v.y * m.r[1].y) + v.z * m.r[2].y,
+	          (v.x * m.r[0].z + v.y * m.r[1].z) + v.z * m.r[2].z);
+}
+RSB_HD M3 operator*(const M3& a, const M3& b) {
+	M3 o;
+	for (int i = 0; i < 3; i++) {
+		const V3 ai = a.r[i];
+		o.r[i] = V3((ai.x * b.r[0].x + ai.y * b.r[1].x) + ai.z * b.r[2].x,
+		            (ai.x * b.r[0].y + ai.y * b.r[1].y) + ai.z * b.r[2].y,
+		            (ai.x * b.r[0].z + ai.y * b.r[1].z) + ai.z * b.r[2].z);
+	}
+	return o;
+}
+RSB_HD M3 transpose(const M3& m) { return M3(m.col(0), m.col(1), m.col(2)); }
+RSB_HD M3 scaled(const M3& m, const V3& s) { return M3(m.r[0] * s, m.r[1] * s, m.r[2] * s); }
+RSB_HD float cofac(const M3& m, int r1, int c1, int r2, int c2) { return m.r[r1][c1] * m.r[r2][c2] - m.r[r1][c2] * m.r[r2][c1]; }
+RSB_HD M3 inverse(const M3& m) {
+	V3 co(cofac(m, 1, 1, 2, 2), cofac(m, 1, 2, 2, 0), cofac(m, 1, 0, 2, 1));
+	float det = dot(m.r[0], co);
+	float s = 1.0f / det;
+	return M3(V3(co.x * s, cofac(m, 0, 2, 2, 1) * s, cofac(m, 0, 1, 1, 2) * s),
+	          V3(co.y * s, cofac(m, 0, 0, 2, 2) * s, cofac(m, 0, 2, 1, 0) * s),
+	          V3(co.z * s, cofac(m, 0, 1, 2, 0) * s, cofac(m, 0, 0, 1, 1) * s));
+}
+
+struct Q4 { float x, y, z, w; };
+RSB_HD Q4 q4(float x, float y, float z, float w) { Q4 q; q.x = x; q.y = y; q.z = z; q.w = w; return q; }
+RSB_HD Q4 qmul(const Q4& a, const Q4& b) {
+	return q4(a.w * b.x + a.x * b.w + a.y * b.z - a.z * b.y,
+	          a.w * b.y + a.y * b.w + a.z * b.x - a.x * b.z,
+	          a.w * b.z + a.z * b.w + a.x * b.y - a.y * b.x,
+	          a.w * b.w - a.x * b.x - a.y * b.y - a.z * b.z);
+}
+RSB_HD float qlen2(const Q4& q) { return (q.x * q.x + q.z * q.z) + (q.y * q.y + q.w * q.w); }
+// btQuaternion(axis, angle) (btQuaternion.h:108-115)
+RSB_HD Q4 q_axis_angle(const V3& axis, float angle) {
+	float d = len(axis);
+	float s = sinf(angle * 0.5f) / d;
+	return q4(axis.x * s, axis.y * s, axis.z * s, cosf(angle * 0.5f));
+}
+// btMatrix3x3::setRotation (btMatrix3x3.h:216-288)
+RSB_HD M3 m3_from_quat(const Q4& q) {
+	float d = qlen2(q);
+	float s = 2.0f / d;
+	float xs = q.x * s, ys = q.y * s, zs = q.z * s;
+	float wx = q.w * xs, wy = q.w * ys, wz = q.w * zs;
+	float xx = q.x * xs, xy = q.x * ys, xz = q.x * zs;
+	float yy = q.y * ys, yz = q.y * zs, zz = q.z * zs;
+	return M3(V3(1.0f - (yy + zz), xy - wz, xz + wy),
+	          V3(xy + wz, 1.0f - (xx + zz), yz - wx),
+	          V3(xz - wy, yz + wx, 1.0f - (xx + yy)));
+}
+// btMatrix3x3::getRotation, SIMD variant (btMatrix3x3.h:421-499)
+RSB_HD Q4 quat_from_m3(const M3& m) {
+	float trace = m.r[0].x + m.r[1].y + m.r[2].z;
+	float t[4];
+	float x;
+	if (trace > 0.f) {
+		x = trace + 1.0f;
+		t[0] = m.r[2].y - m.r[1].z;
+		t[1] = m.r[0].z - m.r[2].x;
+		t[2] = m.r[1].x - m.r[0].y;
+		t[3] = x;
+	} else {
+		int i, j, k;
+		if (m.r[0].x < m.r[1].y) {
+			if (m.r[1].y < m.r[2].z) { i = 2; j = 0; k = 1; } else { i = 1; j = 2; k = 0; }
+		} else {
+			if (m.r[0].x < m.r[2].z) { i = 2; j = 0; k = 1; } else { i = 0; j = 1; k = 2; }
+		}
+		x = m.r[i][i] - m.r[j][j] - m.r[k][k] + 1.0f;
+		t[3] = m.r[k][j] - m.r[j][k];
+		t[j] = m.r[j][i] + m.r[i][j];
+		t[k] = m.r[k][i] + m.r[i][k];
+		t[i] = x;
+	}
+	float s = 0.5f / sqrtf(x);
+	return q4(t[0] * s, t[1] * s, t[2] * s, t[3] * s);
+}
+
+struct Xform { M3 basis; V3 origin; };
+RSB_HD V3 xf_apply(const Xform& t, const V3& v) { return t.basis * v + t.origin; }  // btTransform::operator()
+// btTransform::invXform: (v - origin) * basis  (row-vector product = basis^T * v)
+RSB_HD V3 xf_inv_apply(const Xform& t, const V3& v) { return vmul(v - t.origin, t.basis); }
+
+// btTransformUtil::integrateTransform (btTransformUtil.h:37-87)
+RSB_HD void integrate_transform(const Xform& cur, const V3& linvel, const V3& angvel, float dt, bool noRot, Xform& out) {
+	out.origin = cur.origin + linvel * dt;
+	if (noRot) { out.basis = cur.basis; return; }
+	float fAngle2 = len2(angvel);
+	float fAngle = 0.f;
+	if (fAngle2 > kEps) fAngle = sqrtf(fAngle2);
+	const float kAngMotionThresh = 0.5f * kHalfPi;
+	if (fAngle * dt > kAngMotionThresh) fAngle = kAngMotionThresh / dt;
+	V3 axis;
+	if (fAngle < 0.001f) {
+		axis = angvel * (0.5f * dt - (dt * dt * dt) * 0.020833333333f * fAngle * fAngle);
+	} else {
+		axis = angvel * (sinf(0.5f * fAngle * dt) / fAngle);
+	}
+	Q4 dorn = q4(axis.x, axis.y, axis.z, cosf(fAngle * dt * 0.5f));
+	Q4 orn0 = quat_from_m3(cur.basis);
+	Q4 pred = qmul(dorn, orn0);
+	float l2 = qlen2(pred);
+	if (l2 > kEps) {  // safeNormalize -> normalize: q * (1/sqrt(l2))
+		float inv = 1.0f / sqrtf(l2);
+		pred = q4(pred.x * inv, pred.y * inv, pred.z * inv, pred.w * inv);
+	}
+	if (qlen2(pred) > kEps) out.basis = m3_from_quat(pred);
+	else out.basis = cur.basis;
+}
+
+// btRigidBody::updateInertiaTensor (btRigidBody.cpp:253-256)
+RSB_HD M3 world_inv_inertia(const M3& basis, const V3& invInertiaLocal) {
+	return scaled(basis, invInertiaLocal) * transpose(basis);
+}
+
+// LinearPieceCurve::GetOutput (src/Math/Math.cpp:5-35) over a small sorted knot table.
+template <int N>
+struct Curve { float x[N > 0 ? N : 1]; float y[N > 0 ? N : 1]; };
+template <int N>
+RSB_HD float curve_eval(const Curve<N>& c, float input, float defaultOutput = 1.f) {
+	if (N == 0) return defaultOutput;
+	if (input <= c.x[0]) return c.y[0];
+	for (int i = 1; i < N; i++) {
+		if (c.x[i] > input) {
+			float rangeBetween = c.x[i] - c.x[i - 1];
+			float valDiffBetween = c.y[i] - c.y[i - 1];
+			float f = (input - c.x[i - 1]) / rangeBetween;
+			return c.y[i - 1] + valDiffBetween * f;
+		}
+	}
+	return c.y[N - 1];
+}
+
+}  // namespace rsb

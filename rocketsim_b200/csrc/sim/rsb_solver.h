@@ -1,0 +1,408 @@
+// rsb_solver.h -- islands, sequential-impulse (PGS) contact solve and velocity writeback for
+// one arena (<= 7 dynamic bodies, all islands solved in one group).  Restates
+//   island building / ordering   bt/BulletCollision/CollisionDispatch/btSimulationIslandManager.cpp:40-64,196-445
+//                                bt/BulletCollision/CollisionDispatch/btUnionFind.h (path-compression variant)
+//   btAlignedObjectArray::quickSort (non-stable)  bt/LinearMath/btAlignedObjectArray.h:311-348
+//   solver setup/rows/iterations/writeback        bt/BulletDynamics/ConstraintSolver/btSequentialImpulseConstraintSolver.cpp
+//                                                 :458-491, 517-607, 795-983, 1003-1211, 1467-1599, 1601-1829, 1878-1925
+//   btSolverBody                                  bt/BulletDynamics/ConstraintSolver/btSolverBody.h:105-288
+// including the RocketSim patches: "special" ball-world contacts are skipped in the velocity
+// iterations and replaced by one averaged contact; no speculative penetration term; erp2 0.8;
+// split impulse always on (threshold 1e30) (src/Sim/Arena/Arena.cpp:472-475).
+#pragma once
+#include "rsb_work.h"
+
+namespace rsb {
+
+// ---- union-find over world objects (statics never merge) ----
+struct UF { int id[MAX_BODIES]; int sz[MAX_BODIES]; };
+RSB_HD int uf_find(UF& u, int x) {
+	while (x != u.id[x]) { int p = u.id[x]; u.id[x] = u.id[p]; x = u.id[p]; }
+	return x;
+}
+RSB_HD void uf_unite(UF& u, int p, int q) {
+	int i = uf_find(u, p), j = uf_find(u, q);
+	if (i == j) return;
+	u.id[i] = j; u.sz[j] += u.sz[i];
+}
+
+// btAlignedObjectArray::quickSortInternal on (key,payload) pairs; comparator key<key
+RSB_HD void quicksort_keys(int* key, int* val, int lo, int hi) {
+	// explicit stack (max depth tiny: arrays <= MAX_MANIFOLDS)
+	int stackLo[32], stackHi[32]; int sp = 0;
+	stackLo[0] = lo; stackHi[0] = hi; sp = 1;
+	while (sp > 0) {
+		sp--; lo = stackLo[sp]; hi = stackHi[sp];
+		int i = lo, j = hi;
+		int x = key[(lo + hi) / 2];
+		do {
+			while (key[i] < x) i++;
+			while (x < key[j]) j--;
+			if (i <= j) {
+				int tk = key[i]; key[i] = key[j]; key[j] = tk;
+				int tv = val[i]; val[i] = val[j]; val[j] = tv;
+				i++; j--;
+			}
+		} while (i <= j);
+		// the reference recurses (lo,j) first, then (i,hi); the two ranges are disjoint so order is irrelevant
+		if (i < hi && sp < 32) { stackLo[sp] = i; stackHi[sp] = hi; sp++; }
+		if (lo < j && sp < 32) { stackLo[sp] = lo; stackHi[sp] = j; sp++; }
+	}
+}
+
+
+// calculateSimulationIslands + buildIslands: island tags, wake-ups, and the manifold order
+// handed to the solver.  Returns the number of manifolds to solve (order in w.manifoldOrder).
+RSB_HD int build_islands(const Ctx& cx) {
+	ArenaW& w = *cx.w;
+	const int nb = n_bodies(cx);
+	UF uf;
+	for (int b = 0; b < nb; b++) { uf.id[b] = b; uf.sz[b] = 1; }
+	// findUnions over ALL broadphase pairs whose bodies both merge islands
+	for (int k = 0; k < w.nPairs; k++) {
+		int a = w.pairA[k], b = w.pairB[k];
+		if (a >= STATIC_BASE || b >= STATIC_BASE) continue;
+		if (w.body[a].noResponse || w.body[b].noResponse) continue;
+		uf_unite(uf, a, b);
+	}
+	for (int b = 0; b < nb; b++) w.body[b].islandTag = uf_find(uf, b);
+	// per island: all sleeping? else wake sleepers (ISLAND_SLEEPING -> WANTS_DEACTIVATION)
+	for (int root = 0; root < nb; root++) {
+		bool any = false, allSleeping = true;
+		for (int b = 0; b < nb; b++) if (w.body[b].islandTag == root) {
+			any = true;
+			if (w.body[b].activation == ACT_ACTIVE || w.body[b].activation == ACT_DISABLE_DEACT) { allSleeping = false; break; }
+		}
+		if (!any) continue;
+		for (int b = 0; b < nb; b++) if (w.body[b].islandTag == root) {
+			if (allSleeping) { if (w.body[b].activation != ACT_DISABLE_DEACT && w.body[b].activation != ACT_DISABLE_SIM) w.body[b].activation = ACT_SLEEPING; }
+			else if (w.body[b].activation == ACT_SLEEPING) w.body[b].activation = ACT_WANTS_DEACT;
+		}
+	}
+	// m_islandmanifold: manifolds with an awake body and needsResponse, then quickSort by island id
+	int keys[MAX_MANIFOLDS];
+	int n = 0;
+	for (int m = 0; m < w.nManifolds; m++) {
+		const Manifold& mf = w.manifolds[m];
+		bool s0 = mf.body0 >= STATIC_BASE, s1 = mf.body1 >= STATIC_BASE;
+		bool awake0 = !s0 && w.body[mf.body0].activation != ACT_SLEEPING;
+		bool awake1 = !s1 && w.body[mf.body1].activation != ACT_SLEEPING;
+		if (!(awake0 || awake1)) continue;
+		bool resp = (s0 || !w.body[mf.body0].noResponse) && (s1 || !w.body[mf.body1].noResponse) && (!s0 || !s1);
+		if (!resp) continue;
+		int tag0 = s0 ? -1 : w.body[mf.body0].islandTag;
+		int tag1 = s1 ? -1 : w.body[mf.body1].islandTag;
+		keys[n] = tag0 >= 0 ? tag0 : tag1;
+		w.manifoldOrder[n] = m;
+		n++;
+	}
+	if (n > 1) quicksort_keys(keys, w.manifoldOrder, 0, n - 1);
+	// drop manifolds whose island is asleep (processIslands only calls the solver for awake islands)
+	int outN = 0;
+	for (int k = 0; k < n; k++) {
+		int root = keys[k];
+		bool awake = false;
+		for (int b = 0; b < nb; b++) if (w.body[b].islandTag == root && body_active(w.body[b])) { awake = true; break; }
+		if (awake) w.manifoldOrder[outN++] = w.manifoldOrder[k];
+	}
+	return outN;
+}
+
+RSB_HD V3 sb_vel_no_delta(const SolverBody& b, const V3& rel) {  // getVelocityInLocalPointNoDelta
+	if (b.orig < 0) return v3zero();
+	return b.lin + b.extF + cross(b.ang + b.extT, rel);
+}
+RSB_HD void sb_apply_impulse(SolverBody& b, const V3& lin, const V3& ang, float mag) {
+	if (b.orig >= 0) { b.dLin += lin * mag; b.dAng += ang * mag; }
+}
+RSB_HD void sb_apply_push(SolverBody& b, const V3& lin, const V3& ang, float mag) {
+	if (b.orig >= 0) { b.push += lin * mag; b.turn += ang * mag; }
+}
+RSB_HD float simd_dot3(const V3& a, const V3& b) { return a.x * b.x + (a.y * b.y + a.z * b.z); }  // btSimdDot3 association
+
+// setupContactConstraint (btSequentialImpulseConstraintSolver.cpp:795-983)
+RSB_HD void setup_contact_row(const Ctx& cx, SolverRow& r, int ia, int ib, const V3& normalB, float distance, float restitutionCoef,
+                              float frictionCoef, int isSpecial, const V3& rel1, const V3& rel2) {
+	ArenaW& w = *cx.w;
+	SolverBody& A = w.sbody[ia];
+	SolverBody& B = w.sbody[ib];
+	const bool hasA = A.orig >= 0, hasB = B.orig >= 0;
+	const float dt = cx.p->dt;
+	const float invTimeStep = 1.f / dt;
+	const float erp = 0.8f;
+	float cfm = 0.f; cfm *= invTimeStep;
+	r.bodyA = ia; r.bodyB = ib;
+	V3 torqueAxis0 = cross(rel1, normalB);
+	r.angA = hasA ? (w.body[A.orig].invInertiaW * torqueAxis0) : v3zero();
+	V3 torqueAxis1 = cross(rel2, normalB);
+	r.angB = hasB ? (w.body[B.orig].invInertiaW * (-torqueAxis1)) : v3zero();
+	float denom0 = 0.f, denom1 = 0.f;
+	if (hasA) { V3 vec = cross(r.angA, rel1); denom0 = w.body[A.orig].invMass + dot(normalB, vec); }
+	if (hasB) { V3 vec = cross(-r.angB, rel2); denom1 = w.body[B.orig].invMass + dot(normalB, vec); }
+	r.jacDiagInv = 1.f / (denom0 + denom1 + cfm);
+	if (hasA) { r.n1 = normalB; r.rp1xn = torqueAxis0; } else { r.n1 = v3zero(); r.rp1xn = v3zero(); }
+	if (hasB) { r.n2 = -normalB; r.rp2xn = -torqueAxis1; } else { r.n2 = v3zero(); r.rp2xn = v3zero(); }
+	float restitution = 0.f;
+	float penetration = distance + 0.f;
+	{
+		V3 vel1 = hasA ? vel_at(rigid_of(cx, A.orig), rel1) : v3zero();
+		V3 vel2 = hasB ? vel_at(rigid_of(cx, B.orig), rel2) : v3zero();
+		V3 vel = vel1 - vel2;
+		float rel_vel = dot(normalB, vel);
+		r.friction = frictionCoef;
+		// restitutionCurve with velocity threshold 0.2
+		restitution = (fabsf(rel_vel) < 0.2f) ? 0.f : (restitutionCoef * -rel_vel);
+		if (restitution <= 0.f) restitution = 0.f;
+	}
+	r.applied = 0.f;  // warm start of a fresh point: appliedImpulse 0 * 0.85
+	r.appliedPush = 0.f;
+	{
+		V3 eFA = hasA ? A.extF : v3zero(), eTA = hasA ? A.extT : v3zero();
+		V3 eFB = hasB ? B.extF : v3zero(), eTB = hasB ? B.extT : v3zero();
+		float vel1Dotn = dot(r.n1, A.lin + eFA) + dot(r.rp1xn, A.ang + eTA);
+		float vel2Dotn = dot(r.n2, B.lin + eFB) + dot(r.rp2xn, B.ang + eTB);
+		float rel_vel = vel1Dotn + vel2Dotn;
+		float positionalError = 0.f;
+		float velocityError = restitution - rel_vel;
+		if (penetration > 0.f) positionalError = 0.f;
+		else positionalError = -penetration * erp * invTimeStep;
+		float penetrationImpulse = positionalError * r.jacDiagInv;
+		float velocityImpulse = velocityError * r.jacDiagInv;
+		// split impulse: penetration (<= 1e30 threshold) always goes to rhsPenetration
+		r.rhs = velocityImpulse;
+		r.rhsPen = penetrationImpulse;
+		r.cfm = cfm * r.jacDiagInv;
+		r.lower = 0.f; r.upper = 1e10f;
+	}
+	r.isSpecial = isSpecial;
+}
+
+// setupFrictionConstraint (btSequentialImpulseConstraintSolver.cpp:517-607)
+RSB_HD void setup_friction_row(const Ctx& cx, SolverRow& r, const V3& axis, int ia, int ib, float frictionCoef, const V3& rel1, const V3& rel2, int frictionIndex) {
+	ArenaW& w = *cx.w;
+	SolverBody& A = w.sbody[ia];
+	SolverBody& B = w.sbody[ib];
+	const bool hasA = A.orig >= 0, hasB = B.orig >= 0;
+	r.bodyA = ia; r.bodyB = ib; r.frictionIndex = frictionIndex;
+	r.friction = frictionCoef;
+	r.applied = 0.f; r.appliedPush = 0.f;
+	if (hasA) {
+		r.n1 = axis; V3 ft = cross(rel1, r.n1); r.rp1xn = ft; r.angA = w.body[A.orig].invInertiaW * ft;
+	} else { r.n1 = v3zero(); r.rp1xn = v3zero(); r.angA = v3zero(); }
+	if (hasB) {
+		r.n2 = -axis; V3 ft = cross(rel2, r.n2); r.rp2xn = ft; r.angB = w.body[B.orig].invInertiaW * ft;
+	} else { r.n2 = v3zero(); r.rp2xn = v3zero(); r.angB = v3zero(); }
+	float denom0 = 0.f, denom1 = 0.f;
+	if (hasA) { V3 vec = cross(r.angA, rel1); denom0 = w.body[A.orig].invMass + dot(axis, vec); }
+	if (hasB) { V3 vec = cross(-r.angB, rel2); denom1 = w.body[B.orig].invMass + dot(axis, vec); }
+	r.jacDiagInv = 1.f / (denom0 + denom1);
+	float vel1Dotn = dot(r.n1, hasA ? A.lin + A.extF : v3zero()) + dot(r.rp1xn, hasA ? A.ang : v3zero());
+	float vel2Dotn = dot(r.n2, hasB ? B.lin + B.extF : v3zero()) + dot(r.rp2xn, hasB ? B.ang : v3zero());
+	float rel_vel = vel1Dotn + vel2Dotn;
+	float velocityError = 0.f - rel_vel;
+	float velocityImpulse = velocityError * r.jacDiagInv;
+	r.rhs = 0.f + velocityImpulse;
+	r.rhsPen = 0.f;
+	r.cfm = 0.f;
+	r.lower = -r.friction; r.upper = r.friction;
+	r.isSpecial = 0;
+}
+
+// convertContactInner: friction direction + friction row (btSequentialImpulseConstraintSolver.cpp:1069-1162)
+RSB_HD void add_friction_for(const Ctx& cx, int ia, int ib, const V3& normalB, float frictionCoef, const V3& rel1, const V3& rel2, int frictionIndex) {
+	ArenaW& w = *cx.w;
+	V3 vel1 = sb_vel_no_delta(w.sbody[ia], rel1);
+	V3 vel2 = sb_vel_no_delta(w.sbody[ib], rel2);
+	V3 vel = vel1 - vel2;
+	float rel_vel = dot(normalB, vel);
+	V3 dir1 = vel - normalB * rel_vel;
+	float lat_rel_vel = len2(dir1);
+	if (lat_rel_vel > kEps) {
+		dir1 *= 1.f / sqrtf(lat_rel_vel);
+	} else {
+		V3 dir2;
+		plane_space1(normalB, dir1, dir2);
+	}
+	setup_friction_row(cx, w.frows[w.nFrictionRows], dir1, ia, ib, frictionCoef, rel1, rel2, frictionIndex);
+	w.nFrictionRows++;
+}
+
+RSB_HD int get_or_init_solver_body(const Ctx& cx, int obj, int* companion, int& fixedId) {
+	ArenaW& w = *cx.w;
+	if (obj < STATIC_BASE) {
+		if (companion[obj] >= 0) return companion[obj];
+		int id = w.nSolverBodies++;
+		SolverBody& sb = w.sbody[id];
+		const RigidS& rb = rigid_of(cx, obj);
+		const BodyW& bw = w.body[obj];
+		sb.dLin = sb.dAng = sb.push = sb.turn = v3zero();
+		sb.xf.basis = rb.basis; sb.xf.origin = rb.pos;
+		sb.invMassV = V3(bw.invMass, bw.invMass, bw.invMass);
+		sb.orig = obj;
+		sb.lin = rb.vel; sb.ang = rb.angvel;
+		sb.extF = bw.totalForce * bw.invMass * cx.p->dt;
+		sb.extT = vmul(bw.totalTorque, bw.invInertiaW) * cx.p->dt;
+		companion[obj] = id;
+		return id;
+	}
+	if (fixedId < 0) {
+		fixedId = w.nSolverBodies++;
+		SolverBody& sb = w.sbody[fixedId];
+		sb.dLin = sb.dAng = sb.push = sb.turn = v3zero();
+		sb.xf.basis = m3identity(); sb.xf.origin = v3zero();
+		sb.invMassV = v3zero(); sb.orig = -1;
+		sb.lin = sb.ang = sb.extF = sb.extT = v3zero();
+	}
+	return fixedId;
+}
+
+// Row kernels (SSE2 variants, btSequentialImpulseConstraintSolver.cpp:149-232, 318-349)
+RSB_HD float resolve_row(SolverBody& A, SolverBody& B, SolverRow& c, bool upperLimit) {
+	float deltaImpulse = c.rhs - c.applied * c.cfm;
+	float dv1 = simd_dot3(c.n1, A.dLin) + simd_dot3(c.rp1xn, A.dAng);
+	float dv2 = simd_dot3(c.n2, B.dLin) + simd_dot3(c.rp2xn, B.dAng);
+	deltaImpulse = deltaImpulse - dv1 * c.jacDiagInv;
+	deltaImpulse = deltaImpulse - dv2 * c.jacDiagInv;
+	float sum = c.applied + deltaImpulse;
+	if (sum < c.lower) { deltaImpulse = c.lower - c.applied; c.applied = c.lower; }
+	else if (upperLimit && !(sum < c.upper)) { deltaImpulse = c.upper - c.applied; c.applied = c.upper; }
+	else c.applied = sum;
+	sb_apply_impulse(A, c.n1 * A.invMassV, c.angA, deltaImpulse);
+	sb_apply_impulse(B, c.n2 * B.invMassV, c.angB, deltaImpulse);
+	return deltaImpulse * (1.f / c.jacDiagInv);
+}
+RSB_HD float resolve_split(SolverBody& A, SolverBody& B, SolverRow& c) {
+	if (c.rhsPen == 0.f) return 0.f;
+	float deltaImpulse = c.rhsPen - c.appliedPush * c.cfm;
+	float dv1 = simd_dot3(c.n1, A.push) + simd_dot3(c.rp1xn, A.turn);
+	float dv2 = simd_dot3(c.n2, B.push) + simd_dot3(c.rp2xn, B.turn);
+	deltaImpulse = deltaImpulse - dv1 * c.jacDiagInv;
+	deltaImpulse = deltaImpulse - dv2 * c.jacDiagInv;
+	float sum = c.appliedPush + deltaImpulse;
+	if (sum < c.lower) { deltaImpulse = c.lower - c.appliedPush; c.appliedPush = c.lower; }
+	else c.appliedPush = sum;
+	sb_apply_push(A, c.n1 * A.invMassV, c.angA, deltaImpulse);
+	sb_apply_push(B, c.n2 * B.invMassV, c.angB, deltaImpulse);
+	return deltaImpulse * (1.f / c.jacDiagInv);
+}
+
+// solveGroup for the whole arena: every awake dynamic body is converted (so that bodies
+// without contacts still receive their external force impulse), contacts -> rows, special
+// contacts, iterations, writeback.
+RSB_HD void solve_arena(const Ctx& cx, int nSolveManifolds) {
+	ArenaW& w = *cx.w;
+	const int nb = n_bodies(cx);
+	const float dt = cx.p->dt;
+	int companion[MAX_BODIES];
+	for (int b = 0; b < nb; b++) { companion[b] = -1; w.spNum[b] = 0; w.spTotalDist[b] = 0.f; w.spTotalNormal[b] = v3zero(); w.spFriction[b] = 0.f; w.spRestitution[b] = 0.f; }
+	int fixedId = -1;
+	w.nSolverBodies = 0; w.nRows = 0; w.nFrictionRows = 0;
+
+	// convertBodies: bodies of awake islands, in island order (sorted by island id), then body order
+	for (int root = 0; root < nb; root++) {
+		bool awake = false;
+		for (int b = 0; b < nb; b++) if (w.body[b].islandTag == root && body_active(w.body[b])) { awake = true; break; }
+		if (!awake) continue;
+		for (int b = 0; b < nb; b++) if (w.body[b].islandTag == root) get_or_init_solver_body(cx, b, companion, fixedId);
+	}
+
+	// convertContacts
+	for (int k = 0; k < nSolveManifolds; k++) {
+		Manifold& mf = w.manifolds[w.manifoldOrder[k]];
+		int ia = get_or_init_solver_body(cx, mf.body0, companion, fixedId);
+		int ib = get_or_init_solver_body(cx, mf.body1, companion, fixedId);
+		for (int j = 0; j < mf.nPts; j++) {
+			ContactPt& cp = mf.pts[j];
+			if (!(cp.dist <= mf.processingThresh)) continue;
+			if (w.nRows >= MAX_ROWS) { cx.s->errorFlags |= ERR_MANIFOLD_OVERFLOW; break; }
+			V3 org0 = mf.body0 < STATIC_BASE ? rigid_of(cx, mf.body0).pos : static_origin(cx, mf.body0);
+			V3 org1 = mf.body1 < STATIC_BASE ? rigid_of(cx, mf.body1).pos : static_origin(cx, mf.body1);
+			V3 rel1 = cp.posA - org0;
+			V3 rel2 = cp.posB - org1;
+			int frictionIndex = w.nRows;
+			SolverRow& row = w.rows[w.nRows++];
+			setup_contact_row(cx, row, ia, ib, cp.normalB, cp.dist, cp.restitution, cp.friction, cp.isSpecial, rel1, rel2);
+			row.frictionIndex = w.nFrictionRows;
+			if (cp.isSpecial) {
+				for (int i = 0; i < 2; i++) {
+					int obj = i ? mf.body1 : mf.body0;
+					if (obj < STATIC_BASE) {
+						w.spNum[obj]++;
+						w.spFriction[obj] = cp.friction;
+						w.spRestitution[obj] = cp.restitution;
+						w.spTotalNormal[obj] += cp.normalB;
+						w.spTotalDist[obj] += len(i ? rel2 : rel1);
+					}
+				}
+			}
+			add_friction_for(cx, ia, ib, cp.normalB, cp.friction, rel1, rel2, frictionIndex);
+		}
+	}
+	// special contacts, per converted body in solver-body order (convertContactSpecial, :1164-1211)
+	for (int sbi = 0; sbi < w.nSolverBodies; sbi++) {
+		int b = w.sbody[sbi].orig;
+		if (b < 0 || w.spNum[b] <= 0) continue;
+		if (w.nRows >= MAX_ROWS) { cx.s->errorFlags |= ERR_MANIFOLD_OVERFLOW; break; }
+		float distance = w.spTotalDist[b] / (float)w.spNum[b];
+		V3 normal = w.spTotalNormal[b] / (float)w.spNum[b];
+		int frictionIndex = w.nRows;
+		int ia = companion[b];
+		int ib = get_or_init_solver_body(cx, STATIC_BASE, companion, fixedId);
+		V3 rel1 = normal * -distance;
+		V3 rel2 = v3zero();
+		SolverRow& row = w.rows[w.nRows++];
+		setup_contact_row(cx, row, ia, ib, normal, distance, w.spRestitution[b], w.spFriction[b], 0, rel1, rel2);
+		row.frictionIndex = w.nFrictionRows;
+		add_friction_for(cx, ia, ib, normal, w.spFriction[b], rel1, rel2, frictionIndex);
+		w.spNum[b] = 0;
+	}
+
+	// split impulse iterations (:1778-1810)
+	for (int it = 0; it < 10; it++) {
+		float lsr = 0.f;
+		for (int j = 0; j < w.nRows; j++) {
+			SolverRow& c = w.rows[j];
+			float residual = resolve_split(w.sbody[c.bodyA], w.sbody[c.bodyB], c);
+			float r2 = residual * residual;
+			if (r2 > lsr) lsr = r2;
+		}
+		if (lsr <= 0.f || it >= 9) break;
+	}
+	// velocity iterations (:1601-1776): non-special contacts, then friction rows
+	for (int it = 0; it < 10; it++) {
+		for (int j = 0; j < w.nRows; j++) {
+			SolverRow& c = w.rows[j];
+			if (c.isSpecial) continue;
+			resolve_row(w.sbody[c.bodyA], w.sbody[c.bodyB], c, false);
+		}
+		for (int j = 0; j < w.nFrictionRows; j++) {
+			SolverRow& c = w.frows[j];
+			float totalImpulse = w.rows[c.frictionIndex].applied;
+			if (totalImpulse > 0.f) {
+				c.lower = -(c.friction * totalImpulse);
+				c.upper = c.friction * totalImpulse;
+				resolve_row(w.sbody[c.bodyA], w.sbody[c.bodyB], c, true);
+			}
+		}
+	}
+	// writeBackBodies (:1878-1904, btSolverBody.h:265-287)
+	for (int i = 0; i < w.nSolverBodies; i++) {
+		SolverBody& sb = w.sbody[i];
+		if (sb.orig < 0) continue;
+		RigidS& rb = rigid_of(cx, sb.orig);
+		sb.lin += sb.dLin;
+		sb.ang += sb.dAng;
+		if (sb.push.x != 0.f || sb.push.y != 0.f || sb.push.z != 0.f || sb.turn.x != 0.f || sb.turn.y != 0.f || sb.turn.z != 0.f) {
+			Xform nt;
+			bool noRot = (sb.orig == 0) && cx.p->ballNoRot;
+			integrate_transform(sb.xf, sb.push, sb.turn * 0.1f, dt, noRot, nt);
+			sb.xf = nt;
+		}
+		rb.vel = sb.lin + sb.extF;
+		rb.angvel = sb.ang + sb.extT;
+		rb.pos = sb.xf.origin;
+		rb.basis = sb.xf.basis;
+	}
+}
+
+}  // namespace rsb

@@ -1,0 +1,190 @@
+// rsb_state.h -- device-resident data model of the batched arena tick.
+//
+//   ArenaS  : everything the reference keeps alive BETWEEN ticks for one arena: the rigid
+//             body pose/velocity of ball and cars (Bullet units), CarState/BallState game
+//             fields (reference src/Sim/Car/Car.h:17-120, src/Sim/Ball/Ball.h:18-57), the
+//             wheel values that the reference consumes one tick late, pad
+//             state, the respawn RNG and the broadphase cell history stamps.
+//             One contiguous record per arena: a warp owns an arena and streams its record
+//             with coalesced 16-byte accesses.
+//   ArenaW  : per-tick scratch of one arena (wheel ray results, swept AABBs, contact
+//             manifolds, solver rows).  Never read across ticks.
+//   BatchParams / Scene : read-only constants shared by all arenas of a batch / game mode.
+#pragma once
+
+#include "rsb_math.h"
+
+namespace rsb {
+
+constexpr int MAX_CARS = 6;          // 3v3
+constexpr int MAX_BODIES = MAX_CARS + 1;  // dynamic bodies: ball (index 0) + cars (1..n)
+constexpr int MAX_PADS = 40;         // Soccar 34, Hoops 20
+constexpr int MAX_WHEELS = MAX_CARS * 4;
+constexpr int MAX_MANIFOLDS = 48;
+constexpr int MAX_POINTS = MAX_MANIFOLDS * 4;
+constexpr int MAX_ROWS = MAX_POINTS + MAX_BODIES;
+constexpr int MAX_EVENTS_PER_ARENA = 8;
+
+enum GameMode : int { SOCCAR = 0, HOOPS = 1, HEATSEEKER = 2, SNOWDAY = 3, DROPSHOT = 4, THE_VOID = 5 };
+
+// ---------------------------------------------------------------- persistent state
+struct RigidS {
+	V3 pos;      // world transform origin (Bullet units)
+	M3 basis;    // world transform basis (row-major)
+	V3 vel;      // linear velocity (bt/s)
+	V3 angvel;   // rad/s
+};
+
+struct CtrlS {
+	float throttle, steer, pitch, yaw, roll;
+	uint8_t jump, boost, handbrake, _pad;
+};
+
+struct CarS {
+	RigidS rb;
+	// --- CarState game fields (Car.h:17-120) ---
+	V3 flipRelTorque;
+	V3 worldContactNormal;
+	float jumpTime, flipTime, airTime, airTimeSinceJump;
+	float boost, timeSinceBoosted, boostingTime, supersonicTime;
+	float handbrakeVal, autoFlipTimer, autoFlipTorqueScale;
+	float carContactCooldown, demoRespawnTimer;
+	uint32_t carContactOtherID;
+	uint8_t isOnGround, hasJumped, hasDoubleJumped, hasFlipped;
+	uint8_t isFlipping, isJumping, isBoosting, isSupersonic;
+	uint8_t isAutoFlipping, worldContactHas, isDemoed, bhValid;
+	uint8_t wheelsWithContact[4];
+	// ballHitInfo (BallHitInfo.h:9-28), vectors in UU
+	V3 bhRelPos, bhBallPos, bhExtraVel;
+	uint64_t bhTickHit, bhTickExtra;
+	CtrlS lastControls;
+	CtrlS controls;  // Car::controls (Car.h:149)
+	uint64_t tickCountSinceUpdate;
+	// --- state the reference keeps outside CarState ---
+	float wSteer[4], wEngine[4], wBrake[4], wLatFriction[4], wLongFriction[4], wExtraPushback[4];
+	V3 velImpulseCache;  // Car::_velocityImpulseCache, Bullet units
+};
+
+struct BallS {
+	RigidS rb;
+	float hsYTargetDir, hsCurTargetSpeed, hsTimeSinceHit;  // BallState::HeatseekerInfo
+	V3 velImpulseCache;  // Ball::_velocityImpulseCache, Bullet units
+	uint64_t tickCountSinceUpdate;
+	uint8_t groundStickApplied;  // Ball::_groundStickApplied (Ball.h:82)
+	uint8_t _pad[7];
+};
+
+struct PadS {
+	float cooldown;
+	uint32_t prevLockedCarID;
+	uint8_t isActive;
+	uint8_t _pad[3];
+};
+
+struct ArenaS {
+	uint64_t tickCount;
+	uint32_t rng;          // minstd_rand0 state of the respawn RNG (Math.cpp:44-64)
+	uint32_t stampCounter; // broadphase cell-history counter
+	// btRSBroadphase dynamic proxies: cell of the AABB min corner and the order in which
+	// bodies last (re-)entered their 27-cell neighbourhood (btRSBroadphase.cpp:184-202,286-323)
+	int32_t cellIdx[MAX_BODIES];
+	uint32_t cellStamp[MAX_BODIES];
+	uint32_t errorFlags;
+	uint32_t goalScoredTick;  // debug
+	BallS ball;
+	CarS cars[MAX_CARS];
+	PadS pads[MAX_PADS];
+};
+
+enum ErrorFlags : uint32_t {
+	ERR_MANIFOLD_OVERFLOW = 1u, ERR_NAN = 2u, ERR_EVENT_OVERFLOW = 4u, ERR_BVH_STACK = 8u, ERR_EPA_FAIL = 16u,
+	ERR_TRI_OVERFLOW = 32u,
+};
+
+// ---------------------------------------------------------------- batch constants
+struct CarCfgD {            // derived from CarConfig (CarConfig.h:21-38) in Car::_BulletSetup (Car.cpp:195-292)
+	V3 hitboxHalf;          // (hitboxSize * UU_TO_BT) / 2 as passed to btBoxShape
+	V3 hitboxImplicit;      // hitboxHalf - 0.04 (btBoxShape.cpp:17-26: shrunk by the DEFAULT margin)
+	float hitboxMargin;     // min(0.04, 0.1 * min half extent) (setSafeMargin, btConvexInternalShape.h:63-78)
+	V3 hitboxOffset;        // compound child origin
+	V3 invInertiaLocal;
+	V3 wheelConn[4];        // chassisConnectionPointCS
+	float wheelRadius[4];
+	float suspRest[4];      // suspensionRestLength1 (config rest - travel), Bullet units
+	float forceScale[4];
+	float dodgeDeadzone;
+	int threeWheels;
+};
+
+struct PadCfgD {
+	V3 posBT, boxMin, boxMax;
+	float cylRadBT;
+	int isBig;
+};
+
+struct MutD {  // MutatorConfig (MutatorConfig.h:16-79), raw values in reference units
+	V3 gravity;
+	float carMass, carWorldFriction, carWorldRestitution;
+	float ballMass, ballMaxSpeed, ballDrag, ballWorldFriction, ballWorldRestitution;
+	float jumpAccel, jumpImmediateForce, boostAccelGround, boostAccelAir, boostUsedPerSecond;
+	float respawnDelay, bumpCooldownTime, boostPadCooldown_Big, boostPadCooldown_Small, carSpawnBoostAmount;
+	float ballHitExtraForceScale, bumpForceScale, ballRadius;
+	float rechargeBoostPerSecond, rechargeBoostDelay, goalBaseThresholdY;
+	int unlimitedFlips, unlimitedDoubleJumps, rechargeBoostEnabled, demoMode, enableTeamDemos;
+};
+
+constexpr int PUCK_POINTS = 40;
+
+struct BatchParams {
+	int mode, nCars, nPads, nArenas;
+	float dt;
+	MutD mut;
+	V3 gravityBT;
+	// ball rigid body / shape (Ball.cpp:53-115)
+	int ballIsSphere, ballNoRot;
+	float ballRadiusBT, ballInvMass, ballMass;
+	V3 ballInvInertiaLocal;
+	V3 puckPts[PUCK_POINTS];
+	V3 puckLocalAabbMin, puckLocalAabbMax;  // recalcLocalAabb result
+	CarCfgD carCfg[MAX_CARS];
+	int team[MAX_CARS];
+	PadCfgD pads[MAX_PADS];
+	int padGrid[8 * 10];  // BoostPadGrid (BoostPadGrid.h:10-29): pad index or -1
+};
+
+// ---------------------------------------------------------------- static scene (per game mode)
+struct BvhNode { uint16_t qmin[3]; uint16_t qmax[3]; int32_t idx; };  // btQuantizedBvhNode (16 B)
+struct SubtreeHdr { uint16_t qmin[3]; uint16_t qmax[3]; int32_t root; int32_t size; };
+struct TriInfo { int32_t flags; float a01, a12, a20; };  // btTriangleInfo, flags = -1 when absent
+
+struct MeshD {
+	const BvhNode* nodes; int nNodes;
+	const SubtreeHdr* hdrs; int nHdrs;
+	const int32_t* tris;   // 3 indices per triangle
+	const float* verts;    // 4 floats per vertex (16-byte stride like btVector3)
+	const TriInfo* info;
+	int nTris, nVerts;
+	V3 bvhMin, bvhMax, bvhQuant;  // quantization frame
+	V3 aabbMin, aabbMax;          // shape local AABB (= world: meshes sit at the origin)
+	int group, mask;              // collision filter (HOOPS_NET for the 505-vertex mesh)
+};
+
+struct PlaneD { V3 n; float d; V3 pos; V3 aabbMin, aabbMax; };  // world plane n.x = d ; body origin pos
+
+constexpr int MAX_MESHES = 20;
+constexpr int MAX_PLANES = 6;
+constexpr int MAX_STATICS = MAX_MESHES + MAX_PLANES;
+
+struct Scene {
+	int nMeshes, nPlanes;
+	MeshD meshes[MAX_MESHES];
+	PlaneD planes[MAX_PLANES];
+	// btRSBroadphase grid (btRSBroadphase.cpp:43-84): static object lists per cell, CSR
+	V3 gridMin, gridMax;
+	float cellSize;
+	int cellsX, cellsY, cellsZ;
+	const int32_t* cellStart;   // [totalCells+1]
+	const uint8_t* cellStatics; // static object indices (0..nMeshes-1 meshes, then planes)
+};
+
+}  // namespace rsb

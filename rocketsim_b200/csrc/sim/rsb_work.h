@@ -1,0 +1,153 @@
+// rsb_work.h -- per-tick scratch (ArenaW) and the execution context of one arena.
+#pragma once
+#include "rsb_state.h"
+#include "rsb_consts.h"
+
+namespace rsb {
+
+// Object ids used inside a tick: dynamic bodies 0..nBodies-1 (0 = ball, 1+i = car i);
+// static objects are STATIC_BASE + index (meshes first, then planes) -- the reference's
+// world object order (Arena.cpp:480-496, 1004-1068).
+constexpr int OBJ_NONE = -1;
+constexpr int STATIC_BASE = 64;
+
+enum Activation : int { ACT_ACTIVE = 1, ACT_SLEEPING = 2, ACT_WANTS_DEACT = 3, ACT_DISABLE_DEACT = 4, ACT_DISABLE_SIM = 5 };
+
+struct WheelW {  // btWheelInfoRL working values (btVehicleRL.h:9-27, btWheelInfo.h)
+	V3 hardPointWS, wheelDirWS, wheelAxleWS;
+	V3 contactPointWS, contactNormalWS;
+	V3 impulse;
+	M3 wtBasis;  // wheel world transform basis
+	float suspLen, suspRelVel, clippedInv, suspForce;
+	int isInContact, isInContactWithWorld, groundObj;
+};
+
+struct BodyW {  // btRigidBody working values of one dynamic body
+	M3 invInertiaW;
+	V3 totalForce, totalTorque;
+	V3 invInertiaLocal;
+	float invMass;
+	Xform interp;       // predicted transform (m_interpolationWorldTransform)
+	V3 aabbMin, aabbMax;
+	int activation;     // Activation
+	int noResponse;     // CF_NO_CONTACT_RESPONSE
+	int islandTag;
+	float friction, restitution;
+};
+
+struct ContactPt {  // btManifoldPoint subset
+	V3 localA, localB;
+	V3 posA, posB;      // world
+	V3 normalB;         // m_normalWorldOnB
+	float dist;
+	float friction, restitution;
+	int isSpecial;
+	int partId0, index0, partId1, index1;
+};
+
+struct Manifold {  // btPersistentManifold subset
+	int body0, body1;   // object ids (dynamic index or STATIC_BASE+k)
+	int nPts;
+	float breakingThresh, processingThresh;
+	ContactPt pts[4];
+};
+
+struct SolverBody {
+	V3 dLin, dAng, push, turn;
+	V3 lin, ang, extF, extT;
+	V3 invMassV;
+	Xform xf;
+	int orig;  // dynamic body index or -1 (fixed)
+};
+
+struct SolverRow {
+	V3 n1, n2, rp1xn, rp2xn, angA, angB;
+	float jacDiagInv, rhs, rhsPen, cfm, lower, upper, friction, applied, appliedPush;
+	int bodyA, bodyB, frictionIndex, isSpecial;
+};
+
+struct ArenaW {
+	BodyW body[MAX_BODIES];
+	WheelW wheels[MAX_WHEELS];
+	int padLocked[MAX_PADS];  // BoostPadState::curLockedCar as car index, -1 none
+	// broadphase pairs in creation order
+	int nPairs;
+	int pairA[MAX_MANIFOLDS], pairB[MAX_MANIFOLDS];
+	int nManifolds;
+	Manifold manifolds[MAX_MANIFOLDS];
+	int manifoldOrder[MAX_MANIFOLDS];
+	int nSolverBodies, nRows, nFrictionRows;
+	SolverBody sbody[MAX_BODIES + 1];
+	SolverRow rows[MAX_ROWS];
+	SolverRow frows[MAX_ROWS];
+	// special (ball-world) contact accumulation per body (btCollisionObject::m_specialResolveInfo)
+	int spNum[MAX_BODIES];
+	float spFriction[MAX_BODIES], spRestitution[MAX_BODIES], spTotalDist[MAX_BODIES];
+	V3 spTotalNormal[MAX_BODIES];
+};
+
+struct EventSink {
+	struct Ev { uint32_t arena, type, a, b; uint64_t tick; };
+	Ev* buf;
+	uint32_t* count;
+	uint32_t cap;
+};
+
+struct Ctx {
+	ArenaS* s;
+	ArenaW* w;
+	const BatchParams* p;
+	const Scene* sc;
+	EventSink ev;
+	int arena;
+	int lane, nlanes;  // SPMD position inside the arena's warp (host check: 0 / 1)
+};
+
+#if defined(__CUDA_ARCH__)
+#define RSB_SYNC() __syncwarp()
+#else
+#define RSB_SYNC() ((void)0)
+#endif
+#define RSB_FOR_LANES(i, n) for (int i = cx.lane; i < (n); i += cx.nlanes)
+
+RSB_HD RigidS& rigid_of(const Ctx& cx, int b) { return b == 0 ? cx.s->ball.rb : cx.s->cars[b - 1].rb; }
+RSB_HD int n_bodies(const Ctx& cx) { return cx.p->nCars + 1; }
+
+RSB_HD void push_event(const Ctx& cx, uint32_t type, uint32_t a, uint32_t b) {
+	if (!cx.ev.buf) return;
+#if defined(__CUDA_ARCH__)
+	uint32_t i = atomicAdd(cx.ev.count, 1u);
+#else
+	uint32_t i = (*cx.ev.count)++;
+#endif
+	if (i < cx.ev.cap) {
+		EventSink::Ev e; e.arena = (uint32_t)cx.arena; e.type = type; e.a = a; e.b = b; e.tick = cx.s->tickCount;
+		cx.ev.buf[i] = e;
+	} else {
+		cx.s->errorFlags |= ERR_EVENT_OVERFLOW;
+	}
+}
+
+RSB_HD bool body_active(const BodyW& b) { return b.activation != ACT_SLEEPING && b.activation != ACT_DISABLE_SIM; }
+
+// ---- btRigidBody helpers on (RigidS, BodyW) pairs ----
+RSB_HD V3 vel_at(const RigidS& rb, const V3& rel) { return rb.vel + cross(rb.angvel, rel); }  // getVelocityInLocalPoint
+RSB_HD void apply_central_impulse(RigidS& rb, const BodyW& bw, const V3& imp) { rb.vel += imp * bw.invMass; }
+RSB_HD void apply_torque_impulse(RigidS& rb, const BodyW& bw, const V3& t) { rb.angvel += bw.invInertiaW * t; }
+RSB_HD void apply_impulse(RigidS& rb, const BodyW& bw, const V3& imp, const V3& rel) {
+	if (bw.invMass != 0.f) {
+		apply_central_impulse(rb, bw, imp);
+		apply_torque_impulse(rb, bw, cross(rel, imp));
+	}
+}
+RSB_HD void apply_central_force(BodyW& bw, const V3& f) { bw.totalForce += f; }
+RSB_HD void apply_torque(BodyW& bw, const V3& t) { bw.totalTorque += t; }
+// btRigidBody::computeImpulseDenominator (btRigidBody.h:495-504)
+RSB_HD float impulse_denominator(const RigidS& rb, const BodyW& bw, const V3& pos, const V3& normal) {
+	V3 r0 = pos - rb.pos;
+	V3 c0 = cross(r0, normal);
+	V3 vec = cross(vmul(c0, bw.invInertiaW), r0);
+	return bw.invMass + dot(normal, vec);
+}
+
+}  // namespace rsb
