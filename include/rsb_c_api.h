@@ -102,6 +102,10 @@ int rsb_set_ball_internals(RsbBatch* b, const uint32_t* arena_idx, int n, const 
  * (all arenas when arena_idx == NULL; then seeds[a] applies to arena a). */
 int rsb_reset_to_random_kickoff(RsbBatch* b, const uint32_t* arena_idx, int n, const int32_t* seeds);
 
+/* Debug probe: per wheel {isInContact, isInContactWithWorld, suspLen, contactPoint xyz, contactNormal xyz,
+ * suspRelVel, clippedInv, impulse xyz} of the last tick for arena `arena`; out is [n_cars*4][14]. */
+int rsb_debug_get_wheels(RsbBatch* b, int arena, float* out);
+
 /* Static-scene introspection for the scene-builder unit tests. */
 int rsb_scene_counts(int game_mode, int mesh, int* counts5);
 int rsb_scene_dump(int game_mode, int mesh, void* nodes, void* headers, float* quant9, void* triinfo);

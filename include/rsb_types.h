@@ -171,13 +171,23 @@ typedef struct RsbCarInternal {
 	float longFriction[4];
 	float extraPushback[4];
 	float velocityImpulseCache[4]; /* Bullet units */
+	/* exact rigid-body position / linear velocity in Bullet units (CarState carries them x50,
+	 * which does not round-trip bit-exactly); applied by the setter when hasRigidBody != 0 */
+	float rbPos[4];
+	float rbVel[4];
+	uint64_t tickCountSinceUpdate;
+	uint32_t hasRigidBody;
+	uint32_t _pad;
 } RsbCarInternal;
 
 typedef struct RsbBallInternal {
 	float velocityImpulseCache[4]; /* Bullet units */
 	uint8_t groundStickApplied;
 	uint8_t _pad[3];
-	uint32_t _pad2[3];
+	uint32_t hasRigidBody;
+	uint64_t tickCountSinceUpdate;
+	float rbPos[4];
+	float rbVel[4];
 } RsbBallInternal;
 
 /* Events produced by a step (goal callback Arena.cpp:748-752, bump callback :399-400). */

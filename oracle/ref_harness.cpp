@@ -120,6 +120,11 @@ void ref_get_car_internal(RefArena* r, uint32_t id, RsbCarInternal* o) {
 		o->latFriction[i] = w.m_latFriction; o->longFriction[i] = w.m_longFriction; o->extraPushback[i] = w.m_extraPushback;
 	}
 	memcpy(o->velocityImpulseCache, &c->_velocityImpulseCache, 16);
+	const btVector3& org = c->_rigidBody.getWorldTransform().getOrigin();
+	for (int k = 0; k < 3; k++) { o->rbPos[k] = org[k]; o->rbVel[k] = c->_rigidBody.m_linearVelocity[k]; }
+	o->rbPos[3] = o->rbVel[3] = 0.f;
+	o->tickCountSinceUpdate = c->_internalState.tickCountSinceUpdate;
+	o->hasRigidBody = 1; o->_pad = 0;
 }
 void ref_set_car_internal(RefArena* r, uint32_t id, const RsbCarInternal* o) {
 	Car* c = r->cars[id - 1];
@@ -129,6 +134,11 @@ void ref_set_car_internal(RefArena* r, uint32_t id, const RsbCarInternal* o) {
 		w.m_latFriction = o->latFriction[i]; w.m_longFriction = o->longFriction[i]; w.m_extraPushback = o->extraPushback[i];
 	}
 	memcpy(&c->_velocityImpulseCache, o->velocityImpulseCache, 16);
+	if (o->hasRigidBody) {
+		c->_rigidBody.getWorldTransform().setOrigin(btVector3(o->rbPos[0], o->rbPos[1], o->rbPos[2]));
+		c->_rigidBody.m_linearVelocity = btVector3(o->rbVel[0], o->rbVel[1], o->rbVel[2]);
+		c->_internalState.tickCountSinceUpdate = o->tickCountSinceUpdate;
+	}
 }
 void ref_get_ball_state(RefArena* r, RsbBallState* out) {
 	BallState s = r->arena->ball->GetState();
@@ -143,10 +153,19 @@ void ref_get_ball_internal(RefArena* r, RsbBallInternal* o) {
 	memset(o, 0, sizeof(*o));
 	memcpy(o->velocityImpulseCache, &r->arena->ball->_velocityImpulseCache, 16);
 	o->groundStickApplied = r->arena->ball->_groundStickApplied;
+	const btVector3& org = r->arena->ball->_rigidBody.getWorldTransform().getOrigin();
+	for (int k = 0; k < 3; k++) { o->rbPos[k] = org[k]; o->rbVel[k] = r->arena->ball->_rigidBody.m_linearVelocity[k]; }
+	o->tickCountSinceUpdate = r->arena->ball->_internalState.tickCountSinceUpdate;
+	o->hasRigidBody = 1;
 }
 void ref_set_ball_internal(RefArena* r, const RsbBallInternal* o) {
 	memcpy(&r->arena->ball->_velocityImpulseCache, o->velocityImpulseCache, 16);
 	r->arena->ball->_groundStickApplied = o->groundStickApplied;
+	if (o->hasRigidBody) {
+		r->arena->ball->_rigidBody.getWorldTransform().setOrigin(btVector3(o->rbPos[0], o->rbPos[1], o->rbPos[2]));
+		r->arena->ball->_rigidBody.m_linearVelocity = btVector3(o->rbVel[0], o->rbVel[1], o->rbVel[2]);
+		r->arena->ball->_internalState.tickCountSinceUpdate = o->tickCountSinceUpdate;
+	}
 }
 void ref_get_pad_states(RefArena* r, RsbBoostPadState* out) {
 	auto& pads = r->arena->_boostPads;

@@ -293,6 +293,9 @@ RSB_GLOBAL void get_car_internals_kernel(const ArenaS* S, RsbCarInternal* out, i
 	RsbCarInternal o;
 	for (int k = 0; k < 4; k++) { o.steerAngle[k] = c.wSteer[k]; o.engineForce[k] = c.wEngine[k]; o.brake[k] = c.wBrake[k]; o.latFriction[k] = c.wLatFriction[k]; o.longFriction[k] = c.wLongFriction[k]; o.extraPushback[k] = c.wExtraPushback[k]; }
 	o.velocityImpulseCache[0] = c.velImpulseCache.x; o.velocityImpulseCache[1] = c.velImpulseCache.y; o.velocityImpulseCache[2] = c.velImpulseCache.z; o.velocityImpulseCache[3] = 0.f;
+	o.rbPos[0] = c.rb.pos.x; o.rbPos[1] = c.rb.pos.y; o.rbPos[2] = c.rb.pos.z; o.rbPos[3] = 0.f;
+	o.rbVel[0] = c.rb.vel.x; o.rbVel[1] = c.rb.vel.y; o.rbVel[2] = c.rb.vel.z; o.rbVel[3] = 0.f;
+	o.tickCountSinceUpdate = c.tickCountSinceUpdate; o.hasRigidBody = 1; o._pad = 0;
 	out[i] = o;
 }
 RSB_GLOBAL void set_car_internals_kernel(ArenaS* S, const uint32_t* ai, const uint32_t* ci, const RsbCarInternal* in, int n) {
@@ -301,12 +304,20 @@ RSB_GLOBAL void set_car_internals_kernel(ArenaS* S, const uint32_t* ai, const ui
 	const RsbCarInternal& o = in[i];
 	for (int k = 0; k < 4; k++) { c.wSteer[k] = o.steerAngle[k]; c.wEngine[k] = o.engineForce[k]; c.wBrake[k] = o.brake[k]; c.wLatFriction[k] = o.latFriction[k]; c.wLongFriction[k] = o.longFriction[k]; c.wExtraPushback[k] = o.extraPushback[k]; }
 	c.velImpulseCache = V3(o.velocityImpulseCache[0], o.velocityImpulseCache[1], o.velocityImpulseCache[2]);
+	if (o.hasRigidBody) {
+		c.rb.pos = V3(o.rbPos[0], o.rbPos[1], o.rbPos[2]); c.rb.vel = V3(o.rbVel[0], o.rbVel[1], o.rbVel[2]);
+		c.tickCountSinceUpdate = o.tickCountSinceUpdate;
+	}
 }
 RSB_GLOBAL void get_ball_internals_kernel(const ArenaS* S, RsbBallInternal* out, int nArenas) {
 	KERNEL_1D(i, nArenas);
 	RsbBallInternal o; memset(&o, 0, sizeof(o));
 	o.velocityImpulseCache[0] = S[i].ball.velImpulseCache.x; o.velocityImpulseCache[1] = S[i].ball.velImpulseCache.y; o.velocityImpulseCache[2] = S[i].ball.velImpulseCache.z;
 	o.groundStickApplied = S[i].ball.groundStickApplied;
+	const BallS& bb = S[i].ball;
+	o.rbPos[0] = bb.rb.pos.x; o.rbPos[1] = bb.rb.pos.y; o.rbPos[2] = bb.rb.pos.z;
+	o.rbVel[0] = bb.rb.vel.x; o.rbVel[1] = bb.rb.vel.y; o.rbVel[2] = bb.rb.vel.z;
+	o.tickCountSinceUpdate = bb.tickCountSinceUpdate; o.hasRigidBody = 1;
 	out[i] = o;
 }
 RSB_GLOBAL void set_ball_internals_kernel(ArenaS* S, const uint32_t* ai, const RsbBallInternal* in, int n) {
@@ -314,6 +325,10 @@ RSB_GLOBAL void set_ball_internals_kernel(ArenaS* S, const uint32_t* ai, const R
 	BallS& b = S[ai[i]].ball;
 	b.velImpulseCache = V3(in[i].velocityImpulseCache[0], in[i].velocityImpulseCache[1], in[i].velocityImpulseCache[2]);
 	b.groundStickApplied = in[i].groundStickApplied != 0;
+	if (in[i].hasRigidBody) {
+		b.rb.pos = V3(in[i].rbPos[0], in[i].rbPos[1], in[i].rbPos[2]); b.rb.vel = V3(in[i].rbVel[0], in[i].rbVel[1], in[i].rbVel[2]);
+		b.tickCountSinceUpdate = in[i].tickCountSinceUpdate;
+	}
 }
 RSB_GLOBAL void get_obs_kernel(const ArenaS* S, float* out, int nArenas, int nCars) {
 	KERNEL_1D(i, nArenas);
@@ -927,6 +942,21 @@ int rsb_reset_to_random_kickoff(RsbBatch* b, const uint32_t* ai, int n, const in
 int rsb_bench_fill_controls_device(RsbBatch* b, void* d_seq, int n_ticks, uint32_t tick0, uint64_t seed) {
 	API_BEGIN set_device(b);
 	LAUNCH_1D(fill_controls_kernel, b->hp.nArenas * b->hp.nCars, b, (CtrlS*)d_seq, b->hp.nArenas, b->hp.nCars, n_ticks, tick0, seed);
+	API_END
+}
+
+// ---- debug probe: wheel values of the last tick (layout of oracle ref_get_wheel_debug) ----
+int rsb_debug_get_wheels(RsbBatch* b, int arena, float* out) {
+	API_BEGIN set_device(b);
+	std::vector<ArenaW> w(1);
+	d2h(w.data(), b->dW + arena, sizeof(ArenaW), b->stream);
+	for (int k = 0; k < b->hp.nCars * 4; k++) {
+		const WheelW& x = w[0].wheels[k]; float* p = out + 14 * k;
+		p[0] = (float)x.isInContact; p[1] = (float)x.isInContactWithWorld; p[2] = x.suspLen;
+		p[3] = x.contactPointWS.x; p[4] = x.contactPointWS.y; p[5] = x.contactPointWS.z;
+		p[6] = x.contactNormalWS.x; p[7] = x.contactNormalWS.y; p[8] = x.contactNormalWS.z;
+		p[9] = x.suspRelVel; p[10] = x.clippedInv; p[11] = x.impulse.x; p[12] = x.impulse.y; p[13] = x.impulse.z;
+	}
 	API_END
 }
 

@@ -68,7 +68,7 @@ RSB_HD float len2(const V3& a) { return dot(a, a); }
 RSB_HD float len(const V3& a) { return sqrtf(dot(a, a)); }
 RSB_HD bool is_zero(const V3& a) { return a.x == 0.f && a.y == 0.f && a.z == 0.f; }
 RSB_HD bool fuzzy_zero(const V3& a) { return len2(a) < kEps * kEps; }
-RSB_HD V3 normalized(const V3& a) { return a * (1.0f / sqrtf(len2(a))); }  // btVector3::normalize
+RSB_HD V3 normalized(const V3& a) { return a * (1.0f / sqrtf(len2(a))); }  // btVector3::normalize (reference: rsqrtss + 1 NR step)
 // btVector3::safeNormalize (btVector3.h:292-305)
 RSB_HD V3 safe_normalized(const V3& a) {
 	float l2 = len2(a);

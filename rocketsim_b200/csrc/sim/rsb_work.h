@@ -66,6 +66,28 @@ struct SolverRow {
 	int bodyA, bodyB, frictionIndex, isSpecial;
 };
 
+// ---- EPA scratch (see rsb_epa.h) ----
+constexpr int EPA_MAX_VERTICES = 128, EPA_MAX_FACES = 256, EPA_MAX_ITERATIONS = 255;
+constexpr float GJK2_ACCURACY = 0.0001f, GJK2_MIN_DISTANCE = 0.0001f, GJK2_DUPLICATED_EPS = 0.0001f;
+constexpr float EPA_ACCURACY = 0.0001f, EPA_PLANE_EPS = 0.00001f;
+
+struct SV { V3 d, w; };
+struct Simplex2 { SV c[4]; float p[4]; int rank; };
+
+struct EpaFace {
+	V3 n; float d;
+	int16_t c[3];      // vertex indices into EpaScratch::sv
+	int16_t f[3];      // adjacent faces
+	int16_t l[2];      // list links (prev, next), -1 = none
+	uint8_t e[3];
+	uint8_t pass;
+};
+struct EpaScratch {
+	SV sv[EPA_MAX_VERTICES + 4];
+	EpaFace fc[EPA_MAX_FACES];
+	int16_t stackF[EPA_MAX_FACES + 8]; uint8_t stackE[EPA_MAX_FACES + 8]; uint8_t stackS[EPA_MAX_FACES + 8];
+};
+
 struct ArenaW {
 	BodyW body[MAX_BODIES];
 	WheelW wheels[MAX_WHEELS];
@@ -84,6 +106,7 @@ struct ArenaW {
 	int spNum[MAX_BODIES];
 	float spFriction[MAX_BODIES], spRestitution[MAX_BODIES], spTotalDist[MAX_BODIES];
 	V3 spTotalNormal[MAX_BODIES];
+	EpaScratch epa;
 };
 
 struct EventSink {

@@ -88,12 +88,15 @@ BoostPadState = np.dtype({"names": ["isActive", "cooldown", "prevLockedCarID"], 
 
 CarInternal = np.dtype({
     "names": ["steerAngle", "engineForce", "brake", "latFriction", "longFriction", "extraPushback",
-              "velocityImpulseCache"],
-    "formats": [("<f4", 4)] * 7,
-    "itemsize": 112,
+              "velocityImpulseCache", "rbPos", "rbVel", "tickCountSinceUpdate", "hasRigidBody"],
+    "formats": [("<f4", 4)] * 9 + ["<u8", "<u4"],
+    "offsets": [16 * i for i in range(9)] + [144, 152],
+    "itemsize": 160,
 })
-BallInternal = np.dtype({"names": ["velocityImpulseCache", "groundStickApplied"], "formats": [("<f4", 4), "u1"],
-                         "offsets": [0, 16], "itemsize": 32})
+BallInternal = np.dtype({"names": ["velocityImpulseCache", "groundStickApplied", "hasRigidBody", "tickCountSinceUpdate",
+                                   "rbPos", "rbVel"],
+                         "formats": [("<f4", 4), "u1", "<u4", "<u8", ("<f4", 4), ("<f4", 4)],
+                         "offsets": [0, 16, 20, 24, 32, 48], "itemsize": 64})
 
 Event = np.dtype({"names": ["arena", "type", "a", "b", "tick"], "formats": ["<u4", "<u4", "<u4", "<u4", "<u8"],
                   "itemsize": 24})
@@ -106,5 +109,5 @@ CAR_OCTANE, CAR_DOMINUS, CAR_PLANK, CAR_BREAKOUT, CAR_HYBRID, CAR_MERC, CAR_PSYC
 SIZES = {
     "RsbVec": 16, "RsbRotMat": 48, "RsbCarControls": 24, "RsbBallHitInfo": 80, "RsbCarState": 352,
     "RsbBallState": 144, "RsbMutatorConfig": 128, "RsbCarConfig": 112, "RsbBoostPadState": 12,
-    "RsbCarInternal": 112, "RsbBallInternal": 32, "RsbEvent": 24,
+    "RsbCarInternal": 160, "RsbBallInternal": 64, "RsbEvent": 24,
 }

@@ -12,6 +12,8 @@ ap.add_argument("mode", type=int); ap.add_argument("cpt", type=int); ap.add_argu
 ap.add_argument("--sync", action="store_true"); ap.add_argument("--seed", type=int, default=1)
 ap.add_argument("--planes", action="store_true"); ap.add_argument("--verbose", action="store_true")
 ap.add_argument("--stop", type=float, default=1e-3)
+ap.add_argument("--drive", type=int, default=0)
+ap.add_argument("--aim", action="store_true", help="place every car on a circle around the ball, facing it")
 a = ap.parse_args()
 
 L = rsb_lib.load(pu.build_hostcheck())
@@ -23,11 +25,24 @@ for t in teams: ref.add_car(t)
 b = pu.ArenaBatch(a.mode, 1, teams, lib=L)
 ref.seed_rng(a.seed); b.seed_rng(0, a.seed)
 ref.reset_kickoff(a.seed)
+if a.aim:
+    n = len(teams)
+    for i, cid in enumerate(ref.car_ids):
+        st = ref.car_state(cid)
+        ang = 2 * np.pi * i / n + 0.3
+        r = 900.0 + 150 * i
+        st['pos']['x'] = r * np.cos(ang); st['pos']['y'] = r * np.sin(ang); st['pos']['z'] = 17.0
+        yaw = ang + np.pi
+        cy, sy = np.float32(np.cos(yaw)), np.float32(np.sin(yaw))
+        st['rotMat']['forward'] = (cy, sy, 0, 0); st['rotMat']['right'] = (-sy, cy, 0, 0); st['rotMat']['up'] = (0, 0, 1, 0)
+        ref.set_car_state(cid, st)
 pu.sync_from_ref(b, ref)
 sched = pu.ControlSchedule(len(teams), a.seed)
 worst = {}
 for tick in range(a.ticks):
     c = sched.at(tick)
+    if tick < a.drive:
+        c['throttle'] = 1; c['boost'] = 1; c['steer'] = 0; c['jump'] = 0; c['handbrake'] = 0; c['pitch'] = 0; c['yaw'] = 0; c['roll'] = 0
     for i, cid in enumerate(ref.car_ids): ref.set_controls(cid, c[i])
     b.set_controls(c[None])
     ref.step(1); b.step(1)

@@ -45,7 +45,7 @@ def build_hostcheck(force: bool = False) -> str:
     for f in os.listdir(os.path.join(ROOT, "include")):
         newest = max(newest, os.path.getmtime(os.path.join(ROOT, "include", f)))
     if force or not os.path.exists(HOSTCHECK_LIB) or os.path.getmtime(HOSTCHECK_LIB) < newest:
-        cmd = ["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-DRSB_HOSTCHECK", "-x", "c++", src,
+        cmd = ["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-DRSB_HOSTCHECK", *os.environ.get("RSB_HOSTCHECK_FLAGS", "").split(), "-x", "c++", src,
                "-o", HOSTCHECK_LIB, "-I" + os.path.join(ROOT, "rocketsim_b200", "csrc")]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
