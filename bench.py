@@ -1,0 +1,304 @@
+#!/usr/bin/env python
+"""bench.py -- arena-ticks/s of the batched Arena::Step on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # CUDA arm (this repo)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU Arena::Step on the host cores
+
+Workload (BASELINE.json configs[1]): Soccar 2v2, 4,096 arenas per GPU, README bench inputs (each car
+redraws its controls every 2..60 ticks, include/rsb_bench_inputs.h), kickoff reset on goal inside the
+measured loop (device-side auto reset; the reference arm does `if IsBallScored() ResetToRandomKickoff`).
+One "step" = TICKS_PER_STEP consecutive ticks of every arena = one launch of the fused tick kernel.
+
+  value  : arena-ticks/s with the control sequences already resident in HBM (device timed, CUDA events).
+  e2e    : same through the C ABI with HOST buffers: per step one H2D copy of the step's control
+           sequence (pinned) + launch + D2H of every CarState and BallState.
+  roofline: algorithmic bytes per arena-tick (B = 2*(nCars*308+108+nPads*12+8)+nCars*24)
+           x arena-ticks per launch / measured kernel time, against the measured HBM peak.
+  cpu_baseline: oracle/_ref (the unmodified reference) on all host cores, bounded sample.
+
+Arenas are independent: N GPUs = N independent batches (weak scaling), no collective on the data path;
+torch.distributed is used only for the barrier and the max-over-ranks of the timing.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+MODE_NAMES = {0: "soccar", 1: "hoops", 2: "heatseeker", 3: "snowday", 5: "the_void"}
+SEED = 1234
+
+
+def algorithmic_bytes(n_cars: int, n_pads: int) -> int:
+    return 2 * (n_cars * 308 + 108 + n_pads * 12 + 8) + n_cars * 24
+
+
+def n_pads_of(mode: int) -> int:
+    return {0: 34, 1: 20, 2: 34, 3: 34, 5: 0}[mode]
+
+
+def measured_hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+        except Exception:
+            pass
+    return 6500.0, "fallback (B200_PROFILING.md: ~6.5 TB/s measured copy bandwidth)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons with nvidia-smi while the timed region runs."""
+
+    def __init__(self, gpu_index: int):
+        super().__init__(daemon=True)
+        self.gpu = gpu_index
+        self.stop_flag = threading.Event()
+        self.sm, self.reasons, self.sm_max = [], set(), None
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_throttle_reasons.active,clocks_event_reasons.hw_slowdown," \
+            "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                out = [x.strip() for x in out]
+                if len(out) >= 7:
+                    self.sm.append(float(out[0]))
+                    self.sm_max = float(out[1])
+                    for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), out[3:7]):
+                        if v.lower().startswith("active"):
+                            self.reasons.add(name)
+            except Exception:
+                pass
+            self.stop_flag.wait(0.05)
+
+    def result(self):
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.sm_max,
+                "reasons": sorted(self.reasons), "samples": len(self.sm)}
+
+
+def run_reference(args):
+    """The reference's own CPU implementation (oracle/_ref) on the host cores, same workload/metric."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import refsim
+    from rocketsim_b200 import synthetic_meshes as sm
+    if not refsim.available():
+        refsim.build()
+    refsim.init_from_mem(sm.mesh_sets())
+    cores = os.cpu_count() or 1
+    threads = cores
+    # README style (README.md:10-11): one arena per thread is the reference's fastest configuration (more arenas per
+    # thread only add cache pressure: measured 375k -> 28k arena-ticks/s from 1 to 64 arenas/thread on 8 cores).
+    # Bounded sample: a reference "step" = 64 x ticks_per_step ticks of `threads` arenas; construction is untimed.
+    apt = 1
+    ticks = 64 * args.ticks_per_step
+    if args.warmup > 0:
+        refsim.bench(args.mode, args.cars_per_team, threads, apt, max(1, ticks * args.warmup // 8), SEED)
+    v, wall = refsim.bench(args.mode, args.cars_per_team, threads, apt, ticks * max(1, args.steps), SEED)
+    value = v
+    n_cars = 2 * args.cars_per_team
+    sample = f"{threads} threads x {apt} arena x {ticks * max(1, args.steps)} ticks ({wall:.1f} s), oracle/_ref"
+    line = {
+        "impl": "reference", "metric": "arena_ticks_per_s", "value": value, "unit": "arena-ticks/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": wall * 1e3 / max(1, args.steps), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{MODE_NAMES[args.mode]} {args.cars_per_team}v{args.cars_per_team}, README bench inputs, "
+                               f"{args.arenas} arenas/GPU on the CUDA arm; CPU arm: bounded sample", "ticks_per_step": args.ticks_per_step,
+                   "n_cars": n_cars, "meshes": "synthetic .cmf (SURVEY F4)"},
+        "cpu_baseline": {"value": value, "unit": "arena-ticks/s", "cores": threads, "kind": "reference", "sample": sample},
+        "e2e": {"value": value, "unit": "arena-ticks/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_cuda(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (rocketsim_b200 has no CPU path)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    from rocketsim_b200 import lib as rlib, synthetic_meshes as sm, types as T
+    from rocketsim_b200.arena_batch import ArenaBatch
+
+    L = rlib.load()
+    rlib.init_from_mem(sm.mesh_sets(), L)
+    n_cars = 2 * args.cars_per_team
+    teams = [0] * args.cars_per_team + [1] * args.cars_per_team
+    A, TPS = args.arenas, args.ticks_per_step
+    batch = ArenaBatch(args.mode, A, teams, seed=SEED + rank * A, device=local_rank, lib=L)
+    stream = torch.cuda.current_stream()
+    batch.set_stream(stream.cuda_stream)
+    # arena ids are global: rank r owns arenas [r*A, (r+1)*A) (contiguous shard)
+    seeds = (SEED + rank * A + np.arange(A)).astype(np.int32)
+    batch.reset_to_random_kickoff(seeds)
+    batch.set_auto_reset(True, SEED + rank * A)
+
+    n_steps_total = args.warmup + args.steps
+    ctrl_bytes = TPS * A * n_cars * 24
+    # pre-generated control sequences, resident in HBM, one per step (different ticks -> different data)
+    d_seq = [torch.empty(ctrl_bytes, dtype=torch.uint8, device="cuda") for _ in range(n_steps_total)]
+    for i, buf in enumerate(d_seq):
+        rlib.check(L, L.rsb_bench_fill_controls_device(batch.h, C.c_void_p(buf.data_ptr()), TPS, i * TPS, SEED + rank))
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > L2 (126 MB)
+    torch.cuda.synchronize()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_device(i):
+        rlib.check(L, L.rsb_step_with_controls_device(batch.h, C.c_void_p(d_seq[i].data_ptr()), TPS))
+
+    # ---- device-resident arm ("value")
+    for i in range(args.warmup):
+        step_device(i)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    ev0.record(stream)
+    for k in range(args.steps):
+        flush.zero_()  # L2 flush between timed iterations
+        kev[k][0].record(stream)
+        step_device(args.warmup + k)
+        kev[k][1].record(stream)
+    ev1.record(stream)
+    barrier()
+    total_ms = ev0.elapsed_time(ev1)
+    kern_ms = [a.elapsed_time(b) for a, b in kev]
+    if rank == 0:
+        sampler.stop_flag.set()
+        sampler.join()
+    err = batch.get_error_flags()
+    ticks_done = batch.get_tick_counts()
+    assert int(ticks_done.min()) == n_steps_total * TPS, "tick counter mismatch: work was skipped"
+
+    # ---- end-to-end arm through the C ABI with host buffers
+    h_seq = [torch.empty(ctrl_bytes, dtype=torch.uint8).pin_memory() for _ in range(args.steps)]
+    for k in range(args.steps):
+        h_seq[k].copy_(d_seq[args.warmup + k])
+    car_out = np.zeros((A, n_cars), dtype=T.CarState)
+    ball_out = np.zeros(A, dtype=T.BallState)
+    d2h_bytes = car_out.nbytes + ball_out.nbytes
+
+    def step_e2e(k):
+        rlib.check(L, L.rsb_step_with_controls(batch.h, C.c_void_p(h_seq[k].data_ptr()), TPS))
+        rlib.check(L, L.rsb_get_car_states(batch.h, rlib.ptr(car_out)))
+        rlib.check(L, L.rsb_get_ball_states(batch.h, rlib.ptr(ball_out)))
+
+    for k in range(min(3, args.steps)):
+        step_e2e(k)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    t_host0 = time.perf_counter()
+    for k in range(args.steps):
+        step_e2e(k)
+    e1.record(stream)
+    barrier()
+    e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - t_host0) * 1e3 * 0)  # device clock; D2H copies synchronise
+    checksum = float(np.abs(car_out["pos"]["x"]).sum())
+
+    t = torch.tensor([total_ms, e2e_ms, float(np.mean(kern_ms))], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, e2e_ms, kern_ms_mean = [float(x) for x in t.cpu()]
+    errs = torch.tensor([int(err.max())], device="cuda")
+    if world > 1:
+        dist.all_reduce(errs, op=dist.ReduceOp.MAX)
+
+    if rank == 0:
+        arena_ticks_total = world * A * TPS * args.steps
+        value = arena_ticks_total / (total_ms * 1e-3)
+        e2e = arena_ticks_total / (e2e_ms * 1e-3)
+        n_pads = n_pads_of(args.mode)
+        Bt = algorithmic_bytes(n_cars, n_pads)
+        peak, peak_src = measured_hbm_peak()
+        achieved = A * TPS * Bt / (kern_ms_mean * 1e-3) / 1e9
+        line = {
+            "metric": "arena_ticks_per_s", "value": value, "unit": "arena-ticks/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{MODE_NAMES[args.mode]} {args.cars_per_team}v{args.cars_per_team}, README bench inputs (redrawn every 2-60 ticks/car), "
+                                   f"{A} arenas/GPU, kickoff reset on goal", "arenas_per_gpu": A, "ticks_per_step": TPS,
+                       "n_cars": n_cars, "meshes": "synthetic .cmf (SURVEY F4)", "l2": "256 MiB flush write between timed steps",
+                       "parallelism": f"replicas x{world} (independent arena shards, no collective)"},
+            "e2e": {"value": e2e, "unit": "arena-ticks/s", "h2d_bytes_per_step": ctrl_bytes, "d2h_bytes_per_step": d2h_bytes,
+                    "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": args.steps,  # one arena_step_kernel launch per step (plus one memset for the L2 flush)
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "kernel": "arena_step_kernel", "kernel_ms": kern_ms_mean,
+                         "bytes_per_arena_tick": Bt, "peak_source": peak_src},
+            "clocks": sampler.result(),
+            "device_error_flags": int(errs.item()), "checksum": checksum,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                from oracle import refsim
+                if refsim.available() or os.path.isdir(refsim.REFERENCE_ROOT):
+                    refsim.init_from_mem(sm.mesh_sets())
+                    cores = os.cpu_count() or 1
+                    apt = 1  # README style: the reference's fastest configuration
+                    v, wall = refsim.bench(args.mode, args.cars_per_team, cores, apt, 2000, SEED)  # calibrate
+                    ticks = int(max(2000, min(5_000_000, 12.0 * v / (cores * apt))))
+                    v, wall = refsim.bench(args.mode, args.cars_per_team, cores, apt, ticks, SEED)
+                    line["cpu_baseline"] = {"value": v, "unit": "arena-ticks/s", "cores": cores, "kind": "reference",
+                                            "sample": f"{cores} threads x {apt} arena x {ticks} ticks ({wall:.1f} s), oracle/_ref"}
+                else:
+                    line["cpu_baseline"] = {"value": None, "unit": "arena-ticks/s", "cores": 0, "kind": "reference",
+                                            "sample": "oracle/_ref not built"}
+            except Exception as e:  # the checker must never break the measurement
+                line["cpu_baseline"] = {"value": None, "unit": "arena-ticks/s", "cores": 0, "kind": "reference", "sample": f"failed: {e}"}
+        print(json.dumps(line), flush=True)
+    batch.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--mode", type=int, default=0)
+    ap.add_argument("--cars-per-team", type=int, default=2)
+    ap.add_argument("--arenas", type=int, default=4096, help="arenas per GPU")
+    ap.add_argument("--ticks-per-step", type=int, default=120)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "cuda" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_cuda(args)
+
+
+if __name__ == "__main__":
+    main()

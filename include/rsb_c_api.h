@@ -61,6 +61,13 @@ int rsb_step(RsbBatch* b, int n_ticks);
 /* Like rsb_step(1) repeated n_ticks times with a different control set per tick:
  * d_controls_seq is DEVICE memory [n_ticks][n_arenas][n_cars]. One launch. */
 int rsb_step_with_controls_device(RsbBatch* b, const void* d_controls_seq, int n_ticks);
+/* Same with the control sequence [n_ticks][n_arenas][n_cars] in HOST memory (one H2D copy + one launch):
+ * the reference loop `for t: car->controls = seq[t]; arena->Step(1)` (Car.h:149, Arena.h:132). */
+int rsb_step_with_controls(RsbBatch* b, const RsbCarControls* controls_seq, int n_ticks);
+/* README bench loop on device (README.md:49-53; oracle ref_bench): when enabled, a tick that ends with
+ * IsBallScored() is followed by ResetToRandomKickoff(seed + arena + tick) inside the same launch
+ * (Arena.cpp:113-223, 744-752). Off by default, as in the reference. */
+int rsb_set_auto_reset(RsbBatch* b, int enable, uint32_t seed);
 int rsb_sync(RsbBatch* b);
 
 /* Replace Car::GetState / Car::SetState (src/Sim/Car/Car.h:151-152, Car.cpp:10-36).

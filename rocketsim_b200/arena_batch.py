@@ -60,6 +60,16 @@ class ArenaBatch:
     def step(self, n_ticks: int = 1):
         _lib.check(self.L, self.L.rsb_step(self.h, n_ticks))
 
+    def step_with_controls(self, controls_seq: np.ndarray):
+        """``for t: car->controls = controls_seq[t]; Step(1)`` as one launch; controls_seq is
+        ``[n_ticks, n_arenas, n_cars]`` host memory."""
+        c = np.ascontiguousarray(controls_seq, dtype=T.CarControls).reshape(-1, self.n_arenas, self.n_cars)
+        _lib.check(self.L, self.L.rsb_step_with_controls(self.h, _lib.ptr(c), c.shape[0]))
+
+    def set_auto_reset(self, enable: bool, seed: int = 0):
+        """Device-side ``if (IsBallScored()) ResetToRandomKickoff(seed + arena + tick)`` after every tick."""
+        _lib.check(self.L, self.L.rsb_set_auto_reset(self.h, int(bool(enable)), seed & 0xFFFFFFFF))
+
     def sync(self):
         _lib.check(self.L, self.L.rsb_sync(self.h))
 

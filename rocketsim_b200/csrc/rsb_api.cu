@@ -117,6 +117,8 @@ struct RsbBatch {
 	uint32_t* dEventCount = nullptr;
 	uint32_t eventCap = 0;
 	CtrlS* dCtrl = nullptr;        // staging for rsb_set_controls
+	CtrlS* dCtrlSeq = nullptr;     // staging for rsb_step_with_controls (host sequence)
+	size_t ctrlSeqCap = 0;
 	void* dScratch = nullptr;      // staging for get/set
 	size_t scratchBytes = 0;
 	stream_t stream = 0;
@@ -365,90 +367,10 @@ RSB_GLOBAL void fill_controls_kernel(CtrlS* out, int nArenas, int nCars, int nTi
 }
 
 // Arena::ResetToRandomKickoff (Arena.cpp:113-223) on device, one thread per listed arena.
-struct KickoffTables { K::SpawnPos spawn[5]; K::SpawnPos respawn[4]; int locationAmount; };
-RSB_HD uint32_t minstd_uniform(uint32_t& x, uint32_t range) {
-	// std::uniform_int_distribution<size_t>(0, range-1) on minstd_rand0 (libstdc++ downscaling path)
-	const uint64_t urngrange = 2147483646ull - 1ull;  // max - min
-	const uint64_t scaling = urngrange / range;
-	const uint64_t past = range * scaling;
-	uint64_t ret;
-	do { ret = (uint64_t)minstd_next(x) - 1ull; } while (ret >= past);
-	return (uint32_t)(ret / scaling);
-}
-RSB_GLOBAL void reset_kickoff_kernel(ArenaS* S, const BatchParams* P, const Scene* sc, const uint32_t* ai, const int32_t* seeds, int n, KickoffTables kt) {
+RSB_GLOBAL void reset_kickoff_kernel(ArenaS* S, const BatchParams* P, const uint32_t* ai, const int32_t* seeds, int n) {
 	KERNEL_1D(i, n);
 	const int arena = ai ? (int)ai[i] : i;
-	ArenaS& A = S[arena];
-	const int seed = seeds[i];
-	uint32_t localRng = minstd_seed((uint32_t)seed);
-	uint32_t& rng = (seed == -1) ? A.rng : localRng;
-	int order[5] = {0, 1, 2, 3, 4};
-	const int L = kt.locationAmount;
-	// std::shuffle(first, first+L, g) (libstdc++ bits/stl_algo.h: pairwise draws when range*range fits)
-	{
-		const uint64_t urngrange = 2147483646ull - 1ull;
-		const uint64_t urange = (uint64_t)L;
-		if (urngrange / urange >= urange) {
-			int it = 1;
-			if ((urange % 2) == 0) { uint32_t j = minstd_uniform(rng, 2); int t = order[it]; order[it] = order[j]; order[j] = t; it++; }
-			while (it < L) {
-				const uint32_t swap_range = (uint32_t)it + 1;
-				uint32_t x = minstd_uniform(rng, swap_range * (swap_range + 1));
-				uint32_t p0 = x / (swap_range + 1), p1 = x % (swap_range + 1);
-				int t = order[it]; order[it] = order[p0]; order[p0] = t; it++;
-				t = order[it]; order[it] = order[p1]; order[p1] = t; it++;
-			}
-		} else {
-			for (int it = 1; it < L; it++) { uint32_t j = minstd_uniform(rng, (uint32_t)it + 1); int t = order[it]; order[it] = order[j]; order[j] = t; }
-		}
-	}
-	int nBlue = 0, nOrange = 0;
-	int blue[MAX_CARS], orange[MAX_CARS];
-	for (int c = 0; c < P->nCars; c++) { if (P->team[c] == 0) blue[nBlue++] = c; else orange[nOrange++] = c; }
-	int numAtRespawn[4] = {0, 0, 0, 0};
-	int amount = nBlue > nOrange ? nBlue : nOrange;
-	for (int k = 0; k < amount; k++) {
-		K::SpawnPos sp;
-		if (k < L) {
-			int idx = order[k] < L - 1 ? order[k] : L - 1;
-			sp = kt.spawn[idx];
-		} else {
-			int ridx = (k - L) % L;
-			sp = kt.respawn[ridx];
-			sp.y += 250.f * numAtRespawn[ridx];
-			numAtRespawn[ridx]++;
-		}
-		for (int team = 0; team < 2; team++) {
-			bool isBlue = team == 0;
-			int cnt = isBlue ? nBlue : nOrange;
-			if (k >= cnt) continue;
-			CarS& c = A.cars[isBlue ? blue[k] : orange[k]];
-			car_reset_state(c, P->mut.carSpawnBoostAmount);
-			V3 pos(sp.x, sp.y, K::CAR_SPAWN_REST_Z);
-			float yaw = sp.yaw;
-			if (!isBlue) { pos = pos * V3(-1.f, -1.f, 1.f); yaw = (float)((double)yaw + 3.14159265358979323846); }
-			c.rb.pos = pos * UU_TO_BT;
-			c.rb.basis = basis_from_ypr(yaw, 0.f, 0.f);
-			c.rb.vel = v3zero(); c.rb.angvel = v3zero();
-			c.isOnGround = 1;
-		}
-	}
-	BallS& b = A.ball;
-	b.rb.basis = m3identity(); b.rb.angvel = v3zero();
-	V3 bpos(0.f, 0.f, K::BALL_REST_Z), bvel(0.f, 0.f, 0.f);
-	b.hsYTargetDir = 0.f; b.hsCurTargetSpeed = K::HS_INITIAL_TARGET_SPEED; b.hsTimeSinceHit = 0.f;
-	if (P->mode == HEATSEEKER) {
-		int nextRand = (int)minstd_next(rng);
-		V3 scale(1.f, (nextRand % 2) ? 1.f : -1.f, 1.f);
-		bpos = V3(-1000, -2220, 92.75f) * scale;
-		bvel = V3(0, -65, 650) * scale;
-	} else if (P->mode == SNOWDAY) {
-		bvel.z = kEps;
-	}
-	b.rb.pos = bpos * UU_TO_BT; b.rb.vel = bvel * UU_TO_BT;
-	b.velImpulseCache = v3zero(); b.tickCountSinceUpdate = 0;
-	for (int p = 0; p < P->nPads; p++) { A.pads[p].isActive = 1; A.pads[p].cooldown = 0.f; A.pads[p].prevLockedCarID = 0; }
-	(void)sc;
+	kickoff_reset(S[arena], *P, seeds[i]);
 }
 
 // ------------------------------------------------------------------ parameter setup (host)
@@ -753,7 +675,7 @@ int rsb_batch_destroy(RsbBatch* b) {
 #ifndef RSB_HOSTCHECK
 	cudaDeviceSynchronize();
 #endif
-	dev_free(b->dP); dev_free(b->dS); dev_free(b->dW); dev_free(b->dEvents); dev_free(b->dEventCount); dev_free(b->dCtrl); dev_free(b->dScratch);
+	dev_free(b->dP); dev_free(b->dS); dev_free(b->dW); dev_free(b->dEvents); dev_free(b->dEventCount); dev_free(b->dCtrl); dev_free(b->dCtrlSeq); dev_free(b->dScratch);
 	delete b;
 	API_END
 }
@@ -814,6 +736,27 @@ int rsb_step_with_controls_device(RsbBatch* b, const void* d_seq, int n_ticks) {
 	API_BEGIN
 	set_device(b);
 	if (n_ticks > 0) launch_step(b, n_ticks, (const CtrlS*)d_seq, n_ticks);
+	API_END
+}
+int rsb_step_with_controls(RsbBatch* b, const RsbCarControls* seq, int n_ticks) {
+	API_BEGIN
+	set_device(b);
+	if (n_ticks <= 0) return 0;
+	static_assert(sizeof(CtrlS) == sizeof(RsbCarControls), "control layouts must match");
+	size_t n = (size_t)n_ticks * b->hp.nArenas * b->hp.nCars;
+	if (n > b->ctrlSeqCap) { dev_free(b->dCtrlSeq); b->dCtrlSeq = (CtrlS*)dev_alloc(n * sizeof(CtrlS)); b->ctrlSeqCap = n; }
+	h2d(b->dCtrlSeq, seq, n * sizeof(CtrlS), b->stream);
+	launch_step(b, n_ticks, b->dCtrlSeq, n_ticks);
+	API_END
+}
+int rsb_set_auto_reset(RsbBatch* b, int enable, uint32_t seed) {
+	API_BEGIN
+	set_device(b);
+	b->hp.autoReset = enable ? 1 : 0; b->hp.autoResetSeed = seed;
+#ifndef RSB_HOSTCHECK
+	CUDA_OK(cudaStreamSynchronize(b->stream));
+#endif
+	h2d(b->dP, &b->hp, sizeof(BatchParams), b->stream);
 	API_END
 }
 int rsb_sync(RsbBatch* b) {
@@ -920,22 +863,12 @@ int rsb_reset_to_random_kickoff(RsbBatch* b, const uint32_t* ai, int n, const in
 	API_BEGIN set_device(b);
 	if (!ai) n = b->hp.nArenas; else check_idx(b, ai, nullptr, n);
 	if (n <= 0) return 0;
-	const float P4 = (float)(3.14159265358979323846 / 4), P2 = (float)(3.14159265358979323846 / 2);
-	KickoffTables kt;
-	const int mode = b->hp.mode;
-	const K::SpawnPos soccar[5] = {{-2048, -2560, P4 * 1}, {2048, -2560, P4 * 3}, {-256, -3840, P4 * 2}, {256, -3840, P4 * 2}, {0, -4608, P4 * 2}};
-	const K::SpawnPos hoops[5] = {{-1536, -3072, P4 * 2}, {1536, -3072, P4 * 2}, {-256, -2816, P4 * 2}, {256, -2816, P4 * 2}, {0, -3200, P4 * 2}};
-	const K::SpawnPos heat[5] = {{-1000, -4620, P2}, {1000, -4620, P2}, {-2000, -4620, P2}, {2000, -4620, P2}, {0, 0, 0}};
-	const K::SpawnPos* sp = mode == HOOPS ? hoops : (mode == HEATSEEKER ? heat : soccar);
-	for (int i = 0; i < 5; i++) kt.spawn[i] = sp[i];
-	for (int i = 0; i < 4; i++) kt.respawn[i] = respawn_slot(mode == HOOPS, i);
-	kt.locationAmount = mode == HEATSEEKER ? 4 : 5;
 	size_t idxBytes = ((size_t)n * 4 + 15) & ~(size_t)15;
 	b->ensure_scratch(2 * idxBytes);
 	uint32_t* dai = (uint32_t*)b->dScratch; int32_t* dseed = (int32_t*)((char*)b->dScratch + idxBytes);
 	if (ai) h2d(dai, ai, (size_t)n * 4, b->stream);
 	h2d(dseed, seeds, (size_t)n * 4, b->stream);
-	LAUNCH_1D(reset_kickoff_kernel, n, b, b->dS, b->dP, b->dScene, ai ? dai : nullptr, dseed, n, kt);
+	LAUNCH_1D(reset_kickoff_kernel, n, b, b->dS, b->dP, ai ? dai : nullptr, dseed, n);
 	API_END
 }
 

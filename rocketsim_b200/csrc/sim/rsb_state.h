@@ -150,6 +150,8 @@ struct BatchParams {
 	int team[MAX_CARS];
 	PadCfgD pads[MAX_PADS];
 	int padGrid[8 * 10];  // BoostPadGrid (BoostPadGrid.h:10-29): pad index or -1
+	// README bench loop on device: when set, a goal is followed by ResetToRandomKickoff(autoResetSeed + arena + tick)
+	int autoReset; uint32_t autoResetSeed;
 };
 
 // ---------------------------------------------------------------- static scene (per game mode)

@@ -9,6 +9,7 @@
 #include "rsb_ball.h"
 #include "rsb_collide.h"
 #include "rsb_solver.h"
+#include "rsb_kickoff.h"
 
 namespace rsb {
 
@@ -109,6 +110,7 @@ RSB_HD void arena_tick(const Ctx& cx) {
 		if (P.mode != THE_VOID && is_ball_scored(cx)) {
 			float y = -S.ball.rb.pos.y;
 			push_event(cx, 1u /*RSB_EVENT_GOAL*/, (y < 0.f) ? 0u : 1u, 0u);
+			if (P.autoReset) kickoff_reset(S, P, (int)(P.autoResetSeed + (uint32_t)cx.arena + (uint32_t)S.tickCount));
 		}
 		S.tickCount++;
 	}

@@ -1,0 +1,50 @@
+"""Generates the golden single-step records under tests/golden/*.npz from the ORACLE
+(the unmodified reference compiled into oracle/_ref).  Run in the build container:
+
+    python tests/golden/make_golden.py
+
+Each record holds, for every tick of an oracle rollout driven by the README-style control
+schedule, the complete pre-tick state (CarState + hidden carry-over state + BallState + pads),
+the controls and the post-tick state, so every tick is an independent single-step parity case
+(tests/test_golden.py replays them without needing the oracle).  Synthetic .cmf meshes
+(rocketsim_b200.synthetic_meshes) are used on both sides; see SURVEY.md F4.
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import parity_util as pu  # noqa: E402
+from rocketsim_b200 import synthetic_meshes as sm, types as T  # noqa: E402
+from oracle import refsim  # noqa: E402
+
+# name: (mode, cars per team, seed, ticks, forced-drive ticks, aim cars at ball)
+CASES = {
+    "void_1v1": (T.MODE_THE_VOID, 1, 3, 240, 0, False),
+    "soccar_2v2_kickoff": (T.MODE_SOCCAR, 2, 11, 300, 120, False),
+    "soccar_2v2_aim": (T.MODE_SOCCAR, 2, 5, 240, 90, True),
+    "soccar_3v3_aim": (T.MODE_SOCCAR, 3, 7, 240, 90, True),
+    "hoops_2v2_aim": (T.MODE_HOOPS, 2, 9, 240, 60, True),
+    "heatseeker_1v1": (T.MODE_HEATSEEKER, 1, 13, 240, 60, False),
+    "snowday_3v3_aim": (T.MODE_SNOWDAY, 3, 17, 240, 90, True),
+}
+
+
+def main():
+    refsim.init_from_mem(sm.mesh_sets())
+    for name, (mode, cpt, seed, ticks, drive, aim) in CASES.items():
+        teams = [0] * cpt + [1] * cpt
+        rec = pu.record_rollout(refsim, mode, teams, seed, ticks, drive=drive, aim=aim)
+        path = os.path.join(HERE, name + ".npz")
+        np.savez_compressed(path, **rec)
+        ev = rec["events"]
+        print(f"{name}: {ticks} ticks, {len(ev)} events, {os.path.getsize(path) / 1024:.0f} KiB")
+
+
+if __name__ == "__main__":
+    main()

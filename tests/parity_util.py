@@ -124,3 +124,138 @@ def sync_from_ref(batch: ArenaBatch, ref, arena=0):
     batch.set_ball_internals([arena], np.array([ref.ball_internal()], dtype=T.BallInternal))
     if batch.n_pads:
         batch.set_pad_states([arena], ref.pad_states())
+
+
+# ---------------------------------------------------------------------------------------------
+# Golden records: single-step transitions sampled along an oracle rollout.
+# rec = dict(mode, teams, seed, controls[T,n], car_pre[T,n], carint_pre[T,n], ball_pre[T], ballint_pre[T],
+#            pads_pre[T,p], rng_seed, car_post[T,n], ball_post[T], pads_post[T,p], events[...])
+# "pre" is the COMPLETE reference state before the tick (incl. hidden carry-over state), "post"
+# the reference state after it, so every tick is an independent single-step parity case.
+
+def make_ref_arena(refsim, mode, teams):
+    ref = refsim.RefArena(mode)
+    for t in teams:
+        ref.add_car(t)
+    return ref
+
+
+def aim_cars_at_ball(ref, radius=900.0):
+    """Put every car on a circle around the ball, facing it (produces car-ball and car-car contacts)."""
+    n = len(ref.car_ids)
+    for i, cid in enumerate(ref.car_ids):
+        st = ref.car_state(cid)
+        ang = 2 * np.pi * i / n + 0.3
+        r = radius + 150 * i
+        st["pos"]["x"] = r * np.cos(ang)
+        st["pos"]["y"] = r * np.sin(ang)
+        st["pos"]["z"] = 17.0
+        yaw = ang + np.pi
+        cy, sy = np.float32(np.cos(yaw)), np.float32(np.sin(yaw))
+        st["rotMat"]["forward"] = (cy, sy, 0, 0)
+        st["rotMat"]["right"] = (-sy, cy, 0, 0)
+        st["rotMat"]["up"] = (0, 0, 1, 0)
+        ref.set_car_state(cid, st)
+
+
+def record_rollout(refsim, mode, teams, seed, ticks, drive=0, aim=False):
+    ref = make_ref_arena(refsim, mode, teams)
+    n = len(teams)
+    ref.seed_rng(seed)
+    ref.reset_kickoff(seed)
+    if aim:
+        aim_cars_at_ball(ref)
+    sched = ControlSchedule(n, seed)
+    npads = ref.num_pads
+    rec = dict(mode=np.int32(mode), teams=np.asarray(teams, np.int32), seed=np.int32(seed),
+               controls=np.zeros((ticks, n), T.CarControls),
+               car_pre=np.zeros((ticks, n), T.CarState), carint_pre=np.zeros((ticks, n), T.CarInternal),
+               ball_pre=np.zeros(ticks, T.BallState), ballint_pre=np.zeros(ticks, T.BallInternal),
+               pads_pre=np.zeros((ticks, npads), T.BoostPadState),
+               car_post=np.zeros((ticks, n), T.CarState), ball_post=np.zeros(ticks, T.BallState),
+               pads_post=np.zeros((ticks, npads), T.BoostPadState), scored=np.zeros(ticks, np.uint8))
+    events = []
+    for t in range(ticks):
+        c = sched.at(t)
+        if t < drive:
+            c["throttle"] = 1; c["boost"] = 1; c["steer"] = 0; c["jump"] = 0; c["handbrake"] = 0
+            c["pitch"] = 0; c["yaw"] = 0; c["roll"] = 0
+        rec["controls"][t] = c
+        for i, cid in enumerate(ref.car_ids):
+            rec["car_pre"][t, i] = ref.car_state(cid)
+            rec["carint_pre"][t, i] = ref.car_internal(cid)
+            ref.set_controls(cid, c[i])
+        rec["ball_pre"][t] = ref.ball_state()
+        rec["ballint_pre"][t] = ref.ball_internal()
+        rec["pads_pre"][t] = ref.pad_states()
+        ref.step(1)
+        for i, cid in enumerate(ref.car_ids):
+            rec["car_post"][t, i] = ref.car_state(cid)
+        rec["ball_post"][t] = ref.ball_state()
+        rec["pads_post"][t] = ref.pad_states()
+        rec["scored"][t] = ref.is_ball_scored()
+        for e in ref.drain_events():
+            events.append((t, int(e["type"]), int(e["a"]), int(e["b"])))
+    rec["events"] = np.asarray(events, np.int32).reshape(-1, 4)
+    ref.close()
+    return rec
+
+
+def load_pre_state(batch, rec, t, arena=0):
+    n = rec["car_pre"].shape[1]
+    if n:
+        ai = np.full(n, arena, np.uint32)
+        idx = np.arange(n, dtype=np.uint32)
+        batch.set_car_states(ai, idx, rec["car_pre"][t])
+        batch.set_car_internals(ai, idx, rec["carint_pre"][t])
+    batch.set_ball_states([arena], rec["ball_pre"][t:t + 1])
+    batch.set_ball_internals([arena], rec["ballint_pre"][t:t + 1])
+    if batch.n_pads:
+        batch.set_pad_states([arena], rec["pads_pre"][t])
+
+
+def replay_record(rec, lib, n_arenas=1, ticks=None, tol=1e-4):
+    """Single-step parity of every recorded tick: load pre-state, step once, compare with post-state.
+    All `n_arenas` arenas replay the same record (arena 0 and the last one are checked).
+    Returns dict(worst={field: rel err}, discrete_mismatches=[...], ticks=N)."""
+    teams = [int(x) for x in rec["teams"]]
+    mode = int(rec["mode"])
+    batch = ArenaBatch(mode, n_arenas, teams, lib=lib)
+    T_ = rec["controls"].shape[0] if ticks is None else min(ticks, rec["controls"].shape[0])
+    worst, mism = {}, []
+    check_arenas = sorted({0, n_arenas - 1})
+    my_events = []
+    for t in range(T_):
+        for a in check_arenas:
+            load_pre_state(batch, rec, t, a)
+            batch.seed_rng(a, int(rec["seed"]))
+        ctrl = np.broadcast_to(rec["controls"][t], (n_arenas, len(teams)))
+        batch.set_controls(ctrl)
+        batch.step(1)
+        cs = batch.get_car_states()
+        bs = batch.get_ball_states()
+        ps = batch.get_pad_states() if batch.n_pads else None
+        sc = batch.is_ball_scored()
+        for a in check_arenas:
+            for i in range(len(teams)):
+                bad, errs = compare_car(cs[a, i], rec["car_post"][t, i])
+                if bad:
+                    mism.append((t, a, i, bad))
+                for k, v in errs.items():
+                    worst[k] = max(worst.get(k, 0.0), v)
+            for k, v in compare_ball(bs[a], rec["ball_post"][t]).items():
+                worst["ball_" + k] = max(worst.get("ball_" + k, 0.0), v)
+            if ps is not None:
+                if not (np.array_equal(ps[a]["isActive"], rec["pads_post"][t]["isActive"])
+                        and np.array_equal(ps[a]["prevLockedCarID"], rec["pads_post"][t]["prevLockedCarID"])):
+                    mism.append((t, a, -1, ["pads"]))
+                worst["pad_cooldown"] = max(worst.get("pad_cooldown", 0.0),
+                                            rel_err(ps[a]["cooldown"], rec["pads_post"][t]["cooldown"], 1e-2))
+            if bool(sc[a]) != bool(rec["scored"][t]):
+                mism.append((t, a, -1, ["scored"]))
+        for e in batch.get_events():
+            if int(e["arena"]) == 0:
+                my_events.append((t, int(e["type"]), int(e["a"]), int(e["b"])))
+    err = batch.get_error_flags()
+    batch.close()
+    return dict(worst=worst, discrete_mismatches=mism, ticks=T_, events=my_events, error_flags=int(err.max()))
