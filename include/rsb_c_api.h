@@ -113,6 +113,17 @@ int rsb_reset_to_random_kickoff(RsbBatch* b, const uint32_t* arena_idx, int n, c
  * suspRelVel, clippedInv, impulse xyz} of the last tick for arena `arena`; out is [n_cars*4][14]. */
 int rsb_debug_get_wheels(RsbBatch* b, int arena, float* out);
 
+/* Debug probe: contact points of the last tick of arena `arena`, 16 floats each {obj0, obj1, point#, dist, normalOnB xyz,
+ * posA xyz, posB xyz, friction, restitution, isSpecial}; obj = world object index (meshes, planes, ball, cars). */
+int rsb_debug_get_manifolds(RsbBatch* b, int arena, float* out, int cap_points, int* n_out);
+
+/* Debug probe: solver rows of the last tick (which: 0 contact, 1 friction), 24 floats each {n1, rp1xn, n2, rp2xn, angA, angB,
+ * jacDiagInv, rhs, rhsPenetration, appliedImpulse, appliedPushImpulse, friction}. */
+int rsb_debug_get_solver_rows(RsbBatch* b, int arena, int which, float* out, int cap, int* n_out);
+
+/* Debug probe: solver bodies of the last tick, 12 floats each {linVel, angVel, externalForceImpulse, externalTorqueImpulse}. */
+int rsb_debug_get_solver_bodies(RsbBatch* b, int arena, float* out, int cap, int* n_out);
+
 /* Static-scene introspection for the scene-builder unit tests. */
 int rsb_scene_counts(int game_mode, int mesh, int* counts5);
 int rsb_scene_dump(int game_mode, int mesh, void* nodes, void* headers, float* quant9, void* triinfo);

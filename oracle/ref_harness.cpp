@@ -267,6 +267,54 @@ void ref_get_car_body(RefArena* r, uint32_t id, float* o) {
 	for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) o[3 + i * 3 + j] = t.getBasis()[i][j];
 }
 
+// Contact manifolds alive after the last step (they persist until the next tick's pair wipe):
+// 16 floats per point {obj0, obj1, point#, dist, normalOnB xyz, posA xyz, posB xyz, friction, restitution, isSpecial};
+// obj = index in the world's collision object array (meshes, planes, ball, cars).
+int ref_get_manifolds(RefArena* r, float* out, int cap_points) {
+	btCollisionDispatcher* d = r->arena->_bulletWorld.getDispatcher();
+	int n = 0;
+	for (int m = 0; m < d->getNumManifolds(); m++) {
+		btPersistentManifold* pm = d->getManifoldByIndexInternal(m);
+		for (int k = 0; k < pm->getNumContacts() && n < cap_points; k++, n++) {
+			const btManifoldPoint& p = pm->getContactPoint(k);
+			float* o = out + 16 * n;
+			o[0] = (float)pm->getBody0()->getWorldArrayIndex(); o[1] = (float)pm->getBody1()->getWorldArrayIndex(); o[2] = (float)k;
+			o[3] = p.m_distance1;
+			for (int c = 0; c < 3; c++) { o[4 + c] = p.m_normalWorldOnB[c]; o[7 + c] = p.m_positionWorldOnA[c]; o[10 + c] = p.m_positionWorldOnB[c]; }
+			o[13] = p.m_combinedFriction; o[14] = p.m_combinedRestitution; o[15] = (float)p.m_isSpecial;
+		}
+	}
+	return n;
+}
+
+// Solver rows of the last step (the pools keep their memory after solveGroupCacheFriendlyFinish resets the sizes):
+// which = 0 contact rows, 1 friction rows; 24 floats per row {n1, rp1xn, n2, rp2xn, angA, angB (3 each), jacDiagInv, rhs,
+// rhsPenetration, appliedImpulse, appliedPushImpulse, friction}.
+void ref_get_solver_rows(RefArena* r, int which, int n, float* out) {
+	btSequentialImpulseConstraintSolver* s = r->arena->_bulletWorld.getConstraintSolver();
+	btConstraintArray& pool = which ? s->m_tmpSolverContactFrictionConstraintPool : s->m_tmpSolverContactConstraintPool;
+	if (pool.capacity() < n) n = pool.capacity();
+	for (int i = 0; i < n; i++) {
+		const btSolverConstraint& c = pool[i]; float* o = out + 24 * i;
+		for (int k = 0; k < 3; k++) {
+			o[k] = c.m_contactNormal1[k]; o[3 + k] = c.m_relpos1CrossNormal[k]; o[6 + k] = c.m_contactNormal2[k];
+			o[9 + k] = c.m_relpos2CrossNormal[k]; o[12 + k] = c.m_angularComponentA[k]; o[15 + k] = c.m_angularComponentB[k];
+		}
+		o[18] = c.m_jacDiagABInv; o[19] = c.m_rhs; o[20] = c.m_rhsPenetration; o[21] = c.m_appliedImpulse; o[22] = c.m_appliedPushImpulse; o[23] = c.m_friction;
+	}
+}
+
+// Solver bodies of the last step: 12 floats each {linVel, angVel, externalForceImpulse, externalTorqueImpulse} (as at setup
+// for lin/ang: m_linearVelocity/m_angularVelocity of btSolverBody are not modified by the iterations).
+void ref_get_solver_bodies(RefArena* r, int n, float* out) {
+	btSequentialImpulseConstraintSolver* s = r->arena->_bulletWorld.getConstraintSolver();
+	if (s->m_tmpSolverBodyPool.capacity() < n) n = s->m_tmpSolverBodyPool.capacity();
+	for (int i = 0; i < n; i++) {
+		const btSolverBody& b = s->m_tmpSolverBodyPool[i]; float* o = out + 12 * i;
+		for (int k = 0; k < 3; k++) { o[k] = b.m_linearVelocity[k]; o[3 + k] = b.m_angularVelocity[k]; o[6 + k] = b.m_externalForceImpulse[k]; o[9 + k] = b.m_externalTorqueImpulse[k]; }
+	}
+}
+
 double ref_bench(int mode, int cars_per_team, int n_threads, int arenas_per_thread, int ticks, uint64_t seed, double* wall_s) {
 	std::atomic<int> ready(0);
 	std::atomic<bool> go(false);

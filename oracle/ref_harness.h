@@ -75,6 +75,14 @@ void ref_get_wheel_debug(RefArena*, uint32_t car_id, float* out4x14);
 /* rigid-body transform of car: origin(3) + basis row-major(9) + linvel(3) + angvel(3), Bullet units */
 void ref_get_car_body(RefArena*, uint32_t car_id, float* out18);
 
+/* contact points alive after the last step, 16 floats each (see ref_harness.cpp); returns the count */
+int ref_get_manifolds(RefArena*, float* out, int cap_points);
+
+/* solver rows of the last step (which: 0 contact, 1 friction), 24 floats each (see ref_harness.cpp) */
+void ref_get_solver_rows(RefArena*, int which, int n, float* out);
+
+void ref_get_solver_bodies(RefArena*, int n, float* out); /* 12 floats each: linVel, angVel, extForceImpulse, extTorqueImpulse */
+
 /* ---- CPU throughput harness: T threads x A arenas, README input schedule ---- */
 /* returns arena-ticks/s; writes wall seconds to *wall_s.  mesh data must be initialised first. */
 double ref_bench(int game_mode, int cars_per_team, int n_threads, int arenas_per_thread,

@@ -71,6 +71,9 @@ def lib():
         L.ref_bvh_dump.argtypes = [i32, i32, vp, vp, vp, vp]; L.ref_bvh_dump.restype = i32
         L.ref_get_wheel_debug.argtypes = [vp, u32, vp]
         L.ref_get_car_body.argtypes = [vp, u32, vp]
+        L.ref_get_manifolds.argtypes = [vp, vp, i32]; L.ref_get_manifolds.restype = i32
+        L.ref_get_solver_rows.argtypes = [vp, i32, i32, vp]
+        L.ref_get_solver_bodies.argtypes = [vp, i32, vp]
         L.ref_bench.argtypes = [i32, i32, i32, i32, i32, u64, vp]; L.ref_bench.restype = C.c_double
         _lib = L
     return _lib
@@ -209,6 +212,21 @@ class RefArena:
     def wheel_debug(self, car_id):
         out = np.zeros((4, 14), dtype=np.float32)
         self.L.ref_get_wheel_debug(self.h, car_id, _ptr(out))
+        return out
+
+    def manifolds(self, cap=64):
+        out = np.zeros((cap, 16), dtype=np.float32)
+        n = self.L.ref_get_manifolds(self.h, _ptr(out), cap)
+        return out[:n]
+
+    def solver_rows(self, which, n):
+        out = np.zeros((n, 24), dtype=np.float32)
+        self.L.ref_get_solver_rows(self.h, which, n, _ptr(out))
+        return out
+
+    def solver_bodies(self, n):
+        out = np.zeros((n, 12), dtype=np.float32)
+        self.L.ref_get_solver_bodies(self.h, n, _ptr(out))
         return out
 
     def car_body(self, car_id):

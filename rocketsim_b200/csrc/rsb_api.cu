@@ -893,6 +893,59 @@ int rsb_debug_get_wheels(RsbBatch* b, int arena, float* out) {
 	API_END
 }
 
+// ---- debug probe: contact points of the last tick (layout of oracle ref_get_manifolds) ----
+int rsb_debug_get_manifolds(RsbBatch* b, int arena, float* out, int cap_points, int* n_out) {
+	API_BEGIN set_device(b);
+	std::vector<ArenaW> w(1);
+	d2h(w.data(), b->dW + arena, sizeof(ArenaW), b->stream);
+	const SceneHost& sh = get_scene_dev(b->device, b->hp.mode)->host;
+	const int nStatics = (int)sh.meshes.size() + (int)sh.planes.size();
+	auto world_index = [&](int obj) { return obj >= STATIC_BASE ? obj - STATIC_BASE : nStatics + obj; };
+	int n = 0;
+	for (int m = 0; m < w[0].nManifolds; m++) {
+		const Manifold& mf = w[0].manifolds[m];
+		for (int k = 0; k < mf.nPts && n < cap_points; k++, n++) {
+			const ContactPt& p = mf.pts[k]; float* o = out + 16 * n;
+			o[0] = (float)world_index(mf.body0); o[1] = (float)world_index(mf.body1); o[2] = (float)k; o[3] = p.dist;
+			o[4] = p.normalB.x; o[5] = p.normalB.y; o[6] = p.normalB.z; o[7] = p.posA.x; o[8] = p.posA.y; o[9] = p.posA.z;
+			o[10] = p.posB.x; o[11] = p.posB.y; o[12] = p.posB.z; o[13] = p.friction; o[14] = p.restitution; o[15] = (float)p.isSpecial;
+		}
+	}
+	if (n_out) *n_out = n;
+	API_END
+}
+
+// ---- debug probe: solver rows of the last tick (layout of oracle ref_get_solver_rows) ----
+int rsb_debug_get_solver_rows(RsbBatch* b, int arena, int which, float* out, int cap, int* n_out) {
+	API_BEGIN set_device(b);
+	std::vector<ArenaW> w(1);
+	d2h(w.data(), b->dW + arena, sizeof(ArenaW), b->stream);
+	int n = which ? w[0].nFrictionRows : w[0].nRows;
+	if (n > cap) n = cap;
+	for (int i = 0; i < n; i++) {
+		const SolverRow& c = which ? w[0].frows[i] : w[0].rows[i]; float* o = out + 24 * i;
+		const V3* v[6] = {&c.n1, &c.rp1xn, &c.n2, &c.rp2xn, &c.angA, &c.angB};
+		for (int k = 0; k < 6; k++) { o[3 * k] = v[k]->x; o[3 * k + 1] = v[k]->y; o[3 * k + 2] = v[k]->z; }
+		o[18] = c.jacDiagInv; o[19] = c.rhs; o[20] = c.rhsPen; o[21] = c.applied; o[22] = c.appliedPush; o[23] = c.friction;
+	}
+	if (n_out) *n_out = n;
+	API_END
+}
+
+int rsb_debug_get_solver_bodies(RsbBatch* b, int arena, float* out, int cap, int* n_out) {
+	API_BEGIN set_device(b);
+	std::vector<ArenaW> w(1);
+	d2h(w.data(), b->dW + arena, sizeof(ArenaW), b->stream);
+	int n = w[0].nSolverBodies; if (n > cap) n = cap;
+	for (int i = 0; i < n; i++) {
+		const SolverBody& sb = w[0].sbody[i]; float* o = out + 12 * i;
+		const V3* v[4] = {&sb.lin, &sb.ang, &sb.extF, &sb.extT};
+		for (int k = 0; k < 4; k++) { o[3 * k] = v[k]->x; o[3 * k + 1] = v[k]->y; o[3 * k + 2] = v[k]->z; }
+	}
+	if (n_out) *n_out = n;
+	API_END
+}
+
 // ---- scene introspection ----
 int rsb_scene_num_meshes(int mode) { auto it = g_sceneHost.find(mode); return it == g_sceneHost.end() ? 0 : (int)it->second.meshes.size(); }
 int rsb_scene_counts(int mode, int mesh, int* c) {

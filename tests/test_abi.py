@@ -23,9 +23,9 @@ def test_header_declares_what_lib_binds():
 
 
 def test_cuda_library_exports_every_symbol():
-    if not os.path.exists(lib.LIB_PATH):
+    if os.path.isdir("/usr/local/cuda/bin"):
         from rocketsim_b200 import build
-        build.build_cuda()
+        build.build_cuda()  # incremental: rebuilds only when a source is newer than the library
     L = C.CDLL(lib.LIB_PATH)
     for name in declared_symbols():
         assert hasattr(L, name), name
