@@ -31,11 +31,13 @@ def _newest_source() -> float:
     return newest
 
 
-def build_cuda(force: bool = False, verbose: bool = False) -> str:
-    if not force and os.path.exists(OUT) and os.path.getmtime(OUT) >= _newest_source():
-        return OUT
+def build_cuda(force: bool = False, verbose: bool = False, profile: bool = False) -> str:
+    """profile=True builds the developer variant librsb_prof.so with per-phase cycle counters (-DRSB_PROFILE)."""
+    out = OUT.replace("librsb.so", "librsb_prof.so") if profile else OUT
+    if not force and os.path.exists(out) and os.path.getmtime(out) >= _newest_source():
+        return out
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-I" + os.path.join(HERE, "csrc"), SRC, "-o", OUT]
+    cmd = [nvcc] + NVCC_FLAGS + (["-DRSB_PROFILE"] if profile else []) + ["-I" + os.path.join(HERE, "csrc"), SRC, "-o", out]
     if verbose:
         cmd += ["-Xptxas", "-v"]
     r = subprocess.run(cmd, capture_output=True, text=True)
@@ -43,7 +45,7 @@ def build_cuda(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError("nvcc failed:\n" + r.stdout[-3000:] + r.stderr[-6000:])
     if verbose:
         print(r.stderr)
-    return OUT
+    return out
 
 
 if __name__ == "__main__":

@@ -1,11 +1,10 @@
 // rsb_api.cu -- C ABI (include/rsb_c_api.h), batch management and the CUDA kernels of the
 // batched Arena::Step for sm_100a.
 //
-// One WARP owns one arena: the arena's persistent record (ArenaS) and per-tick scratch
-// (ArenaW) live in HBM/L2 as contiguous per-arena records; the 32 lanes execute the tick as
-// SPMD phases (rsb_tick.h) -- lanes = car x wheel for the suspension rays, lanes = cars for
-// the game logic, lanes = bodies for prediction/integration -- separated by __syncwarp().
-// rsb_step(n) is ONE launch that loops n ticks inside the kernel.
+// One thread block owns a chunk of arenas for a whole launch: their persistent records (ArenaS)
+// are staged HBM -> shared memory once, n ticks run as block-synchronous item-parallel phases
+// (rsb_tick.h: one thread per wheel / car / body / arena depending on the phase), and the
+// records go back to HBM once.  rsb_step(n) is ONE launch that loops n ticks inside the kernel.
 //
 // Build modes:
 //   nvcc (product):  the only execution path is CUDA; every entry point fails loudly
@@ -122,6 +121,7 @@ struct RsbBatch {
 	void* dScratch = nullptr;      // staging for get/set
 	size_t scratchBytes = 0;
 	stream_t stream = 0;
+	int numSMs = 1;
 	void ensure_scratch(size_t n) { if (n > scratchBytes) { dev_free(dScratch); dScratch = dev_alloc(n); scratchBytes = n; } }
 };
 
@@ -222,35 +222,115 @@ static thread_local int g_hostIdx = 0;
 #define LAUNCH_1D(kern, n, b, ...) do { int _ln = (n); for (g_hostIdx = 0; g_hostIdx < _ln; g_hostIdx++) kern(__VA_ARGS__); } while (0)
 #endif
 
-constexpr int WARPS_PER_BLOCK = 4;
+// ---- the hot kernel -------------------------------------------------------------------------
+// Block-synchronous phase execution: a block keeps a CHUNK of arenas (their ArenaS records plus the
+// batch constants and the scene header) resident in shared memory for all n_ticks ticks of the
+// launch, deals the items of each tick phase (rsb_tick.h) over its threads and separates phases
+// with __syncthreads().  All warps of an SM therefore run the same phase code at the same time
+// (one instruction-cache working set), suspension rays / car logic / body integration use one
+// thread per wheel / car / body, and HBM sees each arena record once per launch in and once out.
+constexpr int STEP_THREADS = 256;
+constexpr int S_WORDS8 = (int)(sizeof(ArenaS) / 8);
+constexpr int S_STRIDE = (int)sizeof(ArenaS) + 8;  // +8 B: de-phases the shared-memory banks of neighbouring arenas
+static_assert(sizeof(ArenaS) % 8 == 0, "ArenaS is copied in 8-byte words");
+constexpr size_t SMEM_P_BYTES = (sizeof(BatchParams) + 15) & ~(size_t)15;
+constexpr size_t SMEM_SC_BYTES = (sizeof(Scene) + 15) & ~(size_t)15;
+constexpr size_t SMEM_MAX = 227 * 1024;
+constexpr int APB_MAX = (int)((SMEM_MAX - SMEM_P_BYTES - SMEM_SC_BYTES) / S_STRIDE);
 
-// The hot kernel: one warp per arena, n_ticks ticks per launch.
-RSB_GLOBAL void
+struct StepArgs {
+	ArenaS* S; ArenaW* W; const BatchParams* P; const Scene* sc; EventSink ev;
+	int nArenas, nTicks; const CtrlS* ctrlSeq; int nCtrl; int apb;
+};
+
 #ifndef RSB_HOSTCHECK
-__launch_bounds__(WARPS_PER_BLOCK * 32)
-#endif
-arena_step_kernel(ArenaS* S, ArenaW* W, const BatchParams* P, const Scene* sc, EventSink ev, int nArenas, int nTicks, const CtrlS* ctrlSeq, int nCtrl) {
-#ifndef RSB_HOSTCHECK
-	const int arena = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
-	if (arena >= nArenas) return;
-	Ctx cx; cx.lane = threadIdx.x & 31; cx.nlanes = 32;
+#if defined(RSB_PROFILE)
+__device__ unsigned long long g_prof[16];  // developer builds: cycles per phase summed over blocks
+#define PHASE_PROF_BEGIN() long long _pt0 = clock64()
+#define PHASE_PROF_END(i) do { if (threadIdx.x == 0) atomicAdd(&g_prof[i], (unsigned long long)(clock64() - _pt0)); } while (0)
 #else
-	const int arena = g_hostIdx;
-	if (arena >= nArenas) return;
-	Ctx cx; cx.lane = 0; cx.nlanes = 1;
+#define PHASE_PROF_BEGIN() ((void)0)
+#define PHASE_PROF_END(i) ((void)0)
 #endif
-	cx.s = S + arena; cx.w = W + arena; cx.p = P; cx.sc = sc; cx.ev = ev; cx.arena = arena;
-	const int nCars = P->nCars;
-	for (int t = 0; t < nTicks; t++) {
-		if (ctrlSeq) {
-			int ct = t < nCtrl ? t : nCtrl - 1;
-			const CtrlS* src = ctrlSeq + ((size_t)ct * nArenas + arena) * nCars;
-			RSB_FOR_LANES(ci, nCars) cx.s->cars[ci].controls = src[ci];
-			RSB_SYNC();
+
+template <int PH>
+__device__ __forceinline__ void run_phase_block(const StepArgs& a, const BatchParams* sP, const Scene* sSc, unsigned char* sS, int a0, int nA, int ptid) {
+	PHASE_PROF_BEGIN();
+	const int n = phase_items(*sP, PH) * nA;
+	for (int i = ptid; i < n; i += STEP_THREADS) {
+		const int ar = i % nA, item = i / nA;
+		Ctx cx;
+		cx.s = (ArenaS*)(sS + (size_t)ar * S_STRIDE); cx.w = a.W + (a0 + ar); cx.p = sP; cx.sc = sSc; cx.ev = a.ev; cx.arena = a0 + ar;
+		phase_run(cx, PH, item);
+	}
+	__syncthreads();
+	PHASE_PROF_END(PH);
+}
+
+__global__ void __launch_bounds__(STEP_THREADS, 1) arena_step_kernel(const StepArgs a) {
+	extern __shared__ __align__(16) unsigned char smem[];
+	BatchParams* sP = (BatchParams*)smem;
+	Scene* sSc = (Scene*)(smem + SMEM_P_BYTES);
+	unsigned char* sS = smem + SMEM_P_BYTES + SMEM_SC_BYTES;
+	const int tid = threadIdx.x;
+	for (int i = tid; i < (int)(sizeof(BatchParams) / 4); i += STEP_THREADS) ((uint32_t*)sP)[i] = ((const uint32_t*)a.P)[i];
+	for (int i = tid; i < (int)(sizeof(Scene) / 4); i += STEP_THREADS) ((uint32_t*)sSc)[i] = ((const uint32_t*)a.sc)[i];
+	// item -> thread permutation: consecutive items go to different warps, so that a phase with few
+	// items (one per arena) spreads over all four schedulers instead of serialising in one warp
+	const int ptid = (tid & 31) * (STEP_THREADS / 32) + (tid >> 5);
+	const int nCars = a.P->nCars;
+	const int nChunks = (a.nArenas + a.apb - 1) / a.apb;
+	for (int chunk = blockIdx.x; chunk < nChunks; chunk += gridDim.x) {
+		const int a0 = chunk * a.apb;
+		const int nA = min(a.apb, a.nArenas - a0);
+		__syncthreads();
+		for (int i = tid; i < nA * S_WORDS8; i += STEP_THREADS) {
+			const int ar = i / S_WORDS8, w = i - ar * S_WORDS8;
+			((uint2*)(sS + (size_t)ar * S_STRIDE))[w] = ((const uint2*)(a.S + a0 + ar))[w];
 		}
-		arena_tick(cx);
+		__syncthreads();
+		for (int t = 0; t < a.nTicks; t++) {
+			if (a.ctrlSeq) {
+				const int ct = t < a.nCtrl ? t : a.nCtrl - 1;
+				const CtrlS* src = a.ctrlSeq + ((size_t)ct * a.nArenas + a0) * nCars;
+				for (int i = tid; i < nA * nCars; i += STEP_THREADS) ((ArenaS*)(sS + (size_t)(i / nCars) * S_STRIDE))->cars[i % nCars].controls = src[i];
+				__syncthreads();
+			}
+			run_phase_block<PH_INIT>(a, sP, sSc, sS, a0, nA, ptid);
+			run_phase_block<PH_PRE_BEGIN>(a, sP, sSc, sS, a0, nA, ptid);
+			run_phase_block<PH_WHEELS>(a, sP, sSc, sS, a0, nA, ptid);
+			run_phase_block<PH_CAR_LOGIC>(a, sP, sSc, sS, a0, nA, ptid);
+			run_phase_block<PH_PADS_BALL>(a, sP, sSc, sS, a0, nA, ptid);
+			run_phase_block<PH_PREDICT>(a, sP, sSc, sS, a0, nA, ptid);
+			run_phase_block<PH_COLLIDE>(a, sP, sSc, sS, a0, nA, ptid);
+			run_phase_block<PH_SOLVE>(a, sP, sSc, sS, a0, nA, ptid);
+			run_phase_block<PH_INTEGRATE>(a, sP, sSc, sS, a0, nA, ptid);
+			run_phase_block<PH_CAR_POST>(a, sP, sSc, sS, a0, nA, ptid);
+			run_phase_block<PH_TAIL>(a, sP, sSc, sS, a0, nA, ptid);
+		}
+		for (int i = tid; i < nA * S_WORDS8; i += STEP_THREADS) {
+			const int ar = i / S_WORDS8, w = i - ar * S_WORDS8;
+			((uint2*)(a.S + a0 + ar))[w] = ((const uint2*)(sS + (size_t)ar * S_STRIDE))[w];
+		}
 	}
 }
+#else
+// host check build (tests only): the same phases, one thread, state in place
+static void arena_step_host(const StepArgs& a) {
+	const int nCars = a.P->nCars;
+	for (int arena = 0; arena < a.nArenas; arena++) {
+		Ctx cx; cx.s = a.S + arena; cx.w = a.W + arena; cx.p = a.P; cx.sc = a.sc; cx.ev = a.ev; cx.arena = arena;
+		for (int t = 0; t < a.nTicks; t++) {
+			if (a.ctrlSeq) {
+				const int ct = t < a.nCtrl ? t : a.nCtrl - 1;
+				const CtrlS* src = a.ctrlSeq + ((size_t)ct * a.nArenas + arena) * nCars;
+				for (int ci = 0; ci < nCars; ci++) cx.s->cars[ci].controls = src[ci];
+			}
+			arena_tick(cx);
+		}
+	}
+}
+#endif
 
 RSB_GLOBAL void set_controls_kernel(ArenaS* S, const RsbCarControls* in, int nArenas, int nCars) {
 	KERNEL_1D(i, nArenas * nCars);
@@ -287,7 +367,7 @@ RSB_GLOBAL void get_misc_kernel(const ArenaS* S, const BatchParams* P, const Sce
 	KERNEL_1D(i, nArenas);
 	if (ticks) ticks[i] = S[i].tickCount;
 	if (errs) errs[i] = S[i].errorFlags;
-	if (scored) { Ctx cx; cx.s = (ArenaS*)&S[i]; cx.w = nullptr; cx.p = P; cx.sc = sc; cx.arena = i; cx.lane = 0; cx.nlanes = 1; cx.ev.buf = nullptr; scored[i] = is_ball_scored(cx) ? 1 : 0; }
+	if (scored) { Ctx cx; cx.s = (ArenaS*)&S[i]; cx.w = nullptr; cx.p = P; cx.sc = sc; cx.arena = i; cx.ev.buf = nullptr; scored[i] = is_ball_scored(cx) ? 1 : 0; }
 }
 RSB_GLOBAL void get_car_internals_kernel(const ArenaS* S, RsbCarInternal* out, int nArenas, int nCars) {
 	KERNEL_1D(i, nArenas * nCars);
@@ -605,6 +685,16 @@ int rsb_batch_create(int device, int game_mode, int n_arenas, int n_cars, const 
 #endif
 	RsbBatch* b = new RsbBatch();
 	b->device = device;
+#ifndef RSB_HOSTCHECK
+	{
+		cudaDeviceProp prop;
+		CUDA_OK(cudaGetDeviceProperties(&prop, device));
+		b->numSMs = prop.multiProcessorCount;
+		if ((size_t)prop.sharedMemPerBlockOptin < SMEM_MAX) throw std::runtime_error("device offers less than 227 KB of shared memory per block: rocketsim_b200 targets sm_100a");
+		static std::mutex attrMutex; std::lock_guard<std::mutex> lk(attrMutex);
+		CUDA_OK(cudaFuncSetAttribute(arena_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
+	}
+#endif
 	BatchParams& P = b->hp;
 	memset(&P, 0, sizeof(P));
 	P.mode = game_mode; P.nCars = n_cars; P.nArenas = n_arenas;
@@ -643,7 +733,7 @@ int rsb_batch_create(int device, int game_mode, int n_arenas, int n_cars, const 
 		A.ball.rb.basis = m3identity();
 		A.ball.hsCurTargetSpeed = K::HS_INITIAL_TARGET_SPEED;
 		for (int p = 0; p < P.nPads; p++) { A.pads[p].isActive = 1; }
-		Ctx cx; cx.s = &A; cx.w = &tmpW; cx.p = &P; cx.sc = &hsc; cx.arena = a; cx.lane = 0; cx.nlanes = 1; cx.ev.buf = nullptr;
+		Ctx cx; cx.s = &A; cx.w = &tmpW; cx.p = &P; cx.sc = &hsc; cx.arena = a; cx.ev.buf = nullptr;
 		for (int c = 0; c < n_cars; c++) {
 			tmpW.body[c + 1].invInertiaLocal = P.carCfg[c].invInertiaLocal;
 			car_respawn(cx, c);  // AddCar -> Respawn(gameMode, -1, carSpawnBoostAmount)
@@ -700,12 +790,23 @@ static EventSink sink_of(RsbBatch* b) { EventSink e; e.buf = b->dEvents; e.count
 
 static void launch_step(RsbBatch* b, int n_ticks, const CtrlS* seq, int nCtrl) {
 	const BatchParams& P = b->hp;
+	StepArgs a; a.S = b->dS; a.W = b->dW; a.P = b->dP; a.sc = b->dScene; a.ev = sink_of(b);
+	a.nArenas = P.nArenas; a.nTicks = n_ticks; a.ctrlSeq = seq; a.nCtrl = nCtrl; a.apb = 1;
 #ifndef RSB_HOSTCHECK
-	int blocks = (P.nArenas + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
-	arena_step_kernel<<<blocks, WARPS_PER_BLOCK * 32, 0, b->stream>>>(b->dS, b->dW, b->dP, b->dScene, sink_of(b), P.nArenas, n_ticks, seq, nCtrl);
+	// chunk size: fill every SM once if the batch fits (one wave), else the fewest equal waves
+	const int sms = b->numSMs;
+	const int chunksMin = (P.nArenas + APB_MAX - 1) / APB_MAX;
+	const int waves = (chunksMin + sms - 1) / sms;
+	a.apb = (P.nArenas + waves * sms - 1) / (waves * sms);
+	if (a.apb < 1) a.apb = 1;
+	if (a.apb > APB_MAX) a.apb = APB_MAX;
+	const int nChunks = (P.nArenas + a.apb - 1) / a.apb;
+	const int grid = nChunks < sms ? nChunks : sms;
+	const size_t smem = SMEM_P_BYTES + SMEM_SC_BYTES + (size_t)a.apb * S_STRIDE;
+	arena_step_kernel<<<grid, STEP_THREADS, smem, b->stream>>>(a);
 	CUDA_OK(cudaGetLastError());
 #else
-	for (g_hostIdx = 0; g_hostIdx < P.nArenas; g_hostIdx++) arena_step_kernel(b->dS, b->dW, b->dP, b->dScene, sink_of(b), P.nArenas, n_ticks, seq, nCtrl);
+	arena_step_host(a);
 #endif
 }
 
@@ -943,6 +1044,20 @@ int rsb_debug_get_solver_bodies(RsbBatch* b, int arena, float* out, int cap, int
 		for (int k = 0; k < 4; k++) { o[3 * k] = v[k]->x; o[3 * k + 1] = v[k]->y; o[3 * k + 2] = v[k]->z; }
 	}
 	if (n_out) *n_out = n;
+	API_END
+}
+
+// ---- developer profile counters (non-zero only in -DRSB_PROFILE builds) ----
+int rsb_debug_profile(uint64_t* out16, int reset) {
+	API_BEGIN
+	for (int i = 0; i < 16; i++) out16[i] = 0;
+#if defined(RSB_PROFILE) && !defined(RSB_HOSTCHECK)
+	CUDA_OK(cudaDeviceSynchronize());
+	CUDA_OK(cudaMemcpyFromSymbol(out16, g_prof, sizeof(unsigned long long) * 16));
+	if (reset) { unsigned long long z[16] = {0}; CUDA_OK(cudaMemcpyToSymbol(g_prof, z, sizeof(z))); }
+#else
+	(void)reset;
+#endif
 	API_END
 }
 

@@ -1,7 +1,7 @@
 // rsb_tick.h -- one arena tick = Arena::Step body (reference src/Sim/Arena/Arena.cpp:689-756)
 // + btDiscreteDynamicsWorld::stepSimulation / internalSingleStepSimulation
 // (bt/BulletDynamics/Dynamics/btDiscreteDynamicsWorld.cpp:325-437, 889-991, 1029-1044),
-// written as SPMD phases over the lanes of the warp that owns the arena.
+// written as a sequence of item-parallel phases (see Phase below).
 #pragma once
 #include "rsb_work.h"
 #include "rsb_ray.h"
@@ -33,42 +33,68 @@ RSB_HD void init_body_work(const Ctx& cx, int b) {
 	bw.islandTag = b;
 }
 
-RSB_HD void arena_tick(const Ctx& cx) {
+// ---------------------------------------------------------------- phases of one tick
+// A tick is a fixed sequence of PHASES; every phase is a flat list of independent ITEMS
+// (arena x wheel, arena x car, arena x body, arena) that any thread may execute.  The CUDA
+// kernel (rsb_api.cu) keeps a chunk of arenas resident in shared memory, deals the items of a
+// phase over all threads of the block and separates phases with __syncthreads(); the host
+// check build runs the same phases with one thread.  Order = Arena::Step T0..T6.
+enum Phase : int {
+	PH_INIT = 0,     // T0  working rigid-body values + ball sleep gate        item = body
+	PH_PRE_BEGIN,    // T1  Car::_PreTickUpdate head (respawn RNG, sequential)  item = arena
+	PH_WHEELS,       // T1  suspension rays                                     item = car x wheel
+	PH_CAR_LOGIC,    // T1  friction, game logic, suspension/boost forces       item = car
+	PH_PADS_BALL,    // T2  pads + ball pre-tick                                 item = pad | ball
+	PH_PREDICT,      // T3  gravity, damping, predicted transform               item = body
+	PH_COLLIDE,      // T3  AABBs, broadphase pairs, narrowphase, contact hooks item = arena
+	PH_SOLVE,        // T3  islands + sequential-impulse solve                   item = arena
+	PH_INTEGRATE,    // T3  integrateTransforms                                  item = body
+	PH_CAR_POST,     // T4  Car::_PostTickUpdate / _FinishPhysicsTick           item = car
+	PH_TAIL,         // T4-T6 pad pickups, ball finish, goal, tick counter      item = arena
+	PH_COUNT
+};
+
+RSB_HD int phase_items(const BatchParams& P, int phase) {
+	const int nCars = P.nCars, nb = nCars + 1;
+	switch (phase) {
+	case PH_INIT: case PH_PREDICT: case PH_INTEGRATE: return nb;
+	case PH_WHEELS: return nCars * 4;
+	case PH_CAR_LOGIC: case PH_CAR_POST: return nCars;
+	case PH_PADS_BALL: return ((P.mode != THE_VOID && nCars != 0) ? P.nPads : 0) + 1;
+	default: return 1;
+	}
+}
+
+RSB_HD void phase_run(const Ctx& cx, int phase, int item) {
 	const BatchParams& P = *cx.p;
 	ArenaS& S = *cx.s;
 	ArenaW& W = *cx.w;
-	const int nCars = P.nCars, nb = nCars + 1;
+	const int nCars = P.nCars;
 	const float dt = P.dt;
 	const bool hasArenaStuff = (P.mode != THE_VOID);
 	const bool ballOnly = (nCars == 0);
-
-	// ---- T0: working rigid-body values + ball sleep gate
-	RSB_FOR_LANES(b, nb) init_body_work(cx, b);
-	RSB_SYNC();
-
-	// ---- T1: cars pre-tick (Car::_PreTickUpdate)
-	if (cx.lane == 0) {  // sequential: respawns draw from the arena RNG in car order
+	switch (phase) {
+	case PH_INIT: init_body_work(cx, item); break;
+	case PH_PRE_BEGIN:  // sequential: respawns draw from the arena RNG in car order
 		for (int ci = 0; ci < nCars; ci++) car_pretick_begin(cx, ci);
-	}
-	RSB_SYNC();
-	RSB_FOR_LANES(k, nCars * 4) {
-		int ci = k >> 2, wi = k & 3;
+		break;
+	case PH_WHEELS: {
+		int ci = item >> 2, wi = item & 3;
 		if (!S.cars[ci].isDemoed) wheel_trace(cx, ci, wi);
+		break;
 	}
-	RSB_SYNC();
-	RSB_FOR_LANES(ci, nCars) {
-		if (!S.cars[ci].isDemoed) car_pretick_logic(cx, ci);
+	case PH_CAR_LOGIC:
+		if (!S.cars[item].isDemoed) car_pretick_logic(cx, item);
+		break;
+	case PH_PADS_BALL: {
+		const int nPadItems = (hasArenaStuff && !ballOnly) ? P.nPads : 0;
+		if (item < nPadItems) pad_pretick(cx, item);
+		else ball_pretick(cx);
+		break;
 	}
-	RSB_SYNC();
-
-	// ---- T2: pads + ball pre-tick
-	if (hasArenaStuff && !ballOnly) { RSB_FOR_LANES(i, P.nPads) pad_pretick(cx, i); }
-	if (cx.lane == 0) ball_pretick(cx);
-	RSB_SYNC();
-
-	// ---- T3: world step
-	// applyGravity (active bodies) + predictUnconstraintMotion (damping + predicted transform)
-	RSB_FOR_LANES(b, nb) {
+	case PH_PREDICT: {
+		// applyGravity (active bodies) + predictUnconstraintMotion (damping + predicted transform)
+		const int b = item;
 		BodyW& bw = W.body[b];
 		RigidS& rb = rigid_of(cx, b);
 		if (body_active(bw)) apply_central_force(bw, P.gravityBT * (1.f / bw.invMass));
@@ -77,16 +103,17 @@ RSB_HD void arena_tick(const Ctx& cx) {
 		rb.angvel *= powf(1.f - 0.f, dt);
 		Xform cur; cur.basis = rb.basis; cur.origin = rb.pos;
 		integrate_transform(cur, rb.vel, rb.angvel, dt, (b == 0) && P.ballNoRot, bw.interp);
+		break;
 	}
-	RSB_SYNC();
-	if (cx.lane == 0) {
-		collide_world(cx);                    // updateAabbs, pairs, narrowphase + contact hooks
-		int nSolve = build_islands(cx);       // calculateSimulationIslands + buildIslands
-		solve_arena(cx, nSolve);              // solveConstraints
+	case PH_COLLIDE: collide_world(cx); break;  // updateAabbs, pairs, narrowphase + contact hooks
+	case PH_SOLVE: {
+		int nSolve = build_islands(cx);  // calculateSimulationIslands + buildIslands
+		solve_arena(cx, nSolve);          // solveConstraints
+		break;
 	}
-	RSB_SYNC();
-	// integrateTransforms (active bodies) + clearForces
-	RSB_FOR_LANES(b, nb) {
+	case PH_INTEGRATE: {
+		// integrateTransforms (active bodies) + clearForces
+		const int b = item;
 		BodyW& bw = W.body[b];
 		RigidS& rb = rigid_of(cx, b);
 		if (body_active(bw)) {
@@ -95,13 +122,10 @@ RSB_HD void arena_tick(const Ctx& cx) {
 			integrate_transform(cur, rb.vel, rb.angvel, dt, (b == 0) && P.ballNoRot, pred);
 			rb.pos = pred.origin; rb.basis = pred.basis;
 		}
+		break;
 	}
-	RSB_SYNC();
-
-	// ---- T4: cars post-tick + pad checks
-	RSB_FOR_LANES(ci, nCars) car_posttick(cx, ci);
-	RSB_SYNC();
-	if (cx.lane == 0) {
+	case PH_CAR_POST: car_posttick(cx, item); break;
+	case PH_TAIL:
 		if (hasArenaStuff) for (int ci = 0; ci < nCars; ci++) pad_grid_check(cx, ci);
 		// ---- T5: pads post-tick, ball finish
 		if (hasArenaStuff && !ballOnly) for (int i = 0; i < P.nPads; i++) pad_posttick(cx, i);
@@ -113,8 +137,17 @@ RSB_HD void arena_tick(const Ctx& cx) {
 			if (P.autoReset) kickoff_reset(S, P, (int)(P.autoResetSeed + (uint32_t)cx.arena + (uint32_t)S.tickCount));
 		}
 		S.tickCount++;
+		break;
+	default: break;
 	}
-	RSB_SYNC();
+}
+
+// One whole tick of one arena on one thread (host check build, single-arena helpers).
+RSB_HD void arena_tick(const Ctx& cx) {
+	for (int ph = 0; ph < PH_COUNT; ph++) {
+		const int n = phase_items(*cx.p, ph);
+		for (int i = 0; i < n; i++) phase_run(cx, ph, i);
+	}
 }
 
 }  // namespace rsb

@@ -122,16 +122,8 @@ struct Ctx {
 	const BatchParams* p;
 	const Scene* sc;
 	EventSink ev;
-	int arena;
-	int lane, nlanes;  // SPMD position inside the arena's warp (host check: 0 / 1)
+	int arena;  // global arena index inside the batch
 };
-
-#if defined(__CUDA_ARCH__)
-#define RSB_SYNC() __syncwarp()
-#else
-#define RSB_SYNC() ((void)0)
-#endif
-#define RSB_FOR_LANES(i, n) for (int i = cx.lane; i < (n); i += cx.nlanes)
 
 RSB_HD RigidS& rigid_of(const Ctx& cx, int b) { return b == 0 ? cx.s->ball.rb : cx.s->cars[b - 1].rb; }
 RSB_HD int n_bodies(const Ctx& cx) { return cx.p->nCars + 1; }
