@@ -124,8 +124,9 @@ int rsb_debug_get_solver_rows(RsbBatch* b, int arena, int which, float* out, int
 /* Debug probe: solver bodies of the last tick, 12 floats each {linVel, angVel, externalForceImpulse, externalTorqueImpulse}. */
 int rsb_debug_get_solver_bodies(RsbBatch* b, int arena, float* out, int cap, int* n_out);
 
-/* Developer builds (-DRSB_PROFILE) only: cycles spent per tick phase summed over warps (16 counters); zeros otherwise. */
-int rsb_debug_profile(uint64_t* out16, int reset);
+/* Developer builds (-DRSB_PROFILE) only: per tick phase p: out[p] block wall cycles, out[16+p] busy-thread cycles,
+ * out[32+p] busy threads, out[48+p] slowest-thread cycles (each summed over blocks and ticks); zeros otherwise. */
+int rsb_debug_profile(uint64_t* out64, int reset);
 
 /* Static-scene introspection for the scene-builder unit tests. */
 int rsb_scene_counts(int game_mode, int mesh, int* counts5);

@@ -15,6 +15,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <cstddef>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -96,6 +97,9 @@ static SceneDev* get_scene_dev(int device, int mode) {
 	sc.cellsX = h.cellsX; sc.cellsY = h.cellsY; sc.cellsZ = h.cellsZ;
 	sc.cellStart = (const int32_t*)up(h.cellStart.data(), h.cellStart.size() * 4);
 	sc.cellStatics = (const uint8_t*)up(h.cellStatics.data(), h.cellStatics.size());
+	sc.cellHdrStart = (const int32_t*)up(h.cellHdrStart.data(), h.cellHdrStart.size() * 4);
+	sc.cellHdrs = (const uint16_t*)up(h.cellHdrs.data(), h.cellHdrs.size() * 2);
+	sc.cellHdrsRay = (const uint16_t*)up(h.cellHdrsRay.data(), h.cellHdrsRay.size() * 2);
 	sd->dScene = (Scene*)up(&sc, sizeof(sc));
 #ifndef RSB_HOSTCHECK
 	CUDA_OK(cudaDeviceSynchronize());
@@ -111,6 +115,7 @@ struct RsbBatch {
 	BatchParams* dP = nullptr;
 	ArenaS* dS = nullptr;
 	ArenaW* dW = nullptr;
+	ArenaH* dH = nullptr;          // global mirror of the hot per-tick scratch
 	const Scene* dScene = nullptr;
 	EventSink::Ev* dEvents = nullptr;
 	uint32_t* dEventCount = nullptr;
@@ -122,6 +127,7 @@ struct RsbBatch {
 	size_t scratchBytes = 0;
 	stream_t stream = 0;
 	int numSMs = 1;
+	size_t smemBudget = 0;
 	void ensure_scratch(size_t n) { if (n > scratchBytes) { dev_free(dScratch); dScratch = dev_alloc(n); scratchBytes = n; } }
 };
 
@@ -230,40 +236,90 @@ static thread_local int g_hostIdx = 0;
 // (one instruction-cache working set), suspension rays / car logic / body integration use one
 // thread per wheel / car / body, and HBM sees each arena record once per launch in and once out.
 constexpr int STEP_THREADS = 256;
-constexpr int S_WORDS8 = (int)(sizeof(ArenaS) / 8);
-constexpr int S_STRIDE = (int)sizeof(ArenaS) + 8;  // +8 B: de-phases the shared-memory banks of neighbouring arenas
-static_assert(sizeof(ArenaS) % 8 == 0, "ArenaS is copied in 8-byte words");
+static_assert(offsetof(ArenaS, cars) % 8 == 0 && sizeof(CarS) % 8 == 0 && sizeof(BodyW) % 8 == 0 && sizeof(WheelW) % 8 == 0 && sizeof(Manifold) % 8 == 0, "records are staged in 8-byte words");
 constexpr size_t SMEM_P_BYTES = (sizeof(BatchParams) + 15) & ~(size_t)15;
 constexpr size_t SMEM_SC_BYTES = (sizeof(Scene) + 15) & ~(size_t)15;
 constexpr size_t SMEM_MAX = 227 * 1024;
-constexpr int APB_MAX = (int)((SMEM_MAX - SMEM_P_BYTES - SMEM_SC_BYTES) / S_STRIDE);
+
+// Shared-memory layout of one resident arena: [ArenaS prefix (header, ball, pads, nCars cars) | BodyW x nb |
+// WheelW x 4 nCars | padLocked x nPads], padded so that neighbouring arenas start in different banks.
+struct ArenaLayout {
+	int sBytes, bodyOff, wheelOff, wheelBytes, solvBytes, padOff, miscOff, pairOff, mfOff, stride;
+	RSB_HD static ArenaLayout make(int nCars, int nPads) {
+		ArenaLayout L;
+		L.sBytes = (int)offsetof(ArenaS, cars) + nCars * (int)sizeof(CarS);
+		L.bodyOff = L.sBytes;
+		L.wheelOff = L.bodyOff + (nCars + 1) * (int)sizeof(BodyW);
+		// the wheel scratch and the solver scratch share one region (the wheels are dead after the car pre-tick)
+		L.wheelBytes = nCars * 4 * (int)sizeof(WheelW);
+		L.solvBytes = (solv_bytes(nCars + 1) + 7) & ~7;
+		L.padOff = L.wheelOff + (L.wheelBytes > L.solvBytes ? L.wheelBytes : L.solvBytes);
+		L.miscOff = L.padOff + ((nPads * 4 + 7) & ~7);
+		L.pairOff = L.miscOff + 16;
+		L.mfOff = L.pairOff + (((int)sizeof(PairList) + 7) & ~7);
+		int end = L.mfOff + MAX_MANIFOLDS * (int)sizeof(Manifold);
+		L.stride = end + 8;  // 8-byte aligned, and (stride / 4) odd multiples de-phase the banks
+		if (((L.stride / 4) & 3) == 0) L.stride += 8;
+		return L;
+	}
+};
 
 struct StepArgs {
-	ArenaS* S; ArenaW* W; const BatchParams* P; const Scene* sc; EventSink ev;
+	ArenaS* S; ArenaH* H; ArenaW* W; const BatchParams* P; const Scene* sc; EventSink ev;
 	int nArenas, nTicks; const CtrlS* ctrlSeq; int nCtrl; int apb;
+	int mirror;  // keep the full debug mirror (ArenaH) up to date: single-tick launches only
+	ArenaLayout lay;
 };
 
 #ifndef RSB_HOSTCHECK
 #if defined(RSB_PROFILE)
-__device__ unsigned long long g_prof[16];  // developer builds: cycles per phase summed over blocks
+// developer builds: per phase [0..15] block wall cycles, [16..31] sum of busy-thread cycles, [32..47] busy-thread count,
+// [48..63] sum over blocks of the slowest thread's cycles
+__device__ unsigned long long g_prof[64];
 #define PHASE_PROF_BEGIN() long long _pt0 = clock64()
-#define PHASE_PROF_END(i) do { if (threadIdx.x == 0) atomicAdd(&g_prof[i], (unsigned long long)(clock64() - _pt0)); } while (0)
+#define PHASE_PROF_ITEMS(i, had) do { if (had) { unsigned long long _d = (unsigned long long)(clock64() - _pt0); atomicAdd(&g_prof[16 + i], _d); atomicAdd(&g_prof[32 + i], 1ull); atomicMax(&s_profMax, _d); } } while (0)
+#define PHASE_PROF_END(i) do { if (threadIdx.x == 0) { atomicAdd(&g_prof[i], (unsigned long long)(clock64() - _pt0)); atomicAdd(&g_prof[48 + i], s_profMax); s_profMax = 0; } __syncthreads(); } while (0)
 #else
 #define PHASE_PROF_BEGIN() ((void)0)
+#define PHASE_PROF_ITEMS(i, had) ((void)0)
 #define PHASE_PROF_END(i) ((void)0)
 #endif
 
+__device__ __forceinline__ Ctx make_ctx(const StepArgs& a, const BatchParams* sP, const Scene* sSc, unsigned char* sS, int a0, int ar) {
+	Ctx cx;
+	unsigned char* base = sS + (size_t)ar * a.lay.stride;
+	cx.s = (ArenaS*)base; cx.body = (BodyW*)(base + a.lay.bodyOff); cx.wheels = (WheelW*)(base + a.lay.wheelOff);
+	cx.padLocked = (int*)(base + a.lay.padOff); cx.misc = (int*)(base + a.lay.miscOff);
+	cx.pl = (PairList*)(base + a.lay.pairOff); cx.mf = (Manifold*)(base + a.lay.mfOff); cx.solv = base + a.lay.wheelOff;
+	cx.w = a.W + (a0 + ar); cx.p = sP; cx.sc = sSc; cx.ev = a.ev; cx.arena = a0 + ar;
+	return cx;
+}
+
 template <int PH>
 __device__ __forceinline__ void run_phase_block(const StepArgs& a, const BatchParams* sP, const Scene* sSc, unsigned char* sS, int a0, int nA, int ptid) {
+#if defined(RSB_PROFILE)
+	__shared__ unsigned long long s_profMax;
+#endif
 	PHASE_PROF_BEGIN();
 	const int n = phase_items(*sP, PH) * nA;
 	for (int i = ptid; i < n; i += STEP_THREADS) {
 		const int ar = i % nA, item = i / nA;
-		Ctx cx;
-		cx.s = (ArenaS*)(sS + (size_t)ar * S_STRIDE); cx.w = a.W + (a0 + ar); cx.p = sP; cx.sc = sSc; cx.ev = a.ev; cx.arena = a0 + ar;
+		const Ctx cx = make_ctx(a, sP, sSc, sS, a0, ar);
 		phase_run(cx, PH, item);
 	}
+	PHASE_PROF_ITEMS(PH, ptid < n);
 	__syncthreads();
+	if (a.mirror && (PH == PH_CAR_LOGIC || PH == PH_DYN_SOLVE)) {
+		// single-tick launches keep the debug mirror complete: the wheel scratch and the solver scratch alias each other
+		const int words = (PH == PH_CAR_LOGIC ? a.lay.wheelBytes : a.lay.solvBytes) / 4;
+		for (int i = threadIdx.x; i < nA * words; i += STEP_THREADS) {
+			const int ar = i / words, w = i - ar * words;
+			const uint32_t v = ((const uint32_t*)(sS + (size_t)ar * a.lay.stride + a.lay.wheelOff))[w];
+			ArenaH* dst = a.H + a0 + ar;
+			if (PH == PH_CAR_LOGIC) ((uint32_t*)dst->wheels)[w] = v; else ((uint32_t*)dst->solv)[w] = v;
+		}
+		__syncthreads();
+	}
 	PHASE_PROF_END(PH);
 }
 
@@ -278,39 +334,63 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) arena_step_kernel(const StepA
 	// item -> thread permutation: consecutive items go to different warps, so that a phase with few
 	// items (one per arena) spreads over all four schedulers instead of serialising in one warp
 	const int ptid = (tid & 31) * (STEP_THREADS / 32) + (tid >> 5);
-	const int nCars = a.P->nCars;
+	const int nCars = a.P->nCars, nPads = a.P->nPads, nb = nCars + 1;
+	const int sWords = a.lay.sBytes / 8, strideWords = a.lay.stride / 8;
 	const int nChunks = (a.nArenas + a.apb - 1) / a.apb;
 	for (int chunk = blockIdx.x; chunk < nChunks; chunk += gridDim.x) {
 		const int a0 = chunk * a.apb;
 		const int nA = min(a.apb, a.nArenas - a0);
 		__syncthreads();
-		for (int i = tid; i < nA * S_WORDS8; i += STEP_THREADS) {
-			const int ar = i / S_WORDS8, w = i - ar * S_WORDS8;
-			((uint2*)(sS + (size_t)ar * S_STRIDE))[w] = ((const uint2*)(a.S + a0 + ar))[w];
+		// stage the records: persistent prefix from HBM, per-tick scratch zeroed
+		for (int i = tid; i < nA * strideWords; i += STEP_THREADS) {
+			const int ar = i / strideWords, w = i - ar * strideWords;
+			uint2 v = make_uint2(0u, 0u);
+			if (w < sWords) v = ((const uint2*)(a.S + a0 + ar))[w];
+			((uint2*)(sS + (size_t)ar * a.lay.stride))[w] = v;
 		}
 		__syncthreads();
 		for (int t = 0; t < a.nTicks; t++) {
 			if (a.ctrlSeq) {
 				const int ct = t < a.nCtrl ? t : a.nCtrl - 1;
 				const CtrlS* src = a.ctrlSeq + ((size_t)ct * a.nArenas + a0) * nCars;
-				for (int i = tid; i < nA * nCars; i += STEP_THREADS) ((ArenaS*)(sS + (size_t)(i / nCars) * S_STRIDE))->cars[i % nCars].controls = src[i];
+				for (int i = tid; i < nA * nCars; i += STEP_THREADS) ((ArenaS*)(sS + (size_t)(i / nCars) * a.lay.stride))->cars[i % nCars].controls = src[i];
 				__syncthreads();
 			}
 			run_phase_block<PH_INIT>(a, sP, sSc, sS, a0, nA, ptid);
 			run_phase_block<PH_PRE_BEGIN>(a, sP, sSc, sS, a0, nA, ptid);
 			run_phase_block<PH_WHEELS>(a, sP, sSc, sS, a0, nA, ptid);
 			run_phase_block<PH_CAR_LOGIC>(a, sP, sSc, sS, a0, nA, ptid);
-			run_phase_block<PH_PADS_BALL>(a, sP, sSc, sS, a0, nA, ptid);
 			run_phase_block<PH_PREDICT>(a, sP, sSc, sS, a0, nA, ptid);
-			run_phase_block<PH_COLLIDE>(a, sP, sSc, sS, a0, nA, ptid);
-			run_phase_block<PH_SOLVE>(a, sP, sSc, sS, a0, nA, ptid);
-			run_phase_block<PH_INTEGRATE>(a, sP, sSc, sS, a0, nA, ptid);
+			run_phase_block<PH_PAIRS>(a, sP, sSc, sS, a0, nA, ptid);
+			run_phase_block<PH_NARROW_STATIC>(a, sP, sSc, sS, a0, nA, ptid);
+			run_phase_block<PH_DYN_SOLVE>(a, sP, sSc, sS, a0, nA, ptid);
+			run_phase_block<PH_FINISH_BODY>(a, sP, sSc, sS, a0, nA, ptid);
 			run_phase_block<PH_CAR_POST>(a, sP, sSc, sS, a0, nA, ptid);
+			run_phase_block<PH_PADS_POST>(a, sP, sSc, sS, a0, nA, ptid);
 			run_phase_block<PH_TAIL>(a, sP, sSc, sS, a0, nA, ptid);
 		}
-		for (int i = tid; i < nA * S_WORDS8; i += STEP_THREADS) {
-			const int ar = i / S_WORDS8, w = i - ar * S_WORDS8;
-			((uint2*)(a.S + a0 + ar))[w] = ((const uint2*)(sS + (size_t)ar * S_STRIDE))[w];
+		// records back to HBM; the last tick's hot scratch goes to its global mirror (debug probes)
+		for (int i = tid; i < nA * sWords; i += STEP_THREADS) {
+			const int ar = i / sWords, w = i - ar * sWords;
+			((uint2*)(a.S + a0 + ar))[w] = ((const uint2*)(sS + (size_t)ar * a.lay.stride))[w];
+		}
+		if (a.mirror) {
+			const int bodyWords = nb * (int)sizeof(BodyW) / 4;
+			const int tailWords = (a.lay.stride - 8 - a.lay.padOff) / 4;  // padLocked, misc, pairs, manifold headers
+			const int hotWords = bodyWords + tailWords;
+			for (int i = tid; i < nA * hotWords; i += STEP_THREADS) {
+				const int ar = i / hotWords; int w = i - ar * hotWords;
+				const unsigned char* base = sS + (size_t)ar * a.lay.stride;
+				ArenaH* dst = a.H + a0 + ar;
+				if (w < bodyWords) { ((uint32_t*)dst->body)[w] = ((const uint32_t*)(base + a.lay.bodyOff))[w]; continue; }
+				w -= bodyWords;
+				const int off = a.lay.padOff + w * 4;
+				const uint32_t v = *(const uint32_t*)(base + off);
+				if (off < a.lay.miscOff) { if (w < nPads) ((uint32_t*)dst->padLocked)[w] = v; }
+				else if (off < a.lay.pairOff) ((uint32_t*)dst->misc)[(off - a.lay.miscOff) / 4] = v;
+				else if (off < a.lay.mfOff) { if (off - a.lay.pairOff < (int)sizeof(PairList)) ((uint32_t*)&dst->pairs)[(off - a.lay.pairOff) / 4] = v; }
+				else if (off - a.lay.mfOff < MAX_MANIFOLDS * (int)sizeof(Manifold)) ((uint32_t*)dst->mf)[(off - a.lay.mfOff) / 4] = v;
+			}
 		}
 	}
 }
@@ -320,6 +400,8 @@ static void arena_step_host(const StepArgs& a) {
 	const int nCars = a.P->nCars;
 	for (int arena = 0; arena < a.nArenas; arena++) {
 		Ctx cx; cx.s = a.S + arena; cx.w = a.W + arena; cx.p = a.P; cx.sc = a.sc; cx.ev = a.ev; cx.arena = arena;
+		cx.body = a.H[arena].body; cx.wheels = a.H[arena].wheels; cx.padLocked = a.H[arena].padLocked; cx.misc = a.H[arena].misc;
+		cx.pl = &a.H[arena].pairs; cx.mf = a.H[arena].mf; cx.solv = a.H[arena].solv;
 		for (int t = 0; t < a.nTicks; t++) {
 			if (a.ctrlSeq) {
 				const int ct = t < a.nCtrl ? t : a.nCtrl - 1;
@@ -367,7 +449,7 @@ RSB_GLOBAL void get_misc_kernel(const ArenaS* S, const BatchParams* P, const Sce
 	KERNEL_1D(i, nArenas);
 	if (ticks) ticks[i] = S[i].tickCount;
 	if (errs) errs[i] = S[i].errorFlags;
-	if (scored) { Ctx cx; cx.s = (ArenaS*)&S[i]; cx.w = nullptr; cx.p = P; cx.sc = sc; cx.arena = i; cx.ev.buf = nullptr; scored[i] = is_ball_scored(cx) ? 1 : 0; }
+	if (scored) { Ctx cx; cx.s = (ArenaS*)&S[i]; cx.w = nullptr; cx.body = nullptr; cx.wheels = nullptr; cx.padLocked = nullptr; cx.misc = nullptr; cx.pl = nullptr; cx.mf = nullptr; cx.solv = nullptr; cx.p = P; cx.sc = sc; cx.arena = i; cx.ev.buf = nullptr; scored[i] = is_ball_scored(cx) ? 1 : 0; }
 }
 RSB_GLOBAL void get_car_internals_kernel(const ArenaS* S, RsbCarInternal* out, int nArenas, int nCars) {
 	KERNEL_1D(i, nArenas * nCars);
@@ -692,7 +774,10 @@ int rsb_batch_create(int device, int game_mode, int n_arenas, int n_cars, const 
 		b->numSMs = prop.multiProcessorCount;
 		if ((size_t)prop.sharedMemPerBlockOptin < SMEM_MAX) throw std::runtime_error("device offers less than 227 KB of shared memory per block: rocketsim_b200 targets sm_100a");
 		static std::mutex attrMutex; std::lock_guard<std::mutex> lk(attrMutex);
-		CUDA_OK(cudaFuncSetAttribute(arena_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
+		cudaFuncAttributes fa;
+		CUDA_OK(cudaFuncGetAttributes(&fa, arena_step_kernel));
+		b->smemBudget = SMEM_MAX - fa.sharedSizeBytes;  // dynamic shared memory left beside the kernel's static part
+		CUDA_OK(cudaFuncSetAttribute(arena_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smemBudget));
 	}
 #endif
 	BatchParams& P = b->hp;
@@ -709,12 +794,20 @@ int rsb_batch_create(int device, int game_mode, int n_arenas, int n_cars, const 
 		P.team[i] = teams ? teams[i] : (i < (n_cars + 1) / 2 ? 0 : 1);
 	}
 	fill_pads(game_mode, P);
+	{
+		ArenaS tmpS; memset(&tmpS, 0, sizeof(tmpS));
+		Ctx cx; cx.s = &tmpS; cx.w = nullptr; cx.body = nullptr; cx.wheels = nullptr; cx.padLocked = nullptr; cx.misc = nullptr; cx.pl = nullptr; cx.mf = nullptr; cx.solv = nullptr; cx.p = &P; cx.sc = nullptr; cx.arena = 0; cx.ev.buf = nullptr;
+		for (int bidx = 0; bidx <= n_cars; bidx++) P.motionDisc[bidx] = body_angular_motion_disc(cx, bidx);
+		P.boundRadius[0] = P.ballIsSphere ? P.ballRadiusBT : (sqrtf(P.ballRadiusBT * P.ballRadiusBT + (K::PUCK_HEIGHT * UU_TO_BT / 2) * (K::PUCK_HEIGHT * UU_TO_BT / 2)) + 0.04f);
+		for (int c = 0; c < n_cars; c++) P.boundRadius[c + 1] = len(P.carCfg[c].hitboxHalf) + 0.04f;
+	}
 	b->dScene = get_scene_dev(device, game_mode)->dScene;
 	const SceneHost& sh = get_scene_dev(device, game_mode)->host;
 	b->dP = (BatchParams*)dev_alloc(sizeof(BatchParams));
 	h2d(b->dP, &P, sizeof(P), 0);
 	b->dS = (ArenaS*)dev_alloc(sizeof(ArenaS) * (size_t)n_arenas);
 	b->dW = (ArenaW*)dev_alloc(sizeof(ArenaW) * (size_t)n_arenas);
+	b->dH = (ArenaH*)dev_alloc(sizeof(ArenaH) * (size_t)n_arenas);
 	b->eventCap = (uint32_t)std::max(4096, n_arenas * 4);
 	b->dEvents = (EventSink::Ev*)dev_alloc(sizeof(EventSink::Ev) * b->eventCap);
 	b->dEventCount = (uint32_t*)dev_alloc(sizeof(uint32_t));
@@ -723,6 +816,7 @@ int rsb_batch_create(int device, int game_mode, int n_arenas, int n_cars, const 
 	// initial arena record: Arena ctor + AddCar/Respawn (Arena.cpp:50-62, 416-540)
 	std::vector<ArenaS> init((size_t)n_arenas);
 	ArenaW tmpW; memset(&tmpW, 0, sizeof(tmpW));
+	ArenaH tmpH; memset(&tmpH, 0, sizeof(tmpH));
 	Scene hsc; memset(&hsc, 0, sizeof(hsc));
 	hsc.gridMin = sh.gridMin; hsc.gridMax = sh.gridMax; hsc.cellSize = sh.cellSize; hsc.cellsX = sh.cellsX; hsc.cellsY = sh.cellsY; hsc.cellsZ = sh.cellsZ;
 	for (int a = 0; a < n_arenas; a++) {
@@ -734,8 +828,9 @@ int rsb_batch_create(int device, int game_mode, int n_arenas, int n_cars, const 
 		A.ball.hsCurTargetSpeed = K::HS_INITIAL_TARGET_SPEED;
 		for (int p = 0; p < P.nPads; p++) { A.pads[p].isActive = 1; }
 		Ctx cx; cx.s = &A; cx.w = &tmpW; cx.p = &P; cx.sc = &hsc; cx.arena = a; cx.ev.buf = nullptr;
+		cx.body = tmpH.body; cx.wheels = tmpH.wheels; cx.padLocked = tmpH.padLocked; cx.misc = tmpH.misc; cx.pl = &tmpH.pairs; cx.mf = tmpH.mf; cx.solv = tmpH.solv;
 		for (int c = 0; c < n_cars; c++) {
-			tmpW.body[c + 1].invInertiaLocal = P.carCfg[c].invInertiaLocal;
+			tmpH.body[c + 1].invInertiaLocal = P.carCfg[c].invInertiaLocal;
 			car_respawn(cx, c);  // AddCar -> Respawn(gameMode, -1, carSpawnBoostAmount)
 		}
 		// broadphase proxies are created from the body transforms at construction time:
@@ -746,7 +841,9 @@ int rsb_batch_create(int device, int game_mode, int n_arenas, int n_cars, const 
 			body_shape_aabb(cx, bidx, m3identity(), org, mn, mx);
 			int i, j, k;
 			A.cellIdx[bidx] = grid_cell_of(hsc, mn, i, j, k);
+			A.cellI[bidx] = (uint8_t)i; A.cellJ[bidx] = (uint8_t)j; A.cellK[bidx] = (uint8_t)k;
 			A.cellStamp[bidx] = (uint32_t)bidx + 1;
+			A.dynOrder[bidx] = (uint8_t)bidx;
 		}
 		A.stampCounter = (uint32_t)n_cars + 2;
 	}
@@ -765,7 +862,7 @@ int rsb_batch_destroy(RsbBatch* b) {
 #ifndef RSB_HOSTCHECK
 	cudaDeviceSynchronize();
 #endif
-	dev_free(b->dP); dev_free(b->dS); dev_free(b->dW); dev_free(b->dEvents); dev_free(b->dEventCount); dev_free(b->dCtrl); dev_free(b->dCtrlSeq); dev_free(b->dScratch);
+	dev_free(b->dP); dev_free(b->dS); dev_free(b->dW); dev_free(b->dH); dev_free(b->dEvents); dev_free(b->dEventCount); dev_free(b->dCtrl); dev_free(b->dCtrlSeq); dev_free(b->dScratch);
 	delete b;
 	API_END
 }
@@ -790,11 +887,13 @@ static EventSink sink_of(RsbBatch* b) { EventSink e; e.buf = b->dEvents; e.count
 
 static void launch_step(RsbBatch* b, int n_ticks, const CtrlS* seq, int nCtrl) {
 	const BatchParams& P = b->hp;
-	StepArgs a; a.S = b->dS; a.W = b->dW; a.P = b->dP; a.sc = b->dScene; a.ev = sink_of(b);
-	a.nArenas = P.nArenas; a.nTicks = n_ticks; a.ctrlSeq = seq; a.nCtrl = nCtrl; a.apb = 1;
+	StepArgs a; a.S = b->dS; a.H = b->dH; a.W = b->dW; a.P = b->dP;
+	a.lay = ArenaLayout::make(P.nCars, P.nPads); a.sc = b->dScene; a.ev = sink_of(b);
+	a.nArenas = P.nArenas; a.nTicks = n_ticks; a.ctrlSeq = seq; a.nCtrl = nCtrl; a.apb = 1; a.mirror = (n_ticks == 1) ? 1 : 0;
 #ifndef RSB_HOSTCHECK
 	// chunk size: fill every SM once if the batch fits (one wave), else the fewest equal waves
 	const int sms = b->numSMs;
+	const int APB_MAX = (int)((b->smemBudget - SMEM_P_BYTES - SMEM_SC_BYTES) / a.lay.stride);
 	const int chunksMin = (P.nArenas + APB_MAX - 1) / APB_MAX;
 	const int waves = (chunksMin + sms - 1) / sms;
 	a.apb = (P.nArenas + waves * sms - 1) / (waves * sms);
@@ -802,7 +901,7 @@ static void launch_step(RsbBatch* b, int n_ticks, const CtrlS* seq, int nCtrl) {
 	if (a.apb > APB_MAX) a.apb = APB_MAX;
 	const int nChunks = (P.nArenas + a.apb - 1) / a.apb;
 	const int grid = nChunks < sms ? nChunks : sms;
-	const size_t smem = SMEM_P_BYTES + SMEM_SC_BYTES + (size_t)a.apb * S_STRIDE;
+	const size_t smem = SMEM_P_BYTES + SMEM_SC_BYTES + (size_t)a.apb * a.lay.stride;
 	arena_step_kernel<<<grid, STEP_THREADS, smem, b->stream>>>(a);
 	CUDA_OK(cudaGetLastError());
 #else
@@ -982,8 +1081,8 @@ int rsb_bench_fill_controls_device(RsbBatch* b, void* d_seq, int n_ticks, uint32
 // ---- debug probe: wheel values of the last tick (layout of oracle ref_get_wheel_debug) ----
 int rsb_debug_get_wheels(RsbBatch* b, int arena, float* out) {
 	API_BEGIN set_device(b);
-	std::vector<ArenaW> w(1);
-	d2h(w.data(), b->dW + arena, sizeof(ArenaW), b->stream);
+	std::vector<ArenaH> w(1);
+	d2h(w.data(), b->dH + arena, sizeof(ArenaH), b->stream);
 	for (int k = 0; k < b->hp.nCars * 4; k++) {
 		const WheelW& x = w[0].wheels[k]; float* p = out + 14 * k;
 		p[0] = (float)x.isInContact; p[1] = (float)x.isInContactWithWorld; p[2] = x.suspLen;
@@ -995,18 +1094,36 @@ int rsb_debug_get_wheels(RsbBatch* b, int arena, float* out) {
 }
 
 // ---- debug probe: contact points of the last tick (layout of oracle ref_get_manifolds) ----
+// The debug probes read the global mirror of the per-tick scratch, which the kernel keeps complete only for
+// single-tick launches (rsb_step(b, 1) / a 1-tick control sequence).
+struct DebugSnap { std::vector<ArenaH> h; std::vector<ArenaW> w; };
+static DebugSnap debug_snap(RsbBatch* b, int arena) {
+	if (arena < 0 || arena >= b->hp.nArenas) throw std::runtime_error("arena index out of range");
+	DebugSnap s; s.h.resize(1); s.w.resize(1);
+	d2h(s.h.data(), b->dH + arena, sizeof(ArenaH), b->stream);
+	d2h(s.w.data(), b->dW + arena, sizeof(ArenaW), b->stream);
+	return s;
+}
+static SolverView debug_solver_view(DebugSnap& s, int nCars) {
+	SolverView v;
+	v.cnt = (int*)s.h[0].solv; v.sbody = (SolverBody*)(s.h[0].solv + 16);
+	v.rows = (SolverRow*)(v.sbody + (nCars + 2)); v.frows = v.rows + SOLVER_ROWS_FAST;
+	v.orows = s.w[0].rows; v.ofrows = s.w[0].frows;
+	return v;
+}
+
 int rsb_debug_get_manifolds(RsbBatch* b, int arena, float* out, int cap_points, int* n_out) {
 	API_BEGIN set_device(b);
-	std::vector<ArenaW> w(1);
-	d2h(w.data(), b->dW + arena, sizeof(ArenaW), b->stream);
+	DebugSnap s = debug_snap(b, arena);
 	const SceneHost& sh = get_scene_dev(b->device, b->hp.mode)->host;
 	const int nStatics = (int)sh.meshes.size() + (int)sh.planes.size();
 	auto world_index = [&](int obj) { return obj >= STATIC_BASE ? obj - STATIC_BASE : nStatics + obj; };
 	int n = 0;
-	for (int m = 0; m < w[0].nManifolds; m++) {
-		const Manifold& mf = w[0].manifolds[m];
+	for (int m = 0; m < s.h[0].pairs.nManifolds; m++) {
+		const Manifold& mf = s.h[0].mf[m];
+		if (mf.body0 < 0) continue;
 		for (int k = 0; k < mf.nPts && n < cap_points; k++, n++) {
-			const ContactPt& p = mf.pts[k]; float* o = out + 16 * n;
+			const ContactPt& p = s.w[0].points[m * 4 + k]; float* o = out + 16 * n;
 			o[0] = (float)world_index(mf.body0); o[1] = (float)world_index(mf.body1); o[2] = (float)k; o[3] = p.dist;
 			o[4] = p.normalB.x; o[5] = p.normalB.y; o[6] = p.normalB.z; o[7] = p.posA.x; o[8] = p.posA.y; o[9] = p.posA.z;
 			o[10] = p.posB.x; o[11] = p.posB.y; o[12] = p.posB.z; o[13] = p.friction; o[14] = p.restitution; o[15] = (float)p.isSpecial;
@@ -1019,15 +1136,18 @@ int rsb_debug_get_manifolds(RsbBatch* b, int arena, float* out, int cap_points, 
 // ---- debug probe: solver rows of the last tick (layout of oracle ref_get_solver_rows) ----
 int rsb_debug_get_solver_rows(RsbBatch* b, int arena, int which, float* out, int cap, int* n_out) {
 	API_BEGIN set_device(b);
-	std::vector<ArenaW> w(1);
-	d2h(w.data(), b->dW + arena, sizeof(ArenaW), b->stream);
-	int n = which ? w[0].nFrictionRows : w[0].nRows;
-	if (n > cap) n = cap;
-	for (int i = 0; i < n; i++) {
-		const SolverRow& c = which ? w[0].frows[i] : w[0].rows[i]; float* o = out + 24 * i;
-		const V3* v[6] = {&c.n1, &c.rp1xn, &c.n2, &c.rp2xn, &c.angA, &c.angB};
-		for (int k = 0; k < 6; k++) { o[3 * k] = v[k]->x; o[3 * k + 1] = v[k]->y; o[3 * k + 2] = v[k]->z; }
-		o[18] = c.jacDiagInv; o[19] = c.rhs; o[20] = c.rhsPen; o[21] = c.applied; o[22] = c.appliedPush; o[23] = c.friction;
+	DebugSnap s = debug_snap(b, arena);
+	int n = 0;
+	if (s.h[0].misc[0]) {  // the general solver ran this tick
+		const SolverView sv = debug_solver_view(s, b->hp.nCars);
+		n = which ? sv.cnt[2] : sv.cnt[1];
+		if (n > cap) n = cap;
+		for (int i = 0; i < n; i++) {
+			const SolverRow& c = which ? sv.frow(i) : sv.row(i); float* o = out + 24 * i;
+			const V3* v[6] = {&c.n1, &c.rp1xn, &c.n2, &c.rp2xn, &c.angA, &c.angB};
+			for (int k = 0; k < 6; k++) { o[3 * k] = v[k]->x; o[3 * k + 1] = v[k]->y; o[3 * k + 2] = v[k]->z; }
+			o[18] = c.jacDiagInv; o[19] = c.rhs; o[20] = c.rhsPen; o[21] = c.applied; o[22] = c.appliedPush; o[23] = c.friction;
+		}
 	}
 	if (n_out) *n_out = n;
 	API_END
@@ -1035,26 +1155,29 @@ int rsb_debug_get_solver_rows(RsbBatch* b, int arena, int which, float* out, int
 
 int rsb_debug_get_solver_bodies(RsbBatch* b, int arena, float* out, int cap, int* n_out) {
 	API_BEGIN set_device(b);
-	std::vector<ArenaW> w(1);
-	d2h(w.data(), b->dW + arena, sizeof(ArenaW), b->stream);
-	int n = w[0].nSolverBodies; if (n > cap) n = cap;
-	for (int i = 0; i < n; i++) {
-		const SolverBody& sb = w[0].sbody[i]; float* o = out + 12 * i;
-		const V3* v[4] = {&sb.lin, &sb.ang, &sb.extF, &sb.extT};
-		for (int k = 0; k < 4; k++) { o[3 * k] = v[k]->x; o[3 * k + 1] = v[k]->y; o[3 * k + 2] = v[k]->z; }
+	DebugSnap s = debug_snap(b, arena);
+	int n = 0;
+	if (s.h[0].misc[0]) {
+		const SolverView sv = debug_solver_view(s, b->hp.nCars);
+		n = sv.cnt[0]; if (n > cap) n = cap;
+		for (int i = 0; i < n; i++) {
+			const SolverBody& sb = sv.sbody[i]; float* o = out + 12 * i;
+			const V3* v[4] = {&sb.lin, &sb.ang, &sb.extF, &sb.extT};
+			for (int k = 0; k < 4; k++) { o[3 * k] = v[k]->x; o[3 * k + 1] = v[k]->y; o[3 * k + 2] = v[k]->z; }
+		}
 	}
 	if (n_out) *n_out = n;
 	API_END
 }
 
 // ---- developer profile counters (non-zero only in -DRSB_PROFILE builds) ----
-int rsb_debug_profile(uint64_t* out16, int reset) {
+int rsb_debug_profile(uint64_t* out64, int reset) {
 	API_BEGIN
-	for (int i = 0; i < 16; i++) out16[i] = 0;
+	for (int i = 0; i < 64; i++) out64[i] = 0;
 #if defined(RSB_PROFILE) && !defined(RSB_HOSTCHECK)
 	CUDA_OK(cudaDeviceSynchronize());
-	CUDA_OK(cudaMemcpyFromSymbol(out16, g_prof, sizeof(unsigned long long) * 16));
-	if (reset) { unsigned long long z[16] = {0}; CUDA_OK(cudaMemcpyToSymbol(g_prof, z, sizeof(z))); }
+	CUDA_OK(cudaMemcpyFromSymbol(out64, g_prof, sizeof(unsigned long long) * 64));
+	if (reset) { unsigned long long z[64] = {0}; CUDA_OK(cudaMemcpyToSymbol(g_prof, z, sizeof(z))); }
 #else
 	(void)reset;
 #endif

@@ -9,6 +9,10 @@
 // The reference rebuilds the cell lists for every Arena (18k brute-force mesh scans each);
 // here they are built once per game mode and shared by every arena of every batch.
 #pragma once
+#include <algorithm>
+#if defined(__SSE__)
+#include <xmmintrin.h>
+#endif
 #include <cstring>
 #include <stdexcept>
 #include <string>
@@ -41,6 +45,11 @@ struct SceneHost {
 	int cellsX = 0, cellsY = 0, cellsZ = 0;
 	std::vector<int32_t> cellStart;
 	std::vector<uint8_t> cellStatics;
+	// per cell-list entry (= position in cellStatics) of a MESH: the subtree headers of its BVH that can overlap a query
+	// issued from that cell (box = the cell's 27-neighbourhood), in header creation order (AABB queries) and sorted by
+	// root node (ray queries).  Pure culling: skipped headers cannot overlap the quantised query box.
+	std::vector<int32_t> cellHdrStart;
+	std::vector<uint16_t> cellHdrs, cellHdrsRay;
 };
 
 namespace scene_detail {
@@ -350,8 +359,37 @@ inline MeshHost build_mesh(const uint8_t* data, size_t size) {
 	return m;
 }
 
-inline PlaneD make_plane(const V3& posUU, const V3& n) {
+// btVector3::normalize() as compiled for x86-64 (bt/LinearMath/btVector3.h:304-340): rsqrtss estimate + one Newton step.
+// btStaticPlaneShape stores planeNormal.normalized() (btStaticPlaneShape.cpp:19-25), so the reference's arena planes carry
+// e.g. (0, 0, 0.99999994) rather than (0, 0, 1); that value reaches every plane contact normal and friction direction.
+// Scene building is host code, so we run the same instruction sequence on the same CPU.
+inline V3 bullet_normalized_host(const V3& v) {
+#if defined(__SSE__) && !defined(__CUDA_ARCH__)
+	__m128 vec = _mm_set_ps(0.f, v.z, v.y, v.x);
+	__m128 vd = _mm_mul_ps(vec, vec);
+	__m128 z = _mm_movehl_ps(vd, vd);
+	__m128 y = _mm_shuffle_ps(vd, vd, 0x55);
+	vd = _mm_add_ss(vd, y);
+	vd = _mm_add_ss(vd, z);
+	y = _mm_rsqrt_ss(vd);
+	z = _mm_set_ss(1.5f);
+	vd = _mm_mul_ss(vd, _mm_set_ss(0.5f));
+	vd = _mm_mul_ss(vd, y);
+	vd = _mm_mul_ss(vd, y);
+	z = _mm_sub_ss(z, vd);
+	y = _mm_mul_ss(y, z);
+	y = _mm_shuffle_ps(y, y, 0x80);
+	vec = _mm_mul_ps(vec, y);
+	float o[4]; _mm_storeu_ps(o, vec);
+	return V3(o[0], o[1], o[2]);
+#else
+	return v * (1.0f / sqrtf(dot(v, v)));
+#endif
+}
+
+inline PlaneD make_plane(const V3& posUU, const V3& nIn) {
 	PlaneD p;
+	const V3 n = bullet_normalized_host(nIn);
 	p.n = n; p.pos = posUU * UU_TO_BT;
 	p.d = dot(n, p.pos);
 	// btStaticPlaneShape::getAabb (single-axis slab, half-infinite behind the plane)
@@ -454,6 +492,39 @@ inline SceneHost build_scene(int mode, std::vector<MeshHost> meshes) {
 	for (int c = 0; c < total; c++) {
 		s.cellStatics.insert(s.cellStatics.end(), cells[c].begin(), cells[c].end());
 		s.cellStart[c + 1] = (int32_t)s.cellStatics.size();
+	}
+	// header candidate lists per (cell, mesh) entry
+	s.cellHdrStart.assign(1, 0);
+	const float INF = 1e30f;
+	for (int c = 0; c < total; c++) {
+		const int ci = c / (s.cellsY * s.cellsZ), cj = (c / s.cellsZ) % s.cellsY, ck = c % s.cellsZ;
+		V3 cellMin = s.gridMin + V3((float)ci, (float)cj, (float)ck) * s.cellSize;
+		V3 nMin = cellMin - V3(s.cellSize, s.cellSize, s.cellSize) - ct;
+		V3 nMax = cellMin + V3(s.cellSize, s.cellSize, s.cellSize) * 2.f + ct;
+		// positions outside the grid are clamped into the border cells
+		if (ci == 0) nMin.x = -INF; if (cj == 0) nMin.y = -INF; if (ck == 0) nMin.z = -INF;
+		if (ci == s.cellsX - 1) nMax.x = INF; if (cj == s.cellsY - 1) nMax.y = INF; if (ck == s.cellsZ - 1) nMax.z = INF;
+		for (int e = s.cellStart[c]; e < s.cellStart[c + 1]; e++) {
+			const int o = s.cellStatics[e];
+			if (o < (int)s.meshes.size()) {
+				const MeshHost& m = s.meshes[o];
+				if (m.hdrs.size() > 65535) throw std::runtime_error("mesh has too many BVH subtree headers");
+				uint16_t qmin[3], qmax[3];
+				V3 lo = vmin(vmax(nMin, m.bvhMin), m.bvhMax), hi = vmin(vmax(nMax, m.bvhMin), m.bvhMax);  // quantizeWithClamp
+				quantize(m, lo, 0, qmin); quantize(m, hi, 1, qmax);
+				std::vector<uint16_t> list;
+				for (size_t h = 0; h < m.hdrs.size(); h++) {
+					const SubtreeHdr& hd = m.hdrs[h];
+					bool ov = (qmin[0] <= hd.qmax[0]) && (qmax[0] >= hd.qmin[0]) && (qmin[1] <= hd.qmax[1]) && (qmax[1] >= hd.qmin[1]) &&
+					          (qmin[2] <= hd.qmax[2]) && (qmax[2] >= hd.qmin[2]);
+					if (ov) list.push_back((uint16_t)h);
+				}
+				s.cellHdrs.insert(s.cellHdrs.end(), list.begin(), list.end());
+				std::sort(list.begin(), list.end(), [&](uint16_t a, uint16_t b) { return m.hdrs[a].root < m.hdrs[b].root; });
+				s.cellHdrsRay.insert(s.cellHdrsRay.end(), list.begin(), list.end());
+			}
+			s.cellHdrStart.push_back((int32_t)s.cellHdrs.size());
+		}
 	}
 	return s;
 }

@@ -56,7 +56,7 @@ RSB_HD Ang round_angle_ue3(Ang ang) {
 // Ball::_PreTickUpdate
 RSB_HD void ball_pretick(const Ctx& cx) {
 	BallS& b = cx.s->ball;
-	BodyW& bw = cx.w->body[0];
+	BodyW& bw = cx.body[0];
 	const int mode = cx.p->mode;
 	const float dt = cx.p->dt;
 	if (mode == HEATSEEKER) {
@@ -171,7 +171,7 @@ RSB_HD void ball_on_world_collision(const Ctx& cx, const V3& normal) {
 		}
 	} else if (mode == SNOWDAY) {
 		if (!b.groundStickApplied) {
-			apply_central_force(cx.w->body[0], (-normal) * K::PUCK_GROUND_STICK_FORCE);
+			apply_central_force(cx.body[0], (-normal) * K::PUCK_GROUND_STICK_FORCE);
 			b.groundStickApplied = 1;
 		}
 	}
@@ -220,7 +220,7 @@ RSB_HD void pad_pretick(const Ctx& cx, int i) {
 	PadS& p = cx.s->pads[i];
 	if (p.cooldown > 0.f) { float t = p.cooldown - cx.p->dt; p.cooldown = (t > 0.f) ? t : 0.f; }
 	p.isActive = (p.cooldown == 0.f);
-	cx.w->padLocked[i] = -1;
+	cx.padLocked[i] = -1;
 }
 
 // car AABB as btRigidBody::getAabb -> compound shape AABB of the CURRENT transform
@@ -241,7 +241,13 @@ RSB_HD void pad_check_collide(const Ctx& cx, int pi, int ci) {
 		float dx = carPosBT.x - pc.posBT.x, dy = carPosBT.y - pc.posBT.y;
 		if ((dx * dx + dy * dy) < (rad * rad)) colliding = fabsf(carPosBT.z - pc.posBT.z) < (K::PAD_CYL_HEIGHT * UU_TO_BT);
 	}
-	if (colliding) cx.w->padLocked[pi] = ci;
+	if (colliding) {  // cars are visited in index order by the reference loop: the highest index wins
+#if defined(__CUDA_ARCH__)
+		atomicMax(&cx.padLocked[pi], ci);
+#else
+		if (ci > cx.padLocked[pi]) cx.padLocked[pi] = ci;
+#endif
+	}
 }
 
 // BoostPadGrid::CheckCollision
@@ -267,14 +273,26 @@ RSB_HD void pad_posttick(const Ctx& cx, int i) {
 	PadS& p = cx.s->pads[i];
 	const PadCfgD& pc = cx.p->pads[i];
 	uint32_t lockedCarID = 0;
-	int lc = cx.w->padLocked[i];
+	int lc = cx.padLocked[i];
 	if (lc >= 0) {
 		lockedCarID = (uint32_t)(lc + 1);
 		if (p.isActive) {
 			float boostToAdd = pc.isBig ? K::PAD_BOOST_AMOUNT_BIG : K::PAD_BOOST_AMOUNT_SMALL;
 			CarS& c = cx.s->cars[lc];
+#if defined(__CUDA_ARCH__)
+			// pads run one per thread: two pads feeding the same car in one tick must not lose an update
+			unsigned int* addr = (unsigned int*)&c.boost;
+			unsigned int old = *addr, assumed;
+			do {
+				assumed = old;
+				float nb = __uint_as_float(assumed) + boostToAdd;
+				nb = (nb < K::BOOST_MAX) ? nb : K::BOOST_MAX;
+				old = atomicCAS(addr, assumed, __float_as_uint(nb));
+			} while (old != assumed);
+#else
 			float nb = c.boost + boostToAdd;
 			c.boost = (nb < K::BOOST_MAX) ? nb : K::BOOST_MAX;
+#endif
 			p.isActive = 0;
 			p.cooldown = pc.isBig ? cx.p->mut.boostPadCooldown_Big : cx.p->mut.boostPadCooldown_Small;
 		}

@@ -59,13 +59,13 @@ RSB_HD void car_respawn(const Ctx& cx, int ci) {
 	c.rb.basis = basis_from_ypr(yaw, 0.f, 0.f);
 	c.rb.vel = v3zero();
 	c.rb.angvel = v3zero();
-	cx.w->body[ci + 1].invInertiaW = world_inv_inertia(c.rb.basis, cx.w->body[ci + 1].invInertiaLocal);
+	cx.body[ci + 1].invInertiaW = world_inv_inertia(c.rb.basis, cx.body[ci + 1].invInertiaLocal);
 }
 
 // Phase A (per car): input clamp, demo timer / respawn, activation flags (Car.cpp:58-87).
 RSB_HD void car_pretick_begin(const Ctx& cx, int ci) {
 	CarS& c = cx.s->cars[ci];
-	BodyW& bw = cx.w->body[ci + 1];
+	BodyW& bw = cx.body[ci + 1];
 	c.controls.throttle = rs_clamp(c.controls.throttle, -1.f, 1.f);
 	c.controls.steer = rs_clamp(c.controls.steer, -1.f, 1.f);
 	c.controls.pitch = rs_clamp(c.controls.pitch, -1.f, 1.f);
@@ -88,8 +88,8 @@ RSB_HD void car_pretick_begin(const Ctx& cx, int ci) {
 RSB_HD void wheel_trace(const Ctx& cx, int ci, int wi) {
 	CarS& c = cx.s->cars[ci];
 	const CarCfgD& cfg = cx.p->carCfg[ci];
-	const BodyW& bw = cx.w->body[ci + 1];
-	WheelW& w = cx.w->wheels[ci * 4 + wi];
+	const BodyW& bw = cx.body[ci + 1];
+	WheelW& w = cx.wheels[ci * 4 + wi];
 	const RigidS& rb = c.rb;
 
 	// updateWheelTransformsWS
@@ -180,13 +180,13 @@ RSB_HD void wheel_trace(const Ctx& cx, int ci, int wi) {
 RSB_HD void calc_friction_impulses(const Ctx& cx, int ci) {
 	CarS& c = cx.s->cars[ci];
 	const RigidS& rb = c.rb;
-	const BodyW& bw = cx.w->body[ci + 1];
+	const BodyW& bw = cx.body[ci + 1];
 	const CarCfgD& cfg = cx.p->carCfg[ci];
 	const float dt = cx.p->dt;
 	const float mass = 1.f / bw.invMass;  // getMass()
 	const float frictionScale = mass / 3.f;
 	for (int wi = 0; wi < 4; wi++) {
-		WheelW& w = cx.w->wheels[ci * 4 + wi];
+		WheelW& w = cx.wheels[ci * 4 + wi];
 		if (w.groundObj == OBJ_NONE) { w.impulse = v3zero(); continue; }
 		V3 axleDir = w.wtBasis.col(1);
 		V3 surf = w.contactNormalWS;
@@ -212,7 +212,7 @@ RSB_HD void calc_friction_impulses(const Ctx& cx, int ci) {
 				V3 MinvJtA = bw.invInertiaLocal * aJ;
 				if (w.groundObj < STATIC_BASE) {
 					const RigidS& g = rigid_of(cx, w.groundObj);
-					const BodyW& gw = cx.w->body[w.groundObj];
+					const BodyW& gw = cx.body[w.groundObj];
 					rel_pos2 = w.contactPointWS - g.pos;
 					vel2 = vel_at(g, rel_pos2);
 					M3 world2B = transpose(g.basis);
@@ -263,7 +263,7 @@ RSB_HD void calc_friction_impulses(const Ctx& cx, int ci) {
 RSB_HD V3 upwards_dir_from_wheels(const Ctx& cx, int ci) {
 	V3 sum = v3zero();
 	for (int wi = 0; wi < 4; wi++) {
-		const WheelW& w = cx.w->wheels[ci * 4 + wi];
+		const WheelW& w = cx.wheels[ci * 4 + wi];
 		if (w.isInContact) sum += w.contactNormalWS;
 	}
 	if (is_zero(sum)) return cx.s->cars[ci].rb.basis.col(2);
@@ -273,14 +273,14 @@ RSB_HD V3 upwards_dir_from_wheels(const Ctx& cx, int ci) {
 // Car::_UpdateWheels (Car.cpp:339-484)
 RSB_HD void car_update_wheels(const Ctx& cx, int ci, int numWheelsInContact, float forwardSpeed_UU) {
 	CarS& c = cx.s->cars[ci];
-	BodyW& bw = cx.w->body[ci + 1];
+	BodyW& bw = cx.body[ci + 1];
 	const RigidS& rb = c.rb;
 	const CarCfgD& cfg = cx.p->carCfg[ci];
 	const float dt = cx.p->dt;
 	float absForwardSpeed_UU = fabsf(forwardSpeed_UU);
 
 	bool wheelsHaveWorldContact = false;
-	for (int wi = 0; wi < 4; wi++) wheelsHaveWorldContact |= (cx.w->wheels[ci * 4 + wi].isInContactWithWorld != 0);
+	for (int wi = 0; wi < 4; wi++) wheelsHaveWorldContact |= (cx.wheels[ci * 4 + wi].isInContactWithWorld != 0);
 
 	if (c.controls.handbrake) c.handbrakeVal += K::POWERSLIDE_RISE_RATE * dt;
 	else c.handbrakeVal -= K::POWERSLIDE_FALL_RATE * dt;
@@ -323,7 +323,7 @@ RSB_HD void car_update_wheels(const Ctx& cx, int ci, int numWheelsInContact, flo
 	}
 
 	for (int wi = 0; wi < 4; wi++) {
-		const WheelW& w = cx.w->wheels[ci * 4 + wi];
+		const WheelW& w = cx.wheels[ci * 4 + wi];
 		if (w.groundObj == OBJ_NONE) continue;
 		V3 vel = rb.vel, angularVel = rb.angvel;
 		V3 latDir = w.wtBasis.col(1);
@@ -364,7 +364,7 @@ RSB_HD void car_update_wheels(const Ctx& cx, int ci, int numWheelsInContact, flo
 // Car::_UpdateAirTorque (Car.cpp:584-669)
 RSB_HD void car_update_air_torque(const Ctx& cx, int ci, bool updateAirControl) {
 	CarS& c = cx.s->cars[ci];
-	BodyW& bw = cx.w->body[ci + 1];
+	BodyW& bw = cx.body[ci + 1];
 	const RigidS& rb = c.rb;
 	V3 fwdDir = rb.basis.col(0), rightDir = rb.basis.col(1), upDir = rb.basis.col(2);
 	V3 dirPitch_right = -rightDir, dirYaw_up = upDir, dirRoll_forward = -fwdDir;
@@ -425,7 +425,7 @@ RSB_HD void car_update_air_torque(const Ctx& cx, int ci, bool updateAirControl) 
 // Car::_UpdateJump (Car.cpp:535-582)
 RSB_HD void car_update_jump(const Ctx& cx, int ci, bool jumpPressed) {
 	CarS& c = cx.s->cars[ci];
-	BodyW& bw = cx.w->body[ci + 1];
+	BodyW& bw = cx.body[ci + 1];
 	const MutD& mut = cx.p->mut;
 	V3 upDir = c.rb.basis.col(2);
 	if (c.isOnGround && !c.isJumping) {
@@ -468,7 +468,7 @@ RSB_HD float roll_from_basis(const M3& m) {
 // Car::_UpdateAutoFlip (Car.cpp:783-817)
 RSB_HD void car_update_auto_flip(const Ctx& cx, int ci, bool jumpPressed) {
 	CarS& c = cx.s->cars[ci];
-	BodyW& bw = cx.w->body[ci + 1];
+	BodyW& bw = cx.body[ci + 1];
 	V3 upDir = c.rb.basis.col(2), fwdDir = c.rb.basis.col(0);
 	if (jumpPressed && c.worldContactHas && c.worldContactNormal.z > K::CAR_AUTOFLIP_NORMZ_THRESH) {
 		float roll = roll_from_basis(c.rb.basis);
@@ -494,7 +494,7 @@ RSB_HD void car_update_auto_flip(const Ctx& cx, int ci, bool jumpPressed) {
 // Car::_UpdateDoubleJumpOrFlip (Car.cpp:671-781)
 RSB_HD void car_update_double_jump_or_flip(const Ctx& cx, int ci, bool jumpPressed, float forwardSpeed_UU) {
 	CarS& c = cx.s->cars[ci];
-	BodyW& bw = cx.w->body[ci + 1];
+	BodyW& bw = cx.body[ci + 1];
 	const MutD& mut = cx.p->mut;
 	const CarCfgD& cfg = cx.p->carCfg[ci];
 	const float dt = cx.p->dt;
@@ -563,7 +563,7 @@ RSB_HD void car_update_double_jump_or_flip(const Ctx& cx, int ci, bool jumpPress
 // Car::_UpdateAutoRoll (Car.cpp:819-853)
 RSB_HD void car_update_auto_roll(const Ctx& cx, int ci, int numWheelsInContact) {
 	CarS& c = cx.s->cars[ci];
-	BodyW& bw = cx.w->body[ci + 1];
+	BodyW& bw = cx.body[ci + 1];
 	V3 groundUpDir = (numWheelsInContact > 0) ? upwards_dir_from_wheels(cx, ci) : c.worldContactNormal;
 	V3 groundDownDir = -groundUpDir;
 	V3 forwardDir = c.rb.basis.col(0), rightDir = c.rb.basis.col(1);
@@ -582,11 +582,11 @@ RSB_HD void car_update_auto_roll(const Ctx& cx, int ci, int numWheelsInContact) 
 // btVehicleRL::updateSuspension + applyFrictionImpulses (btVehicleRL.cpp:270-303, 383-395)
 RSB_HD void vehicle_second(const Ctx& cx, int ci) {
 	CarS& c = cx.s->cars[ci];
-	const BodyW& bw = cx.w->body[ci + 1];
+	const BodyW& bw = cx.body[ci + 1];
 	const CarCfgD& cfg = cx.p->carCfg[ci];
 	const float dt = cx.p->dt;
 	for (int wi = 0; wi < 4; wi++) {
-		WheelW& w = cx.w->wheels[ci * 4 + wi];
+		WheelW& w = cx.wheels[ci * 4 + wi];
 		if (w.isInContact) {
 			float force = (cfg.suspRest[wi] - w.suspLen) * K::SUSPENSION_STIFFNESS * w.clippedInv;
 			float dampingVelScale = (w.suspRelVel < 0.f) ? K::WHEELS_DAMPING_COMPRESSION : K::WHEELS_DAMPING_RELAXATION;
@@ -598,7 +598,7 @@ RSB_HD void vehicle_second(const Ctx& cx, int ci) {
 		}
 	}
 	for (int wi = 0; wi < 4; wi++) {
-		const WheelW& w = cx.w->wheels[ci * 4 + wi];
+		const WheelW& w = cx.wheels[ci * 4 + wi];
 		if (w.suspForce != 0.f) {
 			V3 contactPointOffset = w.contactPointWS - c.rb.pos;
 			float baseForceScale = (w.suspForce * dt) + c.wExtraPushback[wi];
@@ -608,7 +608,7 @@ RSB_HD void vehicle_second(const Ctx& cx, int ci) {
 	}
 	V3 upDir = c.rb.basis.col(2);
 	for (int wi = 0; wi < 4; wi++) {
-		const WheelW& w = cx.w->wheels[ci * 4 + wi];
+		const WheelW& w = cx.wheels[ci * 4 + wi];
 		if (!is_zero(w.impulse)) {
 			V3 wheelContactOffset = w.contactPointWS - c.rb.pos;
 			float contactUpDot = dot(upDir, wheelContactOffset);
@@ -621,7 +621,7 @@ RSB_HD void vehicle_second(const Ctx& cx, int ci) {
 // Car::_UpdateBoost (Car.cpp:486-533)
 RSB_HD void car_update_boost(const Ctx& cx, int ci) {
 	CarS& c = cx.s->cars[ci];
-	BodyW& bw = cx.w->body[ci + 1];
+	BodyW& bw = cx.body[ci + 1];
 	const MutD& mut = cx.p->mut;
 	const float dt = cx.p->dt;
 	bool hasBoost = c.boost > 0.f;
@@ -661,7 +661,7 @@ RSB_HD void car_pretick_logic(const Ctx& cx, int ci) {
 	bool jumpPressed = c.controls.jump && !c.lastControls.jump;
 	int numWheelsInContact = 0;
 	for (int wi = 0; wi < 4; wi++) {
-		int inContact = cx.w->wheels[ci * 4 + wi].isInContact;
+		int inContact = cx.wheels[ci * 4 + wi].isInContact;
 		c.wheelsWithContact[wi] = (uint8_t)inContact;
 		numWheelsInContact += inContact;
 	}

@@ -89,27 +89,43 @@ RSB_HD bool aabb_overlap(const V3& min1, const V3& max1, const V3& min2, const V
 	return overlap;
 }
 
-// updateSingleAabb for the dynamic bodies + btRSBroadphase::setAabb cell bookkeeping
-RSB_HD void update_aabbs(const Ctx& cx) {
-	const int nb = n_bodies(cx);
+// body b leaves its place in the stamp order and becomes the newest entry
+RSB_HD void dyn_order_move_to_back(ArenaS& S, int nb, int b) {
+	int pos = 0;
+	while (pos < nb && S.dynOrder[pos] != b) pos++;
+	for (int q = pos; q + 1 < nb; q++) S.dynOrder[q] = S.dynOrder[q + 1];
+	S.dynOrder[nb - 1] = (uint8_t)b;
+}
+
+// updateSingleAabb of one dynamic body (current U predicted transform, +-0.02) and the grid cell of its min corner
+RSB_HD void update_aabb(const Ctx& cx, int b) {
 	const V3 ct(kContactBreaking, kContactBreaking, kContactBreaking);
+	BodyW& bw = cx.body[b];
+	const RigidS& rb = rigid_of(cx, b);
+	V3 mn, mx, mn2, mx2;
+	body_shape_aabb(cx, b, rb.basis, rb.pos, mn, mx);
+	mn -= ct; mx += ct;
+	body_shape_aabb(cx, b, bw.interp.basis, bw.interp.origin, mn2, mx2);
+	mn2 -= ct; mx2 += ct;
+	mn = vmin(mn, mn2); mx = vmax(mx, mx2);
+	bw.aabbMin = mn; bw.aabbMax = mx;
+	int i, j, k;
+	bw.newCell = grid_cell_of(*cx.sc, mn, i, j, k);
+	bw.newI = i; bw.newJ = j; bw.newK = k;
+}
+
+// btRSBroadphase::setAabb cell bookkeeping, in body order (a body that changed cell is re-registered last)
+RSB_HD void apply_cell_changes(const Ctx& cx) {
+	const int nb = n_bodies(cx);
 	for (int b = 0; b < nb; b++) {
-		BodyW& bw = cx.w->body[b];
-		const RigidS& rb = rigid_of(cx, b);
-		V3 mn, mx, mn2, mx2;
-		body_shape_aabb(cx, b, rb.basis, rb.pos, mn, mx);
-		mn -= ct; mx += ct;
-		body_shape_aabb(cx, b, bw.interp.basis, bw.interp.origin, mn2, mx2);
-		mn2 -= ct; mx2 += ct;
-		mn = vmin(mn, mn2); mx = vmax(mx, mx2);
-		bool changed = !(mn.x == bw.aabbMin.x && mn.y == bw.aabbMin.y && mn.z == bw.aabbMin.z && mx.x == bw.aabbMax.x && mx.y == bw.aabbMax.y && mx.z == bw.aabbMax.z);
-		bw.aabbMin = mn; bw.aabbMax = mx;
-		(void)changed;
-		int i, j, k;
-		int newIdx = grid_cell_of(*cx.sc, mn, i, j, k);
-		if (newIdx != cx.s->cellIdx[b]) {
-			cx.s->cellIdx[b] = newIdx;
-			if (nb > 1) cx.s->cellStamp[b] = ++cx.s->stampCounter;
+		const BodyW& bw = cx.body[b];
+		if (bw.newCell != cx.s->cellIdx[b]) {
+			cx.s->cellIdx[b] = bw.newCell;
+			cx.s->cellI[b] = (uint8_t)bw.newI; cx.s->cellJ[b] = (uint8_t)bw.newJ; cx.s->cellK[b] = (uint8_t)bw.newK;
+			if (nb > 1) {
+				cx.s->cellStamp[b] = ++cx.s->stampCounter;
+				dyn_order_move_to_back(*cx.s, nb, b);
+			}
 		}
 	}
 }
@@ -123,53 +139,40 @@ RSB_HD void body_filter(const Ctx& cx, int obj, int& group, int& mask) {
 	else { group = FILT_DEFAULT | FILT_DROPSHOT_FLOOR; mask = FILT_ALL; }
 }
 
-RSB_HD void add_pair(const Ctx& cx, int a, int b) {
-	ArenaW& w = *cx.w;
+RSB_HD void add_pair(const Ctx& cx, int a, int b, int entry = 0) {
 	int ga, ma, gb, mb;
 	body_filter(cx, a, ga, ma); body_filter(cx, b, gb, mb);
 	if (!((ga & mb) && (gb & ma))) return;  // needsBroadphaseCollision
-	if (w.nPairs >= MAX_MANIFOLDS) { cx.s->errorFlags |= ERR_MANIFOLD_OVERFLOW; return; }
-	w.pairA[w.nPairs] = a; w.pairB[w.nPairs] = b; w.nPairs++;
+	if (cx.pl->nPairs >= MAX_MANIFOLDS) { set_error(cx, ERR_MANIFOLD_OVERFLOW); return; }
+	cx.pl->a[cx.pl->nPairs] = a; cx.pl->b[cx.pl->nPairs] = b; cx.pl->entry[cx.pl->nPairs] = (uint16_t)entry; cx.pl->nPairs++;
 }
 
 // calculateOverlappingPairs: pair list in creation order; (proxy0, proxy1) sorted by handle id
 // (statics first; ball before cars; lower car index first).
 RSB_HD void compute_pairs(const Ctx& cx) {
-	ArenaW& w = *cx.w;
 	const Scene& sc = *cx.sc;
 	const int nb = n_bodies(cx);
-	w.nPairs = 0;
+	cx.pl->nPairs = 0;
 	for (int b = 0; b < nb; b++) {
-		const BodyW& bw = w.body[b];
+		const BodyW& bw = cx.body[b];
 		int cell = cx.s->cellIdx[b];
 		for (int s = sc.cellStart[cell]; s < sc.cellStart[cell + 1]; s++) {
 			int obj = STATIC_BASE + sc.cellStatics[s];
 			V3 mn, mx; static_proxy_aabb(cx, obj, mn, mx);
-			if (aabb_overlap(bw.aabbMin, bw.aabbMax, mn, mx)) add_pair(cx, obj, b);
+			if (aabb_overlap(bw.aabbMin, bw.aabbMax, mn, mx)) add_pair(cx, obj, b, s);
 		}
 		if (nb > 1) {
-			const int cY = sc.cellsY, cZ = sc.cellsZ;
-			int ci = cell / (cY * cZ), cj = (cell / cZ) % cY, ck = cell % cZ;
-			uint32_t lastStamp = 0; bool first = true;
-			for (int iter = 0; iter < nb; iter++) {
-				int best = -1; uint32_t bestStamp = 0xffffffffu;
-				for (int o = 0; o < nb; o++) {
-					uint32_t st = cx.s->cellStamp[o];
-					if (!first && st <= lastStamp) continue;
-					if (st < bestStamp) { bestStamp = st; best = o; }
-				}
-				if (best < 0) break;
-				first = false; lastStamp = bestStamp;
-				int o = best;
+			// dynamic proxies registered in b's cell, in the cell list's order (ascending stamp)
+			const int ci = cx.s->cellI[b], cj = cx.s->cellJ[b], ck = cx.s->cellK[b];
+			for (int q = 0; q < nb; q++) {
+				const int o = cx.s->dynOrder[q];
 				if (o == b) continue;
-				int idx = cx.s->cellIdx[o];
-				int oi = idx / (cY * cZ), oj = (idx / cZ) % cY, ok = idx % cZ;
-				if (abs(oi - ci) > 1 || abs(oj - cj) > 1 || abs(ok - ck) > 1) continue;
-				const BodyW& ow = w.body[o];
+				if (abs((int)cx.s->cellI[o] - ci) > 1 || abs((int)cx.s->cellJ[o] - cj) > 1 || abs((int)cx.s->cellK[o] - ck) > 1) continue;
+				const BodyW& ow = cx.body[o];
 				if (!aabb_overlap(bw.aabbMin, bw.aabbMax, ow.aabbMin, ow.aabbMax)) continue;
 				int lo = b < o ? b : o, hi = b < o ? o : b;
 				bool exists = false;
-				for (int k = 0; k < w.nPairs; k++) if (w.pairA[k] == lo && w.pairB[k] == hi) { exists = true; break; }
+				for (int k = 0; k < cx.pl->nPairs; k++) if (cx.pl->a[k] == lo && cx.pl->b[k] == hi) { exists = true; break; }
 				if (!exists) add_pair(cx, lo, hi);
 			}
 		}
@@ -189,16 +192,15 @@ RSB_HD float body_angular_motion_disc(const Ctx& cx, int obj) {
 	return radius + len(center);
 }
 
-RSB_HD int new_manifold(const Ctx& cx, int body0, int body1) {
-	ArenaW& w = *cx.w;
-	if (w.nManifolds >= MAX_MANIFOLDS) { cx.s->errorFlags |= ERR_MANIFOLD_OVERFLOW; return -1; }
-	Manifold& m = w.manifolds[w.nManifolds];
-	m.body0 = body0; m.body1 = body1; m.nPts = 0;
-	float t0 = body_angular_motion_disc(cx, body0) * kContactBreaking;
-	float t1 = body_angular_motion_disc(cx, body1) * kContactBreaking;
+// manifold of broadphase pair `slot` (btCollisionDispatcher::getNewManifold, btCollisionDispatcher.cpp:70-104)
+RSB_HD int new_manifold(const Ctx& cx, int slot, int body0, int body1) {
+	Manifold& m = cx.mf[slot];
+	m.body0 = body0; m.body1 = body1; m.nPts = 0; m.pts = cx.w->points + slot * 4;
+	float t0 = (body0 >= STATIC_BASE ? kLargeFloat : cx.p->motionDisc[body0]) * kContactBreaking;
+	float t1 = (body1 >= STATIC_BASE ? kLargeFloat : cx.p->motionDisc[body1]) * kContactBreaking;
 	m.breakingThresh = t0 < t1 ? t0 : t1;
 	m.processingThresh = kLargeFloat;
-	return w.nManifolds++;
+	return slot;
 }
 
 RSB_HD Xform obj_xform(const Ctx& cx, int obj) {
@@ -384,8 +386,7 @@ RSB_HD void on_car_car_collision(const Ctx& cx, int c1, int c2, ContactPt& cp) {
 // are "A"/"B"; (normalOnB, pointOnB, depth) as reported by the detector.  triMesh/triIndex
 // identify the triangle when B is an arena mesh (else triMesh < 0).
 RSB_HD void add_contact_point(const Ctx& cx, int mi, const V3& normalOnB, const V3& pointInWorld, float depth, int triMesh, int triIndex) {
-	ArenaW& w = *cx.w;
-	Manifold& m = w.manifolds[mi];
+	Manifold& m = cx.mf[mi];
 	if (depth > m.breakingThresh) return;
 	ContactPt pt;
 	V3 pointA = pointInWorld + normalOnB * depth;
@@ -400,10 +401,10 @@ RSB_HD void add_contact_point(const Ctx& cx, int mi, const V3& normalOnB, const 
 	// combined friction / restitution (btManifoldResult.cpp:56-77)
 	{
 		bool s0 = m.body0 >= STATIC_BASE, s1 = m.body1 >= STATIC_BASE;
-		float fa = s0 ? K::ARENA_COLLISION_BASE_FRICTION : w.body[m.body0].friction;
-		float fb = s1 ? K::ARENA_COLLISION_BASE_FRICTION : w.body[m.body1].friction;
-		float ra = s0 ? K::ARENA_COLLISION_BASE_RESTITUTION : w.body[m.body0].restitution;
-		float rb = s1 ? K::ARENA_COLLISION_BASE_RESTITUTION : w.body[m.body1].restitution;
+		float fa = s0 ? K::ARENA_COLLISION_BASE_FRICTION : cx.body[m.body0].friction;
+		float fb = s1 ? K::ARENA_COLLISION_BASE_FRICTION : cx.body[m.body1].friction;
+		float ra = s0 ? K::ARENA_COLLISION_BASE_RESTITUTION : cx.body[m.body0].restitution;
+		float rb = s1 ? K::ARENA_COLLISION_BASE_RESTITUTION : cx.body[m.body1].restitution;
 		if (s0 || s1) { pt.friction = (fa < fb) ? fa : fb; pt.restitution = (ra > rb) ? ra : rb; }
 		else { pt.friction = fa * fb; pt.restitution = ra * rb; }
 	}
@@ -416,7 +417,7 @@ RSB_HD void add_contact_point(const Ctx& cx, int mi, const V3& normalOnB, const 
 
 	// ---- Arena::_BulletContactAddedCallback ----
 	const bool d0 = m.body0 < STATIC_BASE, d1 = m.body1 < STATIC_BASE;
-	if ((d0 && w.body[m.body0].noResponse) || (d1 && w.body[m.body1].noResponse)) return;
+	if ((d0 && cx.body[m.body0].noResponse) || (d1 && cx.body[m.body1].noResponse)) return;
 	// manifold orders used here: (car, ball) (carHi, carLo) (car, world) (ball, world)
 	if (d0 && m.body0 > 0) {
 		int car = m.body0 - 1;
@@ -442,7 +443,7 @@ RSB_HD void add_contact_point(const Ctx& cx, int mi, const V3& normalOnB, const 
 
 // btPersistentManifold::refreshContactPoints (btPersistentManifold.cpp:263-329)
 RSB_HD void refresh_contact_points(const Ctx& cx, int mi) {
-	Manifold& m = cx.w->manifolds[mi];
+	Manifold& m = cx.mf[mi];
 	Xform tA = obj_xform(cx, m.body0), tB = obj_xform(cx, m.body1);
 	for (int i = m.nPts - 1; i >= 0; i--) {
 		ContactPt& p = m.pts[i];
@@ -550,9 +551,9 @@ RSB_HD bool triangle_vs_aabb(const V3 t[3], const V3& mn, const V3& mx) {  // Te
 // btConvexConcaveCollisionAlgorithm::processCollision + btConvexTriangleCallback::processTriangle
 // (btConvexConcaveCollisionAlgorithm.cpp:71-250) over the BVH's AABB query
 // (btQuantizedBvh.cpp:655-729: subtree headers in order, stackless walk inside each).
-RSB_HD void convex_vs_mesh(const Ctx& cx, int mi, int body, const Convex& shape, const Xform& xf, int meshIdx) {
+RSB_HD void convex_vs_mesh(const Ctx& cx, int mi, int body, const Convex& shape, const Xform& xf, int meshIdx, int entry) {
 	const MeshD& mesh = cx.sc->meshes[meshIdx];
-	Manifold& mf = cx.w->manifolds[mi];
+	Manifold& mf = cx.mf[mi];
 	// convex AABB in triangle space (mesh at origin, identity): shape->getAabb(convexInTriangleSpace)
 	V3 amin, amax;
 	if (shape.kind == SH_SPHERE) { float mg = shape.margin + 0.08f; V3 e(mg, mg, mg); amin = xf.origin - e; amax = xf.origin + e; }
@@ -562,8 +563,10 @@ RSB_HD void convex_vs_mesh(const Ctx& cx, int mi, int body, const Convex& shape,
 	uint16_t qmin[3], qmax[3];
 	bvh_quantize_clamped(mesh, amin, 0, qmin);
 	bvh_quantize_clamped(mesh, amax, 1, qmax);
-	for (int h = 0; h < mesh.nHdrs; h++) {
-		const SubtreeHdr hd = mesh.hdrs[h];
+	// only the headers that can overlap a query from this broadphase cell (same order as the full header loop)
+	const int hEnd = cx.sc->cellHdrStart[entry + 1];
+	for (int hi = cx.sc->cellHdrStart[entry]; hi < hEnd; hi++) {
+		const SubtreeHdr hd = mesh.hdrs[cx.sc->cellHdrs[hi]];
 		if (!quant_overlap(qmin, qmax, hd.qmin, hd.qmax)) continue;
 		int cur = hd.root;
 		const int end = hd.root + hd.size;
@@ -617,7 +620,7 @@ RSB_HD void convex_vs_mesh(const Ctx& cx, int mi, int body, const Convex& shape,
 
 // btConvexPlaneCollisionAlgorithm::processCollision (btConvexPlaneCollisionAlgorithm.cpp:92-161)
 RSB_HD void convex_vs_plane(const Ctx& cx, int mi, const Convex& shape, const Xform& xf, const PlaneD& pl) {
-	Manifold& mf = cx.w->manifolds[mi];
+	Manifold& mf = cx.mf[mi];
 	const V3 planeNormal = pl.n;
 	M3 planeInConvexBasis = transpose(xf.basis) * m3identity();
 	V3 convexInPlaneOrigin = (m3identity() * xf.origin) + (m3identity() * (-pl.pos));
@@ -649,47 +652,66 @@ RSB_HD void convex_world_aabb(const Ctx& cx, const Convex& s, const Xform& t, V3
 	else transform_aabb_mm(cx.p->puckLocalAabbMin, cx.p->puckLocalAabbMax, s.margin, t.basis, t.origin, mn, mx);
 }
 
-// performDiscreteCollisionDetection for one arena
-RSB_HD void collide_world(const Ctx& cx) {
-	ArenaW& w = *cx.w;
+// performDiscreteCollisionDetection, split so that the per-body work runs on one thread per body:
+//   collide_pairs         (arena)  cell bookkeeping + broadphase pair list; manifold slot k <-> pair k
+//   collide_static_pairs  (body b) narrowphase + contact hooks of b's pairs with static objects
+//   collide_dynamic_pairs (arena)  ball-car and car-car pairs, in pair order (their hooks touch two bodies)
+// Manifold order (= solver row order) is the pair order whatever the execution order.
+RSB_HD void collide_pairs(const Ctx& cx) {
+	apply_cell_changes(cx);
+	compute_pairs(cx);
+	cx.pl->nManifolds = cx.pl->nPairs;
+	for (int k = 0; k < cx.pl->nPairs; k++) { cx.mf[k].body0 = -1; cx.mf[k].nPts = 0; }
+}
+
+RSB_HD bool pair_needs_collision(const Ctx& cx, int a, int b) {
+	// btCollisionDispatcher::needsCollision: skip when both are inactive (statics are inactive)
+	bool actA = a >= STATIC_BASE ? false : body_active(cx.body[a]);
+	bool actB = body_active(cx.body[b]);
+	return actA || actB;
+}
+
+RSB_HD void collide_static_pairs(const Ctx& cx, int b) {
 	const BatchParams& P = *cx.p;
 	const Scene& sc = *cx.sc;
-	w.nManifolds = 0;
-	update_aabbs(cx);
-	compute_pairs(cx);
-	for (int k = 0; k < w.nPairs; k++) {
-		const int a = w.pairA[k], b = w.pairB[k];
-		const bool sa = a >= STATIC_BASE;
-		// btCollisionDispatcher::needsCollision: skip when both are inactive (statics are inactive)
-		bool actA = sa ? false : body_active(w.body[a]);
-		bool actB = body_active(w.body[b]);
-		if (!actA && !actB) continue;
-		if (sa) {
-			const int sk = a - STATIC_BASE;
-			const bool isMesh = sk < sc.nMeshes;
-			const RigidS& rb = rigid_of(cx, b);
-			if (b == 0) {
-				Convex shape = ball_convex(P);
-				Xform xf; xf.basis = rb.basis; xf.origin = rb.pos;
-				int mi = new_manifold(cx, 0, a);
-				if (mi < 0) continue;
-				if (isMesh) convex_vs_mesh(cx, mi, 0, shape, xf, sk);
-				else convex_vs_plane(cx, mi, shape, xf, sc.planes[sk - sc.nMeshes]);
-			} else {
-				const CarCfgD& cfg = P.carCfg[b - 1];
-				Convex shape = car_box(cfg);
-				Xform xf = car_child_xform(rb, cfg);
-				// btCompoundLeafCallback::ProcessChildShape: child AABB vs the other shape's AABB
-				V3 cmn, cmx, omn, omx;
-				convex_world_aabb(cx, shape, xf, cmn, cmx);
-				static_aabb(cx, a, omn, omx);
-				if (!aabb_overlap(cmn, cmx, omn, omx)) continue;
-				int mi = new_manifold(cx, b, a);
-				if (mi < 0) continue;
-				if (isMesh) convex_vs_mesh(cx, mi, b, shape, xf, sk);
-				else convex_vs_plane(cx, mi, shape, xf, sc.planes[sk - sc.nMeshes]);
-			}
-		} else if (a == 0) {
+	const int nPairs = cx.pl->nPairs;
+	for (int k = 0; k < nPairs; k++) {
+		if (cx.pl->b[k] != b) continue;
+		const int a = cx.pl->a[k];
+		if (a < STATIC_BASE) continue;
+		if (!pair_needs_collision(cx, a, b)) continue;
+		const int sk = a - STATIC_BASE;
+		const bool isMesh = sk < sc.nMeshes;
+		const RigidS& rb = rigid_of(cx, b);
+		if (b == 0) {
+			Convex shape = ball_convex(P);
+			Xform xf; xf.basis = rb.basis; xf.origin = rb.pos;
+			int mi = new_manifold(cx, k, 0, a);
+			if (isMesh) convex_vs_mesh(cx, mi, 0, shape, xf, sk, cx.pl->entry[k]);
+			else convex_vs_plane(cx, mi, shape, xf, sc.planes[sk - sc.nMeshes]);
+		} else {
+			const CarCfgD& cfg = P.carCfg[b - 1];
+			Convex shape = car_box(cfg);
+			Xform xf = car_child_xform(rb, cfg);
+			// btCompoundLeafCallback::ProcessChildShape: child AABB vs the other shape's AABB
+			V3 cmn, cmx, omn, omx;
+			convex_world_aabb(cx, shape, xf, cmn, cmx);
+			static_aabb(cx, a, omn, omx);
+			if (!aabb_overlap(cmn, cmx, omn, omx)) continue;
+			int mi = new_manifold(cx, k, b, a);
+			if (isMesh) convex_vs_mesh(cx, mi, b, shape, xf, sk, cx.pl->entry[k]);
+			else convex_vs_plane(cx, mi, shape, xf, sc.planes[sk - sc.nMeshes]);
+		}
+	}
+}
+
+RSB_HD void collide_dynamic_pairs(const Ctx& cx) {
+	const BatchParams& P = *cx.p;
+	for (int k = 0; k < cx.pl->nPairs; k++) {
+		const int a = cx.pl->a[k], b = cx.pl->b[k];
+		if (a >= STATIC_BASE) continue;
+		if (!pair_needs_collision(cx, a, b)) continue;
+		if (a == 0) {
 			// (ball, car): swapped compound -> convex-convex(box of the car, ball shape); manifold (car, ball)
 			const CarCfgD& cfg = P.carCfg[b - 1];
 			const RigidS& rc = rigid_of(cx, b);
@@ -700,8 +722,7 @@ RSB_HD void collide_world(const Ctx& cx) {
 			convex_world_aabb(cx, box, xfc, cmn, cmx);
 			convex_world_aabb(cx, ball, xfb, omn, omx);
 			if (!aabb_overlap(cmn, cmx, omn, omx)) continue;
-			int mi = new_manifold(cx, b, 0);
-			if (mi < 0) continue;
+			int mi = new_manifold(cx, k, b, 0);
 			convex_convex(cx, mi, box, xfc, ball, xfb, -1, -1);
 			refresh_contact_points(cx, mi);
 		} else {
@@ -716,8 +737,7 @@ RSB_HD void collide_world(const Ctx& cx) {
 			if (!aabb_overlap(amn, amx, cmn, cmx)) continue;
 			convex_world_aabb(cx, boxB, xfB, bmn, bmx);   // child of B vs box A
 			if (!aabb_overlap(bmn, bmx, amn, amx)) continue;
-			int mi = new_manifold(cx, b, a);
-			if (mi < 0) continue;
+			int mi = new_manifold(cx, k, b, a);
 			box_box(cx, mi, boxB, xfB, boxA, xfA);
 			refresh_contact_points(cx, mi);
 		}

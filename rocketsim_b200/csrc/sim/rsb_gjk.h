@@ -44,7 +44,7 @@ RSB_HD_NOINLINE bool epa_penetration(const Ctx& cx, const Convex& A, const Xform
 
 // GJK closest points + addContactPoint.  A/B with world transforms; triMesh/triIndex forwarded.
 RSB_HD_NOINLINE void convex_convex(const Ctx& cx, int mi, const Convex& A, const Xform& xfA, const Convex& B, const Xform& xfB, int triMesh, int triIndex) {
-	const float breaking = cx.w->manifolds[mi].breakingThresh;
+	const float breaking = cx.mf[mi].breakingThresh;
 	float maxDist2 = A.margin + B.margin + breaking;
 	maxDist2 *= maxDist2;
 

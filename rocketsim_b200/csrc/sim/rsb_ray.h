@@ -107,8 +107,10 @@ RSB_HD bool ray_aabb2(const V3& rayFrom, const V3& invDir, const unsigned sign[3
 	return (tmin < lambda_max) && (tmax > lambda_min);
 }
 
-// walkStacklessQuantizedTreeAgainstRay over the whole node array + triangle tests
-RSB_HD bool ray_mesh(const MeshD& m, const V3& from, const V3& to, float& hitFraction, V3& outNormal) {
+// walkStacklessQuantizedTreeAgainstRay + triangle tests.  The reference walks the whole node array from node 0; a
+// subtree is only entered through ancestors whose boxes contain it, so walking just the candidate subtrees of the
+// ray-origin cell (Scene::cellHdrsRay, ascending root = the same leaf order) visits the same leaves.
+RSB_HD bool ray_mesh(const Scene& sc, const MeshD& m, int entry, const V3& from, const V3& to, float& hitFraction, V3& outNormal) {
 	V3 rayDirection = safe_normalized(to - from);
 	float lambda_max = dot(rayDirection, to - from);
 	V3 inv(rayDirection.x == 0.f ? kLargeFloat : 1.f / rayDirection.x,
@@ -120,8 +122,12 @@ RSB_HD bool ray_mesh(const MeshD& m, const V3& from, const V3& to, float& hitFra
 	bvh_quantize_clamped(m, rayAabbMin, 0, qmin);
 	bvh_quantize_clamped(m, rayAabbMax, 1, qmax);
 	bool any = false;
-	int cur = 0;
-	const int end = m.nNodes;
+	const int hEnd = sc.cellHdrStart[entry + 1];
+	for (int hi = sc.cellHdrStart[entry]; hi < hEnd; hi++) {
+	const SubtreeHdr hd = m.hdrs[sc.cellHdrsRay[hi]];
+	if (!quant_overlap(qmin, qmax, hd.qmin, hd.qmax)) continue;
+	int cur = hd.root;
+	const int end = hd.root + hd.size;
 	while (cur < end) {
 		const BvhNode nd = m.nodes[cur];
 		bool rayBoxOverlap = false;
@@ -140,6 +146,7 @@ RSB_HD bool ray_mesh(const MeshD& m, const V3& from, const V3& to, float& hitFra
 		}
 		if (rayBoxOverlap || isLeaf) cur++;
 		else cur += -nd.idx;
+	}
 	}
 	return any;
 }
@@ -237,7 +244,7 @@ RSB_HD bool cast_vehicle_ray(const Ctx& cx, int self, const V3& from, const V3& 
 			if (k < sc.nMeshes) {
 				const MeshD& m = sc.meshes[k];
 				if (!((m.group & FILT_ALL) != 0 && (rayGroup & m.mask))) continue;
-				if (ray_mesh(m, from, to, closest, normal)) obj = STATIC_BASE + k;
+				if (ray_mesh(sc, m, s, from, to, closest, normal)) obj = STATIC_BASE + k;
 			} else {
 				if (ray_plane(sc.planes[k - sc.nMeshes], from, to, closest, normal)) obj = STATIC_BASE + k;
 			}
@@ -246,25 +253,25 @@ RSB_HD bool cast_vehicle_ray(const Ctx& cx, int self, const V3& from, const V3& 
 	// dynamic proxies registered in the ray-origin cell, in cell-list order (= ascending stamp)
 	{
 		const int nb = n_bodies(cx);
-		const int cY = sc.cellsY, cZ = sc.cellsZ;
-		uint32_t lastStamp = 0; bool first = true;
-		for (int iter = 0; iter < nb; iter++) {
-			int best = -1; uint32_t bestStamp = 0xffffffffu;
-			for (int b = 0; b < nb; b++) {
-				uint32_t st = cx.s->cellStamp[b];
-				if (!first && st <= lastStamp) continue;
-				if (st < bestStamp) { bestStamp = st; best = b; }
-			}
-			if (best < 0) break;
-			first = false; lastStamp = bestStamp;
-			int b = best;
+		for (int q = 0; q < nb; q++) {
+			const int b = cx.s->dynOrder[q];
 			if (b == self) continue;
 			if (closest == 0.f) break;
-			int idx = cx.s->cellIdx[b];
-			int bi = idx / (cY * cZ), bj = (idx / cZ) % cY, bk = idx % cZ;
-			if (abs(bi - ci) > 1 || abs(bj - cj) > 1 || abs(bk - ck) > 1) continue;
+			if (abs((int)cx.s->cellI[b] - ci) > 1 || abs((int)cx.s->cellJ[b] - cj) > 1 || abs((int)cx.s->cellK[b] - ck) > 1) continue;
 			const RigidS& rb = rigid_of(cx, b);
 			Xform xf; Convex shp;
+			{
+				// conservative cull (ours, not in the reference): the cast can only hit when the segment passes within the
+				// body's bounding sphere; 0.25 bt of slack covers the cast's own 1e-2 termination tolerance many times over
+				const float R = P.boundRadius[b] + 0.25f;
+				const V3 centre = (b == 0) ? rb.pos : (rb.basis * P.carCfg[b - 1].hitboxOffset + rb.pos);
+				const V3 d = to - from, m = centre - from;
+				const float dd = dot(d, d);
+				float t = dd > 0.f ? dot(m, d) / dd : 0.f;
+				t = t < 0.f ? 0.f : (t > 1.f ? 1.f : t);
+				const V3 c = m - d * t;
+				if (dot(c, c) > R * R) continue;
+			}
 			if (b == 0) {
 				xf.basis = rb.basis; xf.origin = rb.pos;
 				shp = ball_convex(P);
@@ -278,7 +285,7 @@ RSB_HD bool cast_vehicle_ray(const Ctx& cx, int self, const V3& from, const V3& 
 		}
 	}
 	if (obj == OBJ_NONE) return false;
-	if (obj < STATIC_BASE && cx.w->body[obj].noResponse) return false;
+	if (obj < STATIC_BASE && cx.body[obj].noResponse) return false;
 	out.obj = obj;
 	out.fraction = closest;
 	out.point = lerp(from, to, closest);

@@ -54,56 +54,56 @@ RSB_HD void quicksort_keys(int* key, int* val, int lo, int hi) {
 // calculateSimulationIslands + buildIslands: island tags, wake-ups, and the manifold order
 // handed to the solver.  Returns the number of manifolds to solve (order in w.manifoldOrder).
 RSB_HD int build_islands(const Ctx& cx) {
-	ArenaW& w = *cx.w;
 	const int nb = n_bodies(cx);
 	UF uf;
 	for (int b = 0; b < nb; b++) { uf.id[b] = b; uf.sz[b] = 1; }
 	// findUnions over ALL broadphase pairs whose bodies both merge islands
-	for (int k = 0; k < w.nPairs; k++) {
-		int a = w.pairA[k], b = w.pairB[k];
+	for (int k = 0; k < cx.pl->nPairs; k++) {
+		int a = cx.pl->a[k], b = cx.pl->b[k];
 		if (a >= STATIC_BASE || b >= STATIC_BASE) continue;
-		if (w.body[a].noResponse || w.body[b].noResponse) continue;
+		if (cx.body[a].noResponse || cx.body[b].noResponse) continue;
 		uf_unite(uf, a, b);
 	}
-	for (int b = 0; b < nb; b++) w.body[b].islandTag = uf_find(uf, b);
+	for (int b = 0; b < nb; b++) cx.body[b].islandTag = uf_find(uf, b);
 	// per island: all sleeping? else wake sleepers (ISLAND_SLEEPING -> WANTS_DEACTIVATION)
 	for (int root = 0; root < nb; root++) {
 		bool any = false, allSleeping = true;
-		for (int b = 0; b < nb; b++) if (w.body[b].islandTag == root) {
+		for (int b = 0; b < nb; b++) if (cx.body[b].islandTag == root) {
 			any = true;
-			if (w.body[b].activation == ACT_ACTIVE || w.body[b].activation == ACT_DISABLE_DEACT) { allSleeping = false; break; }
+			if (cx.body[b].activation == ACT_ACTIVE || cx.body[b].activation == ACT_DISABLE_DEACT) { allSleeping = false; break; }
 		}
 		if (!any) continue;
-		for (int b = 0; b < nb; b++) if (w.body[b].islandTag == root) {
-			if (allSleeping) { if (w.body[b].activation != ACT_DISABLE_DEACT && w.body[b].activation != ACT_DISABLE_SIM) w.body[b].activation = ACT_SLEEPING; }
-			else if (w.body[b].activation == ACT_SLEEPING) w.body[b].activation = ACT_WANTS_DEACT;
+		for (int b = 0; b < nb; b++) if (cx.body[b].islandTag == root) {
+			if (allSleeping) { if (cx.body[b].activation != ACT_DISABLE_DEACT && cx.body[b].activation != ACT_DISABLE_SIM) cx.body[b].activation = ACT_SLEEPING; }
+			else if (cx.body[b].activation == ACT_SLEEPING) cx.body[b].activation = ACT_WANTS_DEACT;
 		}
 	}
 	// m_islandmanifold: manifolds with an awake body and needsResponse, then quickSort by island id
-	int keys[MAX_MANIFOLDS];
+	int keys[MAX_MANIFOLDS], order[MAX_MANIFOLDS];
 	int n = 0;
-	for (int m = 0; m < w.nManifolds; m++) {
-		const Manifold& mf = w.manifolds[m];
+	for (int m = 0; m < cx.pl->nManifolds; m++) {
+		const Manifold& mf = cx.mf[m];
+		if (mf.body0 < 0) continue;  // pair without a manifold
 		bool s0 = mf.body0 >= STATIC_BASE, s1 = mf.body1 >= STATIC_BASE;
-		bool awake0 = !s0 && w.body[mf.body0].activation != ACT_SLEEPING;
-		bool awake1 = !s1 && w.body[mf.body1].activation != ACT_SLEEPING;
+		bool awake0 = !s0 && cx.body[mf.body0].activation != ACT_SLEEPING;
+		bool awake1 = !s1 && cx.body[mf.body1].activation != ACT_SLEEPING;
 		if (!(awake0 || awake1)) continue;
-		bool resp = (s0 || !w.body[mf.body0].noResponse) && (s1 || !w.body[mf.body1].noResponse) && (!s0 || !s1);
+		bool resp = (s0 || !cx.body[mf.body0].noResponse) && (s1 || !cx.body[mf.body1].noResponse) && (!s0 || !s1);
 		if (!resp) continue;
-		int tag0 = s0 ? -1 : w.body[mf.body0].islandTag;
-		int tag1 = s1 ? -1 : w.body[mf.body1].islandTag;
+		int tag0 = s0 ? -1 : cx.body[mf.body0].islandTag;
+		int tag1 = s1 ? -1 : cx.body[mf.body1].islandTag;
 		keys[n] = tag0 >= 0 ? tag0 : tag1;
-		w.manifoldOrder[n] = m;
+		order[n] = m;
 		n++;
 	}
-	if (n > 1) quicksort_keys(keys, w.manifoldOrder, 0, n - 1);
+	if (n > 1) quicksort_keys(keys, order, 0, n - 1);
 	// drop manifolds whose island is asleep (processIslands only calls the solver for awake islands)
 	int outN = 0;
 	for (int k = 0; k < n; k++) {
 		int root = keys[k];
 		bool awake = false;
-		for (int b = 0; b < nb; b++) if (w.body[b].islandTag == root && body_active(w.body[b])) { awake = true; break; }
-		if (awake) w.manifoldOrder[outN++] = w.manifoldOrder[k];
+		for (int b = 0; b < nb; b++) if (cx.body[b].islandTag == root && body_active(cx.body[b])) { awake = true; break; }
+		if (awake) cx.pl->manifoldOrder[outN++] = (uint8_t)order[k];
 	}
 	return outN;
 }
@@ -123,9 +123,9 @@ RSB_HD float simd_dot3(const V3& a, const V3& b) { return a.x * b.x + (a.y * b.y
 // setupContactConstraint (btSequentialImpulseConstraintSolver.cpp:795-983)
 RSB_HD void setup_contact_row(const Ctx& cx, SolverRow& r, int ia, int ib, const V3& normalB, float distance, float restitutionCoef,
                               float frictionCoef, int isSpecial, const V3& rel1, const V3& rel2) {
-	ArenaW& w = *cx.w;
-	SolverBody& A = w.sbody[ia];
-	SolverBody& B = w.sbody[ib];
+	const SolverView sv = solver_view(cx);
+	SolverBody& A = sv.sbody[ia];
+	SolverBody& B = sv.sbody[ib];
 	const bool hasA = A.orig >= 0, hasB = B.orig >= 0;
 	const float dt = cx.p->dt;
 	const float invTimeStep = 1.f / dt;
@@ -133,12 +133,12 @@ RSB_HD void setup_contact_row(const Ctx& cx, SolverRow& r, int ia, int ib, const
 	float cfm = 0.f; cfm *= invTimeStep;
 	r.bodyA = ia; r.bodyB = ib;
 	V3 torqueAxis0 = cross(rel1, normalB);
-	r.angA = hasA ? (w.body[A.orig].invInertiaW * torqueAxis0) : v3zero();
+	r.angA = hasA ? (cx.body[A.orig].invInertiaW * torqueAxis0) : v3zero();
 	V3 torqueAxis1 = cross(rel2, normalB);
-	r.angB = hasB ? (w.body[B.orig].invInertiaW * (-torqueAxis1)) : v3zero();
+	r.angB = hasB ? (cx.body[B.orig].invInertiaW * (-torqueAxis1)) : v3zero();
 	float denom0 = 0.f, denom1 = 0.f;
-	if (hasA) { V3 vec = cross(r.angA, rel1); denom0 = w.body[A.orig].invMass + dot(normalB, vec); }
-	if (hasB) { V3 vec = cross(-r.angB, rel2); denom1 = w.body[B.orig].invMass + dot(normalB, vec); }
+	if (hasA) { V3 vec = cross(r.angA, rel1); denom0 = cx.body[A.orig].invMass + dot(normalB, vec); }
+	if (hasB) { V3 vec = cross(-r.angB, rel2); denom1 = cx.body[B.orig].invMass + dot(normalB, vec); }
 	r.jacDiagInv = 1.f / (denom0 + denom1 + cfm);
 	if (hasA) { r.n1 = normalB; r.rp1xn = torqueAxis0; } else { r.n1 = v3zero(); r.rp1xn = v3zero(); }
 	if (hasB) { r.n2 = -normalB; r.rp2xn = -torqueAxis1; } else { r.n2 = v3zero(); r.rp2xn = v3zero(); }
@@ -179,22 +179,22 @@ RSB_HD void setup_contact_row(const Ctx& cx, SolverRow& r, int ia, int ib, const
 
 // setupFrictionConstraint (btSequentialImpulseConstraintSolver.cpp:517-607)
 RSB_HD void setup_friction_row(const Ctx& cx, SolverRow& r, const V3& axis, int ia, int ib, float frictionCoef, const V3& rel1, const V3& rel2, int frictionIndex) {
-	ArenaW& w = *cx.w;
-	SolverBody& A = w.sbody[ia];
-	SolverBody& B = w.sbody[ib];
+	const SolverView sv = solver_view(cx);
+	SolverBody& A = sv.sbody[ia];
+	SolverBody& B = sv.sbody[ib];
 	const bool hasA = A.orig >= 0, hasB = B.orig >= 0;
 	r.bodyA = ia; r.bodyB = ib; r.frictionIndex = frictionIndex;
 	r.friction = frictionCoef;
 	r.applied = 0.f; r.appliedPush = 0.f;
 	if (hasA) {
-		r.n1 = axis; V3 ft = cross(rel1, r.n1); r.rp1xn = ft; r.angA = w.body[A.orig].invInertiaW * ft;
+		r.n1 = axis; V3 ft = cross(rel1, r.n1); r.rp1xn = ft; r.angA = cx.body[A.orig].invInertiaW * ft;
 	} else { r.n1 = v3zero(); r.rp1xn = v3zero(); r.angA = v3zero(); }
 	if (hasB) {
-		r.n2 = -axis; V3 ft = cross(rel2, r.n2); r.rp2xn = ft; r.angB = w.body[B.orig].invInertiaW * ft;
+		r.n2 = -axis; V3 ft = cross(rel2, r.n2); r.rp2xn = ft; r.angB = cx.body[B.orig].invInertiaW * ft;
 	} else { r.n2 = v3zero(); r.rp2xn = v3zero(); r.angB = v3zero(); }
 	float denom0 = 0.f, denom1 = 0.f;
-	if (hasA) { V3 vec = cross(r.angA, rel1); denom0 = w.body[A.orig].invMass + dot(axis, vec); }
-	if (hasB) { V3 vec = cross(-r.angB, rel2); denom1 = w.body[B.orig].invMass + dot(axis, vec); }
+	if (hasA) { V3 vec = cross(r.angA, rel1); denom0 = cx.body[A.orig].invMass + dot(axis, vec); }
+	if (hasB) { V3 vec = cross(-r.angB, rel2); denom1 = cx.body[B.orig].invMass + dot(axis, vec); }
 	r.jacDiagInv = 1.f / (denom0 + denom1);
 	float vel1Dotn = dot(r.n1, hasA ? A.lin + A.extF : v3zero()) + dot(r.rp1xn, hasA ? A.ang : v3zero());
 	float vel2Dotn = dot(r.n2, hasB ? B.lin + B.extF : v3zero()) + dot(r.rp2xn, hasB ? B.ang : v3zero());
@@ -210,9 +210,9 @@ RSB_HD void setup_friction_row(const Ctx& cx, SolverRow& r, const V3& axis, int 
 
 // convertContactInner: friction direction + friction row (btSequentialImpulseConstraintSolver.cpp:1069-1162)
 RSB_HD void add_friction_for(const Ctx& cx, int ia, int ib, const V3& normalB, float frictionCoef, const V3& rel1, const V3& rel2, int frictionIndex) {
-	ArenaW& w = *cx.w;
-	V3 vel1 = sb_vel_no_delta(w.sbody[ia], rel1);
-	V3 vel2 = sb_vel_no_delta(w.sbody[ib], rel2);
+	const SolverView sv = solver_view(cx);
+	V3 vel1 = sb_vel_no_delta(sv.sbody[ia], rel1);
+	V3 vel2 = sb_vel_no_delta(sv.sbody[ib], rel2);
 	V3 vel = vel1 - vel2;
 	float rel_vel = dot(normalB, vel);
 	V3 dir1 = vel - normalB * rel_vel;
@@ -223,18 +223,18 @@ RSB_HD void add_friction_for(const Ctx& cx, int ia, int ib, const V3& normalB, f
 		V3 dir2;
 		plane_space1(normalB, dir1, dir2);
 	}
-	setup_friction_row(cx, w.frows[w.nFrictionRows], dir1, ia, ib, frictionCoef, rel1, rel2, frictionIndex);
-	w.nFrictionRows++;
+	setup_friction_row(cx, sv.frow(sv.cnt[2]), dir1, ia, ib, frictionCoef, rel1, rel2, frictionIndex);
+	sv.cnt[2]++;
 }
 
 RSB_HD int get_or_init_solver_body(const Ctx& cx, int obj, int* companion, int& fixedId) {
-	ArenaW& w = *cx.w;
+	const SolverView sv = solver_view(cx);
 	if (obj < STATIC_BASE) {
 		if (companion[obj] >= 0) return companion[obj];
-		int id = w.nSolverBodies++;
-		SolverBody& sb = w.sbody[id];
+		int id = sv.cnt[0]++;
+		SolverBody& sb = sv.sbody[id];
 		const RigidS& rb = rigid_of(cx, obj);
-		const BodyW& bw = w.body[obj];
+		const BodyW& bw = cx.body[obj];
 		sb.dLin = sb.dAng = sb.push = sb.turn = v3zero();
 		sb.xf.basis = rb.basis; sb.xf.origin = rb.pos;
 		sb.invMassV = V3(bw.invMass, bw.invMass, bw.invMass);
@@ -246,8 +246,8 @@ RSB_HD int get_or_init_solver_body(const Ctx& cx, int obj, int* companion, int& 
 		return id;
 	}
 	if (fixedId < 0) {
-		fixedId = w.nSolverBodies++;
-		SolverBody& sb = w.sbody[fixedId];
+		fixedId = sv.cnt[0]++;
+		SolverBody& sb = sv.sbody[fixedId];
 		sb.dLin = sb.dAng = sb.push = sb.turn = v3zero();
 		sb.xf.basis = m3identity(); sb.xf.origin = v3zero();
 		sb.invMassV = v3zero(); sb.orig = -1;
@@ -290,48 +290,50 @@ RSB_HD float resolve_split(SolverBody& A, SolverBody& B, SolverRow& c) {
 // without contacts still receive their external force impulse), contacts -> rows, special
 // contacts, iterations, writeback.
 RSB_HD void solve_arena(const Ctx& cx, int nSolveManifolds) {
-	ArenaW& w = *cx.w;
+	const SolverView sv = solver_view(cx);
 	const int nb = n_bodies(cx);
 	const float dt = cx.p->dt;
 	int companion[MAX_BODIES];
-	for (int b = 0; b < nb; b++) { companion[b] = -1; w.spNum[b] = 0; w.spTotalDist[b] = 0.f; w.spTotalNormal[b] = v3zero(); w.spFriction[b] = 0.f; w.spRestitution[b] = 0.f; }
+	// special (ball-world) contact accumulation per body (btCollisionObject::m_specialResolveInfo)
+	int spNum[MAX_BODIES]; float spFriction[MAX_BODIES], spRestitution[MAX_BODIES], spTotalDist[MAX_BODIES]; V3 spTotalNormal[MAX_BODIES];
+	for (int b = 0; b < nb; b++) { companion[b] = -1; spNum[b] = 0; spTotalDist[b] = 0.f; spTotalNormal[b] = v3zero(); spFriction[b] = 0.f; spRestitution[b] = 0.f; }
 	int fixedId = -1;
-	w.nSolverBodies = 0; w.nRows = 0; w.nFrictionRows = 0;
+	sv.cnt[0] = 0; sv.cnt[1] = 0; sv.cnt[2] = 0;
 
 	// convertBodies: bodies of awake islands, in island order (sorted by island id), then body order
 	for (int root = 0; root < nb; root++) {
 		bool awake = false;
-		for (int b = 0; b < nb; b++) if (w.body[b].islandTag == root && body_active(w.body[b])) { awake = true; break; }
+		for (int b = 0; b < nb; b++) if (cx.body[b].islandTag == root && body_active(cx.body[b])) { awake = true; break; }
 		if (!awake) continue;
-		for (int b = 0; b < nb; b++) if (w.body[b].islandTag == root) get_or_init_solver_body(cx, b, companion, fixedId);
+		for (int b = 0; b < nb; b++) if (cx.body[b].islandTag == root) get_or_init_solver_body(cx, b, companion, fixedId);
 	}
 
 	// convertContacts
 	for (int k = 0; k < nSolveManifolds; k++) {
-		Manifold& mf = w.manifolds[w.manifoldOrder[k]];
+		Manifold& mf = cx.mf[cx.pl->manifoldOrder[k]];
 		int ia = get_or_init_solver_body(cx, mf.body0, companion, fixedId);
 		int ib = get_or_init_solver_body(cx, mf.body1, companion, fixedId);
 		for (int j = 0; j < mf.nPts; j++) {
 			ContactPt& cp = mf.pts[j];
 			if (!(cp.dist <= mf.processingThresh)) continue;
-			if (w.nRows >= MAX_ROWS) { cx.s->errorFlags |= ERR_MANIFOLD_OVERFLOW; break; }
+			if (sv.cnt[1] >= MAX_ROWS) { set_error(cx, ERR_MANIFOLD_OVERFLOW); break; }
 			V3 org0 = mf.body0 < STATIC_BASE ? rigid_of(cx, mf.body0).pos : static_origin(cx, mf.body0);
 			V3 org1 = mf.body1 < STATIC_BASE ? rigid_of(cx, mf.body1).pos : static_origin(cx, mf.body1);
 			V3 rel1 = cp.posA - org0;
 			V3 rel2 = cp.posB - org1;
-			int frictionIndex = w.nRows;
-			SolverRow& row = w.rows[w.nRows++];
+			int frictionIndex = sv.cnt[1];
+			SolverRow& row = sv.row(sv.cnt[1]++);
 			setup_contact_row(cx, row, ia, ib, cp.normalB, cp.dist, cp.restitution, cp.friction, cp.isSpecial, rel1, rel2);
-			row.frictionIndex = w.nFrictionRows;
+			row.frictionIndex = sv.cnt[2];
 			if (cp.isSpecial) {
 				for (int i = 0; i < 2; i++) {
 					int obj = i ? mf.body1 : mf.body0;
 					if (obj < STATIC_BASE) {
-						w.spNum[obj]++;
-						w.spFriction[obj] = cp.friction;
-						w.spRestitution[obj] = cp.restitution;
-						w.spTotalNormal[obj] += cp.normalB;
-						w.spTotalDist[obj] += len(i ? rel2 : rel1);
+						spNum[obj]++;
+						spFriction[obj] = cp.friction;
+						spRestitution[obj] = cp.restitution;
+						spTotalNormal[obj] += cp.normalB;
+						spTotalDist[obj] += len(i ? rel2 : rel1);
 					}
 				}
 			}
@@ -339,30 +341,30 @@ RSB_HD void solve_arena(const Ctx& cx, int nSolveManifolds) {
 		}
 	}
 	// special contacts, per converted body in solver-body order (convertContactSpecial, :1164-1211)
-	for (int sbi = 0; sbi < w.nSolverBodies; sbi++) {
-		int b = w.sbody[sbi].orig;
-		if (b < 0 || w.spNum[b] <= 0) continue;
-		if (w.nRows >= MAX_ROWS) { cx.s->errorFlags |= ERR_MANIFOLD_OVERFLOW; break; }
-		float distance = w.spTotalDist[b] / (float)w.spNum[b];
-		V3 normal = w.spTotalNormal[b] / (float)w.spNum[b];
-		int frictionIndex = w.nRows;
+	for (int sbi = 0; sbi < sv.cnt[0]; sbi++) {
+		int b = sv.sbody[sbi].orig;
+		if (b < 0 || spNum[b] <= 0) continue;
+		if (sv.cnt[1] >= MAX_ROWS) { set_error(cx, ERR_MANIFOLD_OVERFLOW); break; }
+		float distance = spTotalDist[b] / (float)spNum[b];
+		V3 normal = spTotalNormal[b] / (float)spNum[b];
+		int frictionIndex = sv.cnt[1];
 		int ia = companion[b];
 		int ib = get_or_init_solver_body(cx, STATIC_BASE, companion, fixedId);
 		V3 rel1 = normal * -distance;
 		V3 rel2 = v3zero();
-		SolverRow& row = w.rows[w.nRows++];
-		setup_contact_row(cx, row, ia, ib, normal, distance, w.spRestitution[b], w.spFriction[b], 0, rel1, rel2);
-		row.frictionIndex = w.nFrictionRows;
-		add_friction_for(cx, ia, ib, normal, w.spFriction[b], rel1, rel2, frictionIndex);
-		w.spNum[b] = 0;
+		SolverRow& row = sv.row(sv.cnt[1]++);
+		setup_contact_row(cx, row, ia, ib, normal, distance, spRestitution[b], spFriction[b], 0, rel1, rel2);
+		row.frictionIndex = sv.cnt[2];
+		add_friction_for(cx, ia, ib, normal, spFriction[b], rel1, rel2, frictionIndex);
+		spNum[b] = 0;
 	}
 
 	// split impulse iterations (:1778-1810)
 	for (int it = 0; it < 10; it++) {
 		float lsr = 0.f;
-		for (int j = 0; j < w.nRows; j++) {
-			SolverRow& c = w.rows[j];
-			float residual = resolve_split(w.sbody[c.bodyA], w.sbody[c.bodyB], c);
+		for (int j = 0; j < sv.cnt[1]; j++) {
+			SolverRow& c = sv.row(j);
+			float residual = resolve_split(sv.sbody[c.bodyA], sv.sbody[c.bodyB], c);
 			float r2 = residual * residual;
 			if (r2 > lsr) lsr = r2;
 		}
@@ -370,24 +372,24 @@ RSB_HD void solve_arena(const Ctx& cx, int nSolveManifolds) {
 	}
 	// velocity iterations (:1601-1776): non-special contacts, then friction rows
 	for (int it = 0; it < 10; it++) {
-		for (int j = 0; j < w.nRows; j++) {
-			SolverRow& c = w.rows[j];
+		for (int j = 0; j < sv.cnt[1]; j++) {
+			SolverRow& c = sv.row(j);
 			if (c.isSpecial) continue;
-			resolve_row(w.sbody[c.bodyA], w.sbody[c.bodyB], c, false);
+			resolve_row(sv.sbody[c.bodyA], sv.sbody[c.bodyB], c, false);
 		}
-		for (int j = 0; j < w.nFrictionRows; j++) {
-			SolverRow& c = w.frows[j];
-			float totalImpulse = w.rows[c.frictionIndex].applied;
+		for (int j = 0; j < sv.cnt[2]; j++) {
+			SolverRow& c = sv.frow(j);
+			float totalImpulse = sv.row(c.frictionIndex).applied;
 			if (totalImpulse > 0.f) {
 				c.lower = -(c.friction * totalImpulse);
 				c.upper = c.friction * totalImpulse;
-				resolve_row(w.sbody[c.bodyA], w.sbody[c.bodyB], c, true);
+				resolve_row(sv.sbody[c.bodyA], sv.sbody[c.bodyB], c, true);
 			}
 		}
 	}
 	// writeBackBodies (:1878-1904, btSolverBody.h:265-287)
-	for (int i = 0; i < w.nSolverBodies; i++) {
-		SolverBody& sb = w.sbody[i];
+	for (int i = 0; i < sv.cnt[0]; i++) {
+		SolverBody& sb = sv.sbody[i];
 		if (sb.orig < 0) continue;
 		RigidS& rb = rigid_of(cx, sb.orig);
 		sb.lin += sb.dLin;
@@ -403,6 +405,29 @@ RSB_HD void solve_arena(const Ctx& cx, int nSolveManifolds) {
 		rb.pos = sb.xf.origin;
 		rb.basis = sb.xf.basis;
 	}
+}
+
+// Does any manifold handed to the solver carry a contact point?  If not, solveGroup degenerates to the
+// per-body write-back v += externalForceImpulse (no rows, no push): solve_body_no_contacts, one thread per body.
+RSB_HD bool solver_has_rows(const Ctx& cx, int nSolveManifolds) {
+	for (int k = 0; k < nSolveManifolds; k++) if (cx.mf[cx.pl->manifoldOrder[k]].nPts > 0) return true;
+	return false;
+}
+
+RSB_HD void solve_body_no_contacts(const Ctx& cx, int b) {
+	const int nb = n_bodies(cx);
+	const int root = cx.body[b].islandTag;
+	bool awake = false;  // convertBodies only visits islands with an active body
+	for (int o = 0; o < nb; o++) if (cx.body[o].islandTag == root && body_active(cx.body[o])) { awake = true; break; }
+	if (!awake) return;
+	const BodyW& bw = cx.body[b];
+	RigidS& rb = rigid_of(cx, b);
+	V3 extF = bw.totalForce * bw.invMass * cx.p->dt;
+	V3 extT = vmul(bw.totalTorque, bw.invInertiaW) * cx.p->dt;
+	V3 lin = rb.vel; lin += v3zero();
+	V3 ang = rb.angvel; ang += v3zero();
+	rb.vel = lin + extF;
+	rb.angvel = ang + extT;
 }
 
 }  // namespace rsb

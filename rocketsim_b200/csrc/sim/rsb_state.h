@@ -20,7 +20,7 @@ constexpr int MAX_CARS = 6;          // 3v3
 constexpr int MAX_BODIES = MAX_CARS + 1;  // dynamic bodies: ball (index 0) + cars (1..n)
 constexpr int MAX_PADS = 40;         // Soccar 34, Hoops 20
 constexpr int MAX_WHEELS = MAX_CARS * 4;
-constexpr int MAX_MANIFOLDS = 48;
+constexpr int MAX_MANIFOLDS = 32;    // broadphase pairs per arena and tick (= manifold slots)
 constexpr int MAX_POINTS = MAX_MANIFOLDS * 4;
 constexpr int MAX_ROWS = MAX_POINTS + MAX_BODIES;
 constexpr int MAX_EVENTS_PER_ARENA = 8;
@@ -86,14 +86,18 @@ struct ArenaS {
 	uint32_t rng;          // minstd_rand0 state of the respawn RNG (Math.cpp:44-64)
 	uint32_t stampCounter; // broadphase cell-history counter
 	// btRSBroadphase dynamic proxies: cell of the AABB min corner and the order in which
-	// bodies last (re-)entered their 27-cell neighbourhood (btRSBroadphase.cpp:184-202,286-323)
+	// bodies last (re-)entered their 27-cell neighbourhood (btRSBroadphase.cpp:184-202,286-323).
+	// dynOrder lists the bodies by ascending stamp (= the order of every cell's dynHandles vector),
+	// cellI/J/K are the grid coordinates of cellIdx.
 	int32_t cellIdx[MAX_BODIES];
 	uint32_t cellStamp[MAX_BODIES];
+	uint8_t dynOrder[MAX_BODIES + 1];
+	uint8_t cellI[MAX_BODIES + 1], cellJ[MAX_BODIES + 1], cellK[MAX_BODIES + 1];
 	uint32_t errorFlags;
 	uint32_t goalScoredTick;  // debug
 	BallS ball;
-	CarS cars[MAX_CARS];
 	PadS pads[MAX_PADS];
+	CarS cars[MAX_CARS];   // last: a batch with fewer cars stages only the used prefix of the record
 };
 
 enum ErrorFlags : uint32_t {
@@ -152,6 +156,8 @@ struct BatchParams {
 	int padGrid[8 * 10];  // BoostPadGrid (BoostPadGrid.h:10-29): pad index or -1
 	// README bench loop on device: when set, a goal is followed by ResetToRandomKickoff(autoResetSeed + arena + tick)
 	int autoReset; uint32_t autoResetSeed;
+	float boundRadius[MAX_BODIES]; // radius of a sphere around the shape centre that contains the shape incl. margins
+	float motionDisc[MAX_BODIES];  // btCollisionShape::getAngularMotionDisc of each dynamic body's shape (constant per batch)
 };
 
 // ---------------------------------------------------------------- static scene (per game mode)
@@ -187,6 +193,11 @@ struct Scene {
 	int cellsX, cellsY, cellsZ;
 	const int32_t* cellStart;   // [totalCells+1]
 	const uint8_t* cellStatics; // static object indices (0..nMeshes-1 meshes, then planes)
+	// per cellStatics entry of a mesh: candidate BVH subtree headers for queries issued from that cell
+	// (creation order for AABB queries, root order for ray queries); see rsb_scene.h
+	const int32_t* cellHdrStart;
+	const uint16_t* cellHdrs;
+	const uint16_t* cellHdrsRay;
 };
 
 }  // namespace rsb

@@ -14,7 +14,7 @@
 namespace rsb {
 
 RSB_HD void init_body_work(const Ctx& cx, int b) {
-	BodyW& bw = cx.w->body[b];
+	BodyW& bw = cx.body[b];
 	const BatchParams& P = *cx.p;
 	const RigidS& rb = rigid_of(cx, b);
 	if (b == 0) {
@@ -40,27 +40,30 @@ RSB_HD void init_body_work(const Ctx& cx, int b) {
 // phase over all threads of the block and separates phases with __syncthreads(); the host
 // check build runs the same phases with one thread.  Order = Arena::Step T0..T6.
 enum Phase : int {
-	PH_INIT = 0,     // T0  working rigid-body values + ball sleep gate        item = body
-	PH_PRE_BEGIN,    // T1  Car::_PreTickUpdate head (respawn RNG, sequential)  item = arena
-	PH_WHEELS,       // T1  suspension rays                                     item = car x wheel
-	PH_CAR_LOGIC,    // T1  friction, game logic, suspension/boost forces       item = car
-	PH_PADS_BALL,    // T2  pads + ball pre-tick                                 item = pad | ball
-	PH_PREDICT,      // T3  gravity, damping, predicted transform               item = body
-	PH_COLLIDE,      // T3  AABBs, broadphase pairs, narrowphase, contact hooks item = arena
-	PH_SOLVE,        // T3  islands + sequential-impulse solve                   item = arena
-	PH_INTEGRATE,    // T3  integrateTransforms                                  item = body
-	PH_CAR_POST,     // T4  Car::_PostTickUpdate / _FinishPhysicsTick           item = car
-	PH_TAIL,         // T4-T6 pad pickups, ball finish, goal, tick counter      item = arena
+	PH_INIT = 0,       // T0  working rigid-body values + ball sleep gate                 item = body
+	PH_PRE_BEGIN,      // T1  Car::_PreTickUpdate head (respawn RNG, sequential)           item = arena
+	PH_WHEELS,         // T1  suspension rays                                              item = car x wheel
+	PH_CAR_LOGIC,      // T1  friction, game logic, suspension/boost forces; T2 pads+ball  item = car | pad | ball
+	PH_PREDICT,        // T3  gravity, damping, predicted transform, swept AABB            item = body
+	PH_PAIRS,          // T3  broadphase cell bookkeeping + pair list                      item = arena
+	PH_NARROW_STATIC,  // T3  narrowphase + contact hooks vs static objects                item = body
+	PH_DYN_SOLVE,      // T3  ball-car / car-car narrowphase, islands, solver (if rows)    item = arena
+	PH_FINISH_BODY,    // T3  contact-free solver write-back, integrateTransforms          item = body
+	PH_CAR_POST,       // T4  Car::_PostTickUpdate / _FinishPhysicsTick, pad grid check    item = car
+	PH_PADS_POST,      // T5  pads give boost / start cooldown                             item = pad
+	PH_TAIL,           // T5-T6 ball finish, goal (+ kickoff auto reset), tick counter     item = arena
 	PH_COUNT
 };
 
 RSB_HD int phase_items(const BatchParams& P, int phase) {
 	const int nCars = P.nCars, nb = nCars + 1;
+	const int nPadItems = (P.mode != THE_VOID && nCars != 0) ? P.nPads : 0;
 	switch (phase) {
-	case PH_INIT: case PH_PREDICT: case PH_INTEGRATE: return nb;
+	case PH_INIT: case PH_PREDICT: case PH_NARROW_STATIC: case PH_FINISH_BODY: return nb;
 	case PH_WHEELS: return nCars * 4;
-	case PH_CAR_LOGIC: case PH_CAR_POST: return nCars;
-	case PH_PADS_BALL: return ((P.mode != THE_VOID && nCars != 0) ? P.nPads : 0) + 1;
+	case PH_CAR_LOGIC: return nCars + nPadItems + 1;
+	case PH_CAR_POST: return nCars;
+	case PH_PADS_POST: return nPadItems;
 	default: return 1;
 	}
 }
@@ -68,7 +71,6 @@ RSB_HD int phase_items(const BatchParams& P, int phase) {
 RSB_HD void phase_run(const Ctx& cx, int phase, int item) {
 	const BatchParams& P = *cx.p;
 	ArenaS& S = *cx.s;
-	ArenaW& W = *cx.w;
 	const int nCars = P.nCars;
 	const float dt = P.dt;
 	const bool hasArenaStuff = (P.mode != THE_VOID);
@@ -83,19 +85,18 @@ RSB_HD void phase_run(const Ctx& cx, int phase, int item) {
 		if (!S.cars[ci].isDemoed) wheel_trace(cx, ci, wi);
 		break;
 	}
-	case PH_CAR_LOGIC:
-		if (!S.cars[item].isDemoed) car_pretick_logic(cx, item);
-		break;
-	case PH_PADS_BALL: {
+	case PH_CAR_LOGIC: {
+		// cars, pads and the ball do not read each other's pre-tick results: one phase
 		const int nPadItems = (hasArenaStuff && !ballOnly) ? P.nPads : 0;
-		if (item < nPadItems) pad_pretick(cx, item);
+		if (item < nCars) { if (!S.cars[item].isDemoed) car_pretick_logic(cx, item); }
+		else if (item < nCars + nPadItems) pad_pretick(cx, item - nCars);
 		else ball_pretick(cx);
 		break;
 	}
 	case PH_PREDICT: {
-		// applyGravity (active bodies) + predictUnconstraintMotion (damping + predicted transform)
+		// applyGravity (active bodies) + predictUnconstraintMotion (damping + predicted transform) + updateSingleAabb
 		const int b = item;
-		BodyW& bw = W.body[b];
+		BodyW& bw = cx.body[b];
 		RigidS& rb = rigid_of(cx, b);
 		if (body_active(bw)) apply_central_force(bw, P.gravityBT * (1.f / bw.invMass));
 		float linDamp = (b == 0) ? P.mut.ballDrag : 0.f;
@@ -103,18 +104,24 @@ RSB_HD void phase_run(const Ctx& cx, int phase, int item) {
 		rb.angvel *= powf(1.f - 0.f, dt);
 		Xform cur; cur.basis = rb.basis; cur.origin = rb.pos;
 		integrate_transform(cur, rb.vel, rb.angvel, dt, (b == 0) && P.ballNoRot, bw.interp);
+		update_aabb(cx, b);
 		break;
 	}
-	case PH_COLLIDE: collide_world(cx); break;  // updateAabbs, pairs, narrowphase + contact hooks
-	case PH_SOLVE: {
-		int nSolve = build_islands(cx);  // calculateSimulationIslands + buildIslands
-		solve_arena(cx, nSolve);          // solveConstraints
+	case PH_PAIRS: collide_pairs(cx); break;
+	case PH_NARROW_STATIC: collide_static_pairs(cx, item); break;
+	case PH_DYN_SOLVE: {
+		collide_dynamic_pairs(cx);
+		const int nSolve = build_islands(cx);  // calculateSimulationIslands + buildIslands
+		const bool rows = solver_has_rows(cx, nSolve);
+		cx.misc[0] = rows ? 1 : 0; cx.misc[1] = nSolve;
+		if (rows) solve_arena(cx, nSolve);     // solveConstraints
 		break;
 	}
-	case PH_INTEGRATE: {
-		// integrateTransforms (active bodies) + clearForces
+	case PH_FINISH_BODY: {
 		const int b = item;
-		BodyW& bw = W.body[b];
+		if (!cx.misc[0]) solve_body_no_contacts(cx, b);
+		// integrateTransforms (active bodies) + clearForces
+		BodyW& bw = cx.body[b];
 		RigidS& rb = rigid_of(cx, b);
 		if (body_active(bw)) {
 			Xform cur; cur.basis = rb.basis; cur.origin = rb.pos;
@@ -124,11 +131,12 @@ RSB_HD void phase_run(const Ctx& cx, int phase, int item) {
 		}
 		break;
 	}
-	case PH_CAR_POST: car_posttick(cx, item); break;
+	case PH_CAR_POST:
+		car_posttick(cx, item);
+		if (hasArenaStuff) pad_grid_check(cx, item);
+		break;
+	case PH_PADS_POST: pad_posttick(cx, item); break;
 	case PH_TAIL:
-		if (hasArenaStuff) for (int ci = 0; ci < nCars; ci++) pad_grid_check(cx, ci);
-		// ---- T5: pads post-tick, ball finish
-		if (hasArenaStuff && !ballOnly) for (int i = 0; i < P.nPads; i++) pad_posttick(cx, i);
 		ball_finish_tick(cx);
 		// ---- T6: goal event, tick counter
 		if (P.mode != THE_VOID && is_ball_scored(cx)) {

@@ -29,6 +29,7 @@ struct BodyW {  // btRigidBody working values of one dynamic body
 	float invMass;
 	Xform interp;       // predicted transform (m_interpolationWorldTransform)
 	V3 aabbMin, aabbMax;
+	int newCell, newI, newJ, newK;  // broadphase cell of this tick's AABB min corner (applied in PH_PAIRS)
 	int activation;     // Activation
 	int noResponse;     // CF_NO_CONTACT_RESPONSE
 	int islandTag;
@@ -45,11 +46,20 @@ struct ContactPt {  // btManifoldPoint subset
 	int partId0, index0, partId1, index1;
 };
 
-struct Manifold {  // btPersistentManifold subset
+struct Manifold {  // btPersistentManifold subset; slot k belongs to broadphase pair k, body0 < 0 = not created
 	int body0, body1;   // object ids (dynamic index or STATIC_BASE+k)
 	int nPts;
 	float breakingThresh, processingThresh;
-	ContactPt pts[4];
+	int _pad;
+	ContactPt* pts;     // 4 points of this slot in the cold scratch (ArenaW::points)
+};
+
+// broadphase pair list in creation order (btHashedOverlappingPairCache array) + solver manifold order
+struct PairList {
+	int nPairs, nManifolds;
+	uint8_t a[MAX_MANIFOLDS], b[MAX_MANIFOLDS];
+	uint8_t manifoldOrder[MAX_MANIFOLDS];
+	uint16_t entry[MAX_MANIFOLDS];  // static pairs: position of the static object in the cell list (Scene::cellStatics)
 };
 
 struct SolverBody {
@@ -88,24 +98,29 @@ struct EpaScratch {
 	int16_t stackF[EPA_MAX_FACES + 8]; uint8_t stackE[EPA_MAX_FACES + 8]; uint8_t stackS[EPA_MAX_FACES + 8];
 };
 
-struct ArenaW {
+// Solver scratch of the common case (few rows): counters, solver bodies and the first SOLVER_ROWS_FAST rows of
+// each pool.  In the kernel it ALIASES the wheel scratch, which is dead once the car pre-tick is over.
+constexpr int SOLVER_ROWS_FAST = 6;
+constexpr int SOLV_BYTES_MAX = 16 + (MAX_BODIES + 1) * (int)sizeof(SolverBody) + 2 * SOLVER_ROWS_FAST * (int)sizeof(SolverRow);
+RSB_HD constexpr int solv_bytes(int nb) { return 16 + (nb + 1) * (int)sizeof(SolverBody) + 2 * SOLVER_ROWS_FAST * (int)sizeof(SolverRow); }
+
+// Hot per-tick scratch: lives in shared memory next to the arena record while a launch runs (the kernel
+// lays out only the used prefix of each array); ArenaH is its full-size global mirror (debug probes, host check).
+struct ArenaH {
 	BodyW body[MAX_BODIES];
 	WheelW wheels[MAX_WHEELS];
 	int padLocked[MAX_PADS];  // BoostPadState::curLockedCar as car index, -1 none
-	// broadphase pairs in creation order
-	int nPairs;
-	int pairA[MAX_MANIFOLDS], pairB[MAX_MANIFOLDS];
-	int nManifolds;
-	Manifold manifolds[MAX_MANIFOLDS];
-	int manifoldOrder[MAX_MANIFOLDS];
-	int nSolverBodies, nRows, nFrictionRows;
-	SolverBody sbody[MAX_BODIES + 1];
-	SolverRow rows[MAX_ROWS];
+	int misc[4];              // [0] = this tick needs the general solver, [1] = #manifolds handed to it
+	PairList pairs;
+	Manifold mf[MAX_MANIFOLDS];
+	alignas(8) unsigned char solv[SOLV_BYTES_MAX];
+};
+
+// Cold per-tick scratch (global memory): only touched when there are contacts.
+struct ArenaW {
+	ContactPt points[MAX_POINTS];
+	SolverRow rows[MAX_ROWS];    // overflow beyond SOLVER_ROWS_FAST (indexed like the full pool)
 	SolverRow frows[MAX_ROWS];
-	// special (ball-world) contact accumulation per body (btCollisionObject::m_specialResolveInfo)
-	int spNum[MAX_BODIES];
-	float spFriction[MAX_BODIES], spRestitution[MAX_BODIES], spTotalDist[MAX_BODIES];
-	V3 spTotalNormal[MAX_BODIES];
 	EpaScratch epa;
 };
 
@@ -118,12 +133,44 @@ struct EventSink {
 
 struct Ctx {
 	ArenaS* s;
+	BodyW* body;       // hot scratch (see ArenaH)
+	WheelW* wheels;
+	int* padLocked;
+	int* misc;
+	PairList* pl;
+	Manifold* mf;
+	unsigned char* solv;  // solver scratch (see SolverView)
 	ArenaW* w;
 	const BatchParams* p;
 	const Scene* sc;
 	EventSink ev;
 	int arena;  // global arena index inside the batch
 };
+
+struct SolverView {
+	int* cnt;  // [0] solver bodies, [1] contact rows, [2] friction rows
+	SolverBody* sbody;
+	SolverRow *rows, *frows, *orows, *ofrows;
+	RSB_HD SolverRow& row(int j) const { return j < SOLVER_ROWS_FAST ? rows[j] : orows[j]; }
+	RSB_HD SolverRow& frow(int j) const { return j < SOLVER_ROWS_FAST ? frows[j] : ofrows[j]; }
+};
+RSB_HD SolverView solver_view(const Ctx& cx) {
+	SolverView v;
+	v.cnt = (int*)cx.solv;
+	v.sbody = (SolverBody*)(cx.solv + 16);
+	v.rows = (SolverRow*)(v.sbody + (cx.p->nCars + 2));
+	v.frows = v.rows + SOLVER_ROWS_FAST;
+	v.orows = cx.w->rows; v.ofrows = cx.w->frows;
+	return v;
+}
+
+RSB_HD void set_error(const Ctx& cx, uint32_t flag) {
+#if defined(__CUDA_ARCH__)
+	atomicOr(&cx.s->errorFlags, flag);
+#else
+	set_error(cx, flag);
+#endif
+}
 
 RSB_HD RigidS& rigid_of(const Ctx& cx, int b) { return b == 0 ? cx.s->ball.rb : cx.s->cars[b - 1].rb; }
 RSB_HD int n_bodies(const Ctx& cx) { return cx.p->nCars + 1; }
@@ -139,7 +186,7 @@ RSB_HD void push_event(const Ctx& cx, uint32_t type, uint32_t a, uint32_t b) {
 		EventSink::Ev e; e.arena = (uint32_t)cx.arena; e.type = type; e.a = a; e.b = b; e.tick = cx.s->tickCount;
 		cx.ev.buf[i] = e;
 	} else {
-		cx.s->errorFlags |= ERR_EVENT_OVERFLOW;
+		set_error(cx, ERR_EVENT_OVERFLOW);
 	}
 }
 

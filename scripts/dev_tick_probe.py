@@ -47,3 +47,10 @@ for i, cid in enumerate(ref.car_ids):
     d = np.abs(rw - mw).max()
     if d > 1e-6:
         print("car", i, "wheel diff", d); print(mw); print(rw)
+for which in (0, 1):
+    rows = np.zeros((64, 24), np.float32)
+    L.rsb_debug_get_solver_rows(b.h, 0, which, vp(rows), 64, C.byref(n)); mr = rows[: n.value]
+    rr = ref.solver_rows(which, n.value)
+    for i in range(n.value):
+        print("row", which, i, "n1 mine", mr[i, 0:3], "ref", rr[i, 0:3], "rp1xn mine", mr[i, 3:6], "ref", rr[i, 3:6])
+print("solver bodies full"); print(sb); print(rb)

@@ -14,9 +14,8 @@ L = rlib.load(path); rlib.init_from_mem(sm.mesh_sets(), L)
 b = ArenaBatch(mode, A, [0] * cpt + [1] * cpt, seed=1234, lib=L)
 b.reset_to_random_kickoff((1234 + np.arange(A)).astype(np.int32)); b.set_auto_reset(True, 1234)
 seq = torch.empty(TICKS * A * 2 * cpt * 24, dtype=torch.uint8, device="cuda")
-names = ["T0 init", "T1 pretick_begin(lane0)", "T1 wheel rays", "T1 car logic", "T2 pads+ball", "T3 predict", "T3 collide(lane0)",
-         "T3 islands(lane0)", "T3 solve(lane0)", "T3 integrate", "T4 car posttick", "T4-6 tail(lane0)"]
-out = (C.c_uint64 * 16)()
+names = ["INIT", "PRE_BEGIN", "WHEELS", "CAR_LOGIC", "PREDICT", "PAIRS", "NARROW_STATIC", "DYN_SOLVE", "FINISH_BODY", "CAR_POST", "PADS_POST", "TAIL"]
+out = (C.c_uint64 * 64)()
 for rep in range(3):
     rlib.check(L, L.rsb_bench_fill_controls_device(b.h, C.c_void_p(seq.data_ptr()), TICKS, rep * TICKS, 1234))
     L.rsb_debug_profile(out, 1)
@@ -24,7 +23,9 @@ for rep in range(3):
     rlib.check(L, L.rsb_step_with_controls_device(b.h, C.c_void_p(seq.data_ptr()), TICKS)); b.sync()
     dt = time.perf_counter() - t0
     L.rsb_debug_profile(out, 1)
-    tot = sum(out)
+    tot = sum(out[:16])
     print(f"rep {rep}: {A * TICKS / dt / 1e6:.2f} M arena-ticks/s ({dt * 1e3:.1f} ms)")
     for i, n in enumerate(names):
-        print(f"  {n:28s} {100.0 * out[i] / max(tot, 1):5.1f} %   {out[i] / (A * TICKS):9.0f} cycles/arena-tick")
+        nblk = TICKS * min(148, A)  # block-phases executed (one block per SM when the batch fits)
+        print(f"  {n:16s} {100.0 * out[i] / max(tot, 1):5.1f} %  wall/block-tick {out[i] / (TICKS * 147):8.0f}  slowest thread {out[48 + i] / (TICKS * 147):8.0f}"
+              f"  mean busy thread {out[16 + i] / max(out[32 + i], 1):8.0f}  busy threads/block {out[32 + i] / (TICKS * 147):6.1f}")

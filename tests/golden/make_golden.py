@@ -14,6 +14,8 @@ import sys
 
 import numpy as np
 
+ONLY = sys.argv[1:]  # optional: regenerate only the named cases
+
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
@@ -32,12 +34,18 @@ CASES = {
     "hoops_2v2_aim": (T.MODE_HOOPS, 2, 9, 240, 60, True),
     "heatseeker_1v1": (T.MODE_HEATSEEKER, 1, 13, 240, 60, False),
     "snowday_3v3_aim": (T.MODE_SNOWDAY, 3, 17, 240, 90, True),
+    # cars driven into side walls / back walls / corners, ball fired at a ramp: arena-mesh BVH paths
+    "soccar_3v3_walls": (T.MODE_SOCCAR, 3, 21, 300, 150, "walls"),
+    "hoops_2v2_walls": (T.MODE_HOOPS, 2, 23, 300, 150, "walls"),
+    "snowday_2v2_walls": (T.MODE_SNOWDAY, 2, 25, 300, 150, "walls"),
 }
 
 
 def main():
     refsim.init_from_mem(sm.mesh_sets())
     for name, (mode, cpt, seed, ticks, drive, aim) in CASES.items():
+        if ONLY and name not in ONLY:
+            continue
         teams = [0] * cpt + [1] * cpt
         rec = pu.record_rollout(refsim, mode, teams, seed, ticks, drive=drive, aim=aim)
         path = os.path.join(HERE, name + ".npz")

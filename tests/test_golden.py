@@ -2,7 +2,7 @@
 the unmodified reference by tests/golden/make_golden.py).
 
 Bar (BASELINE.json north_star): discrete state bit-exact per single step; float state within
-1e-4 relative, `max|a-b| / max(||b||, eps_field)` with eps pos 1 uu, vel 1 uu/s, angVel 0.05 rad/s,
+1e-4 relative, `max|a-b| / max(||b||, eps_field)` with eps pos 1 uu, vel 1 uu/s, angVel 0.01 rad/s,
 rotMat 1.
 """
 import glob
@@ -41,7 +41,7 @@ def check(res, name):
 
 
 def test_golden_files_present():
-    assert len(GOLDEN) >= 7
+    assert len(GOLDEN) >= 10
 
 
 @pytest.mark.parametrize("path", GOLDEN, ids=NAMES)
