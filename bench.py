@@ -175,6 +175,7 @@ def run_cuda(args):
 
     # ---- device-resident arm ("value")
     for i in range(args.warmup):
+        flush.zero_()  # also warms torch's fill kernel: no lazy module load inside the timed region
         step_device(i)
     barrier()
     sampler = ClockSampler(local_rank)

@@ -124,6 +124,9 @@ int rsb_debug_get_solver_rows(RsbBatch* b, int arena, int which, float* out, int
 /* Debug probe: solver bodies of the last tick, 12 floats each {linVel, angVel, externalForceImpulse, externalTorqueImpulse}. */
 int rsb_debug_get_solver_bodies(RsbBatch* b, int arena, float* out, int cap, int* n_out);
 
+/* Debug probe: the four per-arena scratch ints of the last tick ([0] solver ran, [1] #manifolds solved, [2..3] developer use). */
+int rsb_debug_get_misc(RsbBatch* b, int arena, int* out4);
+
 /* Developer builds (-DRSB_PROFILE) only: per tick phase p: out[p] block wall cycles, out[16+p] busy-thread cycles,
  * out[32+p] busy threads, out[48+p] slowest-thread cycles (each summed over blocks and ticks); zeros otherwise. */
 int rsb_debug_profile(uint64_t* out64, int reset);

@@ -116,6 +116,7 @@ struct RsbBatch {
 	ArenaS* dS = nullptr;
 	ArenaW* dW = nullptr;
 	ArenaH* dH = nullptr;          // global mirror of the hot per-tick scratch
+	EpaScratch* dE = nullptr;      // EPA working sets, one per thread of the step grid
 	const Scene* dScene = nullptr;
 	EventSink::Ev* dEvents = nullptr;
 	uint32_t* dEventCount = nullptr;
@@ -265,7 +266,7 @@ struct ArenaLayout {
 };
 
 struct StepArgs {
-	ArenaS* S; ArenaH* H; ArenaW* W; const BatchParams* P; const Scene* sc; EventSink ev;
+	ArenaS* S; ArenaH* H; ArenaW* W; EpaScratch* E; const BatchParams* P; const Scene* sc; EventSink ev;
 	int nArenas, nTicks; const CtrlS* ctrlSeq; int nCtrl; int apb;
 	int mirror;  // keep the full debug mirror (ArenaH) up to date: single-tick launches only
 	ArenaLayout lay;
@@ -291,7 +292,7 @@ __device__ __forceinline__ Ctx make_ctx(const StepArgs& a, const BatchParams* sP
 	cx.s = (ArenaS*)base; cx.body = (BodyW*)(base + a.lay.bodyOff); cx.wheels = (WheelW*)(base + a.lay.wheelOff);
 	cx.padLocked = (int*)(base + a.lay.padOff); cx.misc = (int*)(base + a.lay.miscOff);
 	cx.pl = (PairList*)(base + a.lay.pairOff); cx.mf = (Manifold*)(base + a.lay.mfOff); cx.solv = base + a.lay.wheelOff;
-	cx.w = a.W + (a0 + ar); cx.p = sP; cx.sc = sSc; cx.ev = a.ev; cx.arena = a0 + ar;
+	cx.w = a.W + (a0 + ar); cx.epa = a.E + ((size_t)blockIdx.x * STEP_THREADS + threadIdx.x); cx.p = sP; cx.sc = sSc; cx.ev = a.ev; cx.arena = a0 + ar;
 	return cx;
 }
 
@@ -399,7 +400,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) arena_step_kernel(const StepA
 static void arena_step_host(const StepArgs& a) {
 	const int nCars = a.P->nCars;
 	for (int arena = 0; arena < a.nArenas; arena++) {
-		Ctx cx; cx.s = a.S + arena; cx.w = a.W + arena; cx.p = a.P; cx.sc = a.sc; cx.ev = a.ev; cx.arena = arena;
+		Ctx cx; cx.s = a.S + arena; cx.w = a.W + arena; cx.epa = a.E; cx.p = a.P; cx.sc = a.sc; cx.ev = a.ev; cx.arena = arena;
 		cx.body = a.H[arena].body; cx.wheels = a.H[arena].wheels; cx.padLocked = a.H[arena].padLocked; cx.misc = a.H[arena].misc;
 		cx.pl = &a.H[arena].pairs; cx.mf = a.H[arena].mf; cx.solv = a.H[arena].solv;
 		for (int t = 0; t < a.nTicks; t++) {
@@ -449,7 +450,7 @@ RSB_GLOBAL void get_misc_kernel(const ArenaS* S, const BatchParams* P, const Sce
 	KERNEL_1D(i, nArenas);
 	if (ticks) ticks[i] = S[i].tickCount;
 	if (errs) errs[i] = S[i].errorFlags;
-	if (scored) { Ctx cx; cx.s = (ArenaS*)&S[i]; cx.w = nullptr; cx.body = nullptr; cx.wheels = nullptr; cx.padLocked = nullptr; cx.misc = nullptr; cx.pl = nullptr; cx.mf = nullptr; cx.solv = nullptr; cx.p = P; cx.sc = sc; cx.arena = i; cx.ev.buf = nullptr; scored[i] = is_ball_scored(cx) ? 1 : 0; }
+	if (scored) { Ctx cx; cx.s = (ArenaS*)&S[i]; cx.w = nullptr; cx.epa = nullptr; cx.body = nullptr; cx.wheels = nullptr; cx.padLocked = nullptr; cx.misc = nullptr; cx.pl = nullptr; cx.mf = nullptr; cx.solv = nullptr; cx.p = P; cx.sc = sc; cx.arena = i; cx.ev.buf = nullptr; scored[i] = is_ball_scored(cx) ? 1 : 0; }
 }
 RSB_GLOBAL void get_car_internals_kernel(const ArenaS* S, RsbCarInternal* out, int nArenas, int nCars) {
 	KERNEL_1D(i, nArenas * nCars);
@@ -796,7 +797,7 @@ int rsb_batch_create(int device, int game_mode, int n_arenas, int n_cars, const 
 	fill_pads(game_mode, P);
 	{
 		ArenaS tmpS; memset(&tmpS, 0, sizeof(tmpS));
-		Ctx cx; cx.s = &tmpS; cx.w = nullptr; cx.body = nullptr; cx.wheels = nullptr; cx.padLocked = nullptr; cx.misc = nullptr; cx.pl = nullptr; cx.mf = nullptr; cx.solv = nullptr; cx.p = &P; cx.sc = nullptr; cx.arena = 0; cx.ev.buf = nullptr;
+		Ctx cx; cx.s = &tmpS; cx.w = nullptr; cx.epa = nullptr; cx.body = nullptr; cx.wheels = nullptr; cx.padLocked = nullptr; cx.misc = nullptr; cx.pl = nullptr; cx.mf = nullptr; cx.solv = nullptr; cx.p = &P; cx.sc = nullptr; cx.arena = 0; cx.ev.buf = nullptr;
 		for (int bidx = 0; bidx <= n_cars; bidx++) P.motionDisc[bidx] = body_angular_motion_disc(cx, bidx);
 		P.boundRadius[0] = P.ballIsSphere ? P.ballRadiusBT : (sqrtf(P.ballRadiusBT * P.ballRadiusBT + (K::PUCK_HEIGHT * UU_TO_BT / 2) * (K::PUCK_HEIGHT * UU_TO_BT / 2)) + 0.04f);
 		for (int c = 0; c < n_cars; c++) P.boundRadius[c + 1] = len(P.carCfg[c].hitboxHalf) + 0.04f;
@@ -808,6 +809,11 @@ int rsb_batch_create(int device, int game_mode, int n_arenas, int n_cars, const 
 	b->dS = (ArenaS*)dev_alloc(sizeof(ArenaS) * (size_t)n_arenas);
 	b->dW = (ArenaW*)dev_alloc(sizeof(ArenaW) * (size_t)n_arenas);
 	b->dH = (ArenaH*)dev_alloc(sizeof(ArenaH) * (size_t)n_arenas);
+#ifndef RSB_HOSTCHECK
+	b->dE = (EpaScratch*)dev_alloc(sizeof(EpaScratch) * (size_t)b->numSMs * STEP_THREADS);
+#else
+	b->dE = (EpaScratch*)dev_alloc(sizeof(EpaScratch));
+#endif
 	b->eventCap = (uint32_t)std::max(4096, n_arenas * 4);
 	b->dEvents = (EventSink::Ev*)dev_alloc(sizeof(EventSink::Ev) * b->eventCap);
 	b->dEventCount = (uint32_t*)dev_alloc(sizeof(uint32_t));
@@ -827,7 +833,7 @@ int rsb_batch_create(int device, int game_mode, int n_arenas, int n_cars, const 
 		A.ball.rb.basis = m3identity();
 		A.ball.hsCurTargetSpeed = K::HS_INITIAL_TARGET_SPEED;
 		for (int p = 0; p < P.nPads; p++) { A.pads[p].isActive = 1; }
-		Ctx cx; cx.s = &A; cx.w = &tmpW; cx.p = &P; cx.sc = &hsc; cx.arena = a; cx.ev.buf = nullptr;
+		Ctx cx; cx.s = &A; cx.w = &tmpW; cx.epa = nullptr; cx.p = &P; cx.sc = &hsc; cx.arena = a; cx.ev.buf = nullptr;
 		cx.body = tmpH.body; cx.wheels = tmpH.wheels; cx.padLocked = tmpH.padLocked; cx.misc = tmpH.misc; cx.pl = &tmpH.pairs; cx.mf = tmpH.mf; cx.solv = tmpH.solv;
 		for (int c = 0; c < n_cars; c++) {
 			tmpH.body[c + 1].invInertiaLocal = P.carCfg[c].invInertiaLocal;
@@ -862,7 +868,7 @@ int rsb_batch_destroy(RsbBatch* b) {
 #ifndef RSB_HOSTCHECK
 	cudaDeviceSynchronize();
 #endif
-	dev_free(b->dP); dev_free(b->dS); dev_free(b->dW); dev_free(b->dH); dev_free(b->dEvents); dev_free(b->dEventCount); dev_free(b->dCtrl); dev_free(b->dCtrlSeq); dev_free(b->dScratch);
+	dev_free(b->dP); dev_free(b->dS); dev_free(b->dW); dev_free(b->dH); dev_free(b->dE); dev_free(b->dEvents); dev_free(b->dEventCount); dev_free(b->dCtrl); dev_free(b->dCtrlSeq); dev_free(b->dScratch);
 	delete b;
 	API_END
 }
@@ -887,7 +893,7 @@ static EventSink sink_of(RsbBatch* b) { EventSink e; e.buf = b->dEvents; e.count
 
 static void launch_step(RsbBatch* b, int n_ticks, const CtrlS* seq, int nCtrl) {
 	const BatchParams& P = b->hp;
-	StepArgs a; a.S = b->dS; a.H = b->dH; a.W = b->dW; a.P = b->dP;
+	StepArgs a; a.S = b->dS; a.H = b->dH; a.W = b->dW; a.E = b->dE; a.P = b->dP;
 	a.lay = ArenaLayout::make(P.nCars, P.nPads); a.sc = b->dScene; a.ev = sink_of(b);
 	a.nArenas = P.nArenas; a.nTicks = n_ticks; a.ctrlSeq = seq; a.nCtrl = nCtrl; a.apb = 1; a.mirror = (n_ticks == 1) ? 1 : 0;
 #ifndef RSB_HOSTCHECK
@@ -1167,6 +1173,13 @@ int rsb_debug_get_solver_bodies(RsbBatch* b, int arena, float* out, int cap, int
 		}
 	}
 	if (n_out) *n_out = n;
+	API_END
+}
+
+int rsb_debug_get_misc(RsbBatch* b, int arena, int* out4) {
+	API_BEGIN set_device(b);
+	DebugSnap s = debug_snap(b, arena);
+	for (int i = 0; i < 4; i++) out4[i] = s.h[0].misc[i];
 	API_END
 }
 

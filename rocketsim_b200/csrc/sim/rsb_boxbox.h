@@ -5,12 +5,13 @@
 //   bt/BulletCollision/CollisionDispatch/btBoxBoxDetector.cpp:60-767
 // with the matrices held as three row vectors instead of 4-float padded rows.
 #pragma once
+#include <stdio.h>
 #include "rsb_work.h"
 #include "rsb_simplex.h"
 
 namespace rsb {
 
-RSB_HD void add_contact_point(const Ctx& cx, int mi, const V3& normalOnB, const V3& pointInWorld, float depth, int triMesh, int triIndex);
+RSB_ACP_ATTR void add_contact_point(const Ctx& cx, int mi, const V3& normalOnB, const V3& pointInWorld, float depth, int triMesh, int triIndex);
 
 // R[i*4+j] of the ODE code is element (row i, col j); a "column j" walk is R + j with stride 4.
 struct Mat12 { float m[12]; };
@@ -31,38 +32,40 @@ RSB_HD void line_closest_approach(const float* pa, const float* ua, const float*
 	else { d = 1.f / d; *alpha = (q1 + uaub * q2) * d; *beta = (uaub * q1 + q2) * d; }
 }
 
-RSB_HD int intersect_rect_quad2(float h[2], float p[8], float ret[16]) {
+// intersectRectQuad2 (btBoxBoxDetector.cpp:160-215): clip quad p against the rectangle +-h, one half-plane at a time.
+// Written with value copies between the clip stages (the reference ping-pongs two pointers between `ret` and a scratch
+// buffer; data-dependent pointers into local arrays are avoided in device code).
+RSB_HD int intersect_rect_quad2(const float h[2], const float p[8], float ret[16]) {
+	float q[16];
 	int nq = 4, nr = 0;
-	float buffer[16];
-	float* q = p;
-	float* r = ret;
+	for (int i = 0; i < 8; i++) q[i] = p[i];
 	bool done = false;
 	for (int dir = 0; dir <= 1 && !done; dir++) {
 		for (int sign = -1; sign <= 1 && !done; sign += 2) {
-			float* pq = q;
-			float* pr = r;
+			float r[16];
 			nr = 0;
-			for (int i = nq; i > 0; i--) {
-				if (sign * pq[dir] < h[dir]) {
-					pr[0] = pq[0]; pr[1] = pq[1]; pr += 2; nr++;
-					if (nr & 8) { q = r; done = true; break; }
+			for (int i = 0; i < nq; i++) {
+				const float pq0 = q[2 * i], pq1 = q[2 * i + 1];
+				const float pqd = dir ? pq1 : pq0, pqo = dir ? pq0 : pq1;
+				if (sign * pqd < h[dir]) {
+					r[2 * nr] = pq0; r[2 * nr + 1] = pq1; nr++;
+					if (nr & 8) { done = true; break; }
 				}
-				float* nextq = (i > 1) ? pq + 2 : q;
-				if ((sign * pq[dir] < h[dir]) ^ (sign * nextq[dir] < h[dir])) {
-					pr[1 - dir] = pq[1 - dir] + (nextq[1 - dir] - pq[1 - dir]) / (nextq[dir] - pq[dir]) * (sign * h[dir] - pq[dir]);
-					pr[dir] = sign * h[dir];
-					pr += 2; nr++;
-					if (nr & 8) { q = r; done = true; break; }
+				const int ni = (i < nq - 1) ? i + 1 : 0;
+				const float nq0 = q[2 * ni], nq1 = q[2 * ni + 1];
+				const float nqd = dir ? nq1 : nq0, nqo = dir ? nq0 : nq1;
+				if ((sign * pqd < h[dir]) ^ (sign * nqd < h[dir])) {
+					const float vo = pqo + (nqo - pqo) / (nqd - pqd) * (sign * h[dir] - pqd);
+					const float vd = sign * h[dir];
+					r[2 * nr + (1 - dir)] = vo; r[2 * nr + dir] = vd; nr++;
+					if (nr & 8) { done = true; break; }
 				}
-				pq += 2;
 			}
-			if (done) break;
-			q = r;
-			r = (q == ret) ? buffer : ret;
+			for (int i = 0; i < nr * 2; i++) q[i] = r[i];
 			nq = nr;
 		}
 	}
-	if (q != ret) for (int i = 0; i < nr * 2; i++) ret[i] = q[i];
+	for (int i = 0; i < nr * 2; i++) ret[i] = q[i];
 	return nr;
 }
 
@@ -111,7 +114,7 @@ RSB_HD void cull_points2(int n, float p[], int m, int i0, int iret[]) {
 }
 
 // boxes 1/2 = (shape, world transform); manifold mi has body0 = owner of box 1.
-RSB_HD_NOINLINE void box_box(const Ctx& cx, int mi, const Convex& box1, const Xform& xf1, const Convex& box2, const Xform& xf2) {
+RSB_HD void box_box(const Ctx& cx, int mi, const Convex& box1, const Xform& xf1, const Convex& box2, const Xform& xf2) {
 	const float fudge_factor = 1.05f;
 	Mat12 R1m = mat12_from(xf1.basis), R2m = mat12_from(xf2.basis);
 	const float* R1 = R1m.m; const float* R2 = R2m.m;
@@ -121,7 +124,7 @@ RSB_HD_NOINLINE void box_box(const Ctx& cx, int mi, const Convex& box1, const Xf
 	const float side1[3] = {2.f * he1.x, 2.f * he1.y, 2.f * he1.z};
 	const float side2[3] = {2.f * he2.x, 2.f * he2.y, 2.f * he2.z};
 	float p[3], pp[3], normalC[3] = {0.f, 0.f, 0.f};
-	const float* normalR = nullptr;
+	float nsel0 = 0.f, nsel1 = 0.f, nsel2 = 0.f; int haveR = 0;  // the selected face normal = column `norm` of R1/R2 (copied: no pointers into local arrays)
 	float A[3], B[3], R11, R12, R13, R21, R22, R23, R31, R32, R33, Q11, Q12, Q13, Q21, Q22, Q23, Q31, Q32, Q33, s, s2, l;
 	int i, j, invert_normal, code;
 	float normal[3], depth;
@@ -140,7 +143,7 @@ RSB_HD_NOINLINE void box_box(const Ctx& cx, int mi, const Convex& box1, const Xf
 #define RSB_TST(expr1, expr2, norm, cc) \
 	s2 = fabsf(expr1) - (expr2); \
 	if (s2 > 0) return; \
-	if (s2 > s) { s = s2; normalR = norm; invert_normal = ((expr1) < 0); code = (cc); }
+	if (s2 > s) { s = s2; nsel0 = (norm)[0]; nsel1 = (norm)[4]; nsel2 = (norm)[8]; haveR = 1; invert_normal = ((expr1) < 0); code = (cc); }
 	s = -3.402823466e+38f;
 	invert_normal = 0;
 	code = 0;
@@ -158,7 +161,7 @@ RSB_HD_NOINLINE void box_box(const Ctx& cx, int mi, const Convex& box1, const Xf
 	if (l > kEps) { \
 		s2 /= l; \
 		if (s2 * fudge_factor > s) { \
-			s = s2; normalR = nullptr; \
+			s = s2; haveR = 0; \
 			normalC[0] = (n1) / l; normalC[1] = (n2) / l; normalC[2] = (n3) / l; \
 			invert_normal = ((expr1) < 0); code = (cc); \
 		} \
@@ -179,11 +182,12 @@ RSB_HD_NOINLINE void box_box(const Ctx& cx, int mi, const Convex& box1, const Xf
 #undef RSB_TST
 	if (!code) return;
 
-	if (normalR) { normal[0] = normalR[0]; normal[1] = normalR[4]; normal[2] = normalR[8]; }
+	if (haveR) { normal[0] = nsel0; normal[1] = nsel1; normal[2] = nsel2; }
 	else { normal[0] = ddot_pq(R1, normalC, 1, 1); normal[1] = ddot_pq(R1 + 4, normalC, 1, 1); normal[2] = ddot_pq(R1 + 8, normalC, 1, 1); }
 	if (invert_normal) { normal[0] = -normal[0]; normal[1] = -normal[1]; normal[2] = -normal[2]; }
 	depth = -s;
 	const V3 negNormal(-normal[0], -normal[1], -normal[2]);
+	V3 outPts[4]; float outDep[4]; int nOut = 0;  // <= maxc = 4 contacts
 
 	if (code > 6) {
 		float pa[3], pb[3], sign;
@@ -203,13 +207,18 @@ RSB_HD_NOINLINE void box_box(const Ctx& cx, int mi, const Convex& box1, const Xf
 		line_closest_approach(pa, ua, pb, ub, &alpha, &beta);
 		for (i = 0; i < 3; i++) pa[i] += ua[i] * alpha;
 		for (i = 0; i < 3; i++) pb[i] += ub[i] * beta;
-		add_contact_point(cx, mi, negNormal, V3(pb[0], pb[1], pb[2]), -depth, -1, -1);
-		return;
+		outPts[0] = V3(pb[0], pb[1], pb[2]); outDep[0] = -depth; nOut = 1;
+		goto emit;
 	}
+	{
 
-	const float *Ra, *Rb, *pa, *pb, *Sa, *Sb;
-	if (code <= 3) { Ra = R1; Rb = R2; pa = p1; pb = p2; Sa = A; Sb = B; }
-	else { Ra = R2; Rb = R1; pa = p2; pb = p1; Sa = B; Sb = A; }
+	// reference/incident box selected by VALUE (element-wise copies; no data-dependent pointers into local arrays)
+	float Ra[12], Rb[12], pa[3], pb[3], Sa[3], Sb[3];
+	{
+		const bool first = code <= 3;
+		for (i = 0; i < 12; i++) { Ra[i] = first ? R1[i] : R2[i]; Rb[i] = first ? R2[i] : R1[i]; }
+		for (i = 0; i < 3; i++) { pa[i] = first ? p1[i] : p2[i]; pb[i] = first ? p2[i] : p1[i]; Sa[i] = first ? A[i] : B[i]; Sb[i] = first ? B[i] : A[i]; }
+	}
 	float normal2[3], nr[3], anr[3];
 	if (code <= 3) { normal2[0] = normal[0]; normal2[1] = normal[1]; normal2[2] = normal[2]; }
 	else { normal2[0] = -normal[0]; normal2[1] = -normal[1]; normal2[2] = -normal[2]; }
@@ -273,11 +282,9 @@ RSB_HD_NOINLINE void box_box(const Ctx& cx, int mi, const Convex& box1, const Xf
 	if (cnum <= maxc) {
 		for (j = 0; j < cnum; j++) {
 			V3 pw(point[j * 3 + 0] + pa[0], point[j * 3 + 1] + pa[1], point[j * 3 + 2] + pa[2]);
-			if (code < 4) add_contact_point(cx, mi, negNormal, pw, -dep[j], -1, -1);
-			else {
-				V3 pw2(point[j * 3 + 0] + pa[0] - normal[0] * dep[j], point[j * 3 + 1] + pa[1] - normal[1] * dep[j], point[j * 3 + 2] + pa[2] - normal[2] * dep[j]);
-				add_contact_point(cx, mi, negNormal, pw2, -dep[j], -1, -1);
-			}
+			if (code < 4) outPts[nOut] = pw;
+			else outPts[nOut] = V3(point[j * 3 + 0] + pa[0] - normal[0] * dep[j], point[j * 3 + 1] + pa[1] - normal[1] * dep[j], point[j * 3 + 2] + pa[2] - normal[2] * dep[j]);
+			outDep[nOut++] = -dep[j];
 		}
 	} else {
 		int i1 = 0;
@@ -287,10 +294,15 @@ RSB_HD_NOINLINE void box_box(const Ctx& cx, int mi, const Convex& box1, const Xf
 		cull_points2(cnum, ret, maxc, i1, iret);
 		for (j = 0; j < maxc; j++) {
 			V3 posInWorld(point[iret[j] * 3 + 0] + pa[0], point[iret[j] * 3 + 1] + pa[1], point[iret[j] * 3 + 2] + pa[2]);
-			if (code < 4) add_contact_point(cx, mi, negNormal, posInWorld, -dep[iret[j]], -1, -1);
-			else add_contact_point(cx, mi, negNormal, posInWorld - nrm * dep[iret[j]], -dep[iret[j]], -1, -1);
+			if (code < 4) outPts[nOut] = posInWorld;
+			else outPts[nOut] = posInWorld - nrm * dep[iret[j]];
+			outDep[nOut++] = -dep[iret[j]];
 		}
 	}
+	}
+emit:
+	// one call site: the contact hook (Arena::_BulletContactAddedCallback and all it pulls in) is inlined here once
+	for (int k = 0; k < nOut; k++) add_contact_point(cx, mi, negNormal, outPts[k], outDep[k], -1, -1);
 }
 
 }  // namespace rsb

@@ -385,7 +385,7 @@ RSB_HD void on_car_car_collision(const Ctx& cx, int c1, int c2, ContactPt& cp) {
 // btManifoldResult::addContactPoint + gContactAddedCallback.  body0/body1 of the manifold
 // are "A"/"B"; (normalOnB, pointOnB, depth) as reported by the detector.  triMesh/triIndex
 // identify the triangle when B is an arena mesh (else triMesh < 0).
-RSB_HD void add_contact_point(const Ctx& cx, int mi, const V3& normalOnB, const V3& pointInWorld, float depth, int triMesh, int triIndex) {
+RSB_ACP_ATTR void add_contact_point(const Ctx& cx, int mi, const V3& normalOnB, const V3& pointInWorld, float depth, int triMesh, int triIndex) {
 	Manifold& m = cx.mf[mi];
 	if (depth > m.breakingThresh) return;
 	ContactPt pt;

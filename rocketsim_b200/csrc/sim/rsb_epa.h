@@ -146,7 +146,7 @@ RSB_HD void gjk2_getsupport(const Mink& sh, const V3& d, SV& sv) { sv.d = d / le
 RSB_HD void gjk2_append(const Mink& sh, Simplex2& s, const V3& v) { s.p[s.rank] = 0.f; gjk2_getsupport(sh, v, s.c[s.rank]); s.rank++; }
 
 // GJK::Evaluate (btGjkEpa2.cpp:198-340)
-RSB_HD_NOINLINE int gjk2_evaluate(Gjk2& g, const V3& guess) {
+RSB_HD_NOINLINE int gjk2_evaluate(Gjk2& g, V3 guess) {
 	unsigned iterations = 0;
 	float sqdist = 0.f, alpha = 0.f;
 	V3 lastw[4];
@@ -386,7 +386,7 @@ RSB_HD bool epa_expand(Epa& e, unsigned pass, int w, int f0, unsigned e0, int& h
 }
 
 // EPA::Evaluate (btGjkEpa2.cpp:645-772)
-RSB_HD_NOINLINE int epa_evaluate(Epa& e, Gjk2& gjk, const V3& guess) {
+RSB_HD_NOINLINE int epa_evaluate(Epa& e, Gjk2& gjk, V3 guess) {
 	EpaScratch& m = *e.m;
 	e.status = EPA_FAILED; e.normal = v3zero(); e.depth = 0.f; e.nextsv = 0;
 	e.hullRoot = -1; e.hullCount = 0; e.stockRoot = -1; e.stockCount = 0;
@@ -460,7 +460,7 @@ RSB_HD_NOINLINE int epa_evaluate(Epa& e, Gjk2& gjk, const V3& guess) {
 }
 
 // btGjkEpaPenetrationDepthSolver::calcPenDepth
-RSB_HD_NOINLINE bool epa_penetration(const Ctx& cx, const Convex& A, const Xform& tA, const Convex& B, const Xform& tB, V3& v, V3& wa, V3& wb) {
+RSB_HD_NOINLINE bool epa_penetration(const Ctx& cx, Convex A, Xform tA, Convex B, Xform tB, V3& v, V3& wa, V3& wb) {
 	const V3 guessVectors[9] = {
 		safe_normalized(tB.origin - tA.origin), safe_normalized(tA.origin - tB.origin),
 		V3(0, 0, 1), V3(0, 1, 0), V3(1, 0, 0), V3(1, 1, 0), V3(1, 1, 1), V3(0, 1, 1), V3(1, 0, 1)};
@@ -471,7 +471,7 @@ RSB_HD_NOINLINE bool epa_penetration(const Ctx& cx, const Convex& A, const Xform
 			mink_init(gjk.shape, A, tA, B, tB, true);
 			int st = gjk2_evaluate(gjk, -guess);
 			if (st == G2_INSIDE) {
-				Epa epa; epa.m = &cx.w->epa;
+				Epa epa; epa.m = cx.epa;
 				int es = epa_evaluate(epa, gjk, -guess);
 				if (es != EPA_FAILED) {
 					V3 w0 = v3zero();

@@ -11,7 +11,7 @@
 
 namespace rsb {
 
-RSB_HD void add_contact_point(const Ctx& cx, int mi, const V3& normalOnB, const V3& pointInWorld, float depth, int triMesh, int triIndex);
+RSB_ACP_ATTR void add_contact_point(const Ctx& cx, int mi, const V3& normalOnB, const V3& pointInWorld, float depth, int triMesh, int triIndex);
 RSB_HD void transform_aabb_he(const V3& he, float margin, const M3& basis, const V3& origin, V3& mn, V3& mx);
 RSB_HD void transform_aabb_mm(const V3& lmin, const V3& lmax, float margin, const M3& basis, const V3& origin, V3& mn, V3& mx);
 
@@ -40,10 +40,12 @@ RSB_HD V3 convex_aabb_center(const Ctx& cx, const Convex& s, const Xform& t) {
 	return (mx + mn) * 0.5f;
 }
 
-RSB_HD_NOINLINE bool epa_penetration(const Ctx& cx, const Convex& A, const Xform& tA, const Convex& B, const Xform& tB, V3& v, V3& wa, V3& wb);
+// (out-of-line functions take their read-only aggregates BY VALUE: with nvcc 12.9 a caller-local object whose last use
+// is being passed by reference to a __noinline__ callee can share its stack slot with the callee's own locals)
+RSB_HD_NOINLINE bool epa_penetration(const Ctx& cx, Convex A, Xform tA, Convex B, Xform tB, V3& v, V3& wa, V3& wb);
 
 // GJK closest points + addContactPoint.  A/B with world transforms; triMesh/triIndex forwarded.
-RSB_HD_NOINLINE void convex_convex(const Ctx& cx, int mi, const Convex& A, const Xform& xfA, const Convex& B, const Xform& xfB, int triMesh, int triIndex) {
+RSB_HD_NOINLINE void convex_convex(const Ctx& cx, int mi, Convex A, Xform xfA, Convex B, Xform xfB, int triMesh, int triIndex) {
 	const float breaking = cx.mf[mi].breakingThresh;
 	float maxDist2 = A.margin + B.margin + breaking;
 	maxDist2 *= maxDist2;

@@ -19,6 +19,12 @@
 #define RSB_HD inline
 #define RSB_HD_NOINLINE
 #endif
+// A/B switch (developer): -DRSB_ACP_NOINLINE makes the contact-add hook one out-of-line function (miscompiles with nvcc 12.9: car-car contacts vanish)
+#if !defined(RSB_ACP_NOINLINE)
+#define RSB_ACP_ATTR RSB_HD
+#else
+#define RSB_ACP_ATTR RSB_HD_NOINLINE
+#endif
 
 namespace rsb {
 

@@ -121,7 +121,6 @@ struct ArenaW {
 	ContactPt points[MAX_POINTS];
 	SolverRow rows[MAX_ROWS];    // overflow beyond SOLVER_ROWS_FAST (indexed like the full pool)
 	SolverRow frows[MAX_ROWS];
-	EpaScratch epa;
 };
 
 struct EventSink {
@@ -141,6 +140,7 @@ struct Ctx {
 	Manifold* mf;
 	unsigned char* solv;  // solver scratch (see SolverView)
 	ArenaW* w;
+	EpaScratch* epa;   // EPA working set of the EXECUTING THREAD (several bodies of one arena may run EPA concurrently)
 	const BatchParams* p;
 	const Scene* sc;
 	EventSink ev;
@@ -168,7 +168,7 @@ RSB_HD void set_error(const Ctx& cx, uint32_t flag) {
 #if defined(__CUDA_ARCH__)
 	atomicOr(&cx.s->errorFlags, flag);
 #else
-	set_error(cx, flag);
+	cx.s->errorFlags |= flag;
 #endif
 }
 
