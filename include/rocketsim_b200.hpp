@@ -1,0 +1,237 @@
+// rocketsim_b200.hpp -- header-only C++ front end over the C ABI (rsb_c_api.h), in the reference's vocabulary.
+//
+// Mirrors the part of RocketSim's public C++ surface that sits on the Arena::Step path:
+//
+//   RocketSim::Init / InitFromMem        src/RocketSim.h:27,32            -> RocketSimB200::Init / InitFromMem
+//   Arena::Create / AddCar / GetCar      src/Sim/Arena/Arena.h:111,71,82  -> Arena::Create / AddCar / GetCar
+//   Arena::Step / IsBallScored           Arena.h:132,144                  -> Arena::Step / IsBallScored
+//   Arena::ResetToRandomKickoff          Arena.h (Arena.cpp:113-223)      -> Arena::ResetToRandomKickoff
+//   Arena::Set/GetMutatorConfig          Arena.h:52-53                    -> same names
+//   SetGoalScoreCallback / SetCarBumpCallback  Arena.h:24-25,102,108      -> same names, dispatched after Step() from the event buffer
+//   Car::controls / GetState / SetState  src/Sim/Car/Car.h:149-152        -> same names
+//   Ball::GetState / SetState            src/Sim/Ball/Ball.h:68-69        -> same names
+//   tickCount, tickTime, GetTickRate()   Arena.h:56-64                    -> same names
+//
+// plus ArenaBatch, the batched front end (N identical arenas advanced in lockstep by one CUDA launch).  A facade
+// `Arena` is an ArenaBatch of one arena.  All compute happens in librsb.so on the GPU; there is no CPU path, and
+// errors surface as std::runtime_error like the reference's RS_ERR_CLOSE (src/Framework.h:67-72).
+//
+// Differences from the reference, by construction of the batched design:
+//   * cars are fixed at the first Step/GetState/SetState of an arena (the device record is sized then): AddCar after
+//     that throws, and RemoveCar is not offered;
+//   * callbacks run on the calling thread right after Step() returns the events of the stepped ticks (the reference
+//     calls them from inside the tick); with Step(n > 1) they arrive in tick order after the n ticks;
+//   * ArenaConfig is the default one only.
+#pragma once
+
+#include <cstdint>
+#include <cstring>
+#include <fstream>
+#include <functional>
+#include <map>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "rsb_c_api.h"
+
+namespace RocketSimB200 {
+
+using Vec = RsbVec;
+using RotMat = RsbRotMat;
+using CarControls = RsbCarControls;
+using CarState = RsbCarState;
+using BallState = RsbBallState;
+using BallHitInfo = RsbBallHitInfo;
+using MutatorConfig = RsbMutatorConfig;
+using CarConfig = RsbCarConfig;
+using BoostPadState = RsbBoostPadState;
+
+enum class GameMode : uint8_t { SOCCAR = 0, HOOPS = 1, HEATSEEKER = 2, SNOWDAY = 3, DROPSHOT = 4, THE_VOID = 5 };
+enum class Team : uint8_t { BLUE = 0, ORANGE = 1 };
+
+inline void Check(int rc) { if (rc != 0) throw std::runtime_error(std::string("RocketSimB200: ") + rsb_last_error()); }
+
+inline CarConfig CarConfigPreset(int preset) { CarConfig c; Check(rsb_car_config_preset(preset, &c)); return c; }
+inline const CarConfig& CAR_CONFIG_OCTANE_() { static const CarConfig c = CarConfigPreset(RSB_CAR_OCTANE); return c; }
+#define RSB200_CAR_CONFIG(name) inline const CarConfig& CAR_CONFIG_##name() { static const CarConfig c = CarConfigPreset(RSB_CAR_##name); return c; }
+RSB200_CAR_CONFIG(OCTANE) RSB200_CAR_CONFIG(DOMINUS) RSB200_CAR_CONFIG(PLANK) RSB200_CAR_CONFIG(BREAKOUT)
+RSB200_CAR_CONFIG(HYBRID) RSB200_CAR_CONFIG(MERC) RSB200_CAR_CONFIG(PSYCLOPS)
+#undef RSB200_CAR_CONFIG
+
+inline MutatorConfig DefaultMutatorConfig(GameMode mode) { MutatorConfig m; Check(rsb_default_mutator_config((int)mode, &m)); return m; }
+
+// RocketSim::InitFromMem (src/RocketSim.cpp:92-185): .cmf bytes per game mode.
+inline void InitFromMem(const std::map<GameMode, std::vector<std::vector<uint8_t>>>& meshFilesMap, bool /*silent*/ = false) {
+	std::vector<int> modes; std::vector<const uint8_t*> ptrs; std::vector<size_t> sizes;
+	for (auto& kv : meshFilesMap)
+		for (auto& f : kv.second) { modes.push_back((int)kv.first); ptrs.push_back(f.data()); sizes.push_back(f.size()); }
+	Check(rsb_init_from_mem((int)modes.size(), modes.data(), ptrs.data(), sizes.data()));
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// ArenaBatch: N identical arenas (same mode, same car slots) on one GPU.
+class ArenaBatch {
+public:
+	ArenaBatch(GameMode mode, int numArenas, const std::vector<Team>& teams, const std::vector<CarConfig>& configs = {},
+	           const MutatorConfig* mutator = nullptr, float tickRate = 120.f, uint32_t seed = 0, int device = 0)
+		: gameMode(mode), numArenas(numArenas), numCars((int)teams.size()) {
+		std::vector<int> t; for (Team x : teams) t.push_back((int)x);
+		if (!configs.empty() && configs.size() != teams.size()) throw std::runtime_error("RocketSimB200: one CarConfig per car slot expected");
+		Check(rsb_batch_create(device, (int)mode, numArenas, numCars, t.data(), configs.empty() ? nullptr : configs.data(), mutator, tickRate, seed, &h_));
+		Check(rsb_batch_info(h_, nullptr, nullptr, &numPads, nullptr));
+	}
+	~ArenaBatch() { if (h_) rsb_batch_destroy(h_); }
+	ArenaBatch(const ArenaBatch&) = delete;
+	ArenaBatch& operator=(const ArenaBatch&) = delete;
+
+	// `car->controls = ...` for every car: controls is [numArenas][numCars]
+	void SetControls(const CarControls* controls) { Check(rsb_set_controls(h_, controls)); }
+	void Step(int ticksToSimulate = 1) { Check(rsb_step(h_, ticksToSimulate)); }
+	// for t: controls = seq[t]; Step(1)  -- one launch; seq is [nTicks][numArenas][numCars]
+	void StepWithControls(const CarControls* seq, int nTicks) { Check(rsb_step_with_controls(h_, seq, nTicks)); }
+	void Sync() { Check(rsb_sync(h_)); }
+	void SetStream(void* cudaStream) { Check(rsb_set_stream(h_, cudaStream)); }
+
+	std::vector<CarState> GetCarStates() { std::vector<CarState> v((size_t)numArenas * numCars); if (!v.empty()) Check(rsb_get_car_states(h_, v.data())); return v; }
+	std::vector<BallState> GetBallStates() { std::vector<BallState> v(numArenas); Check(rsb_get_ball_states(h_, v.data())); return v; }
+	std::vector<BoostPadState> GetPadStates() { std::vector<BoostPadState> v((size_t)numArenas * numPads); if (!v.empty()) Check(rsb_get_pad_states(h_, v.data())); return v; }
+	void SetCarState(uint32_t arena, uint32_t carSlot, const CarState& s) { Check(rsb_set_car_states(h_, &arena, &carSlot, 1, &s)); }
+	void SetBallState(uint32_t arena, const BallState& s) { Check(rsb_set_ball_states(h_, &arena, 1, &s)); }
+	std::vector<uint64_t> GetTickCounts() { std::vector<uint64_t> v(numArenas); Check(rsb_get_tick_counts(h_, v.data())); return v; }
+	std::vector<uint8_t> IsBallScored() { std::vector<uint8_t> v(numArenas); Check(rsb_is_ball_scored(h_, v.data())); return v; }
+	std::vector<RsbEvent> GetEvents(int cap = 65536) { std::vector<RsbEvent> v(cap); int n = 0; Check(rsb_get_events(h_, v.data(), cap, &n)); v.resize(n); return v; }
+	std::vector<uint32_t> GetErrorFlags() { std::vector<uint32_t> v(numArenas); Check(rsb_get_error_flags(h_, v.data())); return v; }
+	// Arena::ResetToRandomKickoff(seed) for every arena (seeds[a]) or for the listed ones
+	void ResetToRandomKickoff(const std::vector<int32_t>& seeds, const std::vector<uint32_t>* arenas = nullptr) {
+		Check(rsb_reset_to_random_kickoff(h_, arenas ? arenas->data() : nullptr, arenas ? (int)arenas->size() : numArenas, seeds.data()));
+	}
+	void SetAutoReset(bool enable, uint32_t seed) { Check(rsb_set_auto_reset(h_, enable ? 1 : 0, seed)); }
+	RsbBatch* Handle() { return h_; }
+
+	const GameMode gameMode;
+	const int numArenas, numCars;
+	int numPads = 0;
+
+private:
+	RsbBatch* h_ = nullptr;
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// Single-arena facade with the reference's object model.
+class Arena;
+
+class Car {
+public:
+	CarControls controls = {};          // Car::controls (Car.h:149)
+	uint32_t id = 0;                    // 1-based, AddCar order (Arena.cpp:64-78)
+	Team team = Team::BLUE;
+	CarConfig config = {};
+	CarState GetState();                // Car::GetState (Car.cpp:10-20)
+	void SetState(const CarState& s);   // Car::SetState (Car.cpp:23-36)
+private:
+	friend class Arena;
+	Arena* arena_ = nullptr;
+};
+
+class Ball {
+public:
+	BallState GetState();               // Ball::GetState (Ball.cpp:27-37)
+	void SetState(const BallState& s);  // Ball::SetState (Ball.cpp:39-51)
+private:
+	friend class Arena;
+	Arena* arena_ = nullptr;
+};
+
+typedef std::function<void(Arena* arena, Team scoringTeam, void* userInfo)> GoalScoreEventFn;
+typedef std::function<void(Arena* arena, Car* bumper, Car* victim, bool isDemo, void* userInfo)> CarBumpEventFn;
+
+class Arena {
+public:
+	GameMode gameMode;
+	Ball* ball;
+	float tickTime;
+	uint64_t tickCount = 0;
+	float GetTickRate() const { return 1 / tickTime; }
+
+	// Arena::Create (Arena.h:111).  The caller deletes the arena, as in the reference.
+	static Arena* Create(GameMode gameMode, float tickRate = 120, int device = 0, uint32_t rngSeed = 0) {
+		if (!(tickRate >= 15 && tickRate <= 120)) throw std::runtime_error("RocketSimB200: Tickrate must be from 15 to 120tps");
+		return new Arena(gameMode, tickRate, device, rngSeed);
+	}
+	~Arena() { delete ball; for (Car* c : cars_) delete c; }
+	Arena(const Arena&) = delete;
+	Arena& operator=(const Arena&) = delete;
+
+	Car* AddCar(Team team, const CarConfig& config = CAR_CONFIG_OCTANE()) {
+		if (batch_) throw std::runtime_error("RocketSimB200: AddCar after the arena's first Step/GetState/SetState is not supported by the batched back end");
+		Car* c = new Car(); c->id = (uint32_t)cars_.size() + 1; c->team = team; c->config = config; c->arena_ = this;
+		cars_.push_back(c);
+		return c;
+	}
+	Car* GetCar(uint32_t id) { return (id >= 1 && id <= cars_.size()) ? cars_[id - 1] : nullptr; }
+	const std::vector<Car*>& GetCars() const { return cars_; }
+
+	const MutatorConfig& GetMutatorConfig() { return mutator_; }
+	void SetMutatorConfig(const MutatorConfig& m) {
+		if (batch_) throw std::runtime_error("RocketSimB200: SetMutatorConfig after the arena's first Step is not supported by the batched back end");
+		mutator_ = m;
+	}
+	void SetGoalScoreCallback(GoalScoreEventFn fn, void* userInfo = nullptr) { goalFn_ = fn; goalInfo_ = userInfo; }
+	void SetCarBumpCallback(CarBumpEventFn fn, void* userInfo = nullptr) { bumpFn_ = fn; bumpInfo_ = userInfo; }
+
+	// Arena::Step (Arena.cpp:689-756): uploads every car's `controls`, advances n ticks in one launch, dispatches callbacks.
+	void Step(int ticksToSimulate = 1) {
+		Realize();
+		std::vector<CarControls> c; for (Car* car : cars_) c.push_back(car->controls);
+		if (!c.empty()) batch_->SetControls(c.data());
+		batch_->Step(ticksToSimulate);
+		tickCount += (uint64_t)ticksToSimulate;
+		for (const RsbEvent& e : batch_->GetEvents(4096)) {
+			if (e.type == RSB_EVENT_GOAL) { if (goalFn_) goalFn_(this, (Team)e.a, goalInfo_); }
+			else if (bumpFn_) bumpFn_(this, GetCar(e.a), GetCar(e.b), e.type == RSB_EVENT_DEMO, bumpInfo_);
+		}
+	}
+	void ResetToRandomKickoff(int seed = -1) { Realize(); batch_->ResetToRandomKickoff({(int32_t)seed}); }
+	bool IsBallScored() { Realize(); return batch_->IsBallScored()[0] != 0; }
+	ArenaBatch& Batch() { Realize(); return *batch_; }
+
+private:
+	friend class Car;
+	friend class Ball;
+	Arena(GameMode mode, float tickRate, int device, uint32_t seed)
+		: gameMode(mode), ball(new Ball()), tickTime(1 / tickRate), mutator_(DefaultMutatorConfig(mode)), device_(device), seed_(seed) { ball->arena_ = this; }
+	void Realize() {
+		if (batch_) return;
+		std::vector<Team> teams; std::vector<CarConfig> cfgs;
+		for (Car* c : cars_) { teams.push_back(c->team); cfgs.push_back(c->config); }
+		batch_.reset(new ArenaBatch(gameMode, 1, teams, cfgs, &mutator_, 1 / tickTime, seed_, device_));
+	}
+	std::vector<Car*> cars_;
+	std::unique_ptr<ArenaBatch> batch_;
+	MutatorConfig mutator_;
+	GoalScoreEventFn goalFn_; void* goalInfo_ = nullptr;
+	CarBumpEventFn bumpFn_; void* bumpInfo_ = nullptr;
+	int device_; uint32_t seed_;
+};
+
+inline CarState Car::GetState() { return arena_->Batch().GetCarStates()[id - 1]; }
+inline void Car::SetState(const CarState& s) { arena_->Batch().SetCarState(0, id - 1, s); }
+inline BallState Ball::GetState() { return arena_->Batch().GetBallStates()[0]; }
+inline void Ball::SetState(const BallState& s) { arena_->Batch().SetBallState(0, s); }
+
+// RocketSim::Init (src/RocketSim.cpp:55-90): reads every *.cmf listed in <folder>/<mode>/index.txt-less directory scan is not
+// portable in a header; callers pass the file lists explicitly.
+inline std::vector<uint8_t> ReadFile(const std::string& path) {
+	std::ifstream f(path, std::ios::binary);
+	if (!f) throw std::runtime_error("RocketSimB200: cannot read " + path);
+	return std::vector<uint8_t>((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+}
+inline void Init(const std::map<GameMode, std::vector<std::string>>& meshPaths, bool silent = false) {
+	std::map<GameMode, std::vector<std::vector<uint8_t>>> files;
+	for (auto& kv : meshPaths) for (auto& p : kv.second) files[kv.first].push_back(ReadFile(p));
+	InitFromMem(files, silent);
+}
+
+}  // namespace RocketSimB200

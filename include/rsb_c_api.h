@@ -35,6 +35,11 @@ int rsb_sizeof(const char* type_name);
  * n_meshes == 0 is valid (THE_VOID only).  Idempotent like the reference. */
 int rsb_init_from_mem(int n_meshes, const int* mesh_modes, const uint8_t* const* mesh_ptrs, const size_t* mesh_sizes);
 
+/* The reference's constant tables: CAR_CONFIG_OCTANE ... CAR_CONFIG_PSYCLOPS (src/Sim/Car/CarConfig/CarConfig.cpp:20-100,
+ * preset = RSB_CAR_*) and MutatorConfig(GameMode) (src/Sim/MutatorConfig/MutatorConfig.cpp:5-40). Host only, no device needed. */
+int rsb_car_config_preset(int preset, RsbCarConfig* out);
+int rsb_default_mutator_config(int game_mode, RsbMutatorConfig* out);
+
 /* Replaces Arena::Create + n_cars x Arena::AddCar (src/Sim/Arena/Arena.h:111,71;
  * Arena.cpp:416-544, 50-62) for n_arenas identical arenas on CUDA device `device`.
  * teams[i] / car_configs[i] describe car slot i (car id = i + 1, the reference's ++_lastCarID).

@@ -127,6 +127,11 @@ struct RsbBatch {
 	void* dScratch = nullptr;      // staging for get/set
 	size_t scratchBytes = 0;
 	stream_t stream = 0;
+#ifndef RSB_HOSTCHECK
+	cudaStream_t copyStream = nullptr;   // H2D of control-sequence chunks, overlapped with the previous chunk's launch
+	cudaEvent_t chunkReady[8] = {};      // chunk c of the sequence has landed in dCtrlSeq
+	cudaEvent_t seqFree = nullptr;       // every launch that reads dCtrlSeq has finished
+#endif
 	int numSMs = 1;
 	size_t smemBudget = 0;
 	void ensure_scratch(size_t n) { if (n > scratchBytes) { dev_free(dScratch); dScratch = dev_alloc(n); scratchBytes = n; } }
@@ -236,7 +241,10 @@ static thread_local int g_hostIdx = 0;
 // with __syncthreads().  All warps of an SM therefore run the same phase code at the same time
 // (one instruction-cache working set), suspension rays / car logic / body integration use one
 // thread per wheel / car / body, and HBM sees each arena record once per launch in and once out.
-constexpr int STEP_THREADS = 256;
+#ifndef RSB_STEP_THREADS
+#define RSB_STEP_THREADS 256
+#endif
+constexpr int STEP_THREADS = RSB_STEP_THREADS;
 static_assert(offsetof(ArenaS, cars) % 8 == 0 && sizeof(CarS) % 8 == 0 && sizeof(BodyW) % 8 == 0 && sizeof(WheelW) % 8 == 0 && sizeof(Manifold) % 8 == 0, "records are staged in 8-byte words");
 constexpr size_t SMEM_P_BYTES = (sizeof(BatchParams) + 15) & ~(size_t)15;
 constexpr size_t SMEM_SC_BYTES = (sizeof(Scene) + 15) & ~(size_t)15;
@@ -680,19 +688,27 @@ static void fill_ball(int mode, BatchParams& P) {
 	P.ballInvInertiaLocal = V3(inertia.x != 0.f ? 1.f / inertia.x : 0.f, inertia.y != 0.f ? 1.f / inertia.y : 0.f, inertia.z != 0.f ? 1.f / inertia.z : 0.f);
 }
 
-static const RsbCarConfig& preset_octane() {
-	static RsbCarConfig c;
-	static bool init = false;
-	if (!init) {
-		memset(&c, 0, sizeof(c));
-		c.hitboxSize = RsbVec{120.507f, 86.6994f, 38.6591f, 0}; c.hitboxPosOffset = RsbVec{13.8757f, 0, 20.755f, 0};
-		c.frontWheels.wheelRadius = 12.50f; c.frontWheels.suspensionRestLength = 38.755f; c.frontWheels.connectionPointOffset = RsbVec{51.25f, 25.90f, 20.755f, 0};
-		c.backWheels.wheelRadius = 15.00f; c.backWheels.suspensionRestLength = 37.055f; c.backWheels.connectionPointOffset = RsbVec{-33.75f, 29.50f, 20.755f, 0};
-		c.threeWheels = 0; c.dodgeDeadzone = 0.5f;
-		init = true;
-	}
+// The seven hitbox / wheel presets (values of src/Sim/Car/CarConfig/CarConfig.cpp:20-100; order = RSB_CAR_*).
+struct PresetRow { float size[3], off[3], fr, br, fs, bs, fo[3], bo[3]; int three; };
+static const PresetRow CAR_PRESETS[7] = {
+	{{120.507f, 86.6994f, 38.6591f}, {13.8757f, 0, 20.755f}, 12.50f, 15.00f, 38.755f, 37.055f, {51.25f, 25.90f, 20.755f}, {-33.75f, 29.50f, 20.755f}, 0},    // OCTANE
+	{{130.427f, 85.7799f, 33.8f}, {9.f, 0, 15.75f}, 12.00f, 13.50f, 33.95f, 33.85f, {50.30f, 31.10f, 15.75f}, {-34.75f, 33.00f, 15.75f}, 0},                // DOMINUS
+	{{131.32f, 87.1704f, 31.8944f}, {9.00857f, 0, 12.0942f}, 12.50f, 17.00f, 31.9242f, 27.9242f, {49.97f, 27.80f, 12.0942f}, {-35.43f, 20.28f, 12.0942f}, 0}, // PLANK
+	{{133.992f, 83.021f, 32.8f}, {12.5f, 0, 11.75f}, 13.50f, 15.00f, 29.7f, 29.666f, {51.50f, 26.67f, 11.75f}, {-35.75f, 35.00f, 11.75f}, 0},               // BREAKOUT
+	{{129.519f, 84.6879f, 36.6591f}, {13.8757f, 0, 20.755f}, 12.50f, 15.00f, 38.755f, 37.055f, {51.25f, 25.90f, 20.755f}, {-34.00f, 29.50f, 20.755f}, 0},   // HYBRID
+	{{123.22f, 79.2103f, 44.1591f}, {11.3757f, 0, 21.505f}, 15.00f, 15.00f, 39.505f, 39.105f, {51.25f, 25.90f, 21.505f}, {-33.75f, 29.50f, 21.505f}, 0},    // MERC
+	{{120.507f + 0.134f, 86.6994f + 0.134f, 38.6591f + 0.134f}, {13.8757f, 0, 15.0f}, 12.50f, 15.00f, 33.0f, 31.3f, {51.25f, 5.000f, 15.000f}, {-33.75f, 29.50f, 15.000f}, 1},  // PSYCLOPS
+};
+static RsbCarConfig car_preset(int k) {
+	const PresetRow& r = CAR_PRESETS[k];
+	RsbCarConfig c; memset(&c, 0, sizeof(c));
+	c.hitboxSize = RsbVec{r.size[0], r.size[1], r.size[2], 0}; c.hitboxPosOffset = RsbVec{r.off[0], r.off[1], r.off[2], 0};
+	c.frontWheels.wheelRadius = r.fr; c.frontWheels.suspensionRestLength = r.fs; c.frontWheels.connectionPointOffset = RsbVec{r.fo[0], r.fo[1], r.fo[2], 0};
+	c.backWheels.wheelRadius = r.br; c.backWheels.suspensionRestLength = r.bs; c.backWheels.connectionPointOffset = RsbVec{r.bo[0], r.bo[1], r.bo[2], 0};
+	c.threeWheels = (uint8_t)r.three; c.dodgeDeadzone = 0.5f;  // CarConfig.h:36
 	return c;
 }
+static const RsbCarConfig& preset_octane() { static const RsbCarConfig c = car_preset(0); return c; }
 
 // scratch layout for the indexed setters: [arena idx | car idx | payload]
 template <class T>
@@ -731,6 +747,17 @@ int rsb_sizeof(const char* n) {
 	if (s == "RsbBallInternal") return sizeof(RsbBallInternal); if (s == "RsbEvent") return sizeof(RsbEvent);
 	if (s == "ArenaS") return sizeof(ArenaS); if (s == "ArenaW") return sizeof(ArenaW);
 	return -1;
+}
+
+int rsb_car_config_preset(int preset, RsbCarConfig* out) {
+	if (preset < 0 || preset > 6 || !out) return fail("car preset must be 0..6 (RSB_CAR_*)");
+	*out = car_preset(preset);
+	return 0;
+}
+int rsb_default_mutator_config(int game_mode, RsbMutatorConfig* out) {
+	if (game_mode < 0 || game_mode > THE_VOID || !out) return fail("bad game mode");
+	default_mutator(game_mode, *out);
+	return 0;
 }
 
 int rsb_init_from_mem(int n_meshes, const int* mesh_modes, const uint8_t* const* mesh_ptrs, const size_t* mesh_sizes) {
@@ -868,6 +895,9 @@ int rsb_batch_destroy(RsbBatch* b) {
 #ifndef RSB_HOSTCHECK
 	cudaDeviceSynchronize();
 #endif
+#ifndef RSB_HOSTCHECK
+	if (b->copyStream) { cudaStreamDestroy(b->copyStream); for (auto& e : b->chunkReady) cudaEventDestroy(e); cudaEventDestroy(b->seqFree); }
+#endif
 	dev_free(b->dP); dev_free(b->dS); dev_free(b->dW); dev_free(b->dH); dev_free(b->dE); dev_free(b->dEvents); dev_free(b->dEventCount); dev_free(b->dCtrl); dev_free(b->dCtrlSeq); dev_free(b->dScratch);
 	delete b;
 	API_END
@@ -951,8 +981,36 @@ int rsb_step_with_controls(RsbBatch* b, const RsbCarControls* seq, int n_ticks) 
 	static_assert(sizeof(CtrlS) == sizeof(RsbCarControls), "control layouts must match");
 	size_t n = (size_t)n_ticks * b->hp.nArenas * b->hp.nCars;
 	if (n > b->ctrlSeqCap) { dev_free(b->dCtrlSeq); b->dCtrlSeq = (CtrlS*)dev_alloc(n * sizeof(CtrlS)); b->ctrlSeqCap = n; }
+#ifndef RSB_HOSTCHECK
+	// Pipeline: the sequence goes up in <= 8 chunks on a copy stream while the step stream already runs the ticks of the
+	// chunks that have landed, so only the first chunk's copy is exposed.
+	const size_t perTick = (size_t)b->hp.nArenas * b->hp.nCars;
+	const int nChunks = n_ticks >= 16 ? 8 : 1;
+	if (!b->copyStream) {
+		CUDA_OK(cudaStreamCreateWithFlags(&b->copyStream, cudaStreamNonBlocking));
+		for (auto& e : b->chunkReady) CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+		CUDA_OK(cudaEventCreateWithFlags(&b->seqFree, cudaEventDisableTiming));
+	}
+	CUDA_OK(cudaEventRecord(b->seqFree, b->stream));           // earlier launches may still read the staging buffer
+	CUDA_OK(cudaStreamWaitEvent(b->copyStream, b->seqFree, 0));
+	int t0 = 0;
+	for (int c = 0; c < nChunks; c++) {
+		const int t1 = (int)((long long)n_ticks * (c + 1) / nChunks);
+		if (t1 > t0) CUDA_OK(cudaMemcpyAsync(b->dCtrlSeq + t0 * perTick, seq + t0 * perTick, (size_t)(t1 - t0) * perTick * sizeof(CtrlS), cudaMemcpyHostToDevice, b->copyStream));
+		CUDA_OK(cudaEventRecord(b->chunkReady[c], b->copyStream));
+		t0 = t1;
+	}
+	t0 = 0;
+	for (int c = 0; c < nChunks; c++) {
+		const int t1 = (int)((long long)n_ticks * (c + 1) / nChunks);
+		CUDA_OK(cudaStreamWaitEvent(b->stream, b->chunkReady[c], 0));
+		if (t1 > t0) launch_step(b, t1 - t0, b->dCtrlSeq + t0 * perTick, t1 - t0);
+		t0 = t1;
+	}
+#else
 	h2d(b->dCtrlSeq, seq, n * sizeof(CtrlS), b->stream);
 	launch_step(b, n_ticks, b->dCtrlSeq, n_ticks);
+#endif
 	API_END
 }
 int rsb_set_auto_reset(RsbBatch* b, int enable, uint32_t seed) {

@@ -157,7 +157,10 @@ RSB_HD void wheel_trace(const Ctx& cx, int ci, int wi) {
 				float rel_vel = dot(hit.normal, vel);
 				float restitution = 0.f * -rel_vel;
 				const float erp = 0.2f;  // btContactSolverInfo::m_erp
-				float positionalError = erp * -wheelTraceDistDelta / cx.p->dt;
+				// solverInfo.m_timeStep is only written inside stepSimulation (btDiscreteDynamicsWorld.cpp:417): on an arena's
+				// very first tick it still holds the constructor default 1/60 (btContactSolverInfo.h:82)
+				const float solverTimeStep = (cx.s->tickCount == 0) ? (1.f / 60.f) : cx.p->dt;
+				float positionalError = erp * -wheelTraceDistDelta / solverTimeStep;
 				float velocityError = -(1.0f + restitution) * rel_vel;
 				float denom0 = impulse_denominator(rb, bw, hit.point, hit.normal);
 				float denom1 = 0.f;

@@ -304,3 +304,19 @@ def replay_record(rec, lib, n_arenas=1, ticks=None, tol=1e-4):
     n_ill = int(np.sum(rec["wheel_on_dynamic"][:T_])) if "wheel_on_dynamic" in rec else 0
     return dict(worst=worst, worst_illcond=worst_ill, n_illcond=n_ill, discrete_mismatches=mism, ticks=T_, events=my_events,
                 error_flags=int(err.max()))
+
+
+def struct_equal(a, b) -> bool:
+    """Bit-exact equality of two structured arrays over their NAMED fields (padding bytes are unspecified: the compiler may
+    widen a field store over them)."""
+    a, b = np.asarray(a), np.asarray(b)
+    if a.shape != b.shape or a.dtype.names != b.dtype.names:
+        return False
+    if a.dtype.names is None:
+        return a.dtype == b.dtype and a.tobytes() == b.tobytes()
+    for name in a.dtype.names:
+        if name.startswith("_pad"):
+            continue
+        if not struct_equal(np.ascontiguousarray(a[name]), np.ascontiguousarray(b[name])):
+            return False
+    return True
