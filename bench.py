@@ -200,10 +200,17 @@ def run_cuda(args):
     ticks_done = batch.get_tick_counts()
     assert int(ticks_done.min()) == n_steps_total * TPS, "tick counter mismatch: work was skipped"
 
-    # ---- end-to-end arm through the C ABI with host buffers
-    h_seq = [torch.empty(ctrl_bytes, dtype=torch.uint8).pin_memory() for _ in range(args.steps)]
-    for k in range(args.steps):
-        h_seq[k].copy_(d_seq[args.warmup + k])
+    # ---- end-to-end arm through the C ABI with host buffers.  A FRESH batch with the same seeds, warmed up the same way,
+    # so that both arms cover the same tick window [W*TPS, (W+K)*TPS) of the same games (the cost of a tick depends on how
+    # far the games have developed).
+    h_seq = [torch.empty(ctrl_bytes, dtype=torch.uint8).pin_memory() for _ in range(n_steps_total)]
+    for k in range(n_steps_total):
+        h_seq[k].copy_(d_seq[k])
+    batch.close()
+    batch = ArenaBatch(args.mode, A, teams, seed=SEED + rank * A, device=local_rank, lib=L)
+    batch.set_stream(stream.cuda_stream)
+    batch.reset_to_random_kickoff(seeds)
+    batch.set_auto_reset(True, SEED + rank * A)
     # result buffers in PINNED host memory (what a training loop would hand in): numpy views over torch pinned tensors
     car_pin = torch.empty(A * n_cars * T.CarState.itemsize, dtype=torch.uint8).pin_memory()
     ball_pin = torch.empty(A * T.BallState.itemsize, dtype=torch.uint8).pin_memory()
@@ -216,14 +223,14 @@ def run_cuda(args):
         rlib.check(L, L.rsb_get_car_states(batch.h, rlib.ptr(car_out)))
         rlib.check(L, L.rsb_get_ball_states(batch.h, rlib.ptr(ball_out)))
 
-    for k in range(min(3, args.steps)):
+    for k in range(args.warmup):
         step_e2e(k)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     t_host0 = time.perf_counter()
     for k in range(args.steps):
-        step_e2e(k)
+        step_e2e(args.warmup + k)
     e1.record(stream)
     barrier()
     t_host1 = time.perf_counter()  # after the barrier: every copy has landed

@@ -245,10 +245,15 @@ static thread_local int g_hostIdx = 0;
 #define RSB_STEP_THREADS 256
 #endif
 constexpr int STEP_THREADS = RSB_STEP_THREADS;
+// resident blocks per SM: each block keeps its own chunk of arenas; blocks drift through the tick phases independently
+#ifndef RSB_BLOCKS_PER_SM
+#define RSB_BLOCKS_PER_SM 1
+#endif
+constexpr int BLOCKS_PER_SM = RSB_BLOCKS_PER_SM;
 static_assert(offsetof(ArenaS, cars) % 8 == 0 && sizeof(CarS) % 8 == 0 && sizeof(BodyW) % 8 == 0 && sizeof(WheelW) % 8 == 0 && sizeof(Manifold) % 8 == 0, "records are staged in 8-byte words");
 constexpr size_t SMEM_P_BYTES = (sizeof(BatchParams) + 15) & ~(size_t)15;
 constexpr size_t SMEM_SC_BYTES = (sizeof(Scene) + 15) & ~(size_t)15;
-constexpr size_t SMEM_MAX = 227 * 1024;
+constexpr size_t SMEM_MAX = (228 * 1024) / BLOCKS_PER_SM - 1024;  // 228 KB per SM, 1 KB reserved per resident block
 
 // Shared-memory layout of one resident arena: [ArenaS prefix (header, ball, pads, nCars cars) | BodyW x nb |
 // WheelW x 4 nCars | padLocked x nPads], padded so that neighbouring arenas start in different banks.
@@ -285,9 +290,13 @@ struct StepArgs {
 // developer builds: per phase [0..15] block wall cycles, [16..31] sum of busy-thread cycles, [32..47] busy-thread count,
 // [48..63] sum over blocks of the slowest thread's cycles
 __device__ unsigned long long g_prof[64];
+
+// [phase NS=0 / DYN=1][bucket: min(7, detector calls of the slowest item) + 8 if it ran EPA][0 = sum of its cycles, 1 = count]
+__device__ unsigned long long g_prof2[2][16][2];
 #define PHASE_PROF_BEGIN() long long _pt0 = clock64()
 #define PHASE_PROF_ITEMS(i, had) do { if (had) { unsigned long long _d = (unsigned long long)(clock64() - _pt0); atomicAdd(&g_prof[16 + i], _d); atomicAdd(&g_prof[32 + i], 1ull); atomicMax(&s_profMax, _d); } } while (0)
-#define PHASE_PROF_END(i) do { if (threadIdx.x == 0) { atomicAdd(&g_prof[i], (unsigned long long)(clock64() - _pt0)); atomicAdd(&g_prof[48 + i], s_profMax); s_profMax = 0; } __syncthreads(); } while (0)
+#define PHASE_PROF_END(i) do { if (threadIdx.x == 0) { atomicAdd(&g_prof[i], (unsigned long long)(clock64() - _pt0)); atomicAdd(&g_prof[48 + i], s_profMax); s_profMax = 0; \
+	if (i == PH_NARROW_STATIC || i == PH_DYN_SOLVE) { int c = (int)(s_profMax2 & 0xfffff); int bk = min(7, c & 255) + ((c >> 8) ? 8 : 0); int ph = (i == PH_DYN_SOLVE); atomicAdd(&g_prof2[ph][bk][0], s_profMax2 >> 20); atomicAdd(&g_prof2[ph][bk][1], 1ull); s_profMax2 = 0; } } __syncthreads(); } while (0)
 #else
 #define PHASE_PROF_BEGIN() ((void)0)
 #define PHASE_PROF_ITEMS(i, had) ((void)0)
@@ -304,6 +313,74 @@ __device__ __forceinline__ Ctx make_ctx(const StepArgs& a, const BatchParams* sP
 	return cx;
 }
 
+// Item -> thread assignment of a phase.  Items of a phase are independent, so any assignment gives the same results; the
+// assignment decides how much a warp diverges:
+//   * arena-level phases (few, long, data-dependent items): consecutive items go to different warps (ptid permutation),
+//     so a narrow phase spreads over all schedulers and at most 4 unrelated items share a warp;
+//   * wheel rays: natural order -- the four wheels of a car and the cars of an arena sit in neighbouring lanes and mostly
+//     take the same path (same broadphase cell, same static list);
+//   * body phases: all balls in the first warp(s), cars dealt over the other warps -- the sphere and the box code paths
+//     never share a warp;
+//   * car logic: cars first, dealt evenly over all warps in low lanes; pad and ball items fill the remaining lanes/rounds.
+template <int PH>
+__device__ __forceinline__ bool map_item(int k, int tid, int ptid, int nA, const BatchParams& P, int& ar, int& item) {
+	constexpr int NW = STEP_THREADS / 32;
+	const int nCars = P.nCars;
+	const int warp = tid >> 5, lane = tid & 31;
+#ifndef RSB_MAP
+#define RSB_MAP 1  // measured: natural order helps the wheel rays (-13 % phase time); the body / car groupings do not
+#endif
+	if (PH == PH_WHEELS && (RSB_MAP & 1)) {
+		const int i = tid + k * STEP_THREADS, per = nCars * 4;
+		if (i >= nA * per) return false;
+		ar = i / per; item = i - ar * per;
+		return true;
+	}
+	if ((PH == PH_INIT || PH == PH_PREDICT || PH == PH_NARROW_STATIC || PH == PH_FINISH_BODY) && (RSB_MAP & 2)) {
+		const int ballWarps = (nA + 31) / 32;
+		if (ballWarps < NW) {
+			if (warp < ballWarps) {
+				if (k > 0) return false;
+				ar = warp * 32 + lane; item = 0;
+				return ar < nA;
+			}
+			const int carWarps = NW - ballWarps;
+			const int c = (warp - ballWarps) + carWarps * (lane + 32 * k);
+			if (c >= nA * nCars) return false;
+			ar = c / nCars; item = 1 + (c - ar * nCars);
+			return true;
+		}
+	}
+	if ((PH == PH_CAR_LOGIC || PH == PH_CAR_POST) && (RSB_MAP & 4)) {
+		const int nCarItems = nA * nCars;
+		const int L0 = (nCarItems + NW - 1) / NW;  // lanes per warp that hold a car in round 0
+		if (L0 <= 32) {
+			if (k == 0 && lane < L0) {
+				const int c = lane * NW + warp;
+				if (c >= nCarItems) return false;
+				ar = c / nCars; item = c - ar * nCars;
+				return true;
+			}
+			if (PH == PH_CAR_POST) return false;
+			const int others = (phase_items(P, PH) - nCars) * nA;
+			const int slots0 = (32 - L0) * NW;
+			int j;
+			if (k == 0) j = (lane - L0) * NW + warp;
+			else j = slots0 + (k - 1) * STEP_THREADS + tid;
+			if (j >= others) return false;
+			ar = j % nA; item = nCars + j / nA;
+			return true;
+		}
+	}
+	const int i = ptid + k * STEP_THREADS;
+	if (i >= phase_items(P, PH) * nA) return false;
+	ar = i % nA; item = i / nA;
+	return true;
+}
+
+template <int PH>
+__device__ __forceinline__ bool phase_thread_busy(int tid, int ptid, int nA, const BatchParams& P) { int ar, item; return map_item<PH>(0, tid, ptid, nA, P, ar, item); }
+
 template <int PH>
 __device__ __forceinline__ void run_phase_block(const StepArgs& a, const BatchParams* sP, const Scene* sSc, unsigned char* sS, int a0, int nA, int ptid) {
 #if defined(RSB_PROFILE)
@@ -311,12 +388,22 @@ __device__ __forceinline__ void run_phase_block(const StepArgs& a, const BatchPa
 #endif
 	PHASE_PROF_BEGIN();
 	const int n = phase_items(*sP, PH) * nA;
-	for (int i = ptid; i < n; i += STEP_THREADS) {
-		const int ar = i % nA, item = i / nA;
+	const int nRounds = (n + STEP_THREADS - 1) / STEP_THREADS + 1;
+	for (int k = 0; k < nRounds; k++) {
+		int ar, item;
+		if (!map_item<PH>(k, threadIdx.x, ptid, nA, *sP, ar, item)) continue;
 		const Ctx cx = make_ctx(a, sP, sSc, sS, a0, ar);
 		phase_run(cx, PH, item);
 	}
-	PHASE_PROF_ITEMS(PH, ptid < n);
+	PHASE_PROF_ITEMS(PH, phase_thread_busy<PH>(threadIdx.x, ptid, nA, *sP));
+#if defined(RSB_PROFILE)
+	__shared__ unsigned long long s_profMax2;
+	if (PH == PH_NARROW_STATIC || PH == PH_DYN_SOLVE) {
+		EpaScratch* es = a.E + ((size_t)blockIdx.x * STEP_THREADS + threadIdx.x);
+		if (phase_thread_busy<PH>(threadIdx.x, ptid, nA, *sP)) { unsigned long long d = (unsigned long long)(clock64() - _pt0); int c = es->profCalls; atomicMax(&s_profMax2, (d << 20) | (unsigned long long)(c & 0xfffff)); }
+		es->profCalls = 0;
+	}
+#endif
 	__syncthreads();
 	if (a.mirror && (PH == PH_CAR_LOGIC || PH == PH_DYN_SOLVE)) {
 		// single-tick launches keep the debug mirror complete: the wheel scratch and the solver scratch alias each other
@@ -332,7 +419,7 @@ __device__ __forceinline__ void run_phase_block(const StepArgs& a, const BatchPa
 	PHASE_PROF_END(PH);
 }
 
-__global__ void __launch_bounds__(STEP_THREADS, 1) arena_step_kernel(const StepArgs a) {
+__global__ void __launch_bounds__(STEP_THREADS, BLOCKS_PER_SM) arena_step_kernel(const StepArgs a) {
 	extern __shared__ __align__(16) unsigned char smem[];
 	BatchParams* sP = (BatchParams*)smem;
 	Scene* sSc = (Scene*)(smem + SMEM_P_BYTES);
@@ -800,7 +887,7 @@ int rsb_batch_create(int device, int game_mode, int n_arenas, int n_cars, const 
 		cudaDeviceProp prop;
 		CUDA_OK(cudaGetDeviceProperties(&prop, device));
 		b->numSMs = prop.multiProcessorCount;
-		if ((size_t)prop.sharedMemPerBlockOptin < SMEM_MAX) throw std::runtime_error("device offers less than 227 KB of shared memory per block: rocketsim_b200 targets sm_100a");
+		if ((size_t)prop.sharedMemPerBlockOptin < 227 * 1024) throw std::runtime_error("device offers less than 227 KB of shared memory per block: rocketsim_b200 targets sm_100a");
 		static std::mutex attrMutex; std::lock_guard<std::mutex> lk(attrMutex);
 		cudaFuncAttributes fa;
 		CUDA_OK(cudaFuncGetAttributes(&fa, arena_step_kernel));
@@ -837,7 +924,7 @@ int rsb_batch_create(int device, int game_mode, int n_arenas, int n_cars, const 
 	b->dW = (ArenaW*)dev_alloc(sizeof(ArenaW) * (size_t)n_arenas);
 	b->dH = (ArenaH*)dev_alloc(sizeof(ArenaH) * (size_t)n_arenas);
 #ifndef RSB_HOSTCHECK
-	b->dE = (EpaScratch*)dev_alloc(sizeof(EpaScratch) * (size_t)b->numSMs * STEP_THREADS);
+	b->dE = (EpaScratch*)dev_alloc(sizeof(EpaScratch) * (size_t)b->numSMs * BLOCKS_PER_SM * STEP_THREADS);
 #else
 	b->dE = (EpaScratch*)dev_alloc(sizeof(EpaScratch));
 #endif
@@ -928,7 +1015,7 @@ static void launch_step(RsbBatch* b, int n_ticks, const CtrlS* seq, int nCtrl) {
 	a.nArenas = P.nArenas; a.nTicks = n_ticks; a.ctrlSeq = seq; a.nCtrl = nCtrl; a.apb = 1; a.mirror = (n_ticks == 1) ? 1 : 0;
 #ifndef RSB_HOSTCHECK
 	// chunk size: fill every SM once if the batch fits (one wave), else the fewest equal waves
-	const int sms = b->numSMs;
+	const int sms = b->numSMs * BLOCKS_PER_SM;  // resident block slots
 	const int APB_MAX = (int)((b->smemBudget - SMEM_P_BYTES - SMEM_SC_BYTES) / a.lay.stride);
 	const int chunksMin = (P.nArenas + APB_MAX - 1) / APB_MAX;
 	const int waves = (chunksMin + sms - 1) / sms;
@@ -1248,6 +1335,15 @@ int rsb_debug_profile(uint64_t* out64, int reset) {
 #if defined(RSB_PROFILE) && !defined(RSB_HOSTCHECK)
 	CUDA_OK(cudaDeviceSynchronize());
 	CUDA_OK(cudaMemcpyFromSymbol(out64, g_prof, sizeof(unsigned long long) * 64));
+	{ static unsigned long long h2[2][16][2]; CUDA_OK(cudaMemcpyFromSymbol(h2, g_prof2, sizeof(h2)));
+	  if (getenv("RSB_PROF2")) for (int ph = 0; ph < 2; ph++) for (int k = 0; k < 16; k++) if (h2[ph][k][1]) printf("prof2 %s slowest-item detector calls %d%s epa %d: n %llu mean cycles %llu\n", ph ? "DYN_SOLVE" : "NARROW_STATIC", k & 7, (k & 7) == 7 ? "+" : "", k >> 3, h2[ph][k][1], h2[ph][k][0] / h2[ph][k][1]);
+	  if (reset) { memset(h2, 0, sizeof(h2)); CUDA_OK(cudaMemcpyToSymbol(g_prof2, h2, sizeof(h2))); } }
+	{ unsigned long long h3[64]; CUDA_OK(cudaMemcpyFromSymbol(h3, g_subprof, sizeof(h3)));
+	  const char* nm[32] = {"DYN dyn pairs", "DYN islands (+has_rows)", "DYN solver: bodies", "DYN solver: rows", "DYN solver: split sweeps", "DYN solver: velocity sweeps", "DYN solver: writeback", "DYN solver: whole",
+	                        "WHEEL transforms", "WHEEL cast: statics", "WHEEL cast: dynamics", "WHEEL post", "NS pair loop head", "NS plane pair", "NS mesh pair", "NS 15",
+	                        "CAR friction", "CAR update_wheels", "CAR air/jump/flip", "CAR vehicle_second", "CAR boost", "PAIRS cells", "PAIRS statics", "PAIRS dynamics", "24", "25", "26", "27", "28", "29", "30", "31"};
+	  if (getenv("RSB_PROF2")) for (int k = 0; k < 32; k++) if (h3[32 + k]) printf("subprof %-28s n %llu mean cycles %llu total Mcycles %llu\n", nm[k], h3[32 + k], h3[k] / h3[32 + k], h3[k] / 1000000);
+	  if (reset) { memset(h3, 0, sizeof(h3)); CUDA_OK(cudaMemcpyToSymbol(g_subprof, h3, sizeof(h3))); } }
 	if (reset) { unsigned long long z[64] = {0}; CUDA_OK(cudaMemcpyToSymbol(g_prof, z, sizeof(z))); }
 #else
 	(void)reset;

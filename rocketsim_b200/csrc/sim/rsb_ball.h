@@ -103,7 +103,7 @@ RSB_HD void ball_pretick(const Ctx& cx) {
 }
 
 // Ball::_OnHit (car-ball contact hook).  relPosUU = contact point local to the ball, in uu.
-RSB_HD void ball_on_hit(const Ctx& cx, int ci, const V3& relPosUU) {
+RSB_HD_NOINLINE void ball_on_hit(Ctx cx, int ci, V3 relPosUU) {
 	BallS& b = cx.s->ball;
 	CarS& c = cx.s->cars[ci];
 	const int mode = cx.p->mode;
@@ -149,7 +149,7 @@ RSB_HD void ball_on_hit(const Ctx& cx, int ci, const V3& relPosUU) {
 }
 
 // Ball::_OnWorldCollision (ball-world contact hook)
-RSB_HD void ball_on_world_collision(const Ctx& cx, const V3& normal) {
+RSB_HD_NOINLINE void ball_on_world_collision(Ctx cx, V3 normal) {
 	BallS& b = cx.s->ball;
 	const int mode = cx.p->mode;
 	if (mode == HEATSEEKER) {

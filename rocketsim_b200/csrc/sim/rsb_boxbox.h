@@ -11,7 +11,7 @@
 
 namespace rsb {
 
-RSB_ACP_ATTR void add_contact_point(const Ctx& cx, int mi, const V3& normalOnB, const V3& pointInWorld, float depth, int triMesh, int triIndex);
+RSB_ACP_ATTR void add_contact_point(const Ctx& cx, int mi, const V3& normalOnB, const V3& pointInWorld, float depth, int triMesh, int triIndex, bool dynPair);
 
 // R[i*4+j] of the ODE code is element (row i, col j); a "column j" walk is R + j with stride 4.
 struct Mat12 { float m[12]; };
@@ -116,6 +116,9 @@ RSB_HD void cull_points2(int n, float p[], int m, int i0, int iret[]) {
 // boxes 1/2 = (shape, world transform); manifold mi has body0 = owner of box 1.
 RSB_HD void box_box(const Ctx& cx, int mi, const Convex& box1, const Xform& xf1, const Convex& box2, const Xform& xf2) {
 	const float fudge_factor = 1.05f;
+#if defined(RSB_PROFILE)
+	if (cx.epa) cx.epa->profCalls += 1;
+#endif
 	Mat12 R1m = mat12_from(xf1.basis), R2m = mat12_from(xf2.basis);
 	const float* R1 = R1m.m; const float* R2 = R2m.m;
 	const float p1[3] = {xf1.origin.x, xf1.origin.y, xf1.origin.z};
@@ -302,7 +305,7 @@ RSB_HD void box_box(const Ctx& cx, int mi, const Convex& box1, const Xform& xf1,
 	}
 emit:
 	// one call site: the contact hook (Arena::_BulletContactAddedCallback and all it pulls in) is inlined here once
-	for (int k = 0; k < nOut; k++) add_contact_point(cx, mi, negNormal, outPts[k], outDep[k], -1, -1);
+	for (int k = 0; k < nOut; k++) add_contact_point(cx, mi, negNormal, outPts[k], outDep[k], -1, -1, true);
 }
 
 }  // namespace rsb

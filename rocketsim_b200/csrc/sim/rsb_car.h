@@ -92,6 +92,7 @@ RSB_HD void wheel_trace(const Ctx& cx, int ci, int wi) {
 	WheelW& w = cx.wheels[ci * 4 + wi];
 	const RigidS& rb = c.rb;
 
+	RSB_SUBPROF_BEGIN();
 	// updateWheelTransformsWS
 	w.isInContact = 0; w.isInContactWithWorld = 0;
 	w.hardPointWS = rb.basis * cfg.wheelConn[wi] + rb.pos;
@@ -122,7 +123,9 @@ RSB_HD void wheel_trace(const Ctx& cx, int ci, int wi) {
 	w.groundObj = OBJ_NONE;
 
 	RayHit hit;
+	RSB_SUBPROF_MARK(8);
 	bool got = cast_vehicle_ray(cx, ci + 1, source, target, hit);
+	RSB_SUBPROF_BEGIN2();
 	const V3 upVec = rb.basis.col(2);
 	if (got) {
 		w.contactPointWS = hit.point;
@@ -177,6 +180,7 @@ RSB_HD void wheel_trace(const Ctx& cx, int ci, int wi) {
 		w.clippedInv = 1.f;
 		c.wExtraPushback[wi] = 0.f;
 	}
+	RSB_SUBPROF_MARK(11);
 }
 
 // btVehicleRL::calcFrictionImpulses (btVehicleRL.cpp:306-380)
@@ -659,7 +663,9 @@ RSB_HD void car_update_boost(const Ctx& cx, int ci) {
 // Phase C (per car): everything of Car::_PreTickUpdate after the traces (Car.cpp:89-130).
 RSB_HD void car_pretick_logic(const Ctx& cx, int ci) {
 	CarS& c = cx.s->cars[ci];
+	RSB_SUBPROF_BEGIN();
 	calc_friction_impulses(cx, ci);
+	RSB_SUBPROF_MARK(16);
 
 	bool jumpPressed = c.controls.jump && !c.lastControls.jump;
 	int numWheelsInContact = 0;
@@ -672,6 +678,7 @@ RSB_HD void car_pretick_logic(const Ctx& cx, int ci) {
 
 	float forwardSpeed_UU = dot(c.rb.vel, c.rb.basis.col(0)) * BT_TO_UU;
 	car_update_wheels(cx, ci, numWheelsInContact, forwardSpeed_UU);
+	RSB_SUBPROF_MARK(17);
 
 	if (numWheelsInContact < 3) car_update_air_torque(cx, ci, numWheelsInContact == 0);
 	else c.isFlipping = 0;
@@ -684,8 +691,11 @@ RSB_HD void car_pretick_logic(const Ctx& cx, int ci) {
 		car_update_auto_roll(cx, ci, numWheelsInContact);
 
 	c.worldContactHas = 0;
+	RSB_SUBPROF_MARK(18);
 	vehicle_second(cx, ci);
+	RSB_SUBPROF_MARK(19);
 	car_update_boost(cx, ci);
+	RSB_SUBPROF_MARK(20);
 }
 
 // Car::_PostTickUpdate + _FinishPhysicsTick (Car.cpp:133-193)

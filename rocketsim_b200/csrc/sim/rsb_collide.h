@@ -98,6 +98,8 @@ RSB_HD void dyn_order_move_to_back(ArenaS& S, int nb, int b) {
 }
 
 // updateSingleAabb of one dynamic body (current U predicted transform, +-0.02) and the grid cell of its min corner
+RSB_HD void body_filter(const Ctx& cx, int obj, int& group, int& mask);
+RSB_HD void static_proxy_aabb(const Ctx& cx, int obj, V3& mn, V3& mx);
 RSB_HD void update_aabb(const Ctx& cx, int b) {
 	const V3 ct(kContactBreaking, kContactBreaking, kContactBreaking);
 	BodyW& bw = cx.body[b];
@@ -112,6 +114,24 @@ RSB_HD void update_aabb(const Ctx& cx, int b) {
 	int i, j, k;
 	bw.newCell = grid_cell_of(*cx.sc, mn, i, j, k);
 	bw.newI = i; bw.newJ = j; bw.newK = k;
+	// static half of calculateOverlappingPairs for this body (its cell is final: PH_PAIRS only commits newCell)
+	{
+		const Scene& sc = *cx.sc;
+		int gb, mb; body_filter(cx, b, gb, mb);
+		int n = 0;
+		const int sEnd = sc.cellStart[bw.newCell + 1];
+		for (int s = sc.cellStart[bw.newCell]; s < sEnd; s++) {
+			const int obj = STATIC_BASE + sc.cellStatics[s];
+			V3 smn, smx; static_proxy_aabb(cx, obj, smn, smx);
+			if (!aabb_overlap(mn, mx, smn, smx)) continue;
+			int ga, ma; body_filter(cx, obj, ga, ma);
+			if (!((ga & mb) && (gb & ma))) continue;  // needsBroadphaseCollision
+			if (n >= MAX_CAND) { n = -1; break; }
+			bw.candObj[n] = (uint8_t)(obj - STATIC_BASE);
+			bw.cand[n++] = (uint16_t)s;
+		}
+		bw.nCand = n;
+	}
 }
 
 // btRSBroadphase::setAabb cell bookkeeping, in body order (a body that changed cell is re-registered last)
@@ -155,11 +175,15 @@ RSB_HD void compute_pairs(const Ctx& cx) {
 	cx.pl->nPairs = 0;
 	for (int b = 0; b < nb; b++) {
 		const BodyW& bw = cx.body[b];
-		int cell = cx.s->cellIdx[b];
-		for (int s = sc.cellStart[cell]; s < sc.cellStart[cell + 1]; s++) {
-			int obj = STATIC_BASE + sc.cellStatics[s];
-			V3 mn, mx; static_proxy_aabb(cx, obj, mn, mx);
-			if (aabb_overlap(bw.aabbMin, bw.aabbMax, mn, mx)) add_pair(cx, obj, b, s);
+		if (bw.nCand >= 0) {
+			for (int q = 0; q < bw.nCand; q++) { add_pair(cx, STATIC_BASE + bw.candObj[q], b, bw.cand[q]); }
+		} else {  // candidate list overflowed: full scan
+			int cell = cx.s->cellIdx[b];
+			for (int s = sc.cellStart[cell]; s < sc.cellStart[cell + 1]; s++) {
+				int obj = STATIC_BASE + sc.cellStatics[s];
+				V3 mn, mx; static_proxy_aabb(cx, obj, mn, mx);
+				if (aabb_overlap(bw.aabbMin, bw.aabbMax, mn, mx)) add_pair(cx, obj, b, s);
+			}
 		}
 		if (nb > 1) {
 			// dynamic proxies registered in b's cell, in the cell list's order (ascending stamp)
@@ -264,7 +288,7 @@ RSB_HD bool clamp_normal(const V3& edge, const V3& tri_normal, const V3& localCo
 
 // btAdjustInternalEdgeContacts with normalAdjustFlags = 0; the triangle's mesh sits at the
 // world origin with identity basis, so "local" == world for B.
-RSB_HD void adjust_internal_edge(const Ctx& cx, ContactPt& cp, const MeshD& mesh, int triIndex) {
+RSB_HD_NOINLINE void adjust_internal_edge(Ctx cx, ContactPt& cp, const MeshD& mesh, int triIndex) {
 	const TriInfo info = mesh.info[triIndex];
 	if (info.flags < 0) return;  // no entry in the triangle info map
 	V3 v0, v1, v2;
@@ -333,7 +357,7 @@ RSB_HD void adjust_internal_edge(const Ctx& cx, ContactPt& cp, const MeshD& mesh
 }
 
 // Car::Demolish + bump logic: Arena::_BtCallback_OnCarCarCollision (Arena.cpp:323-405)
-RSB_HD void on_car_car_collision(const Ctx& cx, int c1, int c2, ContactPt& cp) {
+RSB_HD_NOINLINE void on_car_car_collision(Ctx cx, int c1, int c2, ContactPt& cp) {
 	cp.friction = K::CARCAR_COLLISION_FRICTION;
 	cp.restitution = K::CARCAR_COLLISION_RESTITUTION;
 	const MutD& mut = cx.p->mut;
@@ -385,7 +409,9 @@ RSB_HD void on_car_car_collision(const Ctx& cx, int c1, int c2, ContactPt& cp) {
 // btManifoldResult::addContactPoint + gContactAddedCallback.  body0/body1 of the manifold
 // are "A"/"B"; (normalOnB, pointOnB, depth) as reported by the detector.  triMesh/triIndex
 // identify the triangle when B is an arena mesh (else triMesh < 0).
-RSB_ACP_ATTR void add_contact_point(const Ctx& cx, int mi, const V3& normalOnB, const V3& pointInWorld, float depth, int triMesh, int triIndex) {
+// dynPair: the manifold joins two dynamic bodies (car-ball / car-car); false: (dynamic body, static object).  A constant at
+// every inlined call site, so each site keeps only the hooks it can reach.
+RSB_ACP_ATTR void add_contact_point(const Ctx& cx, int mi, const V3& normalOnB, const V3& pointInWorld, float depth, int triMesh, int triIndex, bool dynPair) {
 	Manifold& m = cx.mf[mi];
 	if (depth > m.breakingThresh) return;
 	ContactPt pt;
@@ -400,7 +426,7 @@ RSB_ACP_ATTR void add_contact_point(const Ctx& cx, int mi, const V3& normalOnB, 
 	pt.partId1 = triMesh >= 0 ? 0 : -1; pt.index1 = triMesh >= 0 ? triIndex : -1;
 	// combined friction / restitution (btManifoldResult.cpp:56-77)
 	{
-		bool s0 = m.body0 >= STATIC_BASE, s1 = m.body1 >= STATIC_BASE;
+		const bool s0 = false, s1 = !dynPair;
 		float fa = s0 ? K::ARENA_COLLISION_BASE_FRICTION : cx.body[m.body0].friction;
 		float fb = s1 ? K::ARENA_COLLISION_BASE_FRICTION : cx.body[m.body1].friction;
 		float ra = s0 ? K::ARENA_COLLISION_BASE_RESTITUTION : cx.body[m.body0].restitution;
@@ -416,7 +442,7 @@ RSB_ACP_ATTR void add_contact_point(const Ctx& cx, int mi, const V3& normalOnB, 
 	ContactPt& cp = m.pts[insertIndex];
 
 	// ---- Arena::_BulletContactAddedCallback ----
-	const bool d0 = m.body0 < STATIC_BASE, d1 = m.body1 < STATIC_BASE;
+	const bool d0 = true, d1 = dynPair;  // body0 of a manifold is always dynamic; body1 is static unless dynPair
 	if ((d0 && cx.body[m.body0].noResponse) || (d1 && cx.body[m.body1].noResponse)) return;
 	// manifold orders used here: (car, ball) (carHi, carLo) (car, world) (ball, world)
 	if (d0 && m.body0 > 0) {
@@ -600,7 +626,7 @@ RSB_HD void convex_vs_mesh(const Ctx& cx, int mi, int body, const Convex& shape,
 							// sphereInTr origin = (center - 0) * I
 							V3 c = vmul(xf.origin - v3zero(), m3identity());
 							if (sphere_triangle(c, shape.margin, t, mf.breakingThresh, point, normal, depth))
-								add_contact_point(cx, mi, m3identity() * normal, m3identity() * point + v3zero(), depth, meshIdx, tri);
+								add_contact_point(cx, mi, m3identity() * normal, m3identity() * point + v3zero(), depth, meshIdx, tri, false);
 						} else {
 							Convex triShape; triShape.kind = SH_TRI; triShape.margin = 0.f; triShape.he = v3zero();
 							triShape.tri[0] = t[0]; triShape.tri[1] = t[1]; triShape.tri[2] = t[2]; triShape.pts = nullptr; triShape.npts = 0;
@@ -633,7 +659,7 @@ RSB_HD void convex_vs_plane(const Ctx& cx, int mi, const Convex& shape, const Xf
 		V3 vtxInPlaneProjected = vtxInPlane - distance * planeNormal;
 		V3 vtxInPlaneWorld = m3identity() * vtxInPlaneProjected + pl.pos;
 		V3 normalOnSurfaceB = m3identity() * planeNormal;
-		add_contact_point(cx, mi, normalOnSurfaceB, vtxInPlaneWorld, distance, -1, -1);
+		add_contact_point(cx, mi, normalOnSurfaceB, vtxInPlaneWorld, distance, -1, -1, false);
 	}
 	if (mf.nPts) refresh_contact_points(cx, mi);
 }
@@ -658,8 +684,11 @@ RSB_HD void convex_world_aabb(const Ctx& cx, const Convex& s, const Xform& t, V3
 //   collide_dynamic_pairs (arena)  ball-car and car-car pairs, in pair order (their hooks touch two bodies)
 // Manifold order (= solver row order) is the pair order whatever the execution order.
 RSB_HD void collide_pairs(const Ctx& cx) {
+	RSB_SUBPROF_BEGIN();
 	apply_cell_changes(cx);
+	RSB_SUBPROF_MARK(21);
 	compute_pairs(cx);
+	RSB_SUBPROF_MARK(22);
 	cx.pl->nManifolds = cx.pl->nPairs;
 	for (int k = 0; k < cx.pl->nPairs; k++) { cx.mf[k].body0 = -1; cx.mf[k].nPts = 0; }
 }
@@ -675,6 +704,7 @@ RSB_HD void collide_static_pairs(const Ctx& cx, int b) {
 	const BatchParams& P = *cx.p;
 	const Scene& sc = *cx.sc;
 	const int nPairs = cx.pl->nPairs;
+	RSB_SUBPROF_BEGIN();
 	for (int k = 0; k < nPairs; k++) {
 		if (cx.pl->b[k] != b) continue;
 		const int a = cx.pl->a[k];
@@ -699,8 +729,10 @@ RSB_HD void collide_static_pairs(const Ctx& cx, int b) {
 			static_aabb(cx, a, omn, omx);
 			if (!aabb_overlap(cmn, cmx, omn, omx)) continue;
 			int mi = new_manifold(cx, k, b, a);
+			RSB_SUBPROF_MARK(12);
 			if (isMesh) convex_vs_mesh(cx, mi, b, shape, xf, sk, cx.pl->entry[k]);
 			else convex_vs_plane(cx, mi, shape, xf, sc.planes[sk - sc.nMeshes]);
+			RSB_SUBPROF_MARK(isMesh ? 14 : 13);
 		}
 	}
 }

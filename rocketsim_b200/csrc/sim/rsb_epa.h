@@ -461,6 +461,9 @@ RSB_HD_NOINLINE int epa_evaluate(Epa& e, Gjk2& gjk, V3 guess) {
 
 // btGjkEpaPenetrationDepthSolver::calcPenDepth
 RSB_HD_NOINLINE bool epa_penetration(const Ctx& cx, Convex A, Xform tA, Convex B, Xform tB, V3& v, V3& wa, V3& wb) {
+#if defined(RSB_PROFILE)
+	if (cx.epa) cx.epa->profCalls += 256;
+#endif
 	const V3 guessVectors[9] = {
 		safe_normalized(tB.origin - tA.origin), safe_normalized(tA.origin - tB.origin),
 		V3(0, 0, 1), V3(0, 1, 0), V3(1, 0, 0), V3(1, 1, 0), V3(1, 1, 1), V3(0, 1, 1), V3(1, 0, 1)};

@@ -11,7 +11,7 @@
 
 namespace rsb {
 
-RSB_ACP_ATTR void add_contact_point(const Ctx& cx, int mi, const V3& normalOnB, const V3& pointInWorld, float depth, int triMesh, int triIndex);
+RSB_ACP_ATTR void add_contact_point(const Ctx& cx, int mi, const V3& normalOnB, const V3& pointInWorld, float depth, int triMesh, int triIndex, bool dynPair);
 RSB_HD void transform_aabb_he(const V3& he, float margin, const M3& basis, const V3& origin, V3& mn, V3& mx);
 RSB_HD void transform_aabb_mm(const V3& lmin, const V3& lmax, float margin, const M3& basis, const V3& origin, V3& mn, V3& mx);
 
@@ -46,6 +46,9 @@ RSB_HD_NOINLINE bool epa_penetration(const Ctx& cx, Convex A, Xform tA, Convex B
 
 // GJK closest points + addContactPoint.  A/B with world transforms; triMesh/triIndex forwarded.
 RSB_HD_NOINLINE void convex_convex(const Ctx& cx, int mi, Convex A, Xform xfA, Convex B, Xform xfB, int triMesh, int triIndex) {
+#if defined(RSB_PROFILE)
+	if (cx.epa) cx.epa->profCalls += 1;
+#endif
 	const float breaking = cx.mf[mi].breakingThresh;
 	float maxDist2 = A.margin + B.margin + breaking;
 	maxDist2 *= maxDist2;
@@ -143,7 +146,7 @@ RSB_HD_NOINLINE void convex_convex(const Ctx& cx, int mi, Convex A, Xform xfA, C
 		V3 posB = convex_aabb_center(cx, B, localB);
 		V3 diff = posA - posB;
 		if (dot(diff, normalInB) < 0.f) normalInB *= -1.f;
-		add_contact_point(cx, mi, normalInB, pointOnB + positionOffset, distance, triMesh, triIndex);
+		add_contact_point(cx, mi, normalInB, pointOnB + positionOffset, distance, triMesh, triIndex, triMesh < 0 && cx.mf[mi].body1 < STATIC_BASE);
 	}
 }
 

@@ -175,7 +175,7 @@ RSB_HD bool ray_plane(const PlaneD& pl, const V3& from, const V3& to, float& hit
 }
 
 // btSubsimplexConvexCast::calcTimeOfImpact with A = point moving from->to, B = static convex.
-RSB_HD bool ray_convex(const Convex& shapeB, const Xform& xfB, const V3& from, const V3& to, float& hitFraction, V3& outNormal) {
+RSB_HD_NOINLINE bool ray_convex(Convex shapeB, Xform xfB, V3 from, V3 to, float& hitFraction, V3& outNormal) {
 	Simplex sx;
 	sx.reset();
 	V3 linVelA = to - from;
@@ -236,6 +236,7 @@ RSB_HD bool cast_vehicle_ray(const Ctx& cx, int self, const V3& from, const V3& 
 	const int rayGroup = FILT_DEFAULT | FILT_DROPSHOT_FLOOR;
 	int ci = 0, cj = 0, ck = 0;
 	const Scene& sc = *cx.sc;
+	RSB_SUBPROF_BEGIN();
 	{
 		int cell = grid_cell_of(sc, from, ci, cj, ck);
 		for (int s = sc.cellStart[cell]; s < sc.cellStart[cell + 1]; s++) {
@@ -244,12 +245,21 @@ RSB_HD bool cast_vehicle_ray(const Ctx& cx, int self, const V3& from, const V3& 
 			if (k < sc.nMeshes) {
 				const MeshD& m = sc.meshes[k];
 				if (!((m.group & FILT_ALL) != 0 && (rayGroup & m.mask))) continue;
+				// conservative cull (ours): every triangle lies inside the mesh AABB, so a segment whose box misses it by more
+				// than the triangle test's edge tolerance cannot be reported by the BVH walk
+				{
+					const float slack = 0.1f;
+					const V3 smn = vmin(from, to), smx = vmax(from, to);
+					if (smn.x > m.aabbMax.x + slack || smx.x < m.aabbMin.x - slack || smn.y > m.aabbMax.y + slack || smx.y < m.aabbMin.y - slack ||
+					    smn.z > m.aabbMax.z + slack || smx.z < m.aabbMin.z - slack) continue;
+				}
 				if (ray_mesh(sc, m, s, from, to, closest, normal)) obj = STATIC_BASE + k;
 			} else {
 				if (ray_plane(sc.planes[k - sc.nMeshes], from, to, closest, normal)) obj = STATIC_BASE + k;
 			}
 		}
 	}
+	RSB_SUBPROF_MARK(9);
 	// dynamic proxies registered in the ray-origin cell, in cell-list order (= ascending stamp)
 	{
 		const int nb = n_bodies(cx);
@@ -284,6 +294,7 @@ RSB_HD bool cast_vehicle_ray(const Ctx& cx, int self, const V3& from, const V3& 
 			if (ray_convex(shp, xf, from, to, closest, normal)) obj = b;
 		}
 	}
+	RSB_SUBPROF_MARK(10);
 	if (obj == OBJ_NONE) return false;
 	if (obj < STATIC_BASE && cx.body[obj].noResponse) return false;
 	out.obj = obj;

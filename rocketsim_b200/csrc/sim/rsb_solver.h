@@ -14,18 +14,6 @@
 
 namespace rsb {
 
-// ---- union-find over world objects (statics never merge) ----
-struct UF { int id[MAX_BODIES]; int sz[MAX_BODIES]; };
-RSB_HD int uf_find(UF& u, int x) {
-	while (x != u.id[x]) { int p = u.id[x]; u.id[x] = u.id[p]; x = u.id[p]; }
-	return x;
-}
-RSB_HD void uf_unite(UF& u, int p, int q) {
-	int i = uf_find(u, p), j = uf_find(u, q);
-	if (i == j) return;
-	u.id[i] = j; u.sz[j] += u.sz[i];
-}
-
 // btAlignedObjectArray::quickSortInternal on (key,payload) pairs; comparator key<key
 RSB_HD void quicksort_keys(int* key, int* val, int lo, int hi) {
 	// explicit stack (max depth tiny: arrays <= MAX_MANIFOLDS)
@@ -52,59 +40,65 @@ RSB_HD void quicksort_keys(int* key, int* val, int lo, int hi) {
 
 
 // calculateSimulationIslands + buildIslands: island tags, wake-ups, and the manifold order
-// handed to the solver.  Returns the number of manifolds to solve (order in w.manifoldOrder).
+// handed to the solver.  Returns the number of manifolds to solve (order in pl->manifoldOrder).
+// <= 7 bodies: the union-find forest lives in one register (4 bits per body) and the per-island predicates are bit masks
+// indexed by root; the unite sequence, the roots it produces and the (non-stable) manifold sort are the reference's.
 RSB_HD int build_islands(const Ctx& cx) {
 	const int nb = n_bodies(cx);
-	UF uf;
-	for (int b = 0; b < nb; b++) { uf.id[b] = b; uf.sz[b] = 1; }
+	uint32_t par = 0x76543210u;  // par[b] = b
 	// findUnions over ALL broadphase pairs whose bodies both merge islands
-	for (int k = 0; k < cx.pl->nPairs; k++) {
-		int a = cx.pl->a[k], b = cx.pl->b[k];
+	const int nPairs = cx.pl->nPairs;
+	for (int k = 0; k < nPairs; k++) {
+		const int a = cx.pl->a[k], b = cx.pl->b[k];
 		if (a >= STATIC_BASE || b >= STATIC_BASE) continue;
 		if (cx.body[a].noResponse || cx.body[b].noResponse) continue;
-		uf_unite(uf, a, b);
+		int i = a, j = b;
+		for (;;) { const int q = (par >> (4 * i)) & 15; if (q == i) break; i = q; }
+		for (;;) { const int q = (par >> (4 * j)) & 15; if (q == j) break; j = q; }
+		if (i != j) par = (par & ~(15u << (4 * i))) | ((uint32_t)j << (4 * i));  // id[root(a)] = root(b)
 	}
-	for (int b = 0; b < nb; b++) cx.body[b].islandTag = uf_find(uf, b);
+	uint32_t tags = 0, rootsActive = 0;
+	for (int b = 0; b < nb; b++) {
+		int r = b;
+		for (;;) { const int q = (par >> (4 * r)) & 15; if (q == r) break; r = q; }
+		cx.body[b].islandTag = r;
+		tags |= (uint32_t)r << (4 * b);
+		const int act = cx.body[b].activation;
+		if (act == ACT_ACTIVE || act == ACT_DISABLE_DEACT) rootsActive |= 1u << r;
+	}
 	// per island: all sleeping? else wake sleepers (ISLAND_SLEEPING -> WANTS_DEACTIVATION)
-	for (int root = 0; root < nb; root++) {
-		bool any = false, allSleeping = true;
-		for (int b = 0; b < nb; b++) if (cx.body[b].islandTag == root) {
-			any = true;
-			if (cx.body[b].activation == ACT_ACTIVE || cx.body[b].activation == ACT_DISABLE_DEACT) { allSleeping = false; break; }
-		}
-		if (!any) continue;
-		for (int b = 0; b < nb; b++) if (cx.body[b].islandTag == root) {
-			if (allSleeping) { if (cx.body[b].activation != ACT_DISABLE_DEACT && cx.body[b].activation != ACT_DISABLE_SIM) cx.body[b].activation = ACT_SLEEPING; }
-			else if (cx.body[b].activation == ACT_SLEEPING) cx.body[b].activation = ACT_WANTS_DEACT;
-		}
+	uint32_t rootsAwake = 0, notSleeping = 0;
+	for (int b = 0; b < nb; b++) {
+		const int r = (tags >> (4 * b)) & 15;
+		int act = cx.body[b].activation;
+		if ((rootsActive >> r) & 1) { if (act == ACT_SLEEPING) { act = ACT_WANTS_DEACT; cx.body[b].activation = act; } }
+		else if (act != ACT_DISABLE_DEACT && act != ACT_DISABLE_SIM && act != ACT_SLEEPING) { act = ACT_SLEEPING; cx.body[b].activation = act; }
+		if (act != ACT_SLEEPING) notSleeping |= 1u << b;
+		if (act != ACT_SLEEPING && act != ACT_DISABLE_SIM) rootsAwake |= 1u << r;  // body_active
 	}
 	// m_islandmanifold: manifolds with an awake body and needsResponse, then quickSort by island id
 	int keys[MAX_MANIFOLDS], order[MAX_MANIFOLDS];
 	int n = 0;
-	for (int m = 0; m < cx.pl->nManifolds; m++) {
+	const int nMf = cx.pl->nManifolds;
+	for (int m = 0; m < nMf; m++) {
 		const Manifold& mf = cx.mf[m];
-		if (mf.body0 < 0) continue;  // pair without a manifold
-		bool s0 = mf.body0 >= STATIC_BASE, s1 = mf.body1 >= STATIC_BASE;
-		bool awake0 = !s0 && cx.body[mf.body0].activation != ACT_SLEEPING;
-		bool awake1 = !s1 && cx.body[mf.body1].activation != ACT_SLEEPING;
+		const int b0 = mf.body0, b1 = mf.body1;
+		if (b0 < 0) continue;  // pair without a manifold
+		const bool s0 = b0 >= STATIC_BASE, s1 = b1 >= STATIC_BASE;
+		const bool awake0 = !s0 && ((notSleeping >> b0) & 1);
+		const bool awake1 = !s1 && ((notSleeping >> b1) & 1);
 		if (!(awake0 || awake1)) continue;
-		bool resp = (s0 || !cx.body[mf.body0].noResponse) && (s1 || !cx.body[mf.body1].noResponse) && (!s0 || !s1);
+		const bool resp = (s0 || !cx.body[b0].noResponse) && (s1 || !cx.body[b1].noResponse) && (!s0 || !s1);
 		if (!resp) continue;
-		int tag0 = s0 ? -1 : cx.body[mf.body0].islandTag;
-		int tag1 = s1 ? -1 : cx.body[mf.body1].islandTag;
-		keys[n] = tag0 >= 0 ? tag0 : tag1;
+		keys[n] = !s0 ? (int)((tags >> (4 * b0)) & 15) : (int)((tags >> (4 * b1)) & 15);
 		order[n] = m;
 		n++;
 	}
 	if (n > 1) quicksort_keys(keys, order, 0, n - 1);
 	// drop manifolds whose island is asleep (processIslands only calls the solver for awake islands)
 	int outN = 0;
-	for (int k = 0; k < n; k++) {
-		int root = keys[k];
-		bool awake = false;
-		for (int b = 0; b < nb; b++) if (cx.body[b].islandTag == root && body_active(cx.body[b])) { awake = true; break; }
-		if (awake) cx.pl->manifoldOrder[outN++] = (uint8_t)order[k];
-	}
+	for (int k = 0; k < n; k++)
+		if ((rootsAwake >> keys[k]) & 1) cx.pl->manifoldOrder[outN++] = (uint8_t)order[k];
 	return outN;
 }
 
@@ -114,6 +108,13 @@ RSB_HD V3 sb_vel_no_delta(const SolverBody& b, const V3& rel) {  // getVelocityI
 }
 RSB_HD void sb_apply_impulse(SolverBody& b, const V3& lin, const V3& ang, float mag) {
 	if (b.orig >= 0) { b.dLin += lin * mag; b.dAng += ang * mag; }
+}
+// same, reporting whether the body's delta velocities changed at all (fixed-point detection of the PGS sweep)
+RSB_HD bool sb_apply_impulse_chg(SolverBody& b, const V3& lin, const V3& ang, float mag) {
+	if (b.orig < 0) return false;
+	const V3 l0 = b.dLin, a0 = b.dAng;
+	b.dLin += lin * mag; b.dAng += ang * mag;
+	return (b.dLin.x != l0.x) | (b.dLin.y != l0.y) | (b.dLin.z != l0.z) | (b.dAng.x != a0.x) | (b.dAng.y != a0.y) | (b.dAng.z != a0.z);
 }
 RSB_HD void sb_apply_push(SolverBody& b, const V3& lin, const V3& ang, float mag) {
 	if (b.orig >= 0) { b.push += lin * mag; b.turn += ang * mag; }
@@ -257,7 +258,9 @@ RSB_HD int get_or_init_solver_body(const Ctx& cx, int obj, int* companion, int& 
 }
 
 // Row kernels (SSE2 variants, btSequentialImpulseConstraintSolver.cpp:149-232, 318-349)
-RSB_HD float resolve_row(SolverBody& A, SolverBody& B, SolverRow& c, bool upperLimit) {
+// returns true when the row changed anything (its applied impulse or a body's delta velocity)
+RSB_HD bool resolve_row(SolverBody& A, SolverBody& B, SolverRow& c, bool upperLimit) {
+	const float applied0 = c.applied;
 	float deltaImpulse = c.rhs - c.applied * c.cfm;
 	float dv1 = simd_dot3(c.n1, A.dLin) + simd_dot3(c.rp1xn, A.dAng);
 	float dv2 = simd_dot3(c.n2, B.dLin) + simd_dot3(c.rp2xn, B.dAng);
@@ -267,9 +270,10 @@ RSB_HD float resolve_row(SolverBody& A, SolverBody& B, SolverRow& c, bool upperL
 	if (sum < c.lower) { deltaImpulse = c.lower - c.applied; c.applied = c.lower; }
 	else if (upperLimit && !(sum < c.upper)) { deltaImpulse = c.upper - c.applied; c.applied = c.upper; }
 	else c.applied = sum;
-	sb_apply_impulse(A, c.n1 * A.invMassV, c.angA, deltaImpulse);
-	sb_apply_impulse(B, c.n2 * B.invMassV, c.angB, deltaImpulse);
-	return deltaImpulse * (1.f / c.jacDiagInv);
+	bool chg = c.applied != applied0;
+	chg |= sb_apply_impulse_chg(A, c.n1 * A.invMassV, c.angA, deltaImpulse);
+	chg |= sb_apply_impulse_chg(B, c.n2 * B.invMassV, c.angB, deltaImpulse);
+	return chg;
 }
 RSB_HD float resolve_split(SolverBody& A, SolverBody& B, SolverRow& c) {
 	if (c.rhsPen == 0.f) return 0.f;
@@ -299,18 +303,18 @@ RSB_HD void solve_arena(const Ctx& cx, int nSolveManifolds) {
 	for (int b = 0; b < nb; b++) { companion[b] = -1; spNum[b] = 0; spTotalDist[b] = 0.f; spTotalNormal[b] = v3zero(); spFriction[b] = 0.f; spRestitution[b] = 0.f; }
 	int fixedId = -1;
 	sv.cnt[0] = 0; sv.cnt[1] = 0; sv.cnt[2] = 0;
+	RSB_SUBPROF_BEGIN();
 
-	// convertBodies: bodies of awake islands, in island order (sorted by island id), then body order
-	for (int root = 0; root < nb; root++) {
-		bool awake = false;
-		for (int b = 0; b < nb; b++) if (cx.body[b].islandTag == root && body_active(cx.body[b])) { awake = true; break; }
-		if (!awake) continue;
-		for (int b = 0; b < nb; b++) if (cx.body[b].islandTag == root) get_or_init_solver_body(cx, b, companion, fixedId);
-	}
+	// convertBodies: the reference converts every body of every awake island.  A body that ends up without a row only
+	// receives v += externalForceImpulse in the write-back, which solve_body_no_contacts reproduces bit for bit on the
+	// body's own thread (PH_FINISH_BODY); solver bodies are therefore created lazily, for bodies that carry a contact.
+	// (Solver-body numbering is internal; the only order that matters -- special contacts per body -- involves the ball alone.)
 
+	RSB_SUBPROF_MARK(2);
 	// convertContacts
 	for (int k = 0; k < nSolveManifolds; k++) {
 		Manifold& mf = cx.mf[cx.pl->manifoldOrder[k]];
+		if (mf.nPts == 0) continue;
 		int ia = get_or_init_solver_body(cx, mf.body0, companion, fixedId);
 		int ib = get_or_init_solver_body(cx, mf.body1, companion, fixedId);
 		for (int j = 0; j < mf.nPts; j++) {
@@ -359,6 +363,7 @@ RSB_HD void solve_arena(const Ctx& cx, int nSolveManifolds) {
 		spNum[b] = 0;
 	}
 
+	RSB_SUBPROF_MARK(3);
 	// split impulse iterations (:1778-1810)
 	for (int it = 0; it < 10; it++) {
 		float lsr = 0.f;
@@ -371,11 +376,16 @@ RSB_HD void solve_arena(const Ctx& cx, int nSolveManifolds) {
 		if (lsr <= 0.f || it >= 9) break;
 	}
 	// velocity iterations (:1601-1776): non-special contacts, then friction rows
+	RSB_SUBPROF_MARK(4);
+	// The reference always runs 10 sweeps (m_leastSquaresResidualThreshold = 0).  A sweep is a deterministic function of
+	// (applied impulses, body delta velocities); once a sweep leaves all of them unchanged it is at a fixed point and the
+	// remaining sweeps would reproduce it bit for bit, so they are skipped.
 	for (int it = 0; it < 10; it++) {
+		bool changed = false;
 		for (int j = 0; j < sv.cnt[1]; j++) {
 			SolverRow& c = sv.row(j);
 			if (c.isSpecial) continue;
-			resolve_row(sv.sbody[c.bodyA], sv.sbody[c.bodyB], c, false);
+			changed |= resolve_row(sv.sbody[c.bodyA], sv.sbody[c.bodyB], c, false);
 		}
 		for (int j = 0; j < sv.cnt[2]; j++) {
 			SolverRow& c = sv.frow(j);
@@ -383,10 +393,12 @@ RSB_HD void solve_arena(const Ctx& cx, int nSolveManifolds) {
 			if (totalImpulse > 0.f) {
 				c.lower = -(c.friction * totalImpulse);
 				c.upper = c.friction * totalImpulse;
-				resolve_row(sv.sbody[c.bodyA], sv.sbody[c.bodyB], c, true);
+				changed |= resolve_row(sv.sbody[c.bodyA], sv.sbody[c.bodyB], c, true);
 			}
 		}
+		if (!changed) break;
 	}
+	RSB_SUBPROF_MARK(5);
 	// writeBackBodies (:1878-1904, btSolverBody.h:265-287)
 	for (int i = 0; i < sv.cnt[0]; i++) {
 		SolverBody& sb = sv.sbody[i];
@@ -404,7 +416,9 @@ RSB_HD void solve_arena(const Ctx& cx, int nSolveManifolds) {
 		rb.angvel = sb.ang + sb.extT;
 		rb.pos = sb.xf.origin;
 		rb.basis = sb.xf.basis;
+		cx.misc[2] |= 1 << sb.orig;  // written back here: PH_FINISH_BODY must not touch this body's velocity again
 	}
+	RSB_SUBPROF_MARK(6);
 }
 
 // Does any manifold handed to the solver carry a contact point?  If not, solveGroup degenerates to the

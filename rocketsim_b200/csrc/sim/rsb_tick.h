@@ -110,16 +110,20 @@ RSB_HD void phase_run(const Ctx& cx, int phase, int item) {
 	case PH_PAIRS: collide_pairs(cx); break;
 	case PH_NARROW_STATIC: collide_static_pairs(cx, item); break;
 	case PH_DYN_SOLVE: {
+		RSB_SUBPROF_BEGIN();
 		collide_dynamic_pairs(cx);
+		RSB_SUBPROF_MARK(0);
 		const int nSolve = build_islands(cx);  // calculateSimulationIslands + buildIslands
+		RSB_SUBPROF_MARK(1);
 		const bool rows = solver_has_rows(cx, nSolve);
-		cx.misc[0] = rows ? 1 : 0; cx.misc[1] = nSolve;
+		cx.misc[0] = rows ? 1 : 0; cx.misc[1] = nSolve; cx.misc[2] = 0;
 		if (rows) solve_arena(cx, nSolve);     // solveConstraints
+		RSB_SUBPROF_MARK(rows ? 7 : 1);
 		break;
 	}
 	case PH_FINISH_BODY: {
 		const int b = item;
-		if (!cx.misc[0]) solve_body_no_contacts(cx, b);
+		if (!((cx.misc[2] >> b) & 1)) solve_body_no_contacts(cx, b);  // bodies the contact solver did not write back
 		// integrateTransforms (active bodies) + clearForces
 		BodyW& bw = cx.body[b];
 		RigidS& rb = rigid_of(cx, b);

@@ -22,6 +22,7 @@ struct WheelW {  // btWheelInfoRL working values (btVehicleRL.h:9-27, btWheelInf
 	int isInContact, isInContactWithWorld, groundObj;
 };
 
+constexpr int MAX_CAND = 14;
 struct BodyW {  // btRigidBody working values of one dynamic body
 	M3 invInertiaW;
 	V3 totalForce, totalTorque;
@@ -34,6 +35,11 @@ struct BodyW {  // btRigidBody working values of one dynamic body
 	int noResponse;     // CF_NO_CONTACT_RESPONSE
 	int islandTag;
 	float friction, restitution;
+	// broadphase: static proxies of the body's (new) cell whose AABB overlaps the body's and that pass the collision filter,
+	// as positions in Scene::cellStatics, found by the body's own thread (PH_PREDICT); nCand < 0 = list overflow, PH_PAIRS rescans
+	int nCand;
+	uint16_t cand[MAX_CAND];
+	uint8_t candObj[MAX_CAND + 2];  // static object index of each candidate
 };
 
 struct ContactPt {  // btManifoldPoint subset
@@ -96,6 +102,9 @@ struct EpaScratch {
 	SV sv[EPA_MAX_VERTICES + 4];
 	EpaFace fc[EPA_MAX_FACES];
 	int16_t stackF[EPA_MAX_FACES + 8]; uint8_t stackE[EPA_MAX_FACES + 8]; uint8_t stackS[EPA_MAX_FACES + 8];
+#if defined(RSB_PROFILE)
+	int profCalls;  // developer builds: narrowphase detector calls of the executing thread in the current phase (+1 GJK/box-box, +256 EPA)
+#endif
 };
 
 // Solver scratch of the common case (few rows): counters, solver bodies and the first SOLVER_ROWS_FAST rows of
@@ -122,6 +131,20 @@ struct ArenaW {
 	SolverRow rows[MAX_ROWS];    // overflow beyond SOLVER_ROWS_FAST (indexed like the full pool)
 	SolverRow frows[MAX_ROWS];
 };
+
+// developer builds (-DRSB_PROFILE): cycle split inside PH_DYN_SOLVE, summed over arenas and ticks
+#if defined(RSB_PROFILE) && defined(__CUDACC__)
+static __device__ unsigned long long g_subprof[64];
+#endif
+#if defined(RSB_PROFILE) && defined(__CUDA_ARCH__)
+#define RSB_SUBPROF_BEGIN() long long _sp0 = clock64()
+#define RSB_SUBPROF_BEGIN2() _sp0 = clock64()
+#define RSB_SUBPROF_MARK(k) do { long long _n = clock64(); atomicAdd(&g_subprof[k], (unsigned long long)(_n - _sp0)); atomicAdd(&g_subprof[32 + (k)], 1ull); _sp0 = _n; } while (0)
+#else
+#define RSB_SUBPROF_BEGIN() ((void)0)
+#define RSB_SUBPROF_BEGIN2() ((void)0)
+#define RSB_SUBPROF_MARK(k) ((void)0)
+#endif
 
 struct EventSink {
 	struct Ev { uint32_t arena, type, a, b; uint64_t tick; };

@@ -9,7 +9,7 @@ A = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 TICKS = int(sys.argv[2]) if len(sys.argv) > 2 else 240
 mode = int(sys.argv[3]) if len(sys.argv) > 3 else 0
 cpt = int(sys.argv[4]) if len(sys.argv) > 4 else 2
-path = os.path.join(R, "rocketsim_b200", "librsb_prof.so")
+path = os.environ.get("RSB_PROF_LIB") or os.path.join(R, "rocketsim_b200", "librsb_prof.so")
 L = rlib.load(path); rlib.init_from_mem(sm.mesh_sets(), L)
 b = ArenaBatch(mode, A, [0] * cpt + [1] * cpt, seed=1234, lib=L)
 b.reset_to_random_kickoff((1234 + np.arange(A)).astype(np.int32)); b.set_auto_reset(True, 1234)
