@@ -47,6 +47,25 @@ def n_pads_of(mode: int) -> int:
     return {0: 34, 1: 20, 2: 34, 3: 34, 5: 0}[mode]
 
 
+def ncu_traffic_per_launch(mode, cars_per_team, arenas, ticks):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE tick-kernel launch from the committed `ncu --set full` capture
+    (profiles/rNN_summary.json, scripts/gpu_round.sh), valid only for the launch shape it was taken on; else None."""
+    best = None
+    pdir = os.path.join(ROOT, "profiles")
+    for name in sorted(os.listdir(pdir)) if os.path.isdir(pdir) else []:
+        if not name.endswith("_summary.json"):
+            continue
+        try:
+            d = json.load(open(os.path.join(pdir, name)))
+            cfg = d["bench"]["config"]
+            if (cfg["arenas_per_gpu"], cfg["ticks_per_step"], cfg["n_cars"]) == (arenas, ticks, 2 * cars_per_team) and \
+                    cfg["workload"].startswith(MODE_NAMES[mode]):
+                best = float(d["ncu_full"]["dram_traffic_bytes_per_launch"])
+        except Exception:
+            continue
+    return best
+
+
 def measured_hbm_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -103,9 +122,10 @@ def run_reference(args):
     threads = cores
     # README style (README.md:10-11): one arena per thread is the reference's fastest configuration (more arenas per
     # thread only add cache pressure: measured 375k -> 28k arena-ticks/s from 1 to 64 arenas/thread on 8 cores).
-    # Bounded sample: a reference "step" = 64 x ticks_per_step ticks of `threads` arenas; construction is untimed.
+    # Bounded sample: a reference "step" = 512 x ticks_per_step ticks of `threads` arenas (about half a second of CPU work
+    # per step at the default 120 ticks); construction is untimed.
     apt = 1
-    ticks = 64 * args.ticks_per_step
+    ticks = 512 * args.ticks_per_step
     if args.warmup > 0:
         refsim.bench(args.mode, args.cars_per_team, threads, apt, max(1, ticks * args.warmup // 8), SEED)
     v, wall = refsim.bench(args.mode, args.cars_per_team, threads, apt, ticks * max(1, args.steps), SEED)
@@ -262,10 +282,12 @@ def run_cuda(args):
                        "n_cars": n_cars, "meshes": "synthetic .cmf (SURVEY F4)", "l2": "256 MiB flush write between timed steps",
                        "parallelism": f"replicas x{world} (independent arena shards, no collective)"},
             "e2e": {"value": e2e, "unit": "arena-ticks/s", "h2d_bytes_per_step": ctrl_bytes, "d2h_bytes_per_step": d2h_bytes,
-                    "ms_per_step": e2e_ms / args.steps},
+                    "ms_per_step": e2e_ms / args.steps, "launches_per_step": 8 + 2,
+                    "path": "rsb_step_with_controls (host control sequence, pinned) + rsb_get_car_states + rsb_get_ball_states (pinned)"},
             "gpu_launches": args.steps,  # one arena_step_kernel launch per step (plus one memset for the L2 flush)
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "arena_step_kernel", "kernel_ms": kern_ms_mean,
+                         "traffic": ncu_traffic_per_launch(args.mode, args.cars_per_team, A, TPS), "traffic_unit": "bytes/launch (ncu, profiles/)",
+                         "kernel": "arena_step_kernel", "kernel_ms": kern_ms_mean,
                          "bytes_per_arena_tick": Bt, "peak_source": peak_src},
             "clocks": sampler.result(),
             "device_error_flags": int(errs.item()), "checksum": checksum,
