@@ -45,7 +45,7 @@ RSB_HD V3 convex_aabb_center(const Ctx& cx, const Convex& s, const Xform& t) {
 RSB_HD_NOINLINE bool epa_penetration(const Ctx& cx, Convex A, Xform tA, Convex B, Xform tB, V3& v, V3& wa, V3& wb);
 
 // GJK closest points + addContactPoint.  A/B with world transforms; triMesh/triIndex forwarded.
-RSB_HD_NOINLINE void convex_convex(const Ctx& cx, int mi, Convex A, Xform xfA, Convex B, Xform xfB, int triMesh, int triIndex) {
+RSB_CC_ATTR void convex_convex(const Ctx& cx, int mi, const Convex& A, const Xform& xfA, const Convex& B, const Xform& xfB, int triMesh, int triIndex) {
 #if defined(RSB_PROFILE)
 	if (cx.epa) cx.epa->profCalls += 1;
 #endif

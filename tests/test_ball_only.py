@@ -1,0 +1,45 @@
+"""Ball-only batches (0 cars): the building block of a batched BallPredTracker (the reference's
+src/Sim/BallPredTracker/BallPredTracker.cpp:25-71 steps a ball-only shadow arena).  Single-step parity against a reference
+arena without cars, for a ball fired at ramps, walls, the ceiling and the goal."""
+import numpy as np
+import pytest
+
+import parity_util as pu
+from rocketsim_b200 import types as T
+
+LAUNCHES = [((0, 0, 300), (1800, 2600, 900)), ((3000, -2000, 150), (2500, 800, -300)), ((-500, 4000, 600), (-300, 2200, 1500)),
+            ((0, 0, 93.15), (0, 0, 0)), ((1000, 1000, 1800), (600, -900, 2000))]
+
+
+def run(lib, oracle, mode, ticks=300):
+    ref = oracle.RefArena(mode)
+    batch = pu.ArenaBatch(mode, len(LAUNCHES), [], lib=lib)
+    worst = 0.0
+    for k, (pos, vel) in enumerate(LAUNCHES):
+        bs = ref.ball_state()
+        bs["pos"]["x"], bs["pos"]["y"], bs["pos"]["z"] = pos
+        bs["vel"]["x"], bs["vel"]["y"], bs["vel"]["z"] = vel
+        bs["angVel"]["x"] = 2.0
+        ref.set_ball_state(bs)
+        for t in range(ticks):
+            batch.set_ball_states([k], np.array([ref.ball_state()], T.BallState))
+            batch.set_ball_internals([k], np.array([ref.ball_internal()], T.BallInternal))
+            ref.step(1)
+            batch.step(1)
+            mine = batch.get_ball_states()[k]
+            worst = max(worst, max(pu.compare_ball(mine, ref.ball_state()).values()))
+            assert bool(batch.is_ball_scored()[k]) == bool(ref.is_ball_scored()), (k, t)
+    assert int(batch.get_error_flags().max()) == 0
+    batch.close(); ref.close()
+    return worst
+
+
+@pytest.mark.parametrize("mode", [T.MODE_SOCCAR, T.MODE_HOOPS, T.MODE_SNOWDAY], ids=["soccar", "hoops", "snowday"])
+def test_ball_only_hostcheck(hostlib, oracle, mode):
+    assert run(hostlib, oracle, mode, ticks=200) <= 1e-4
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", [T.MODE_SOCCAR, T.MODE_HOOPS, T.MODE_HEATSEEKER, T.MODE_SNOWDAY], ids=["soccar", "hoops", "heatseeker", "snowday"])
+def test_ball_only_cuda(cudalib, oracle, mode):
+    assert run(cudalib, oracle, mode) <= 1e-4
