@@ -282,7 +282,7 @@ def run_cuda(args):
                        "n_cars": n_cars, "meshes": "synthetic .cmf (SURVEY F4)", "l2": "256 MiB flush write between timed steps",
                        "parallelism": f"replicas x{world} (independent arena shards, no collective)"},
             "e2e": {"value": e2e, "unit": "arena-ticks/s", "h2d_bytes_per_step": ctrl_bytes, "d2h_bytes_per_step": d2h_bytes,
-                    "ms_per_step": e2e_ms / args.steps, "launches_per_step": 8 + 2,
+                    "ms_per_step": e2e_ms / args.steps, "launches_per_step": 3 + 2,
                     "path": "rsb_step_with_controls (host control sequence, pinned) + rsb_get_car_states + rsb_get_ball_states (pinned)"},
             "gpu_launches": args.steps,  # one arena_step_kernel launch per step (plus one memset for the L2 flush)
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

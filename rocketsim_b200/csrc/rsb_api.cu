@@ -1069,10 +1069,13 @@ int rsb_step_with_controls(RsbBatch* b, const RsbCarControls* seq, int n_ticks) 
 	size_t n = (size_t)n_ticks * b->hp.nArenas * b->hp.nCars;
 	if (n > b->ctrlSeqCap) { dev_free(b->dCtrlSeq); b->dCtrlSeq = (CtrlS*)dev_alloc(n * sizeof(CtrlS)); b->ctrlSeqCap = n; }
 #ifndef RSB_HOSTCHECK
-	// Pipeline: the sequence goes up in <= 8 chunks on a copy stream while the step stream already runs the ticks of the
+	// Pipeline: the sequence goes up in 3 chunks on a copy stream while the step stream already runs the ticks of the
 	// chunks that have landed, so only the first chunk's copy is exposed.
 	const size_t perTick = (size_t)b->hp.nArenas * b->hp.nCars;
-	const int nChunks = n_ticks >= 16 ? 8 : 1;
+	// a short first chunk (so compute starts after ~1/16 of the copy) and two long ones: every extra launch costs a grid
+	// tail (its slowest block), so the sequence is not cut finer than the overlap needs
+	const int nChunks = n_ticks >= 16 ? 3 : 1;
+	auto chunk_end = [&](int c) { return nChunks == 1 ? n_ticks : (c == 0 ? n_ticks / 16 : (c == 1 ? n_ticks / 16 + (n_ticks - n_ticks / 16) / 2 : n_ticks)); };
 	if (!b->copyStream) {
 		CUDA_OK(cudaStreamCreateWithFlags(&b->copyStream, cudaStreamNonBlocking));
 		for (auto& e : b->chunkReady) CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -1082,14 +1085,14 @@ int rsb_step_with_controls(RsbBatch* b, const RsbCarControls* seq, int n_ticks) 
 	CUDA_OK(cudaStreamWaitEvent(b->copyStream, b->seqFree, 0));
 	int t0 = 0;
 	for (int c = 0; c < nChunks; c++) {
-		const int t1 = (int)((long long)n_ticks * (c + 1) / nChunks);
+		const int t1 = chunk_end(c);
 		if (t1 > t0) CUDA_OK(cudaMemcpyAsync(b->dCtrlSeq + t0 * perTick, seq + t0 * perTick, (size_t)(t1 - t0) * perTick * sizeof(CtrlS), cudaMemcpyHostToDevice, b->copyStream));
 		CUDA_OK(cudaEventRecord(b->chunkReady[c], b->copyStream));
 		t0 = t1;
 	}
 	t0 = 0;
 	for (int c = 0; c < nChunks; c++) {
-		const int t1 = (int)((long long)n_ticks * (c + 1) / nChunks);
+		const int t1 = chunk_end(c);
 		CUDA_OK(cudaStreamWaitEvent(b->stream, b->chunkReady[c], 0));
 		if (t1 > t0) launch_step(b, t1 - t0, b->dCtrlSeq + t0 * perTick, t1 - t0);
 		t0 = t1;
