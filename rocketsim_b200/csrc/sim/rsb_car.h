@@ -184,17 +184,19 @@ RSB_HD void wheel_trace(const Ctx& cx, int ci, int wi) {
 }
 
 // btVehicleRL::calcFrictionImpulses (btVehicleRL.cpp:306-380)
-RSB_HD void calc_friction_impulses(const Ctx& cx, int ci) {
+// One wheel of btVehicleRL::calcFrictionImpulses (btVehicleRL.cpp:306-380).  It only reads the wheel's own ray result, last
+// tick's wheel inputs and rigid-body state that nothing writes during the vehicle update, so it runs on the wheel's own thread
+// right after its ray (PH_WHEELS) instead of in a 4-wheel loop on the car's thread.
+RSB_HD void calc_friction_impulse(const Ctx& cx, int ci, int wi) {
 	CarS& c = cx.s->cars[ci];
 	const RigidS& rb = c.rb;
 	const BodyW& bw = cx.body[ci + 1];
-	const CarCfgD& cfg = cx.p->carCfg[ci];
 	const float dt = cx.p->dt;
 	const float mass = 1.f / bw.invMass;  // getMass()
 	const float frictionScale = mass / 3.f;
-	for (int wi = 0; wi < 4; wi++) {
+	{
 		WheelW& w = cx.wheels[ci * 4 + wi];
-		if (w.groundObj == OBJ_NONE) { w.impulse = v3zero(); continue; }
+		if (w.groundObj == OBJ_NONE) { w.impulse = v3zero(); return; }
 		V3 axleDir = w.wtBasis.col(1);
 		V3 surf = w.contactNormalWS;
 		float proj = dot(axleDir, surf);
@@ -262,7 +264,6 @@ RSB_HD void calc_friction_impulses(const Ctx& cx, int ci) {
 		}
 		V3 total = (forwardDir * rollingFriction * c.wLongFriction[wi]) + (axleDir * sideImpulse * c.wLatFriction[wi]);
 		w.impulse = total * frictionScale;
-		(void)cfg;
 	}
 }
 
@@ -664,8 +665,6 @@ RSB_HD void car_update_boost(const Ctx& cx, int ci) {
 RSB_HD void car_pretick_logic(const Ctx& cx, int ci) {
 	CarS& c = cx.s->cars[ci];
 	RSB_SUBPROF_BEGIN();
-	calc_friction_impulses(cx, ci);
-	RSB_SUBPROF_MARK(16);
 
 	bool jumpPressed = c.controls.jump && !c.lastControls.jump;
 	int numWheelsInContact = 0;

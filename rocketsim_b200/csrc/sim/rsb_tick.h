@@ -82,7 +82,7 @@ RSB_HD void phase_run(const Ctx& cx, int phase, int item) {
 		break;
 	case PH_WHEELS: {
 		int ci = item >> 2, wi = item & 3;
-		if (!S.cars[ci].isDemoed) wheel_trace(cx, ci, wi);
+		if (!S.cars[ci].isDemoed) { wheel_trace(cx, ci, wi); calc_friction_impulse(cx, ci, wi); }
 		break;
 	}
 	case PH_CAR_LOGIC: {
