@@ -99,6 +99,9 @@ RSB_HD void dyn_order_move_to_back(ArenaS& S, int nb, int b) {
 
 // updateSingleAabb of one dynamic body (current U predicted transform, +-0.02) and the grid cell of its min corner
 RSB_HD void body_filter(const Ctx& cx, int obj, int& group, int& mask);
+RSB_HD Convex car_box(const CarCfgD& cfg);
+RSB_HD Xform car_child_xform(const RigidS& rb, const CarCfgD& cfg);
+RSB_HD void convex_world_aabb(const Ctx& cx, const Convex& s, const Xform& t, V3& mn, V3& mx);
 RSB_HD void static_proxy_aabb(const Ctx& cx, int obj, V3& mn, V3& mx);
 RSB_HD void update_aabb(const Ctx& cx, int b) {
 	const V3 ct(kContactBreaking, kContactBreaking, kContactBreaking);
@@ -114,6 +117,11 @@ RSB_HD void update_aabb(const Ctx& cx, int b) {
 	int i, j, k;
 	bw.newCell = grid_cell_of(*cx.sc, mn, i, j, k);
 	bw.newI = i; bw.newJ = j; bw.newK = k;
+	if (b > 0) {
+		const CarCfgD& cfg = cx.p->carCfg[b - 1];
+		bw.childXf = car_child_xform(rb, cfg);
+		convex_world_aabb(cx, car_box(cfg), bw.childXf, bw.childMin, bw.childMax);
+	}
 	// static half of calculateOverlappingPairs for this body (its cell is final: PH_PAIRS only commits newCell)
 	{
 		const Scene& sc = *cx.sc;
@@ -721,13 +729,12 @@ RSB_HD void collide_static_pairs(const Ctx& cx, int b) {
 			else convex_vs_plane(cx, mi, shape, xf, sc.planes[sk - sc.nMeshes]);
 		} else {
 			const CarCfgD& cfg = P.carCfg[b - 1];
-			Convex shape = car_box(cfg);
-			Xform xf = car_child_xform(rb, cfg);
 			// btCompoundLeafCallback::ProcessChildShape: child AABB vs the other shape's AABB
-			V3 cmn, cmx, omn, omx;
-			convex_world_aabb(cx, shape, xf, cmn, cmx);
+			V3 omn, omx;
 			static_aabb(cx, a, omn, omx);
-			if (!aabb_overlap(cmn, cmx, omn, omx)) continue;
+			if (!aabb_overlap(cx.body[b].childMin, cx.body[b].childMax, omn, omx)) continue;
+			Convex shape = car_box(cfg);
+			const Xform xf = cx.body[b].childXf;
 			int mi = new_manifold(cx, k, b, a);
 			RSB_SUBPROF_MARK(12);
 			if (isMesh) convex_vs_mesh(cx, mi, b, shape, xf, sk, cx.pl->entry[k]);
@@ -746,14 +753,12 @@ RSB_HD void collide_dynamic_pairs(const Ctx& cx) {
 		if (a == 0) {
 			// (ball, car): swapped compound -> convex-convex(box of the car, ball shape); manifold (car, ball)
 			const CarCfgD& cfg = P.carCfg[b - 1];
-			const RigidS& rc = rigid_of(cx, b);
 			const RigidS& rball = rigid_of(cx, 0);
-			Convex box = car_box(cfg); Xform xfc = car_child_xform(rc, cfg);
 			Convex ball = ball_convex(P); Xform xfb; xfb.basis = rball.basis; xfb.origin = rball.pos;
-			V3 cmn, cmx, omn, omx;
-			convex_world_aabb(cx, box, xfc, cmn, cmx);
+			V3 omn, omx;
 			convex_world_aabb(cx, ball, xfb, omn, omx);
-			if (!aabb_overlap(cmn, cmx, omn, omx)) continue;
+			if (!aabb_overlap(cx.body[b].childMin, cx.body[b].childMax, omn, omx)) continue;
+			Convex box = car_box(cfg); const Xform xfc = cx.body[b].childXf;
 			int mi = new_manifold(cx, k, b, 0);
 			convex_convex(cx, mi, box, xfc, ball, xfb, -1, -1);
 			refresh_contact_points(cx, mi);
@@ -761,14 +766,14 @@ RSB_HD void collide_dynamic_pairs(const Ctx& cx) {
 			// (carLo=a, carHi=b): compound-compound -> ... -> box-box(body0 = box of b, body1 = box of a); manifold (b, a)
 			const CarCfgD& cfgA = P.carCfg[a - 1]; const CarCfgD& cfgB = P.carCfg[b - 1];
 			const RigidS& ra = rigid_of(cx, a); const RigidS& rbb = rigid_of(cx, b);
-			Convex boxA = car_box(cfgA), boxB = car_box(cfgB);
-			Xform xfA = car_child_xform(ra, cfgA), xfB = car_child_xform(rbb, cfgB);
-			V3 amn, amx, bmn, bmx, cmn, cmx;
-			convex_world_aabb(cx, boxA, xfA, amn, amx);   // child of A
+			const V3 amn = cx.body[a].childMin, amx = cx.body[a].childMax;   // child of A
+			V3 cmn, cmx;
 			compound_aabb(cfgB, rbb.basis, rbb.pos, cmn, cmx);  // whole compound B
 			if (!aabb_overlap(amn, amx, cmn, cmx)) continue;
-			convex_world_aabb(cx, boxB, xfB, bmn, bmx);   // child of B vs box A
-			if (!aabb_overlap(bmn, bmx, amn, amx)) continue;
+			if (!aabb_overlap(cx.body[b].childMin, cx.body[b].childMax, amn, amx)) continue;   // child of B vs box A
+			Convex boxA = car_box(cfgA), boxB = car_box(cfgB);
+			const Xform xfA = cx.body[a].childXf, xfB = cx.body[b].childXf;
+			(void)ra;
 			int mi = new_manifold(cx, k, b, a);
 			box_box(cx, mi, boxB, xfB, boxA, xfA);
 			refresh_contact_points(cx, mi);

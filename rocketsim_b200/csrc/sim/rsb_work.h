@@ -35,6 +35,10 @@ struct BodyW {  // btRigidBody working values of one dynamic body
 	int noResponse;     // CF_NO_CONTACT_RESPONSE
 	int islandTag;
 	float friction, restitution;
+	// cars: world transform of the hitbox (compound child) and its AABB at the CURRENT pose, shared by every narrowphase pair of
+	// the body this tick (computed once in PH_PREDICT; the pose does not change before the solver)
+	Xform childXf;
+	V3 childMin, childMax;
 	// broadphase: static proxies of the body's (new) cell whose AABB overlaps the body's and that pass the collision filter,
 	// as positions in Scene::cellStatics, found by the body's own thread (PH_PREDICT); nCand < 0 = list overflow, PH_PAIRS rescans
 	int nCand;
