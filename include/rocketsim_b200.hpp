@@ -108,6 +108,13 @@ public:
 		Check(rsb_reset_to_random_kickoff(h_, arenas ? arenas->data() : nullptr, arenas ? (int)arenas->size() : numArenas, seeds.data()));
 	}
 	void SetAutoReset(bool enable, uint32_t seed) { Check(rsb_set_auto_reset(h_, enable ? 1 : 0, seed)); }
+	// GameEventTracker on the device (shots, goal credits, saves in GetEvents) and Arena::IsBallProbablyGoingIn
+	void SetEventTracker(bool enable, const RsbEventTrackerConfig* cfg = nullptr) { Check(rsb_set_event_tracker(h_, enable ? 1 : 0, cfg)); }
+	std::vector<uint8_t> IsBallProbablyGoingIn(float maxTime = 2.f, float extraMargin = 0, std::vector<uint8_t>* goalTeams = nullptr) {
+		std::vector<uint8_t> v(numArenas), t(numArenas); Check(rsb_is_ball_probably_going_in(h_, maxTime, extraMargin, v.data(), t.data()));
+		if (goalTeams) *goalTeams = t;
+		return v;
+	}
 	RsbBatch* Handle() { return h_; }
 
 	const GameMode gameMode;
@@ -146,6 +153,10 @@ private:
 
 typedef std::function<void(Arena* arena, Team scoringTeam, void* userInfo)> GoalScoreEventFn;
 typedef std::function<void(Arena* arena, Car* bumper, Car* victim, bool isDemo, void* userInfo)> CarBumpEventFn;
+// GameEventTracker callbacks (src/Sim/GameEventTracker/GameEventTracker.h:6-8)
+typedef std::function<void(Arena* arena, Car* shooter, Car* passer, void* userInfo)> ShotEventFn;
+typedef std::function<void(Arena* arena, Car* scorer, Car* passer, void* userInfo)> GoalEventFn;
+typedef std::function<void(Arena* arena, Car* saver, void* userInfo)> SaveEventFn;
 
 class Arena {
 public:
@@ -180,6 +191,16 @@ public:
 	}
 	void SetGoalScoreCallback(GoalScoreEventFn fn, void* userInfo = nullptr) { goalFn_ = fn; goalInfo_ = userInfo; }
 	void SetCarBumpCallback(CarBumpEventFn fn, void* userInfo = nullptr) { bumpFn_ = fn; bumpInfo_ = userInfo; }
+	// GameEventTracker folded into the arena: enable once, then the callbacks fire from Step() like the arena's own
+	void EnableEventTracker(const RsbEventTrackerConfig* cfg = nullptr) { Realize(); batch_->SetEventTracker(true, cfg); }
+	void SetShotCallback(ShotEventFn fn, void* userInfo = nullptr) { shotFn_ = fn; shotInfo_ = userInfo; }
+	void SetGoalCallback(GoalEventFn fn, void* userInfo = nullptr) { goalCreditFn_ = fn; goalCreditInfo_ = userInfo; }
+	void SetSaveCallback(SaveEventFn fn, void* userInfo = nullptr) { saveFn_ = fn; saveInfo_ = userInfo; }
+	bool IsBallProbablyGoingIn(float maxTime = 2.f, float extraMargin = 0, Team* goalTeamOut = nullptr) {
+		Realize(); std::vector<uint8_t> t; bool r = batch_->IsBallProbablyGoingIn(maxTime, extraMargin, &t)[0] != 0;
+		if (r && goalTeamOut) *goalTeamOut = (Team)t[0];
+		return r;
+	}
 
 	// Arena::Step (Arena.cpp:689-756): uploads every car's `controls`, advances n ticks in one launch, dispatches callbacks.
 	void Step(int ticksToSimulate = 1) {
@@ -190,6 +211,9 @@ public:
 		tickCount += (uint64_t)ticksToSimulate;
 		for (const RsbEvent& e : batch_->GetEvents(4096)) {
 			if (e.type == RSB_EVENT_GOAL) { if (goalFn_) goalFn_(this, (Team)e.a, goalInfo_); }
+			else if (e.type == RSB_EVENT_SHOT) { if (shotFn_) shotFn_(this, GetCar(e.a), GetCar(e.b), shotInfo_); }
+			else if (e.type == RSB_EVENT_GOAL_CREDIT) { if (goalCreditFn_) goalCreditFn_(this, GetCar(e.a), GetCar(e.b), goalCreditInfo_); }
+			else if (e.type == RSB_EVENT_SAVE) { if (saveFn_) saveFn_(this, GetCar(e.a), saveInfo_); }
 			else if (bumpFn_) bumpFn_(this, GetCar(e.a), GetCar(e.b), e.type == RSB_EVENT_DEMO, bumpInfo_);
 		}
 	}
@@ -213,6 +237,9 @@ private:
 	MutatorConfig mutator_;
 	GoalScoreEventFn goalFn_; void* goalInfo_ = nullptr;
 	CarBumpEventFn bumpFn_; void* bumpInfo_ = nullptr;
+	ShotEventFn shotFn_; void* shotInfo_ = nullptr;
+	GoalEventFn goalCreditFn_; void* goalCreditInfo_ = nullptr;
+	SaveEventFn saveFn_; void* saveInfo_ = nullptr;
 	int device_; uint32_t seed_;
 };
 

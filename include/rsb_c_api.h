@@ -75,6 +75,16 @@ int rsb_step_with_controls(RsbBatch* b, const RsbCarControls* controls_seq, int 
 int rsb_set_auto_reset(RsbBatch* b, int enable, uint32_t seed);
 int rsb_sync(RsbBatch* b);
 
+/* Replaces GameEventTracker (src/Sim/GameEventTracker/GameEventTracker.h:45-100, .cpp:5-157) used as
+ * `arena->Step(1); tracker.Update(arena);`: when enabled, every tick of every arena ends with the tracker's Update and its
+ * shot / goal / save callbacks arrive through rsb_get_events as RSB_EVENT_SHOT / _GOAL_CREDIT / _SAVE (a = shooter, scorer or
+ * saver car id, b = passer id or 0).  cfg == NULL selects GameEventTrackerConfig's defaults.  Soccar, Snowday and Hoops only
+ * (Arena::IsBallProbablyGoingIn raises for the other modes, Arena.cpp:887). */
+int rsb_set_event_tracker(RsbBatch* b, int enable, const RsbEventTrackerConfig* cfg);
+/* Replaces Arena::IsBallProbablyGoingIn(maxTime, extraMargin, &goalTeam) (Arena.h, Arena.cpp:771-891); out / goal_team_out are
+ * [n_arenas] (goal_team_out may be NULL; it is only meaningful where out is 1). */
+int rsb_is_ball_probably_going_in(RsbBatch* b, float max_time, float extra_margin, uint8_t* out, uint8_t* goal_team_out);
+
 /* Replace Car::GetState / Car::SetState (src/Sim/Car/Car.h:151-152, Car.cpp:10-36).
  * get: out is [n_arenas][n_cars] host memory.  set: n entries addressed by (arena_idx[i], car_idx[i]),
  * car_idx is the 0-based slot (id - 1). */

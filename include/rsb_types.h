@@ -191,7 +191,15 @@ typedef struct RsbBallInternal {
 } RsbBallInternal;
 
 /* Events produced by a step (goal callback Arena.cpp:748-752, bump callback :399-400). */
-enum { RSB_EVENT_GOAL = 1, RSB_EVENT_BUMP = 2, RSB_EVENT_DEMO = 3 };
+enum { RSB_EVENT_GOAL = 1, RSB_EVENT_BUMP = 2, RSB_EVENT_DEMO = 3,
+       /* GameEventTracker events (src/Sim/GameEventTracker/GameEventTracker.h:6-8), produced when the tracker is enabled:
+        * a = shooter / scorer / saver car id, b = passer car id or 0 */
+       RSB_EVENT_SHOT = 4, RSB_EVENT_GOAL_CREDIT = 5, RSB_EVENT_SAVE = 6 };
+
+/* GameEventTrackerConfig (src/Sim/GameEventTracker/GameEventTracker.h:10-38), same field order and defaults. */
+typedef struct RsbEventTrackerConfig {
+	float shotMinSpeed, shotTouchMinDelay, predScoreExtraMargin, shotEventCooldown, shotMinScoreTime, goalMaxTouchTime, passMaxTouchTime;
+} RsbEventTrackerConfig;
 typedef struct RsbEvent {
 	uint32_t arena;
 	uint32_t type;     /* RSB_EVENT_* */

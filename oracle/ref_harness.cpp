@@ -7,6 +7,7 @@
 #include "../include/rsb_bench_inputs.h"
 
 #include "RocketSim.h"
+#include "Sim/GameEventTracker/GameEventTracker.h"
 #include "../libsrc/bullet3-3.24/BulletCollision/CollisionShapes/btBvhTriangleMeshShape.h"
 #include "../libsrc/bullet3-3.24/BulletCollision/CollisionShapes/btTriangleInfoMap.h"
 #include "../libsrc/bullet3-3.24/BulletCollision/CollisionShapes/btOptimizedBvh.h"
@@ -44,6 +45,7 @@ struct RefArena {
 	Arena* arena = nullptr;
 	std::vector<Car*> cars; // in AddCar order (index = id-1)
 	std::vector<RsbEvent> events;
+	GameEventTracker* tracker = nullptr;  // optional: the reference's own shot / goal / save detection, updated after every tick
 };
 
 static thread_local std::string g_err;
@@ -87,7 +89,7 @@ RefArena* ref_arena_create(int game_mode, float tick_rate) {
 	} catch (std::exception& e) { g_err = e.what(); return nullptr; }
 }
 
-void ref_arena_destroy(RefArena* r) { if (r) { delete r->arena; delete r; } }
+void ref_arena_destroy(RefArena* r) { if (r) { delete r->tracker; delete r->arena; delete r; } }
 
 uint32_t ref_add_car(RefArena* r, int team, int car_preset) {
 	Car* c = r->arena->AddCar((Team)team, *preset(car_preset));
@@ -99,7 +101,37 @@ int ref_num_pads(RefArena* r) { return (int)r->arena->_boostPads.size(); }
 void ref_seed_thread_rng(uint32_t seed) { Math::GetRandEngine().seed(seed); }
 void ref_reset_kickoff(RefArena* r, int seed) { r->arena->ResetToRandomKickoff(seed); }
 void ref_set_controls(RefArena* r, uint32_t id, const RsbCarControls* c) { memcpy(&r->cars[id - 1]->controls, c, sizeof(CarControls)); }
-void ref_step(RefArena* r, int n) { r->arena->Step(n); }
+void ref_step(RefArena* r, int n) {
+	if (!r->tracker) { r->arena->Step(n); return; }
+	for (int i = 0; i < n; i++) { r->arena->Step(1); r->tracker->Update(r->arena); }
+}
+
+/* GameEventTracker (src/Sim/GameEventTracker/GameEventTracker.h) with the given config (7 floats, field order of
+ * GameEventTrackerConfig); its callbacks land in the event queue as RSB_EVENT_SHOT / _GOAL_CREDIT / _SAVE. */
+void ref_enable_event_tracker(RefArena* r, const float* cfg7) {
+	delete r->tracker;
+	r->tracker = new GameEventTracker();
+	if (cfg7) {
+		GameEventTrackerConfig& c = r->tracker->config;
+		c.shotMinSpeed = cfg7[0]; c.shotTouchMinDelay = cfg7[1]; c.predScoreExtraMargin = cfg7[2]; c.shotEventCooldown = cfg7[3];
+		c.shotMinScoreTime = cfg7[4]; c.goalMaxTouchTime = cfg7[5]; c.passMaxTouchTime = cfg7[6];
+	}
+	r->tracker->SetShotCallback([](Arena* a, Car* shooter, Car* passer, void* u) {
+		((RefArena*)u)->events.push_back(RsbEvent{ 0, RSB_EVENT_SHOT, shooter->id, passer ? passer->id : 0u, a->tickCount });
+	}, r);
+	r->tracker->SetGoalCallback([](Arena* a, Car* scorer, Car* passer, void* u) {
+		((RefArena*)u)->events.push_back(RsbEvent{ 0, RSB_EVENT_GOAL_CREDIT, scorer->id, passer ? passer->id : 0u, a->tickCount });
+	}, r);
+	r->tracker->SetSaveCallback([](Arena* a, Car* saver, void* u) {
+		((RefArena*)u)->events.push_back(RsbEvent{ 0, RSB_EVENT_SAVE, saver->id, 0u, a->tickCount });
+	}, r);
+}
+int ref_is_ball_probably_going_in(RefArena* r, float maxTime, float extraMargin, int* teamOut) {
+	Team t = Team::BLUE;
+	bool in = r->arena->IsBallProbablyGoingIn(maxTime, extraMargin, &t);
+	if (teamOut) *teamOut = (int)t;
+	return in ? 1 : 0;
+}
 uint64_t ref_tick_count(RefArena* r) { return r->arena->tickCount; }
 int ref_is_ball_scored(RefArena* r) { return r->arena->IsBallScored() ? 1 : 0; }
 

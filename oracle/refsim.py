@@ -56,6 +56,8 @@ def lib():
         L.ref_step.argtypes = [vp, i32]
         L.ref_tick_count.argtypes = [vp]; L.ref_tick_count.restype = u64
         L.ref_is_ball_scored.argtypes = [vp]; L.ref_is_ball_scored.restype = i32
+        L.ref_enable_event_tracker.argtypes = [vp, vp]
+        L.ref_is_ball_probably_going_in.argtypes = [vp, f32, f32, vp]; L.ref_is_ball_probably_going_in.restype = i32
         for n in ("car_state", "car_internal"):
             getattr(L, "ref_get_" + n).argtypes = [vp, u32, vp]
             getattr(L, "ref_set_" + n).argtypes = [vp, u32, vp]
@@ -143,6 +145,15 @@ class RefArena:
     @property
     def tick_count(self):
         return self.L.ref_tick_count(self.h)
+
+    def enable_event_tracker(self, cfg7=None):
+        arr = None if cfg7 is None else np.asarray(cfg7, np.float32)
+        lib().ref_enable_event_tracker(self.h, None if arr is None else _ptr(arr))
+
+    def is_ball_probably_going_in(self, max_time=2.0, extra_margin=0.0):
+        t = C.c_int()
+        r = lib().ref_is_ball_probably_going_in(self.h, max_time, extra_margin, C.byref(t))
+        return bool(r), t.value
 
     def is_ball_scored(self):
         return bool(self.L.ref_is_ball_scored(self.h))

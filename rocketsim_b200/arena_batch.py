@@ -70,6 +70,17 @@ class ArenaBatch:
         """Device-side ``if (IsBallScored()) ResetToRandomKickoff(seed + arena + tick)`` after every tick."""
         _lib.check(self.L, self.L.rsb_set_auto_reset(self.h, int(bool(enable)), seed & 0xFFFFFFFF))
 
+    def set_event_tracker(self, enable: bool = True, config=None):
+        """Device-side ``GameEventTracker`` (shots, goal credits, saves) updated after every tick; events arrive via get_events."""
+        cfg = None if config is None else np.array([config], dtype=T.EventTrackerConfig)
+        _lib.check(self.L, self.L.rsb_set_event_tracker(self.h, int(bool(enable)), _lib.ptr(cfg)))
+
+    def is_ball_probably_going_in(self, max_time: float = 2.0, extra_margin: float = 0.0):
+        """``Arena::IsBallProbablyGoingIn`` for every arena: (going_in[n_arenas] bool, goal_team[n_arenas])."""
+        out = np.zeros(self.n_arenas, np.uint8); team = np.zeros(self.n_arenas, np.uint8)
+        _lib.check(self.L, self.L.rsb_is_ball_probably_going_in(self.h, max_time, extra_margin, _lib.ptr(out), _lib.ptr(team)))
+        return out.astype(bool), team
+
     def sync(self):
         _lib.check(self.L, self.L.rsb_sync(self.h))
 

@@ -1113,6 +1113,42 @@ int rsb_set_auto_reset(RsbBatch* b, int enable, uint32_t seed) {
 	h2d(b->dP, &b->hp, sizeof(BatchParams), b->stream);
 	API_END
 }
+int rsb_set_event_tracker(RsbBatch* b, int enable, const RsbEventTrackerConfig* cfg) {
+	API_BEGIN
+	set_device(b);
+	if (enable && (b->hp.mode == HEATSEEKER || b->hp.mode == THE_VOID))
+		throw std::runtime_error("Arena::IsBallProbablyGoingIn() is not supported for gamemode " + std::to_string(b->hp.mode));  // Arena.cpp:887
+	b->hp.trackerEnabled = enable ? 1 : 0;
+	TrackerCfgD& t = b->hp.tracker;
+	if (cfg) { t.shotMinSpeed = cfg->shotMinSpeed; t.shotTouchMinDelay = cfg->shotTouchMinDelay; t.predScoreExtraMargin = cfg->predScoreExtraMargin; t.shotEventCooldown = cfg->shotEventCooldown;
+	           t.shotMinScoreTime = cfg->shotMinScoreTime; t.goalMaxTouchTime = cfg->goalMaxTouchTime; t.passMaxTouchTime = cfg->passMaxTouchTime; }
+	else { t.shotMinSpeed = 1750; t.shotTouchMinDelay = 0.3f; t.predScoreExtraMargin = 0; t.shotEventCooldown = 1.0f; t.shotMinScoreTime = 2.0f; t.goalMaxTouchTime = 4.0f; t.passMaxTouchTime = 2.0f; }
+#ifndef RSB_HOSTCHECK
+	CUDA_OK(cudaStreamSynchronize(b->stream));
+#endif
+	h2d(b->dP, &b->hp, sizeof(BatchParams), b->stream);
+	API_END
+}
+RSB_GLOBAL void going_in_kernel(ArenaS* S, const BatchParams* P, float maxTime, float extraMargin, uint8_t* in, uint8_t* team, int nArenas) {
+	KERNEL_1D(i, nArenas);
+	Ctx cx; cx.s = &S[i]; cx.w = nullptr; cx.epa = nullptr; cx.body = nullptr; cx.wheels = nullptr; cx.padLocked = nullptr; cx.misc = nullptr; cx.pl = nullptr; cx.mf = nullptr; cx.solv = nullptr; cx.p = P; cx.sc = nullptr; cx.arena = i; cx.ev.buf = nullptr;
+	int t = 0; bool sup;
+	in[i] = is_ball_probably_going_in(cx, maxTime, extraMargin, t, sup) ? 1 : 0;
+	if (team) team[i] = (uint8_t)t;
+}
+int rsb_is_ball_probably_going_in(RsbBatch* b, float max_time, float extra_margin, uint8_t* out, uint8_t* goal_team_out) {
+	API_BEGIN
+	set_device(b);
+	if (b->hp.mode == HEATSEEKER || b->hp.mode == THE_VOID)
+		throw std::runtime_error("Arena::IsBallProbablyGoingIn() is not supported for gamemode " + std::to_string(b->hp.mode));
+	const int n = b->hp.nArenas;
+	b->ensure_scratch((size_t)n * 2);
+	uint8_t* din = (uint8_t*)b->dScratch; uint8_t* dteam = din + n;
+	LAUNCH_1D(going_in_kernel, n, b, b->dS, b->dP, max_time, extra_margin, din, dteam, n);
+	d2h(out, din, (size_t)n, b->stream);
+	if (goal_team_out) d2h(goal_team_out, dteam, (size_t)n, b->stream);
+	API_END
+}
 int rsb_sync(RsbBatch* b) {
 	API_BEGIN
 	set_device(b);

@@ -95,6 +95,10 @@ struct ArenaS {
 	uint8_t cellI[MAX_BODIES + 1], cellJ[MAX_BODIES + 1], cellK[MAX_BODIES + 1];
 	uint32_t errorFlags;
 	uint32_t goalScoredTick;  // debug
+	// GameEventTracker persistent info (GameEventTracker.h:72-87); only advanced when the batch enabled the tracker
+	uint64_t trkLastBallUpdate;
+	float trkShotCooldown;
+	uint8_t trkBallShot, trkShotGoalTeam, trkScoredLast, _trkPad;
 	BallS ball;
 	PadS pads[MAX_PADS];
 	CarS cars[MAX_CARS];   // last: a batch with fewer cars stages only the used prefix of the record
@@ -139,6 +143,8 @@ struct MutD {  // MutatorConfig (MutatorConfig.h:16-79), raw values in reference
 
 constexpr int PUCK_POINTS = 40;
 
+struct TrackerCfgD { float shotMinSpeed, shotTouchMinDelay, predScoreExtraMargin, shotEventCooldown, shotMinScoreTime, goalMaxTouchTime, passMaxTouchTime; };
+
 struct BatchParams {
 	int mode, nCars, nPads, nArenas;
 	float dt;
@@ -156,6 +162,7 @@ struct BatchParams {
 	int padGrid[8 * 10];  // BoostPadGrid (BoostPadGrid.h:10-29): pad index or -1
 	// README bench loop on device: when set, a goal is followed by ResetToRandomKickoff(autoResetSeed + arena + tick)
 	int autoReset; uint32_t autoResetSeed;
+	int trackerEnabled; TrackerCfgD tracker;  // device-side GameEventTracker (rsb_set_event_tracker)
 	float boundRadius[MAX_BODIES]; // radius of a sphere around the shape centre that contains the shape incl. margins
 	float motionDisc[MAX_BODIES];  // btCollisionShape::getAngularMotionDisc of each dynamic body's shape (constant per batch)
 };

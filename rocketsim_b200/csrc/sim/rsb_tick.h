@@ -10,6 +10,7 @@
 #include "rsb_collide.h"
 #include "rsb_solver.h"
 #include "rsb_kickoff.h"
+#include "rsb_tracker.h"
 
 namespace rsb {
 
@@ -143,10 +144,15 @@ RSB_HD void phase_run(const Ctx& cx, int phase, int item) {
 	case PH_TAIL:
 		ball_finish_tick(cx);
 		// ---- T6: goal event, tick counter
-		if (P.mode != THE_VOID && is_ball_scored(cx)) {
-			float y = -S.ball.rb.pos.y;
-			push_event(cx, 1u /*RSB_EVENT_GOAL*/, (y < 0.f) ? 0u : 1u, 0u);
-			if (P.autoReset) kickoff_reset(S, P, (int)(P.autoResetSeed + (uint32_t)cx.arena + (uint32_t)S.tickCount));
+		{
+			const bool scored = P.mode != THE_VOID && is_ball_scored(cx);
+			if (scored) {
+				float y = -S.ball.rb.pos.y;
+				push_event(cx, 1u /*RSB_EVENT_GOAL*/, (y < 0.f) ? 0u : 1u, 0u);
+			}
+			// the caller's loop is Step(); tracker.Update(); if (scored) Reset -- same order here
+			if (P.trackerEnabled) tracker_update(cx, scored, S.tickCount + 1);
+			if (scored && P.autoReset) kickoff_reset(S, P, (int)(P.autoResetSeed + (uint32_t)cx.arena + (uint32_t)S.tickCount));
 		}
 		S.tickCount++;
 		break;

@@ -217,6 +217,18 @@ RSB_HD void push_event(const Ctx& cx, uint32_t type, uint32_t a, uint32_t b) {
 	}
 }
 
+// same with an explicit tick stamp (the tracker reports Arena::tickCount as its Update() sees it, i.e. after the step)
+RSB_HD void push_event_at(const Ctx& cx, uint32_t type, uint32_t a, uint32_t b, uint64_t tick) {
+	if (!cx.ev.buf) return;
+#if defined(__CUDA_ARCH__)
+	uint32_t i = atomicAdd(cx.ev.count, 1u);
+#else
+	uint32_t i = (*cx.ev.count)++;
+#endif
+	if (i < cx.ev.cap) { EventSink::Ev e; e.arena = (uint32_t)cx.arena; e.type = type; e.a = a; e.b = b; e.tick = tick; cx.ev.buf[i] = e; }
+	else set_error(cx, ERR_EVENT_OVERFLOW);
+}
+
 RSB_HD bool body_active(const BodyW& b) { return b.activation != ACT_SLEEPING && b.activation != ACT_DISABLE_SIM; }
 
 // ---- btRigidBody helpers on (RigidS, BodyW) pairs ----

@@ -102,6 +102,9 @@ Event = np.dtype({"names": ["arena", "type", "a", "b", "tick"], "formats": ["<u4
                   "itemsize": 24})
 
 EVENT_GOAL, EVENT_BUMP, EVENT_DEMO = 1, 2, 3
+EVENT_SHOT, EVENT_GOAL_CREDIT, EVENT_SAVE = 4, 5, 6
+EventTrackerConfig = np.dtype([(n, "<f4") for n in ("shotMinSpeed", "shotTouchMinDelay", "predScoreExtraMargin", "shotEventCooldown",
+                                                     "shotMinScoreTime", "goalMaxTouchTime", "passMaxTouchTime")])
 MODE_SOCCAR, MODE_HOOPS, MODE_HEATSEEKER, MODE_SNOWDAY, MODE_DROPSHOT, MODE_THE_VOID = range(6)
 TEAM_BLUE, TEAM_ORANGE = 0, 1
 CAR_OCTANE, CAR_DOMINUS, CAR_PLANK, CAR_BREAKOUT, CAR_HYBRID, CAR_MERC, CAR_PSYCLOPS = range(7)
