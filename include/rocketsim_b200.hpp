@@ -107,6 +107,8 @@ public:
 	void ResetToRandomKickoff(const std::vector<int32_t>& seeds, const std::vector<uint32_t>* arenas = nullptr) {
 		Check(rsb_reset_to_random_kickoff(h_, arenas ? arenas->data() : nullptr, arenas ? (int)arenas->size() : numArenas, seeds.data()));
 	}
+	// BallPredTracker::predData for every arena: [nTicks][numArenas], row 0 = now
+	std::vector<BallState> PredictBall(int nTicks) { std::vector<BallState> v((size_t)nTicks * numArenas); Check(rsb_predict_ball(h_, nTicks, v.data())); return v; }
 	void SetAutoReset(bool enable, uint32_t seed) { Check(rsb_set_auto_reset(h_, enable ? 1 : 0, seed)); }
 	// GameEventTracker on the device (shots, goal credits, saves in GetEvents) and Arena::IsBallProbablyGoingIn
 	void SetEventTracker(bool enable, const RsbEventTrackerConfig* cfg = nullptr) { Check(rsb_set_event_tracker(h_, enable ? 1 : 0, cfg)); }

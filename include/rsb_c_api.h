@@ -81,6 +81,11 @@ int rsb_sync(RsbBatch* b);
  * saver car id, b = passer id or 0).  cfg == NULL selects GameEventTrackerConfig's defaults.  Soccar, Snowday and Hoops only
  * (Arena::IsBallProbablyGoingIn raises for the other modes, Arena.cpp:887). */
 int rsb_set_event_tracker(RsbBatch* b, int enable, const RsbEventTrackerConfig* cfg);
+/* Replaces BallPredTracker::ForceUpdateAllPred / predData (src/Sim/BallPredTracker/BallPredTracker.cpp:58-66) for every arena
+ * of the batch at once: out is [n_ticks][n_arenas]; row 0 = the arena's current Ball::GetState(), row i = the ball state after i
+ * ticks of a ball-only arena of the same game mode, mutators and tick rate started from it (cars are not simulated). */
+int rsb_predict_ball(RsbBatch* b, int n_ticks, RsbBallState* out);
+
 /* Replaces Arena::IsBallProbablyGoingIn(maxTime, extraMargin, &goalTeam) (Arena.h, Arena.cpp:771-891); out / goal_team_out are
  * [n_arenas] (goal_team_out may be NULL; it is only meaningful where out is 1). */
 int rsb_is_ball_probably_going_in(RsbBatch* b, float max_time, float extra_margin, uint8_t* out, uint8_t* goal_team_out);

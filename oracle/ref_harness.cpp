@@ -8,6 +8,7 @@
 
 #include "RocketSim.h"
 #include "Sim/GameEventTracker/GameEventTracker.h"
+#include "Sim/BallPredTracker/BallPredTracker.h"
 #include "../libsrc/bullet3-3.24/BulletCollision/CollisionShapes/btBvhTriangleMeshShape.h"
 #include "../libsrc/bullet3-3.24/BulletCollision/CollisionShapes/btTriangleInfoMap.h"
 #include "../libsrc/bullet3-3.24/BulletCollision/CollisionShapes/btOptimizedBvh.h"
@@ -125,6 +126,12 @@ void ref_enable_event_tracker(RefArena* r, const float* cfg7) {
 	r->tracker->SetSaveCallback([](Arena* a, Car* saver, void* u) {
 		((RefArena*)u)->events.push_back(RsbEvent{ 0, RSB_EVENT_SAVE, saver->id, 0u, a->tickCount });
 	}, r);
+}
+/* BallPredTracker (src/Sim/BallPredTracker/BallPredTracker.cpp): predData of a fresh tracker built on the arena. */
+int ref_ball_pred(RefArena* r, int n_ticks, RsbBallState* out) {
+	BallPredTracker t(r->arena, (size_t)n_ticks);
+	for (size_t i = 0; i < t.predData.size(); i++) memcpy(&out[i], &t.predData[i], sizeof(RsbBallState));
+	return (int)t.predData.size();
 }
 int ref_is_ball_probably_going_in(RefArena* r, float maxTime, float extraMargin, int* teamOut) {
 	Team t = Team::BLUE;

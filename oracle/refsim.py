@@ -57,6 +57,7 @@ def lib():
         L.ref_tick_count.argtypes = [vp]; L.ref_tick_count.restype = u64
         L.ref_is_ball_scored.argtypes = [vp]; L.ref_is_ball_scored.restype = i32
         L.ref_enable_event_tracker.argtypes = [vp, vp]
+        L.ref_ball_pred.argtypes = [vp, i32, vp]; L.ref_ball_pred.restype = i32
         L.ref_is_ball_probably_going_in.argtypes = [vp, f32, f32, vp]; L.ref_is_ball_probably_going_in.restype = i32
         for n in ("car_state", "car_internal"):
             getattr(L, "ref_get_" + n).argtypes = [vp, u32, vp]
@@ -145,6 +146,11 @@ class RefArena:
     @property
     def tick_count(self):
         return self.L.ref_tick_count(self.h)
+
+    def ball_pred(self, n_ticks):
+        out = np.zeros(n_ticks, dtype=T.BallState)
+        n = lib().ref_ball_pred(self.h, n_ticks, _ptr(out))
+        return out[:n]
 
     def enable_event_tracker(self, cfg7=None):
         arr = None if cfg7 is None else np.asarray(cfg7, np.float32)

@@ -81,6 +81,13 @@ class ArenaBatch:
         _lib.check(self.L, self.L.rsb_is_ball_probably_going_in(self.h, max_time, extra_margin, _lib.ptr(out), _lib.ptr(team)))
         return out.astype(bool), team
 
+    def predict_ball(self, n_ticks: int):
+        """Batched ``BallPredTracker``: ``[n_ticks, n_arenas]`` ball states, row 0 = now, row i = after i ticks of a ball-only
+        arena started from the current ball state (``BallPredTracker::ForceUpdateAllPred``)."""
+        out = np.zeros((int(n_ticks), self.n_arenas), dtype=T.BallState)
+        _lib.check(self.L, self.L.rsb_predict_ball(self.h, int(n_ticks), _lib.ptr(out)))
+        return out
+
     def sync(self):
         _lib.check(self.L, self.L.rsb_sync(self.h))
 

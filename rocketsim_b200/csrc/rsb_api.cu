@@ -117,6 +117,10 @@ struct RsbBatch {
 	ArenaW* dW = nullptr;
 	ArenaH* dH = nullptr;          // global mirror of the hot per-tick scratch
 	EpaScratch* dE = nullptr;      // EPA working sets, one per thread of the step grid
+	RsbBallState* traceOut = nullptr;  // consumed by the next launch (rsb_predict_ball)
+	RsbBatch* pred = nullptr;      // ball-only sibling batch used by rsb_predict_ball (created on first use)
+	RsbMutatorConfig mutApi;       // the mutator config the batch was created with
+	float tickRate = 120.f;
 	const Scene* dScene = nullptr;
 	EventSink::Ev* dEvents = nullptr;
 	uint32_t* dEventCount = nullptr;
@@ -282,6 +286,7 @@ struct StepArgs {
 	ArenaS* S; ArenaH* H; ArenaW* W; EpaScratch* E; const BatchParams* P; const Scene* sc; EventSink ev;
 	int nArenas, nTicks; const CtrlS* ctrlSeq; int nCtrl; int apb;
 	int mirror;  // keep the full debug mirror (ArenaH) up to date: single-tick launches only
+	RsbBallState* ballTrace;  // optional [nTicks + 1][nArenas]: Ball::GetState() after every tick (row t + 1), see rsb_predict_ball
 	ArenaLayout lay;
 };
 
@@ -464,6 +469,8 @@ __global__ void __launch_bounds__(STEP_THREADS, BLOCKS_PER_SM) arena_step_kernel
 			run_phase_block<PH_CAR_POST>(a, sP, sSc, sS, a0, nA, ptid);
 			run_phase_block<PH_PADS_POST>(a, sP, sSc, sS, a0, nA, ptid);
 			run_phase_block<PH_TAIL>(a, sP, sSc, sS, a0, nA, ptid);
+			if (a.ballTrace)  // the ball is next written in PH_CAR_LOGIC, several barriers from here
+				for (int i = tid; i < nA; i += STEP_THREADS) ball_to_api(((const ArenaS*)(sS + (size_t)i * a.lay.stride))->ball, a.ballTrace[(size_t)(t + 1) * a.nArenas + a0 + i]);
 		}
 		// records back to HBM; the last tick's hot scratch goes to its global mirror (debug probes)
 		for (int i = tid; i < nA * sWords; i += STEP_THREADS) {
@@ -505,6 +512,7 @@ static void arena_step_host(const StepArgs& a) {
 				for (int ci = 0; ci < nCars; ci++) cx.s->cars[ci].controls = src[ci];
 			}
 			arena_tick(cx);
+			if (a.ballTrace) ball_to_api(cx.s->ball, a.ballTrace[(size_t)(t + 1) * a.nArenas + arena]);
 		}
 	}
 }
@@ -901,6 +909,7 @@ int rsb_batch_create(int device, int game_mode, int n_arenas, int n_cars, const 
 	P.dt = 1 / tick_rate;
 	RsbMutatorConfig mc;
 	if (mutator) mc = *mutator; else default_mutator(game_mode, mc);
+	b->mutApi = mc; b->tickRate = tick_rate;
 	fill_mut(mc, P.mut);
 	P.gravityBT = P.mut.gravity * UU_TO_BT;
 	fill_ball(game_mode, P);
@@ -985,6 +994,7 @@ int rsb_batch_destroy(RsbBatch* b) {
 #ifndef RSB_HOSTCHECK
 	if (b->copyStream) { cudaStreamDestroy(b->copyStream); for (auto& e : b->chunkReady) cudaEventDestroy(e); cudaEventDestroy(b->seqFree); }
 #endif
+	if (b->pred) { rsb_batch_destroy(b->pred); b->pred = nullptr; }
 	dev_free(b->dP); dev_free(b->dS); dev_free(b->dW); dev_free(b->dH); dev_free(b->dE); dev_free(b->dEvents); dev_free(b->dEventCount); dev_free(b->dCtrl); dev_free(b->dCtrlSeq); dev_free(b->dScratch);
 	delete b;
 	API_END
@@ -1013,6 +1023,7 @@ static void launch_step(RsbBatch* b, int n_ticks, const CtrlS* seq, int nCtrl) {
 	StepArgs a; a.S = b->dS; a.H = b->dH; a.W = b->dW; a.E = b->dE; a.P = b->dP;
 	a.lay = ArenaLayout::make(P.nCars, P.nPads); a.sc = b->dScene; a.ev = sink_of(b);
 	a.nArenas = P.nArenas; a.nTicks = n_ticks; a.ctrlSeq = seq; a.nCtrl = nCtrl; a.apb = 1; a.mirror = (n_ticks == 1) ? 1 : 0;
+	a.ballTrace = b->traceOut; b->traceOut = nullptr;
 #ifndef RSB_HOSTCHECK
 	// chunk size: fill every SM once if the batch fits (one wave), else the fewest equal waves
 	const int sms = b->numSMs * BLOCKS_PER_SM;  // resident block slots
@@ -1147,6 +1158,33 @@ int rsb_is_ball_probably_going_in(RsbBatch* b, float max_time, float extra_margi
 	LAUNCH_1D(going_in_kernel, n, b, b->dS, b->dP, max_time, extra_margin, din, dteam, n);
 	d2h(out, din, (size_t)n, b->stream);
 	if (goal_team_out) d2h(goal_team_out, dteam, (size_t)n, b->stream);
+	API_END
+}
+// Ball::GetState -> Ball::SetState across two arenas (BallPredTracker::ForceUpdateAllPred's first line): through the UU-valued
+// BallState, as the reference does, so the x50 / x0.02 round trip of the position is reproduced
+RSB_GLOBAL void copy_ball_kernel(const ArenaS* src, ArenaS* dst, RsbBallState* row0, int nArenas) {
+	KERNEL_1D(i, nArenas);
+	RsbBallState st; ball_to_api(src[i].ball, st);
+	ball_from_api(st, dst[i].ball);
+	row0[i] = st;
+}
+int rsb_predict_ball(RsbBatch* b, int n_ticks, RsbBallState* out) {
+	API_BEGIN
+	set_device(b);
+	if (n_ticks < 1) throw std::runtime_error("n_ticks must be >= 1");
+	if (!b->pred) {
+		RsbBatch* p = nullptr;
+		if (rsb_batch_create(b->device, b->hp.mode, b->hp.nArenas, 0, nullptr, nullptr, &b->mutApi, b->tickRate, 0, &p) != 0) throw std::runtime_error(g_err);
+		b->pred = p;
+	}
+	RsbBatch* p = b->pred;
+	p->stream = b->stream;
+	const size_t rows = (size_t)n_ticks * b->hp.nArenas;
+	b->ensure_scratch(rows * sizeof(RsbBallState));
+	RsbBallState* dTrace = (RsbBallState*)b->dScratch;
+	LAUNCH_1D(copy_ball_kernel, b->hp.nArenas, b, b->dS, p->dS, dTrace, b->hp.nArenas);
+	if (n_ticks > 1) { p->traceOut = dTrace; launch_step(p, n_ticks - 1, nullptr, 0); }
+	d2h(out, dTrace, rows * sizeof(RsbBallState), b->stream);
 	API_END
 }
 int rsb_sync(RsbBatch* b) {
