@@ -107,6 +107,12 @@ public:
 	void ResetToRandomKickoff(const std::vector<int32_t>& seeds, const std::vector<uint32_t>* arenas = nullptr) {
 		Check(rsb_reset_to_random_kickoff(h_, arenas ? arenas->data() : nullptr, arenas ? (int)arenas->size() : numArenas, seeds.data()));
 	}
+	// Arena::Serialize / Arena::DeserializeNew of one arena in RocketSim's own byte format (interchange with the CPU library)
+	std::vector<uint8_t> SerializeArena(uint32_t arena) {
+		size_t n = 0; Check(rsb_serialize_arena(h_, arena, nullptr, 0, &n));
+		std::vector<uint8_t> v(n); Check(rsb_serialize_arena(h_, arena, v.data(), v.size(), &n)); return v;
+	}
+	void DeserializeArena(uint32_t arena, const std::vector<uint8_t>& data) { Check(rsb_deserialize_arena(h_, arena, data.data(), data.size())); }
 	// BallPredTracker::predData for every arena: [nTicks][numArenas], row 0 = now
 	std::vector<BallState> PredictBall(int nTicks) { std::vector<BallState> v((size_t)nTicks * numArenas); Check(rsb_predict_ball(h_, nTicks, v.data())); return v; }
 	void SetAutoReset(bool enable, uint32_t seed) { Check(rsb_set_auto_reset(h_, enable ? 1 : 0, seed)); }

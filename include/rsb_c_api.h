@@ -81,6 +81,14 @@ int rsb_sync(RsbBatch* b);
  * saver car id, b = passer id or 0).  cfg == NULL selects GameEventTrackerConfig's defaults.  Soccar, Snowday and Hoops only
  * (Arena::IsBallProbablyGoingIn raises for the other modes, Arena.cpp:887). */
 int rsb_set_event_tracker(RsbBatch* b, int enable, const RsbEventTrackerConfig* cfg);
+/* Wire compatibility with the CPU library.  rsb_serialize_arena writes arena `arena_idx` in the byte format of
+ * Arena::Serialize (src/Sim/Arena/Arena.cpp:546-574; no version header, like the in-memory DataStreamOut) -- a stream that
+ * RocketSim's Arena::DeserializeNew loads; out == NULL only returns the size in *n_out.  rsb_deserialize_arena is
+ * Arena::DeserializeNew (Arena.cpp:576-644) into an existing arena of the batch: the stream's game mode, tick rate, cars
+ * (ids 1..n_cars, teams, configs) and mutators must equal what the batch was created with. */
+int rsb_serialize_arena(RsbBatch* b, uint32_t arena_idx, uint8_t* out, size_t cap, size_t* n_out);
+int rsb_deserialize_arena(RsbBatch* b, uint32_t arena_idx, const uint8_t* data, size_t n);
+
 /* Replaces BallPredTracker::ForceUpdateAllPred / predData (src/Sim/BallPredTracker/BallPredTracker.cpp:58-66) for every arena
  * of the batch at once: out is [n_ticks][n_arenas]; row 0 = the arena's current Ball::GetState(), row i = the ball state after i
  * ticks of a ball-only arena of the same game mode, mutators and tick rate started from it (cars are not simulated). */

@@ -13,6 +13,7 @@
 #include "../libsrc/bullet3-3.24/BulletCollision/CollisionShapes/btTriangleInfoMap.h"
 #include "../libsrc/bullet3-3.24/BulletCollision/CollisionShapes/btOptimizedBvh.h"
 
+#include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <cstring>
@@ -126,6 +127,23 @@ void ref_enable_event_tracker(RefArena* r, const float* cfg7) {
 	r->tracker->SetSaveCallback([](Arena* a, Car* saver, void* u) {
 		((RefArena*)u)->events.push_back(RsbEvent{ 0, RSB_EVENT_SAVE, saver->id, 0u, a->tickCount });
 	}, r);
+}
+/* Arena::Serialize / Arena::DeserializeNew (Arena.cpp:546-644) through in-memory streams. */
+size_t ref_serialize(RefArena* r, uint8_t* out, size_t cap) {
+	DataStreamOut s; r->arena->Serialize(s);
+	if (out && cap >= s.data.size()) memcpy(out, s.data.data(), s.data.size());
+	return s.data.size();
+}
+RefArena* ref_deserialize_new(const uint8_t* data, size_t n) {
+	try {
+		DataStreamIn in; in.data.assign(data, data + n);
+		RefArena* r = new RefArena();
+		r->arena = Arena::DeserializeNew(in);
+		std::vector<Car*> cars(r->arena->_cars.begin(), r->arena->_cars.end());
+		std::sort(cars.begin(), cars.end(), [](Car* a, Car* b) { return a->id < b->id; });
+		r->cars = cars;
+		return r;
+	} catch (const std::exception& e) { g_err = e.what(); return nullptr; }
 }
 /* BallPredTracker (src/Sim/BallPredTracker/BallPredTracker.cpp): predData of a fresh tracker built on the arena. */
 int ref_ball_pred(RefArena* r, int n_ticks, RsbBallState* out) {

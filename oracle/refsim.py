@@ -58,6 +58,8 @@ def lib():
         L.ref_is_ball_scored.argtypes = [vp]; L.ref_is_ball_scored.restype = i32
         L.ref_enable_event_tracker.argtypes = [vp, vp]
         L.ref_ball_pred.argtypes = [vp, i32, vp]; L.ref_ball_pred.restype = i32
+        L.ref_serialize.argtypes = [vp, vp, C.c_size_t]; L.ref_serialize.restype = C.c_size_t
+        L.ref_deserialize_new.argtypes = [vp, C.c_size_t]; L.ref_deserialize_new.restype = vp
         L.ref_is_ball_probably_going_in.argtypes = [vp, f32, f32, vp]; L.ref_is_ball_probably_going_in.restype = i32
         for n in ("car_state", "car_internal"):
             getattr(L, "ref_get_" + n).argtypes = [vp, u32, vp]
@@ -109,6 +111,24 @@ class RefArena:
             raise RuntimeError(self.L.ref_last_error().decode())
         self.mode = mode
         self.car_ids = []
+
+    def serialize(self) -> bytes:
+        n = self.L.ref_serialize(self.h, None, 0)
+        buf = (C.c_uint8 * n)()
+        self.L.ref_serialize(self.h, buf, n)
+        return bytes(buf)
+
+    @classmethod
+    def deserialize_new(cls, data: bytes, mode: int, n_cars: int):
+        self = cls.__new__(cls)
+        self.L = lib()
+        buf = (C.c_uint8 * len(data)).from_buffer_copy(data)
+        self.h = self.L.ref_deserialize_new(buf, len(data))
+        if not self.h:
+            raise RuntimeError(self.L.ref_last_error().decode())
+        self.mode = mode
+        self.car_ids = list(range(1, n_cars + 1))
+        return self
 
     def close(self):
         if self.h:

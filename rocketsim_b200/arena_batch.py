@@ -88,6 +88,19 @@ class ArenaBatch:
         _lib.check(self.L, self.L.rsb_predict_ball(self.h, int(n_ticks), _lib.ptr(out)))
         return out
 
+    def serialize_arena(self, arena: int) -> bytes:
+        """``Arena::Serialize`` of one arena: bytes that RocketSim's ``Arena::DeserializeNew`` loads."""
+        n = C.c_size_t()
+        _lib.check(self.L, self.L.rsb_serialize_arena(self.h, arena, None, 0, C.byref(n)))
+        buf = (C.c_uint8 * n.value)()
+        _lib.check(self.L, self.L.rsb_serialize_arena(self.h, arena, buf, n.value, C.byref(n)))
+        return bytes(buf)
+
+    def deserialize_arena(self, arena: int, data: bytes):
+        """``Arena::DeserializeNew`` into arena ``arena`` (mode, tick rate, car slots and mutators must match the batch)."""
+        buf = (C.c_uint8 * len(data)).from_buffer_copy(data)
+        _lib.check(self.L, self.L.rsb_deserialize_arena(self.h, arena, buf, len(data)))
+
     def sync(self):
         _lib.check(self.L, self.L.rsb_sync(self.h))
 

@@ -26,6 +26,7 @@
 #include "../../include/rsb_bench_inputs.h"
 #include "sim/rsb_tick.h"
 #include "rsb_scene.h"
+#include "rsb_serialize.h"
 
 using namespace rsb;
 
@@ -120,6 +121,7 @@ struct RsbBatch {
 	RsbBallState* traceOut = nullptr;  // consumed by the next launch (rsb_predict_ball)
 	RsbBatch* pred = nullptr;      // ball-only sibling batch used by rsb_predict_ball (created on first use)
 	RsbMutatorConfig mutApi;       // the mutator config the batch was created with
+	std::vector<RsbCarConfig> carCfgApi;  // the car configs the batch was created with (wire format, rsb_serialize_arena)
 	float tickRate = 120.f;
 	const Scene* dScene = nullptr;
 	EventSink::Ev* dEvents = nullptr;
@@ -915,6 +917,7 @@ int rsb_batch_create(int device, int game_mode, int n_arenas, int n_cars, const 
 	fill_ball(game_mode, P);
 	for (int i = 0; i < n_cars; i++) {
 		fill_car_cfg(car_configs ? car_configs[i] : preset_octane(), P.carCfg[i]);
+		b->carCfgApi.push_back(car_configs ? car_configs[i] : preset_octane());
 		P.team[i] = teams ? teams[i] : (i < (n_cars + 1) / 2 ? 0 : 1);
 	}
 	fill_pads(game_mode, P);
@@ -975,6 +978,7 @@ int rsb_batch_create(int device, int game_mode, int n_arenas, int n_cars, const 
 			A.dynOrder[bidx] = (uint8_t)bidx;
 		}
 		A.stampCounter = (uint32_t)n_cars + 2;
+		A.worldFresh = 1;
 	}
 	h2d(b->dS, init.data(), sizeof(ArenaS) * (size_t)n_arenas, 0);
 #ifndef RSB_HOSTCHECK
@@ -1185,6 +1189,115 @@ int rsb_predict_ball(RsbBatch* b, int n_ticks, RsbBallState* out) {
 	LAUNCH_1D(copy_ball_kernel, b->hp.nArenas, b, b->dS, p->dS, dTrace, b->hp.nArenas);
 	if (n_ticks > 1) { p->traceOut = dTrace; launch_step(p, n_ticks - 1, nullptr, 0); }
 	d2h(out, dTrace, rows * sizeof(RsbBallState), b->stream);
+	API_END
+}
+RSB_GLOBAL void get_controls_kernel(const ArenaS* S, RsbCarControls* out, int nArenas, int nCars) {
+	KERNEL_1D(i, nArenas * nCars);
+	ctrl_to_api(S[i / nCars].cars[i % nCars].controls, out[i]);
+}
+// The arena becomes what Arena::DeserializeNew leaves behind: a NEW physics world (first-step solver quirk, broadphase proxies
+// registered at the construction-time poses: ball at (0,0,radius), cars at the origin -- Ball.cpp:92-93, Car.cpp:211-215) and new
+// cars / ball whose state outside CarState/BallState is at its defaults.
+RSB_GLOBAL void fresh_world_kernel(ArenaS* S, const BatchParams* P, const Scene* sc, uint64_t tickCount) {
+	KERNEL_1D(i, 1);
+	ArenaS& A = S[0];
+	A.tickCount = tickCount;
+	A.worldFresh = 1;
+	A.trkLastBallUpdate = 0; A.trkShotCooldown = 0.f; A.trkBallShot = 0; A.trkScoredLast = 0;
+	Ctx cx; cx.s = &A; cx.w = nullptr; cx.epa = nullptr; cx.body = nullptr; cx.wheels = nullptr; cx.padLocked = nullptr; cx.misc = nullptr; cx.pl = nullptr; cx.mf = nullptr; cx.solv = nullptr; cx.p = P; cx.sc = sc; cx.arena = 0; cx.ev.buf = nullptr;
+	const int nCars = P->nCars;
+	for (int b = 0; b <= nCars; b++) {
+		V3 mn, mx;
+		V3 org = (b == 0) ? V3(0, 0, P->mut.ballRadius * UU_TO_BT) : v3zero();
+		body_shape_aabb(cx, b, m3identity(), org, mn, mx);
+		int ci, cj, ck;
+		A.cellIdx[b] = grid_cell_of(*sc, mn, ci, cj, ck);
+		A.cellI[b] = (uint8_t)ci; A.cellJ[b] = (uint8_t)cj; A.cellK[b] = (uint8_t)ck;
+		A.cellStamp[b] = (uint32_t)b + 1;
+		A.dynOrder[b] = (uint8_t)b;
+	}
+	A.stampCounter = (uint32_t)nCars + 2;
+	A.ball.groundStickApplied = 0;
+	for (int c = 0; c < nCars; c++) {
+		CarS& car = A.cars[c];
+		for (int k = 0; k < 4; k++) { car.wSteer[k] = car.wEngine[k] = car.wBrake[k] = car.wLatFriction[k] = car.wLongFriction[k] = car.wExtraPushback[k] = 0.f; }
+	}
+}
+// Replaces Arena::Serialize (Arena.cpp:546-574) for one arena of the batch.
+int rsb_serialize_arena(RsbBatch* b, uint32_t arena, uint8_t* out, size_t cap, size_t* n_out) {
+	API_BEGIN
+	set_device(b);
+	const BatchParams& P = b->hp;
+	if (arena >= (uint32_t)P.nArenas) throw std::runtime_error("arena index out of range");
+	rsbser::ArenaImage img;
+	img.gameMode = (uint8_t)P.mode; img.tickTime = P.dt; img.lastCarID = (uint32_t)P.nCars; img.mut = b->mutApi;
+	const size_t need = (size_t)std::max(1, P.nCars) * (sizeof(RsbCarState) + sizeof(RsbCarControls)) + sizeof(RsbBallState) + (size_t)MAX_PADS * sizeof(RsbBoostPadState) + 64;
+	b->ensure_scratch(need);
+	char* base = (char*)b->dScratch;
+	RsbCarState* dCars = (RsbCarState*)base; RsbCarControls* dCtl = (RsbCarControls*)(dCars + std::max(1, P.nCars));
+	RsbBallState* dBall = (RsbBallState*)(((uintptr_t)(dCtl + std::max(1, P.nCars)) + 15) & ~(uintptr_t)15);
+	RsbBoostPadState* dPads = (RsbBoostPadState*)(dBall + 1); uint64_t* dTick = (uint64_t*)(dPads + MAX_PADS);
+	ArenaS* S1 = b->dS + arena;
+	std::vector<RsbCarState> cars(P.nCars); std::vector<RsbCarControls> ctl(P.nCars); img.pads.resize(P.nPads);
+	if (P.nCars) {
+		LAUNCH_1D(get_car_states_kernel, P.nCars, b, S1, dCars, 1, P.nCars);
+		LAUNCH_1D(get_controls_kernel, P.nCars, b, S1, dCtl, 1, P.nCars);
+		d2h(cars.data(), dCars, sizeof(RsbCarState) * P.nCars, b->stream); d2h(ctl.data(), dCtl, sizeof(RsbCarControls) * P.nCars, b->stream);
+	}
+	LAUNCH_1D(get_ball_states_kernel, 1, b, S1, dBall, 1);
+	d2h(&img.ball, dBall, sizeof(RsbBallState), b->stream);
+	if (P.nPads) { LAUNCH_1D(get_pad_states_kernel, P.nPads, b, S1, dPads, 1, P.nPads); d2h(img.pads.data(), dPads, sizeof(RsbBoostPadState) * P.nPads, b->stream); }
+	LAUNCH_1D(get_misc_kernel, 1, b, S1, b->dP, b->dScene, dTick, (uint8_t*)nullptr, (uint32_t*)nullptr, 1);
+	d2h(&img.tickCount, dTick, 8, b->stream);
+	for (int i = 0; i < P.nCars; i++) {
+		rsbser::ArenaImage::CarImg c; c.team = (uint8_t)P.team[i]; c.id = (uint32_t)i + 1; c.controls = ctl[i]; c.config = b->carCfgApi[i]; c.state = cars[i];
+		img.cars.push_back(c);
+	}
+	const std::vector<uint8_t> bytes = rsbser::write_arena(img);
+	if (n_out) *n_out = bytes.size();
+	if (out) { if (cap < bytes.size()) throw std::runtime_error("output buffer too small"); memcpy(out, bytes.data(), bytes.size()); }
+	API_END
+}
+// Replaces Arena::DeserializeNew (Arena.cpp:576-644) INTO an existing arena of the batch.  What a batch fixes for all of its
+// arenas (game mode, tick rate, car slots with their teams and configs, mutators) must match the stream.
+int rsb_deserialize_arena(RsbBatch* b, uint32_t arena, const uint8_t* data, size_t n) {
+	API_BEGIN
+	set_device(b);
+	const BatchParams& P = b->hp;
+	if (arena >= (uint32_t)P.nArenas) throw std::runtime_error("arena index out of range");
+	rsbser::ArenaImage img = rsbser::read_arena(data, n, [](int mode) { return mode == HOOPS ? 20 : ((mode == THE_VOID || mode == DROPSHOT) ? 0 : 34); });
+	if (img.gameMode != P.mode) throw std::runtime_error("Arena::Deserialize(): the stream's game mode differs from the batch's");
+	if (img.tickTime != P.dt) throw std::runtime_error("Arena::Deserialize(): the stream's tick rate differs from the batch's");
+	if ((int)img.cars.size() != P.nCars) throw std::runtime_error("Arena::Deserialize(): the stream has " + std::to_string(img.cars.size()) + " cars, the batch has " + std::to_string(P.nCars) + " car slots");
+	if (memcmp(&img.mut, &b->mutApi, offsetof(RsbMutatorConfig, _pad2)) != 0) {
+		RsbMutatorConfig x = img.mut, y = b->mutApi; x._pad0 = y._pad0 = 0; x._pad1[0] = x._pad1[1] = y._pad1[0] = y._pad1[1] = 0;
+		if (memcmp(&x, &y, offsetof(RsbMutatorConfig, _pad2)) != 0) throw std::runtime_error("Arena::Deserialize(): the stream's mutator config differs from the batch's");
+	}
+	std::vector<RsbCarState> st(P.nCars); std::vector<RsbCarControls> ctl(P.nCars); std::vector<uint32_t> ai(std::max(1, P.nCars), arena), ci(std::max(1, P.nCars));
+	for (const auto& c : img.cars) {  // the stream lists cars in any order (unordered_set); ids are the slots + 1
+		if (c.id < 1 || c.id > (uint32_t)P.nCars) throw std::runtime_error("Arena::Deserialize(): car ID " + std::to_string(c.id) + " has no slot in the batch");
+		const int slot = (int)c.id - 1;
+		if (c.team != P.team[slot]) throw std::runtime_error("Arena::Deserialize(): team of car " + std::to_string(c.id) + " differs from the batch's slot");
+		const RsbCarConfig& k = b->carCfgApi[slot];
+		if (memcmp(&c.config.hitboxSize, &k.hitboxSize, 12) || memcmp(&c.config.hitboxPosOffset, &k.hitboxPosOffset, 12) || c.config.dodgeDeadzone != k.dodgeDeadzone ||
+		    c.config.frontWheels.wheelRadius != k.frontWheels.wheelRadius || c.config.backWheels.wheelRadius != k.backWheels.wheelRadius ||
+		    c.config.frontWheels.suspensionRestLength != k.frontWheels.suspensionRestLength || c.config.backWheels.suspensionRestLength != k.backWheels.suspensionRestLength ||
+		    memcmp(&c.config.frontWheels.connectionPointOffset, &k.frontWheels.connectionPointOffset, 12) || memcmp(&c.config.backWheels.connectionPointOffset, &k.backWheels.connectionPointOffset, 12))
+			throw std::runtime_error("Arena::Deserialize(): config of car " + std::to_string(c.id) + " differs from the batch's slot");
+		st[slot] = c.state; ctl[slot] = c.controls; ci[slot] = (uint32_t)slot;
+		// Arena::DeserializeNewCar runs Car::_BulletSetup AFTER the state was read, and _BulletSetup ends with
+		// `_internalState.boost = carSpawnBoostAmount` (Car.cpp:291): a loaded car always starts with the spawn boost
+		st[slot].boost = b->mutApi.carSpawnBoostAmount;
+	}
+	if (P.nCars) {
+		if (rsb_set_car_states(b, ai.data(), ci.data(), P.nCars, st.data()) != 0) throw std::runtime_error(g_err);  // Car::SetState(_internalState)
+		b->ensure_scratch(sizeof(RsbCarControls) * P.nCars);
+		h2d(b->dScratch, ctl.data(), sizeof(RsbCarControls) * P.nCars, b->stream);
+		LAUNCH_1D(set_controls_kernel, P.nCars, b, b->dS + arena, (const RsbCarControls*)b->dScratch, 1, P.nCars);
+	}
+	if (P.nPads && rsb_set_pad_states(b, ai.data(), 1, img.pads.data()) != 0) throw std::runtime_error(g_err);
+	if (rsb_set_ball_states(b, ai.data(), 1, &img.ball) != 0) throw std::runtime_error(g_err);
+	LAUNCH_1D(fresh_world_kernel, 1, b, b->dS + arena, b->dP, b->dScene, img.tickCount);
 	API_END
 }
 int rsb_sync(RsbBatch* b) {

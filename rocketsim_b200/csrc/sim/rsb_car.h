@@ -161,8 +161,9 @@ RSB_HD void wheel_trace(const Ctx& cx, int ci, int wi) {
 				float restitution = 0.f * -rel_vel;
 				const float erp = 0.2f;  // btContactSolverInfo::m_erp
 				// solverInfo.m_timeStep is only written inside stepSimulation (btDiscreteDynamicsWorld.cpp:417): on an arena's
-				// very first tick it still holds the constructor default 1/60 (btContactSolverInfo.h:82)
-				const float solverTimeStep = (cx.s->tickCount == 0) ? (1.f / 60.f) : cx.p->dt;
+				// very first tick -- also the first tick after Arena::DeserializeNew, which builds a new world -- it still holds the
+				// constructor default 1/60 (btContactSolverInfo.h:82)
+				const float solverTimeStep = cx.s->worldFresh ? (1.f / 60.f) : cx.p->dt;
 				float positionalError = erp * -wheelTraceDistDelta / solverTimeStep;
 				float velocityError = -(1.0f + restitution) * rel_vel;
 				float denom0 = impulse_denominator(rb, bw, hit.point, hit.normal);

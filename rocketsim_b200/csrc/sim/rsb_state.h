@@ -98,7 +98,8 @@ struct ArenaS {
 	// GameEventTracker persistent info (GameEventTracker.h:72-87); only advanced when the batch enabled the tracker
 	uint64_t trkLastBallUpdate;
 	float trkShotCooldown;
-	uint8_t trkBallShot, trkShotGoalTeam, trkScoredLast, _trkPad;
+	uint8_t trkBallShot, trkShotGoalTeam, trkScoredLast;
+	uint8_t worldFresh;    // 1 until the arena's physics world has stepped once (a new or freshly deserialised arena)
 	BallS ball;
 	PadS pads[MAX_PADS];
 	CarS cars[MAX_CARS];   // last: a batch with fewer cars stages only the used prefix of the record

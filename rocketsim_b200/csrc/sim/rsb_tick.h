@@ -155,6 +155,7 @@ RSB_HD void phase_run(const Ctx& cx, int phase, int item) {
 			if (scored && P.autoReset) kickoff_reset(S, P, (int)(P.autoResetSeed + (uint32_t)cx.arena + (uint32_t)S.tickCount));
 		}
 		S.tickCount++;
+		S.worldFresh = 0;
 		break;
 	default: break;
 	}
