@@ -1,9 +1,9 @@
 """Developer tool: step the oracle and the host-compiled check build side by side and print
 where they diverge.  usage: dev_parity.py MODE CARS_PER_TEAM TICKS [--sync] [--seed S]"""
 import sys, os, argparse
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests")); import parity_util as pu
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), "tests")); import parity_util as pu
 from rocketsim_b200 import types as T, lib as rsb_lib, synthetic_meshes as sm
 from oracle import refsim
 

@@ -1,7 +1,7 @@
 """Developer tool: replay ONE tick of a golden record on the oracle and on the host check build and
 print contact points and solver rows side by side.  usage: dev_tick_probe.py NAME TICK"""
 import sys, os
-R = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+R = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, R); sys.path.insert(0, os.path.join(R, "tests"))
 import numpy as np, ctypes as C, parity_util as pu
 from rocketsim_b200 import lib, synthetic_meshes as sm
