@@ -107,6 +107,7 @@ public:
 	void ResetToRandomKickoff(const std::vector<int32_t>& seeds, const std::vector<uint32_t>* arenas = nullptr) {
 		Check(rsb_reset_to_random_kickoff(h_, arenas ? arenas->data() : nullptr, arenas ? (int)arenas->size() : numArenas, seeds.data()));
 	}
+	void CloneArena(uint32_t src, uint32_t dst) { Check(rsb_clone_arena(h_, src, dst)); }  // Arena::Clone
 	// Arena::Serialize / Arena::DeserializeNew of one arena in RocketSim's own byte format (interchange with the CPU library)
 	std::vector<uint8_t> SerializeArena(uint32_t arena) {
 		size_t n = 0; Check(rsb_serialize_arena(h_, arena, nullptr, 0, &n));

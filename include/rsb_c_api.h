@@ -87,6 +87,8 @@ int rsb_set_event_tracker(RsbBatch* b, int enable, const RsbEventTrackerConfig* 
  * Arena::DeserializeNew (Arena.cpp:576-644) into an existing arena of the batch: the stream's game mode, tick rate, cars
  * (ids 1..n_cars, teams, configs) and mutators must equal what the batch was created with. */
 int rsb_serialize_arena(RsbBatch* b, uint32_t arena_idx, uint8_t* out, size_t cap, size_t* n_out);
+/* Replaces Arena::Clone (Arena.cpp:646-674): arena `dst` becomes a clone of arena `src` of the same batch. */
+int rsb_clone_arena(RsbBatch* b, uint32_t src, uint32_t dst);
 int rsb_deserialize_arena(RsbBatch* b, uint32_t arena_idx, const uint8_t* data, size_t n);
 
 /* Replaces BallPredTracker::ForceUpdateAllPred / predData (src/Sim/BallPredTracker/BallPredTracker.cpp:58-66) for every arena

@@ -145,6 +145,15 @@ RefArena* ref_deserialize_new(const uint8_t* data, size_t n) {
 		return r;
 	} catch (const std::exception& e) { g_err = e.what(); return nullptr; }
 }
+/* Arena::Clone (Arena.cpp:646-674). */
+RefArena* ref_clone(RefArena* r) {
+	RefArena* c = new RefArena();
+	c->arena = r->arena->Clone(false);
+	std::vector<Car*> cars(c->arena->_cars.begin(), c->arena->_cars.end());
+	std::sort(cars.begin(), cars.end(), [](Car* a, Car* b) { return a->id < b->id; });
+	c->cars = cars;
+	return c;
+}
 /* BallPredTracker (src/Sim/BallPredTracker/BallPredTracker.cpp): predData of a fresh tracker built on the arena. */
 int ref_ball_pred(RefArena* r, int n_ticks, RsbBallState* out) {
 	BallPredTracker t(r->arena, (size_t)n_ticks);

@@ -41,6 +41,7 @@ int ref_is_ball_scored(RefArena*);
 void ref_enable_event_tracker(RefArena*, const float* cfg7);              /* GameEventTracker, GameEventTracker.h:45-100 */
 size_t ref_serialize(RefArena*, uint8_t* out, size_t cap);               /* Arena::Serialize, Arena.cpp:546 */
 RefArena* ref_deserialize_new(const uint8_t* data, size_t n);           /* Arena::DeserializeNew, Arena.cpp:576 */
+RefArena* ref_clone(RefArena*);                                         /* Arena::Clone, Arena.cpp:646 */
 int ref_ball_pred(RefArena*, int n_ticks, RsbBallState* out);            /* BallPredTracker, BallPredTracker.cpp:5-66 */
 int ref_is_ball_probably_going_in(RefArena*, float maxTime, float extraMargin, int* teamOut); /* Arena.cpp:771-891 */                                   /* Arena::IsBallScored, Arena.cpp:893 */
 

@@ -58,6 +58,7 @@ def lib():
         L.ref_is_ball_scored.argtypes = [vp]; L.ref_is_ball_scored.restype = i32
         L.ref_enable_event_tracker.argtypes = [vp, vp]
         L.ref_ball_pred.argtypes = [vp, i32, vp]; L.ref_ball_pred.restype = i32
+        L.ref_clone.argtypes = [vp]; L.ref_clone.restype = vp
         L.ref_serialize.argtypes = [vp, vp, C.c_size_t]; L.ref_serialize.restype = C.c_size_t
         L.ref_deserialize_new.argtypes = [vp, C.c_size_t]; L.ref_deserialize_new.restype = vp
         L.ref_is_ball_probably_going_in.argtypes = [vp, f32, f32, vp]; L.ref_is_ball_probably_going_in.restype = i32
@@ -111,6 +112,11 @@ class RefArena:
             raise RuntimeError(self.L.ref_last_error().decode())
         self.mode = mode
         self.car_ids = []
+
+    def clone(self):
+        c = RefArena.__new__(RefArena)
+        c.L = self.L; c.h = self.L.ref_clone(self.h); c.mode = self.mode; c.car_ids = list(self.car_ids)
+        return c
 
     def serialize(self) -> bytes:
         n = self.L.ref_serialize(self.h, None, 0)

@@ -88,6 +88,10 @@ class ArenaBatch:
         _lib.check(self.L, self.L.rsb_predict_ball(self.h, int(n_ticks), _lib.ptr(out)))
         return out
 
+    def clone_arena(self, src: int, dst: int):
+        """``Arena::Clone``: arena ``dst`` becomes a clone of arena ``src``."""
+        _lib.check(self.L, self.L.rsb_clone_arena(self.h, src, dst))
+
     def serialize_arena(self, arena: int) -> bytes:
         """``Arena::Serialize`` of one arena: bytes that RocketSim's ``Arena::DeserializeNew`` loads."""
         n = C.c_size_t()

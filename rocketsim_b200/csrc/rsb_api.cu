@@ -1223,6 +1223,44 @@ RSB_GLOBAL void fresh_world_kernel(ArenaS* S, const BatchParams* P, const Scene*
 		for (int k = 0; k < 4; k++) { car.wSteer[k] = car.wEngine[k] = car.wBrake[k] = car.wLatFriction[k] = car.wLongFriction[k] = car.wExtraPushback[k] = 0.f; }
 	}
 }
+// Arena::Clone (Arena.cpp:646-674) from arena `src` into arena `dst` of the same batch: a NEW world whose ball, cars and pads are
+// set through GetState -> SetState (so positions take the UU round trip and everything outside the state structs restarts at its
+// defaults), plus the velocity-impulse caches, the controls and the tick counter, which Clone copies explicitly.
+RSB_GLOBAL void clone_arena_kernel(ArenaS* S, const BatchParams* P, const Scene* sc, uint32_t src, uint32_t dst) {
+	KERNEL_1D(i, 1);
+	const ArenaS& A = S[src];
+	ArenaS& B = S[dst];
+	const int nCars = P->nCars;
+	RsbBallState bs; ball_to_api(A.ball, bs); ball_from_api(bs, B.ball);
+	B.ball.velImpulseCache = A.ball.velImpulseCache;
+	B.ball.groundStickApplied = 0;
+	for (int c = 0; c < nCars; c++) {
+		RsbCarState cs; car_to_api(A.cars[c], cs); car_from_api(cs, B.cars[c]);
+		B.cars[c].controls = A.cars[c].controls;
+		B.cars[c].velImpulseCache = A.cars[c].velImpulseCache;
+		for (int k = 0; k < 4; k++) { B.cars[c].wSteer[k] = B.cars[c].wEngine[k] = B.cars[c].wBrake[k] = B.cars[c].wLatFriction[k] = B.cars[c].wLongFriction[k] = B.cars[c].wExtraPushback[k] = 0.f; }
+	}
+	for (int p = 0; p < P->nPads; p++) { B.pads[p].isActive = A.pads[p].isActive; B.pads[p].cooldown = A.pads[p].cooldown; B.pads[p].prevLockedCarID = A.pads[p].prevLockedCarID; }
+	B.rng = A.rng;
+	B.errorFlags = 0;
+	(void)sc;
+}
+int rsb_clone_arena(RsbBatch* b, uint32_t src, uint32_t dst) {
+	API_BEGIN
+	set_device(b);
+	if (src >= (uint32_t)b->hp.nArenas || dst >= (uint32_t)b->hp.nArenas) throw std::runtime_error("arena index out of range");
+	if (src == dst) return 0;
+	uint64_t tick = 0;
+	{
+		b->ensure_scratch(16);
+		LAUNCH_1D(get_misc_kernel, 1, b, b->dS + src, b->dP, b->dScene, (uint64_t*)b->dScratch, (uint8_t*)nullptr, (uint32_t*)nullptr, 1);
+		d2h(&tick, b->dScratch, 8, b->stream);
+	}
+	LAUNCH_1D(clone_arena_kernel, 1, b, b->dS, b->dP, b->dScene, src, dst);
+	LAUNCH_1D(fresh_world_kernel, 1, b, b->dS + dst, b->dP, b->dScene, tick);
+	API_END
+}
+
 // Replaces Arena::Serialize (Arena.cpp:546-574) for one arena of the batch.
 int rsb_serialize_arena(RsbBatch* b, uint32_t arena, uint8_t* out, size_t cap, size_t* n_out) {
 	API_BEGIN

@@ -99,6 +99,37 @@ def run_case(lib, oracle, mode, cpt, presets=None):
     return worst
 
 
+def run_clone(lib, oracle, mode, cpt):
+    """Arena::Clone: clone a mid-game arena on both sides, then the clones must step alike (and the originals too)."""
+    teams = [0] * cpt + [1] * cpt
+    ref = pu.make_ref_arena(oracle, mode, teams)
+    ref.seed_rng(6); ref.reset_kickoff(6)
+    ctrl = advance(ref, 150, seed=6)
+    batch = ArenaBatch(mode, 3, teams, lib=lib)
+    pu.sync_from_ref(batch, ref, 0)
+    ref2 = ref.clone()
+    batch.clone_arena(0, 2)
+    assert int(batch.get_tick_counts()[2]) == int(batch.get_tick_counts()[0])
+    cs = batch.get_car_states()
+    for i, cid in enumerate(ref2.car_ids):
+        bad, errs = pu.compare_car(cs[2, i], ref2.car_state(cid))
+        assert not (set(bad) - {"wheelsWithContact", "isSupersonic"}) and max(v for k, v in errs.items() if k != "airTime") <= 1e-6, (i, bad, errs)
+    worst = compare_step(batch, 2, ref2, ctrl)
+    ref.close(); ref2.close(); batch.close()
+    return worst
+
+
+def test_clone_hostcheck(hostlib, oracle):
+    assert run_clone(hostlib, oracle, T.MODE_SOCCAR, 2) <= TOL
+    assert run_clone(hostlib, oracle, T.MODE_HOOPS, 1) <= TOL
+
+
+@pytest.mark.gpu
+def test_clone_cuda(cudalib, oracle):
+    assert run_clone(cudalib, oracle, T.MODE_SOCCAR, 3) <= TOL
+    assert run_clone(cudalib, oracle, T.MODE_SNOWDAY, 1) <= TOL
+
+
 def test_serialize_hostcheck(hostlib, oracle):
     assert run_case(hostlib, oracle, T.MODE_SOCCAR, 2, presets=[0, 1, 3, 5]) <= TOL
     assert run_case(hostlib, oracle, T.MODE_HOOPS, 1) <= TOL
