@@ -195,3 +195,27 @@ class ArenaBatch:
         else:
             ai, _ = self._idx(arena_idx)
             _lib.check(self.L, self.L.rsb_reset_to_random_kickoff(self.h, _lib.ptr(ai), len(ai), _lib.ptr(s)))
+
+
+class BallPredTracker:
+    """Batched mirror of the reference's ``BallPredTracker`` (``src/Sim/BallPredTracker/BallPredTracker.h``): ``pred_data[i, a]`` is
+    the ball of arena ``a`` after ``i`` ticks of a ball-only arena started from its current state.  The reference re-uses old
+    predictions when the ball still matches them; on the GPU a full re-prediction of every arena is one launch, so
+    ``update_pred_from_batch`` always does ``ForceUpdateAllPred``."""
+
+    def __init__(self, batch: ArenaBatch, num_pred_ticks: int):
+        self.batch = batch
+        self.num_pred_ticks = int(num_pred_ticks)
+        self.pred_data = None
+        self.tick_time = None
+
+    def update_pred_from_batch(self):
+        self.pred_data = self.batch.predict_ball(self.num_pred_ticks)
+        return self.pred_data
+
+    def get_ball_state_for_time(self, pred_time: float, tick_rate: float = 120.0):
+        """``GetBallStateForTime``: the predicted states ``[n_arenas]`` at ``pred_time`` seconds (index clamped to the horizon)."""
+        if self.pred_data is None:
+            raise RuntimeError("BallPredTracker::GetBallStateForTime(): Predicted ball data is empty, update prediction before calling")
+        idx = int(min(max(pred_time * tick_rate, 0), self.num_pred_ticks - 1))
+        return self.pred_data[idx]
