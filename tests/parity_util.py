@@ -320,3 +320,16 @@ def struct_equal(a, b) -> bool:
         if not struct_equal(np.ascontiguousarray(a[name]), np.ascontiguousarray(b[name])):
             return False
     return True
+
+
+def canonical_kickoff(ref, teams):
+    """ResetToRandomKickoff hands the spawn slots to the cars in the iteration order of an unordered_set<Car*>, i.e. in an order
+    that changes from process to process.  Re-deal the freshly reset car states within each team by ascending
+    (x, y) so that a seeded test always runs the same scenario (only valid when the cars of a team share one CarConfig)."""
+    ids = list(ref.car_ids)
+    for team in sorted(set(teams)):
+        members = [cid for cid, t in zip(ids, teams) if t == team]
+        states = [ref.car_state(cid).copy() for cid in members]
+        states.sort(key=lambda st: (round(float(st["pos"]["x"]), 3), round(float(st["pos"]["y"]), 3)))
+        for cid, st in zip(members, states):
+            ref.set_car_state(cid, st)
