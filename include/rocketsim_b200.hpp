@@ -101,7 +101,17 @@ public:
 	void SetBallState(uint32_t arena, const BallState& s) { Check(rsb_set_ball_states(h_, &arena, 1, &s)); }
 	std::vector<uint64_t> GetTickCounts() { std::vector<uint64_t> v(numArenas); Check(rsb_get_tick_counts(h_, v.data())); return v; }
 	std::vector<uint8_t> IsBallScored() { std::vector<uint8_t> v(numArenas); Check(rsb_is_ball_scored(h_, v.data())); return v; }
-	std::vector<RsbEvent> GetEvents(int cap = 65536) { std::vector<RsbEvent> v(cap); int n = 0; Check(rsb_get_events(h_, v.data(), cap, &n)); v.resize(n); return v; }
+	std::vector<RsbEvent> GetEvents(int cap = 65536) {
+		std::vector<RsbEvent> all;
+		for (;;) {  // rc 1 = more than `cap` events pending: nothing is dropped, fetch the next slice
+			std::vector<RsbEvent> v(cap); int n = 0;
+			const int rc = rsb_get_events(h_, v.data(), cap, &n);
+			if (rc != 0 && rc != 1) Check(rc);
+			all.insert(all.end(), v.begin(), v.begin() + n);
+			if (rc == 0) break;
+		}
+		return all;
+	}
 	std::vector<uint32_t> GetErrorFlags() { std::vector<uint32_t> v(numArenas); Check(rsb_get_error_flags(h_, v.data())); return v; }
 	// Arena::ResetToRandomKickoff(seed) for every arena (seeds[a]) or for the listed ones
 	void ResetToRandomKickoff(const std::vector<int32_t>& seeds, const std::vector<uint32_t>* arenas = nullptr) {

@@ -73,6 +73,9 @@ int rsb_step_with_controls(RsbBatch* b, const RsbCarControls* controls_seq, int 
  * IsBallScored() is followed by ResetToRandomKickoff(seed + arena + tick) inside the same launch
  * (Arena.cpp:113-223, 744-752). Off by default, as in the reference. */
 int rsb_set_auto_reset(RsbBatch* b, int enable, uint32_t seed);
+/* Sharded jobs (one batch per GPU): global index of this batch's arena 0.  Auto-reset seeds and the arena ids of events are
+ * formed with the GLOBAL arena index, so per-arena results do not depend on how a job is split over GPUs.  Default 0. */
+int rsb_set_arena_offset(RsbBatch* b, uint32_t global_index_of_arena0);
 int rsb_sync(RsbBatch* b);
 
 /* Replaces GameEventTracker (src/Sim/GameEventTracker/GameEventTracker.h:45-100, .cpp:5-157) used as
@@ -115,7 +118,8 @@ int rsb_set_pad_states(RsbBatch* b, const uint32_t* arena_idx, int n, const RsbB
 int rsb_get_tick_counts(RsbBatch* b, uint64_t* out);
 int rsb_is_ball_scored(RsbBatch* b, uint8_t* out);
 /* Goal / bump / demo events since the last call (the reference delivers them through
- * SetGoalScoreCallback / SetCarBumpCallback, Arena.h:102,108).  Sorted by (arena, tick). */
+ * SetGoalScoreCallback / SetCarBumpCallback, Arena.h:102,108).  Sorted by (arena, tick).  Nothing is dropped when more than `cap`
+ * events are pending: the call hands out the first `cap` and returns 1 (rsb_last_error says how many remain); call again. */
 int rsb_get_events(RsbBatch* b, RsbEvent* out, int cap, int* n_out);
 /* Device-side error flags per arena (manifold overflow etc.), 0 = clean; [n_arenas]. */
 int rsb_get_error_flags(RsbBatch* b, uint32_t* out);

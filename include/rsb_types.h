@@ -176,8 +176,11 @@ typedef struct RsbCarInternal {
 	float rbPos[4];
 	float rbVel[4];
 	uint64_t tickCountSinceUpdate;
-	uint32_t hasRigidBody;
+	uint32_t hasRigidBody;  /* bit 0: rbPos / rbVel / tickCountSinceUpdate are valid; bit 1: rbBasis is valid */
 	uint32_t _pad;
+	/* exact rigid-body basis, 3 rows x 4 floats.  Equal to CarState::rotMat except while a car is demoed: then the state keeps
+	 * the rotMat of the last post-tick update (Car.cpp:133-138) while the body keeps the pose it was integrated to. */
+	float rbBasis[12];
 } RsbCarInternal;
 
 typedef struct RsbBallInternal {

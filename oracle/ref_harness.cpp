@@ -190,7 +190,9 @@ void ref_get_car_internal(RefArena* r, uint32_t id, RsbCarInternal* o) {
 	for (int k = 0; k < 3; k++) { o->rbPos[k] = org[k]; o->rbVel[k] = c->_rigidBody.m_linearVelocity[k]; }
 	o->rbPos[3] = o->rbVel[3] = 0.f;
 	o->tickCountSinceUpdate = c->_internalState.tickCountSinceUpdate;
-	o->hasRigidBody = 1; o->_pad = 0;
+	o->hasRigidBody = 3; o->_pad = 0;
+	const btMatrix3x3& bs = c->_rigidBody.getWorldTransform().getBasis();
+	for (int r3 = 0; r3 < 3; r3++) { for (int k = 0; k < 3; k++) o->rbBasis[4 * r3 + k] = bs[r3][k]; o->rbBasis[4 * r3 + 3] = 0.f; }
 }
 void ref_set_car_internal(RefArena* r, uint32_t id, const RsbCarInternal* o) {
 	Car* c = r->cars[id - 1];
@@ -200,10 +202,15 @@ void ref_set_car_internal(RefArena* r, uint32_t id, const RsbCarInternal* o) {
 		w.m_latFriction = o->latFriction[i]; w.m_longFriction = o->longFriction[i]; w.m_extraPushback = o->extraPushback[i];
 	}
 	memcpy(&c->_velocityImpulseCache, o->velocityImpulseCache, 16);
-	if (o->hasRigidBody) {
+	if (o->hasRigidBody & 1) {
 		c->_rigidBody.getWorldTransform().setOrigin(btVector3(o->rbPos[0], o->rbPos[1], o->rbPos[2]));
 		c->_rigidBody.m_linearVelocity = btVector3(o->rbVel[0], o->rbVel[1], o->rbVel[2]);
 		c->_internalState.tickCountSinceUpdate = o->tickCountSinceUpdate;
+	}
+	if (o->hasRigidBody & 2) {
+		btMatrix3x3 bs(o->rbBasis[0], o->rbBasis[1], o->rbBasis[2], o->rbBasis[4], o->rbBasis[5], o->rbBasis[6], o->rbBasis[8], o->rbBasis[9], o->rbBasis[10]);
+		c->_rigidBody.getWorldTransform().setBasis(bs);
+		c->_rigidBody.updateInertiaTensor();
 	}
 }
 void ref_get_ball_state(RefArena* r, RsbBallState* out) {

@@ -70,6 +70,10 @@ class ArenaBatch:
         """Device-side ``if (IsBallScored()) ResetToRandomKickoff(seed + arena + tick)`` after every tick."""
         _lib.check(self.L, self.L.rsb_set_auto_reset(self.h, int(bool(enable)), seed & 0xFFFFFFFF))
 
+    def set_arena_offset(self, global_index_of_arena0: int):
+        """Sharded jobs: auto-reset seeds and event arena ids use ``offset + local arena index``."""
+        _lib.check(self.L, self.L.rsb_set_arena_offset(self.h, int(global_index_of_arena0)))
+
     def set_event_tracker(self, enable: bool = True, config=None):
         """Device-side ``GameEventTracker`` (shots, goal credits, saves) updated after every tick; events arrive via get_events."""
         cfg = None if config is None else np.array([config], dtype=T.EventTrackerConfig)
@@ -147,39 +151,55 @@ class ArenaBatch:
         return self._get("rsb_get_observations", np.float32, (self.n_arenas, nf))
 
     def get_events(self, cap: int = 65536):
-        out = np.zeros(cap, dtype=T.Event)
-        n = C.c_int()
-        _lib.check(self.L, self.L.rsb_get_events(self.h, _lib.ptr(out), cap, C.byref(n)))
-        return out[: n.value]
+        parts = []
+        while True:  # rc 1 = more events pending than `cap`: nothing is dropped, fetch the next slice
+            out = np.zeros(cap, dtype=T.Event)
+            n = C.c_int()
+            rc = self.L.rsb_get_events(self.h, _lib.ptr(out), cap, C.byref(n))
+            if rc not in (0, 1):
+                _lib.check(self.L, rc)
+            parts.append(out[: n.value])
+            if rc == 0:
+                break
+        return parts[0] if len(parts) == 1 else np.concatenate(parts)
 
     def _idx(self, arena_idx, car_idx=None):
         ai = np.ascontiguousarray(arena_idx, dtype=np.uint32).ravel()
         ci = None if car_idx is None else np.ascontiguousarray(car_idx, dtype=np.uint32).ravel()
+        if ci is not None and len(ci) != len(ai):
+            raise ValueError(f"arena_idx has {len(ai)} entries, car_idx {len(ci)}")
         return ai, ci
+
+    @staticmethod
+    def _payload(arr, n, what, per=1):
+        """The C side reads n * per payload elements: refuse shorter arrays instead of letting it read past the buffer."""
+        if arr.size != n * per:
+            raise ValueError(f"{what}: expected {n * per} elements for {n} index entries, got {arr.size}")
+        return arr
 
     def set_car_states(self, arena_idx, car_idx, states):
         ai, ci = self._idx(arena_idx, car_idx)
-        s = np.ascontiguousarray(states, dtype=T.CarState).ravel()
+        s = self._payload(np.ascontiguousarray(states, dtype=T.CarState).ravel(), len(ai), "set_car_states")
         _lib.check(self.L, self.L.rsb_set_car_states(self.h, _lib.ptr(ai), _lib.ptr(ci), len(ai), _lib.ptr(s)))
 
     def set_car_internals(self, arena_idx, car_idx, internals):
         ai, ci = self._idx(arena_idx, car_idx)
-        s = np.ascontiguousarray(internals, dtype=T.CarInternal).ravel()
+        s = self._payload(np.ascontiguousarray(internals, dtype=T.CarInternal).ravel(), len(ai), "set_car_internals")
         _lib.check(self.L, self.L.rsb_set_car_internals(self.h, _lib.ptr(ai), _lib.ptr(ci), len(ai), _lib.ptr(s)))
 
     def set_ball_states(self, arena_idx, states):
         ai, _ = self._idx(arena_idx)
-        s = np.ascontiguousarray(states, dtype=T.BallState).ravel()
+        s = self._payload(np.ascontiguousarray(states, dtype=T.BallState).ravel(), len(ai), "set_ball_states")
         _lib.check(self.L, self.L.rsb_set_ball_states(self.h, _lib.ptr(ai), len(ai), _lib.ptr(s)))
 
     def set_ball_internals(self, arena_idx, internals):
         ai, _ = self._idx(arena_idx)
-        s = np.ascontiguousarray(internals, dtype=T.BallInternal).ravel()
+        s = self._payload(np.ascontiguousarray(internals, dtype=T.BallInternal).ravel(), len(ai), "set_ball_internals")
         _lib.check(self.L, self.L.rsb_set_ball_internals(self.h, _lib.ptr(ai), len(ai), _lib.ptr(s)))
 
     def set_pad_states(self, arena_idx, states):
         ai, _ = self._idx(arena_idx)
-        s = np.ascontiguousarray(states, dtype=T.BoostPadState).reshape(len(ai), self.n_pads)
+        s = self._payload(np.ascontiguousarray(states, dtype=T.BoostPadState).ravel(), len(ai), "set_pad_states", self.n_pads)
         if self.n_pads:
             _lib.check(self.L, self.L.rsb_set_pad_states(self.h, _lib.ptr(ai), len(ai), _lib.ptr(s)))
 
@@ -194,6 +214,7 @@ class ArenaBatch:
             _lib.check(self.L, self.L.rsb_reset_to_random_kickoff(self.h, None, self.n_arenas, _lib.ptr(s)))
         else:
             ai, _ = self._idx(arena_idx)
+            self._payload(s, len(ai), "reset_to_random_kickoff seeds")
             _lib.check(self.L, self.L.rsb_reset_to_random_kickoff(self.h, _lib.ptr(ai), len(ai), _lib.ptr(s)))
 
 

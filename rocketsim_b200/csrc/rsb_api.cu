@@ -68,7 +68,9 @@ static std::map<int, std::vector<std::vector<uint8_t>>> g_meshFiles;
 static std::map<int, SceneHost> g_sceneHost;                 // built at init
 static std::map<std::pair<int, int>, SceneDev*> g_sceneDev;  // (device, mode) -> uploaded scene
 
+static std::mutex g_sceneMutex;  // g_sceneDev / g_sceneHost lookups, uploads and inserts (batches may be created from several threads)
 static SceneDev* get_scene_dev(int device, int mode) {
+	std::lock_guard<std::mutex> lk(g_sceneMutex);
 	auto key = std::make_pair(device, mode);
 	auto it = g_sceneDev.find(key);
 	if (it != g_sceneDev.end()) return it->second;
@@ -130,6 +132,7 @@ struct RsbBatch {
 	CtrlS* dCtrl = nullptr;        // staging for rsb_set_controls
 	CtrlS* dCtrlSeq = nullptr;     // staging for rsb_step_with_controls (host sequence)
 	size_t ctrlSeqCap = 0;
+	std::vector<EventSink::Ev> pendingEvents;  // downloaded, not yet handed to the caller (rsb_get_events with a small buffer)
 	void* dScratch = nullptr;      // staging for get/set
 	size_t scratchBytes = 0;
 	stream_t stream = 0;
@@ -162,11 +165,13 @@ RSB_HD void ctrl_to_api(const CtrlS& c, RsbCarControls& o) { o.throttle = c.thro
 RSB_HD void ctrl_from_api(const RsbCarControls& c, CtrlS& o) { o.throttle = c.throttle; o.steer = c.steer; o.pitch = c.pitch; o.yaw = c.yaw; o.roll = c.roll; o.jump = c.jump != 0; o.boost = c.boost != 0; o.handbrake = c.handbrake != 0; o._pad = 0; }
 
 // Car::GetState (Car.cpp:10-20)
-RSB_HD void car_to_api(const CarS& c, RsbCarState& o) {
+RSB_HD void car_to_api(const ArenaS& A, int ci, RsbCarState& o) {
+	const CarS& c = A.cars[ci];
 	unsigned char* raw = (unsigned char*)&o;
 	for (size_t i = 0; i < sizeof(RsbCarState); i++) raw[i] = 0;
 	o.pos = to_vec(c.rb.pos * BT_TO_UU);
-	basis_to_rotmat(c.rb.basis, o.rotMat);
+	// _internalState.rotMat is refreshed at the top of Car::_PostTickUpdate, which a demoed car skips (Car.cpp:133-138)
+	basis_to_rotmat(c.isDemoed ? A.demoRotMat[ci] : c.rb.basis, o.rotMat);
 	o.vel = to_vec(c.rb.vel * BT_TO_UU);
 	o.angVel = to_vec(c.rb.angvel);
 	o.tickCountSinceUpdate = c.tickCountSinceUpdate;
@@ -186,9 +191,11 @@ RSB_HD void car_to_api(const CarS& c, RsbCarState& o) {
 	ctrl_to_api(c.lastControls, o.lastControls);
 }
 // Car::SetState (Car.cpp:23-36)
-RSB_HD void car_from_api(const RsbCarState& s, CarS& c) {
+RSB_HD void car_from_api(const RsbCarState& s, ArenaS& A, int ci) {
+	CarS& c = A.cars[ci];
 	c.rb.pos = from_vec(s.pos) * UU_TO_BT;
 	c.rb.basis = rotmat_to_basis(s.rotMat);
+	A.demoRotMat[ci] = c.rb.basis;  // _internalState = state
 	c.rb.vel = from_vec(s.vel) * UU_TO_BT;
 	c.rb.angvel = from_vec(s.angVel);
 	c.velImpulseCache = v3zero();
@@ -313,7 +320,7 @@ __device__ unsigned long long g_prof2[2][16][2];
 __device__ __forceinline__ Ctx make_ctx(const StepArgs& a, const BatchParams* sP, const Scene* sSc, unsigned char* sS, int a0, int ar) {
 	Ctx cx;
 	unsigned char* base = sS + (size_t)ar * a.lay.stride;
-	cx.s = (ArenaS*)base; cx.body = (BodyW*)(base + a.lay.bodyOff); cx.wheels = (WheelW*)(base + a.lay.wheelOff);
+	cx.s = (ArenaS*)base; cx.g = a.S + (a0 + ar); cx.body = (BodyW*)(base + a.lay.bodyOff); cx.wheels = (WheelW*)(base + a.lay.wheelOff);
 	cx.padLocked = (int*)(base + a.lay.padOff); cx.misc = (int*)(base + a.lay.miscOff);
 	cx.pl = (PairList*)(base + a.lay.pairOff); cx.mf = (Manifold*)(base + a.lay.mfOff); cx.solv = base + a.lay.wheelOff;
 	cx.w = a.W + (a0 + ar); cx.epa = a.E + ((size_t)blockIdx.x * STEP_THREADS + threadIdx.x); cx.p = sP; cx.sc = sSc; cx.ev = a.ev; cx.arena = a0 + ar;
@@ -504,7 +511,7 @@ __global__ void __launch_bounds__(STEP_THREADS, BLOCKS_PER_SM) arena_step_kernel
 static void arena_step_host(const StepArgs& a) {
 	const int nCars = a.P->nCars;
 	for (int arena = 0; arena < a.nArenas; arena++) {
-		Ctx cx; cx.s = a.S + arena; cx.w = a.W + arena; cx.epa = a.E; cx.p = a.P; cx.sc = a.sc; cx.ev = a.ev; cx.arena = arena;
+		Ctx cx; cx.s = a.S + arena; cx.g = cx.s; cx.w = a.W + arena; cx.epa = a.E; cx.p = a.P; cx.sc = a.sc; cx.ev = a.ev; cx.arena = arena;
 		cx.body = a.H[arena].body; cx.wheels = a.H[arena].wheels; cx.padLocked = a.H[arena].padLocked; cx.misc = a.H[arena].misc;
 		cx.pl = &a.H[arena].pairs; cx.mf = a.H[arena].mf; cx.solv = a.H[arena].solv;
 		for (int t = 0; t < a.nTicks; t++) {
@@ -526,11 +533,11 @@ RSB_GLOBAL void set_controls_kernel(ArenaS* S, const RsbCarControls* in, int nAr
 }
 RSB_GLOBAL void get_car_states_kernel(const ArenaS* S, RsbCarState* out, int nArenas, int nCars) {
 	KERNEL_1D(i, nArenas * nCars);
-	car_to_api(S[i / nCars].cars[i % nCars], out[i]);
+	car_to_api(S[i / nCars], i % nCars, out[i]);
 }
 RSB_GLOBAL void set_car_states_kernel(ArenaS* S, const uint32_t* ai, const uint32_t* ci, const RsbCarState* in, int n) {
 	KERNEL_1D(i, n);
-	car_from_api(in[i], S[ai[i]].cars[ci[i]]);
+	car_from_api(in[i], S[ai[i]], (int)ci[i]);
 }
 RSB_GLOBAL void get_ball_states_kernel(const ArenaS* S, RsbBallState* out, int nArenas) {
 	KERNEL_1D(i, nArenas);
@@ -565,7 +572,8 @@ RSB_GLOBAL void get_car_internals_kernel(const ArenaS* S, RsbCarInternal* out, i
 	o.velocityImpulseCache[0] = c.velImpulseCache.x; o.velocityImpulseCache[1] = c.velImpulseCache.y; o.velocityImpulseCache[2] = c.velImpulseCache.z; o.velocityImpulseCache[3] = 0.f;
 	o.rbPos[0] = c.rb.pos.x; o.rbPos[1] = c.rb.pos.y; o.rbPos[2] = c.rb.pos.z; o.rbPos[3] = 0.f;
 	o.rbVel[0] = c.rb.vel.x; o.rbVel[1] = c.rb.vel.y; o.rbVel[2] = c.rb.vel.z; o.rbVel[3] = 0.f;
-	o.tickCountSinceUpdate = c.tickCountSinceUpdate; o.hasRigidBody = 1; o._pad = 0;
+	o.tickCountSinceUpdate = c.tickCountSinceUpdate; o.hasRigidBody = 3; o._pad = 0;
+	for (int r = 0; r < 3; r++) { o.rbBasis[4 * r] = c.rb.basis.r[r].x; o.rbBasis[4 * r + 1] = c.rb.basis.r[r].y; o.rbBasis[4 * r + 2] = c.rb.basis.r[r].z; o.rbBasis[4 * r + 3] = 0.f; }
 	out[i] = o;
 }
 RSB_GLOBAL void set_car_internals_kernel(ArenaS* S, const uint32_t* ai, const uint32_t* ci, const RsbCarInternal* in, int n) {
@@ -574,10 +582,12 @@ RSB_GLOBAL void set_car_internals_kernel(ArenaS* S, const uint32_t* ai, const ui
 	const RsbCarInternal& o = in[i];
 	for (int k = 0; k < 4; k++) { c.wSteer[k] = o.steerAngle[k]; c.wEngine[k] = o.engineForce[k]; c.wBrake[k] = o.brake[k]; c.wLatFriction[k] = o.latFriction[k]; c.wLongFriction[k] = o.longFriction[k]; c.wExtraPushback[k] = o.extraPushback[k]; }
 	c.velImpulseCache = V3(o.velocityImpulseCache[0], o.velocityImpulseCache[1], o.velocityImpulseCache[2]);
-	if (o.hasRigidBody) {
+	if (o.hasRigidBody & 1) {
 		c.rb.pos = V3(o.rbPos[0], o.rbPos[1], o.rbPos[2]); c.rb.vel = V3(o.rbVel[0], o.rbVel[1], o.rbVel[2]);
 		c.tickCountSinceUpdate = o.tickCountSinceUpdate;
 	}
+	// the body's own basis; CarState::rotMat (kept in demoRotMat while demoed) is not touched
+	if (o.hasRigidBody & 2) for (int r = 0; r < 3; r++) c.rb.basis.r[r] = V3(o.rbBasis[4 * r], o.rbBasis[4 * r + 1], o.rbBasis[4 * r + 2]);
 }
 RSB_GLOBAL void get_ball_internals_kernel(const ArenaS* S, RsbBallInternal* out, int nArenas) {
 	KERNEL_1D(i, nArenas);
@@ -881,7 +891,8 @@ int rsb_batch_create(int device, int game_mode, int n_arenas, int n_cars, const 
 	{
 		std::lock_guard<std::mutex> lk(g_initMutex);
 		if (!g_initialized) throw std::runtime_error("Cannot create Arena, RocketSim has not been initialized, call rsb_init_from_mem() first");
-		if (g_sceneHost.find(game_mode) == g_sceneHost.end() || (game_mode != THE_VOID && g_sceneHost[game_mode].meshes.empty()))
+		const auto hs = g_sceneHost.find(game_mode);
+		if (hs == g_sceneHost.end() || (game_mode != THE_VOID && hs->second.meshes.empty()))
 			throw std::runtime_error("No arena meshes found for gamemode " + std::to_string(game_mode));  // Arena.cpp:997-1002
 	}
 #ifndef RSB_HOSTCHECK
@@ -928,8 +939,9 @@ int rsb_batch_create(int device, int game_mode, int n_arenas, int n_cars, const 
 		P.boundRadius[0] = P.ballIsSphere ? P.ballRadiusBT : (sqrtf(P.ballRadiusBT * P.ballRadiusBT + (K::PUCK_HEIGHT * UU_TO_BT / 2) * (K::PUCK_HEIGHT * UU_TO_BT / 2)) + 0.04f);
 		for (int c = 0; c < n_cars; c++) P.boundRadius[c + 1] = len(P.carCfg[c].hitboxHalf) + 0.04f;
 	}
-	b->dScene = get_scene_dev(device, game_mode)->dScene;
-	const SceneHost& sh = get_scene_dev(device, game_mode)->host;
+	SceneDev* const sdev = get_scene_dev(device, game_mode);
+	b->dScene = sdev->dScene;
+	const SceneHost& sh = sdev->host;
 	b->dP = (BatchParams*)dev_alloc(sizeof(BatchParams));
 	h2d(b->dP, &P, sizeof(P), 0);
 	b->dS = (ArenaS*)dev_alloc(sizeof(ArenaS) * (size_t)n_arenas);
@@ -1128,6 +1140,16 @@ int rsb_set_auto_reset(RsbBatch* b, int enable, uint32_t seed) {
 	h2d(b->dP, &b->hp, sizeof(BatchParams), b->stream);
 	API_END
 }
+int rsb_set_arena_offset(RsbBatch* b, uint32_t off) {
+	API_BEGIN
+	set_device(b);
+	b->hp.arenaOffset = (int)off;
+#ifndef RSB_HOSTCHECK
+	CUDA_OK(cudaStreamSynchronize(b->stream));
+#endif
+	h2d(b->dP, &b->hp, sizeof(BatchParams), b->stream);
+	API_END
+}
 int rsb_set_event_tracker(RsbBatch* b, int enable, const RsbEventTrackerConfig* cfg) {
 	API_BEGIN
 	set_device(b);
@@ -1235,7 +1257,7 @@ RSB_GLOBAL void clone_arena_kernel(ArenaS* S, const BatchParams* P, const Scene*
 	B.ball.velImpulseCache = A.ball.velImpulseCache;
 	B.ball.groundStickApplied = 0;
 	for (int c = 0; c < nCars; c++) {
-		RsbCarState cs; car_to_api(A.cars[c], cs); car_from_api(cs, B.cars[c]);
+		RsbCarState cs; car_to_api(A, c, cs); car_from_api(cs, B, c);
 		B.cars[c].controls = A.cars[c].controls;
 		B.cars[c].velImpulseCache = A.cars[c].velImpulseCache;
 		for (int k = 0; k < 4; k++) { B.cars[c].wSteer[k] = B.cars[c].wEngine[k] = B.cars[c].wBrake[k] = B.cars[c].wLatFriction[k] = B.cars[c].wLongFriction[k] = B.cars[c].wExtraPushback[k] = 0.f; }
@@ -1424,17 +1446,23 @@ int rsb_seed_rng(RsbBatch* b, uint32_t arena, uint32_t seed) {
 
 int rsb_get_events(RsbBatch* b, RsbEvent* out, int cap, int* n_out) {
 	API_BEGIN set_device(b);
+	// events already downloaded but not yet handed out (the caller's buffer was smaller than what was pending) come first
 	uint32_t cnt = 0;
 	d2h(&cnt, b->dEventCount, 4, b->stream);
 	uint32_t n = std::min(cnt, b->eventCap);
-	std::vector<EventSink::Ev> ev(n);
-	if (n) d2h(ev.data(), b->dEvents, n * sizeof(EventSink::Ev), b->stream);
-	uint32_t zero = 0;
-	h2d(b->dEventCount, &zero, 4, b->stream);
-	std::stable_sort(ev.begin(), ev.end(), [](const EventSink::Ev& x, const EventSink::Ev& y) { return x.arena != y.arena ? x.arena < y.arena : x.tick < y.tick; });
-	int m = (int)std::min<uint32_t>(n, (uint32_t)std::max(cap, 0));
-	for (int i = 0; i < m; i++) { out[i].arena = ev[i].arena; out[i].type = ev[i].type; out[i].a = ev[i].a; out[i].b = ev[i].b; out[i].tick = ev[i].tick; }
-	if (n_out) *n_out = m;
+	if (n) {
+		std::vector<EventSink::Ev> ev(n);
+		d2h(ev.data(), b->dEvents, n * sizeof(EventSink::Ev), b->stream);
+		uint32_t zero = 0;
+		h2d(b->dEventCount, &zero, 4, b->stream);
+		std::stable_sort(ev.begin(), ev.end(), [](const EventSink::Ev& x, const EventSink::Ev& y) { return x.arena != y.arena ? x.arena < y.arena : x.tick < y.tick; });
+		b->pendingEvents.insert(b->pendingEvents.end(), ev.begin(), ev.end());
+	}
+	const size_t m = std::min<size_t>(b->pendingEvents.size(), (size_t)std::max(cap, 0));
+	for (size_t i = 0; i < m; i++) { const EventSink::Ev& e = b->pendingEvents[i]; out[i].arena = e.arena; out[i].type = e.type; out[i].a = e.a; out[i].b = e.b; out[i].tick = e.tick; }
+	b->pendingEvents.erase(b->pendingEvents.begin(), b->pendingEvents.begin() + (long)m);
+	if (n_out) *n_out = (int)m;
+	if (!b->pendingEvents.empty()) { g_err = std::to_string(b->pendingEvents.size()) + " more events pending: call rsb_get_events again"; return 1; }
 	API_END
 }
 

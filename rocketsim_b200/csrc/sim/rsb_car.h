@@ -16,6 +16,9 @@ RSB_HD uint32_t minstd_next(uint32_t& x) {  // std::minstd_rand0 (std::default_r
 	return x;
 }
 RSB_HD uint32_t minstd_seed(uint32_t s) { uint32_t x = s % 2147483647u; return x == 0 ? 1u : x; }
+// std::default_random_engine(int seed): libstdc++ takes the seed as unsigned long, i.e. a negative int is sign-extended to 64 bits
+// before the reduction mod 2^31-1 (bits/random.tcc, linear_congruential_engine::seed)
+RSB_HD uint32_t minstd_seed_int(int seed) { uint32_t x = (uint32_t)((uint64_t)(int64_t)seed % 2147483647ull); return x == 0 ? 1u : x; }
 
 // Angle(yaw,0,0).ToRotMat() -> btMatrix3x3::setEulerYPR(yaw,-0,-0) (MathTypes.cpp:72-77, btMatrix3x3.h:290-328)
 RSB_HD M3 basis_from_ypr(float yaw, float pitch, float roll) {

@@ -398,6 +398,7 @@ RSB_HD_NOINLINE void on_car_car_collision(Ctx cx, int c1, int c2, ContactPt& cp)
 					if (isDemo) {
 						car2.isDemoed = 1;
 						car2.demoRespawnTimer = mut.respawnDelay;
+						cx.g->demoRotMat[c2] = car2.rb.basis;  // what GetState().rotMat keeps showing until the respawn (Car.cpp:133-138)
 					} else {
 						bool groundHit = car2.isOnGround != 0;
 						float baseScale = groundHit ? curve_bump_vel_ground(speedTowardsOtherCar) : curve_bump_vel_air(speedTowardsOtherCar);

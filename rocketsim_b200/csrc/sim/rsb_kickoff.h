@@ -34,7 +34,7 @@ RSB_HD K::SpawnPos kickoff_slot(int mode, int i) {
 }
 
 RSB_HD void kickoff_reset(ArenaS& A, const BatchParams& P, int seed) {
-	uint32_t localRng = minstd_seed((uint32_t)seed);
+	uint32_t localRng = minstd_seed_int(seed);
 	uint32_t& rng = (seed == -1) ? A.rng : localRng;
 	int order[5] = {0, 1, 2, 3, 4};
 	const int L = (P.mode == HEATSEEKER) ? 4 : 5;

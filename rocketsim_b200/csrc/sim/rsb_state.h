@@ -102,7 +102,12 @@ struct ArenaS {
 	uint8_t worldFresh;    // 1 until the arena's physics world has stepped once (a new or freshly deserialised arena)
 	BallS ball;
 	PadS pads[MAX_PADS];
-	CarS cars[MAX_CARS];   // last: a batch with fewer cars stages only the used prefix of the record
+	CarS cars[MAX_CARS];   // last of the staged part: a batch with fewer cars stages only the used prefix of the record
+	// ---- cold tail: never staged into shared memory, touched through Ctx::g (the record in HBM) ----
+	// CarState::rotMat as Car::GetState reports it while a car is demoed: the reference refreshes _internalState.rotMat only at the
+	// top of Car::_PostTickUpdate, which returns early for a demoed car (Car.cpp:133-138), while the victim's rigid body still
+	// goes through the solve + integration of the tick it was demoed in.  Captured at the moment of the demo.
+	M3 demoRotMat[MAX_CARS];
 };
 
 enum ErrorFlags : uint32_t {
@@ -163,6 +168,7 @@ struct BatchParams {
 	int padGrid[8 * 10];  // BoostPadGrid (BoostPadGrid.h:10-29): pad index or -1
 	// README bench loop on device: when set, a goal is followed by ResetToRandomKickoff(autoResetSeed + arena + tick)
 	int autoReset; uint32_t autoResetSeed;
+	int arenaOffset;  // global index of the batch's arena 0 in a sharded job (auto-reset seeds and event arena ids are global)
 	int trackerEnabled; TrackerCfgD tracker;  // device-side GameEventTracker (rsb_set_event_tracker)
 	float boundRadius[MAX_BODIES]; // radius of a sphere around the shape centre that contains the shape incl. margins
 	float motionDisc[MAX_BODIES];  // btCollisionShape::getAngularMotionDisc of each dynamic body's shape (constant per batch)

@@ -152,7 +152,8 @@ RSB_HD void phase_run(const Ctx& cx, int phase, int item) {
 			}
 			// the caller's loop is Step(); tracker.Update(); if (scored) Reset -- same order here
 			if (P.trackerEnabled) tracker_update(cx, scored, S.tickCount + 1);
-			if (scored && P.autoReset) kickoff_reset(S, P, (int)(P.autoResetSeed + (uint32_t)cx.arena + (uint32_t)S.tickCount));
+			// seed = f(global arena index, tick), masked to 31 bits: never negative, never the -1 that selects the arena RNG
+			if (scored && P.autoReset) kickoff_reset(S, P, (int)((P.autoResetSeed + (uint32_t)(P.arenaOffset + cx.arena) + (uint32_t)S.tickCount) & 0x7fffffffu));
 		}
 		S.tickCount++;
 		S.worldFresh = 0;

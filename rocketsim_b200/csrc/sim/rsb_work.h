@@ -158,7 +158,8 @@ struct EventSink {
 };
 
 struct Ctx {
-	ArenaS* s;
+	ArenaS* s;         // the arena record the tick works on (shared memory inside the step kernel)
+	ArenaS* g;         // the same arena's record in HBM (cold tail only; == s in the host check build)
 	BodyW* body;       // hot scratch (see ArenaH)
 	WheelW* wheels;
 	int* padLocked;
@@ -210,7 +211,7 @@ RSB_HD void push_event(const Ctx& cx, uint32_t type, uint32_t a, uint32_t b) {
 	uint32_t i = (*cx.ev.count)++;
 #endif
 	if (i < cx.ev.cap) {
-		EventSink::Ev e; e.arena = (uint32_t)cx.arena; e.type = type; e.a = a; e.b = b; e.tick = cx.s->tickCount;
+		EventSink::Ev e; e.arena = (uint32_t)(cx.p->arenaOffset + cx.arena); e.type = type; e.a = a; e.b = b; e.tick = cx.s->tickCount;
 		cx.ev.buf[i] = e;
 	} else {
 		set_error(cx, ERR_EVENT_OVERFLOW);
@@ -225,7 +226,7 @@ RSB_HD void push_event_at(const Ctx& cx, uint32_t type, uint32_t a, uint32_t b, 
 #else
 	uint32_t i = (*cx.ev.count)++;
 #endif
-	if (i < cx.ev.cap) { EventSink::Ev e; e.arena = (uint32_t)cx.arena; e.type = type; e.a = a; e.b = b; e.tick = tick; cx.ev.buf[i] = e; }
+	if (i < cx.ev.cap) { EventSink::Ev e; e.arena = (uint32_t)(cx.p->arenaOffset + cx.arena); e.type = type; e.a = a; e.b = b; e.tick = tick; cx.ev.buf[i] = e; }
 	else set_error(cx, ERR_EVENT_OVERFLOW);
 }
 

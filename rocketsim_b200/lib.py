@@ -28,7 +28,7 @@ EXPORTS = [
     "rsb_get_error_flags", "rsb_seed_rng", "rsb_get_observations", "rsb_observation_floats",
     "rsb_get_car_internals", "rsb_set_car_internals", "rsb_get_ball_internals", "rsb_set_ball_internals",
     "rsb_reset_to_random_kickoff", "rsb_scene_counts", "rsb_scene_dump", "rsb_scene_num_meshes", "rsb_scene_cells",
-    "rsb_bench_fill_controls_device", "rsb_debug_get_wheels", "rsb_step_with_controls", "rsb_set_auto_reset", "rsb_debug_get_manifolds", "rsb_debug_get_solver_rows", "rsb_debug_profile", "rsb_debug_get_solver_bodies", "rsb_debug_get_misc", "rsb_car_config_preset", "rsb_default_mutator_config", "rsb_set_event_tracker", "rsb_is_ball_probably_going_in", "rsb_predict_ball", "rsb_serialize_arena", "rsb_deserialize_arena", "rsb_clone_arena",
+    "rsb_bench_fill_controls_device", "rsb_debug_get_wheels", "rsb_step_with_controls", "rsb_set_auto_reset", "rsb_debug_get_manifolds", "rsb_debug_get_solver_rows", "rsb_debug_profile", "rsb_debug_get_solver_bodies", "rsb_debug_get_misc", "rsb_car_config_preset", "rsb_default_mutator_config", "rsb_set_event_tracker", "rsb_is_ball_probably_going_in", "rsb_predict_ball", "rsb_serialize_arena", "rsb_deserialize_arena", "rsb_clone_arena", "rsb_set_arena_offset",
 ]
 
 
@@ -52,6 +52,7 @@ def _declare(L):
     L.rsb_sync.argtypes = [vp]
     L.rsb_step_with_controls.argtypes = [vp, vp, i32]
     L.rsb_set_auto_reset.argtypes = [vp, i32, u32]
+    L.rsb_set_arena_offset.argtypes = [vp, u32]
     for n in ("car_states", "ball_states", "pad_states", "tick_counts", "error_flags", "observations", "car_internals",
               "ball_internals"):
         getattr(L, "rsb_get_" + n).argtypes = [vp, vp]

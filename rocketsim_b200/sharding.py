@@ -25,6 +25,20 @@ def shard_bounds(n_total: int, world_size: int, rank: int) -> tuple[int, int]:
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+def local_device(rank: int) -> int:
+    """CUDA device of a rank: LOCAL_RANK when the launcher sets it (torchrun), else rank modulo the GPUs of this node --
+    never the global rank, which exceeds the device count on multi-node jobs."""
+    import os
+    if "LOCAL_RANK" in os.environ:
+        return int(os.environ["LOCAL_RANK"])
+    try:
+        import torch
+        n = torch.cuda.device_count()
+    except Exception:
+        n = 0
+    return rank % n if n > 0 else 0
+
+
 class ShardedArenaBatch:
     """This rank's shard of a job of ``n_total`` arenas.  Construction, stepping and state access are purely local."""
 
@@ -37,7 +51,9 @@ class ShardedArenaBatch:
         # rsb_batch_create seeds arena a of the batch with seed + a: offsetting by lo makes the RNG stream a function of
         # the global arena index only
         self.batch = ArenaBatch(game_mode, self.hi - self.lo, teams, seed=seed + self.lo,
-                                device=rank if device is None else device, lib=lib, **kw)
+                                device=local_device(rank) if device is None else device, lib=lib, **kw)
+        # auto-reset seeds and event arena ids are formed with the global arena index on the device
+        self.batch.set_arena_offset(self.lo)
 
     @property
     def global_ids(self) -> np.ndarray:
@@ -45,6 +61,14 @@ class ShardedArenaBatch:
 
     def reset_to_random_kickoff(self, seed: int):
         self.batch.reset_to_random_kickoff((seed + self.global_ids).astype(np.int32))
+
+    def set_auto_reset(self, enable: bool, seed: int = 0):
+        """Device-side kickoff reset after a goal, seeded with ``seed + GLOBAL arena index + tick``."""
+        self.batch.set_auto_reset(enable, seed)
+
+    def get_events(self, cap: int = 65536):
+        """This shard's events; ``arena`` is the GLOBAL arena index."""
+        return self.batch.get_events(cap)
 
     def local_slice(self, global_array: np.ndarray, axis: int = 0) -> np.ndarray:
         """The rows of a job-wide array (e.g. controls [n_total, n_cars]) that belong to this rank."""

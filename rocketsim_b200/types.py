@@ -88,10 +88,10 @@ BoostPadState = np.dtype({"names": ["isActive", "cooldown", "prevLockedCarID"], 
 
 CarInternal = np.dtype({
     "names": ["steerAngle", "engineForce", "brake", "latFriction", "longFriction", "extraPushback",
-              "velocityImpulseCache", "rbPos", "rbVel", "tickCountSinceUpdate", "hasRigidBody"],
-    "formats": [("<f4", 4)] * 9 + ["<u8", "<u4"],
-    "offsets": [16 * i for i in range(9)] + [144, 152],
-    "itemsize": 160,
+              "velocityImpulseCache", "rbPos", "rbVel", "tickCountSinceUpdate", "hasRigidBody", "rbBasis"],
+    "formats": [("<f4", 4)] * 9 + ["<u8", "<u4", ("<f4", 12)],
+    "offsets": [16 * i for i in range(9)] + [144, 152, 160],
+    "itemsize": 208,
 })
 BallInternal = np.dtype({"names": ["velocityImpulseCache", "groundStickApplied", "hasRigidBody", "tickCountSinceUpdate",
                                    "rbPos", "rbVel"],
@@ -112,5 +112,5 @@ CAR_OCTANE, CAR_DOMINUS, CAR_PLANK, CAR_BREAKOUT, CAR_HYBRID, CAR_MERC, CAR_PSYC
 SIZES = {
     "RsbVec": 16, "RsbRotMat": 48, "RsbCarControls": 24, "RsbBallHitInfo": 80, "RsbCarState": 352,
     "RsbBallState": 144, "RsbMutatorConfig": 128, "RsbCarConfig": 112, "RsbBoostPadState": 12,
-    "RsbCarInternal": 160, "RsbBallInternal": 64, "RsbEvent": 24,
+    "RsbCarInternal": 208, "RsbBallInternal": 64, "RsbEvent": 24,
 }

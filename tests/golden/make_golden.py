@@ -38,6 +38,15 @@ CASES = {
     "soccar_3v3_walls": (T.MODE_SOCCAR, 3, 21, 300, 150, "walls"),
     "hoops_2v2_walls": (T.MODE_HOOPS, 2, 23, 300, 150, "walls"),
     "snowday_2v2_walls": (T.MODE_SNOWDAY, 2, 25, 300, 150, "walls"),
+    # demos: a scripted supersonic ram (the attacker crosses the supersonic threshold on the way in), the demoed ticks and the
+    # respawn (3 s = 360 ticks later); tight circles around the ball (bumps, demos once a car is supersonic); goals with cars in play
+    "soccar_3v3_demo_ram": (T.MODE_SOCCAR, 3, 31, 520, 140, "ram"),
+    "soccar_2v2_demo_charge": (T.MODE_SOCCAR, 2, 11, 500, 150, "charge"),
+    "hoops_2v2_demo_charge": (T.MODE_HOOPS, 2, 12, 500, 150, "charge"),
+    "soccar_3v3_demo_charge": (T.MODE_SOCCAR, 3, 13, 500, 150, "charge"),
+    "snowday_3v3_demo_charge": (T.MODE_SNOWDAY, 3, 14, 500, 150, "charge"),
+    "soccar_2v2_goal": (T.MODE_SOCCAR, 2, 41, 180, 30, "goal"),
+    "hoops_2v2_goal": (T.MODE_HOOPS, 2, 43, 240, 30, "goal"),
 }
 
 
@@ -51,7 +60,9 @@ def main():
         path = os.path.join(HERE, name + ".npz")
         np.savez_compressed(path, **rec)
         ev = rec["events"]
-        print(f"{name}: {ticks} ticks, {len(ev)} events, {os.path.getsize(path) / 1024:.0f} KiB")
+        print(f"{name}: {ticks} ticks, {len(ev)} events (goal/bump/demo = {[int((ev[:, 1] == k).sum()) for k in (1, 2, 3)] if len(ev) else 0}), "
+              f"demoed car-ticks {int(rec['car_post']['isDemoed'].sum())}, supersonic car-ticks {int(rec['car_post']['isSupersonic'].sum())}, "
+              f"scored ticks {int(rec['scored'].sum())}, wheel-on-dynamic ticks {int(rec['wheel_on_dynamic'].sum())}, {os.path.getsize(path) / 1024:.0f} KiB")
 
 
 if __name__ == "__main__":

@@ -32,6 +32,10 @@ FLOAT_CAR = {"pos": 1.0, "vel": 1.0, "angVel": 0.01, "rotMat": 1.0, "boost": 1.0
              "supersonicTime": 1e-2, "handbrakeVal": 1e-2, "autoFlipTimer": 1e-2, "demoRespawnTimer": 1e-2,
              "flipRelTorque": 1.0}
 FLOAT_BALL = {"pos": 1.0, "vel": 1.0, "angVel": 0.01}
+# north_star lists boost amounts among the discrete state; the timers are sums of the same constants on both sides.
+# They are compared BITWISE (in addition to the 1e-4 float comparison above).
+BITEXACT_CAR = ["boost", "jumpTime", "flipTime", "airTime", "airTimeSinceJump", "timeSinceBoosted", "boostingTime", "supersonicTime",
+                "handbrakeVal", "autoFlipTimer", "autoFlipTorqueScale", "demoRespawnTimer"]
 
 
 def build_hostcheck(force: bool = False) -> str:
@@ -83,6 +87,10 @@ def field_as_array(s, name):
 def compare_car(mine, ref):
     """returns (discrete mismatches list, {field: rel err})"""
     bad = [f for f in DISCRETE_CAR if not np.array_equal(mine[f], ref[f])]
+    bad += [f for f in BITEXACT_CAR if np.asarray(mine[f]).tobytes() != np.asarray(ref[f]).tobytes()]
+    if int(mine["carContact"]["otherCarID"]) != int(ref["carContact"]["otherCarID"]) or \
+            np.asarray(mine["carContact"]["cooldownTimer"]).tobytes() != np.asarray(ref["carContact"]["cooldownTimer"]).tobytes():
+        bad.append("carContact")
     errs = {f: rel_err(field_as_array(mine, f), field_as_array(ref, f), eps) for f, eps in FLOAT_CAR.items()}
     return bad, errs
 
@@ -188,15 +196,104 @@ def cars_at_walls(ref, mode):
     ref.set_ball_state(bs)
 
 
+def _place_car(ref, cid, x, y, yaw, vel=(0.0, 0.0, 0.0), supersonic=None, boost=None):
+    st = ref.car_state(cid)
+    st["pos"]["x"], st["pos"]["y"], st["pos"]["z"] = x, y, 17.0
+    cy, sy = np.float32(np.cos(yaw)), np.float32(np.sin(yaw))
+    st["rotMat"]["forward"] = (cy, sy, 0, 0)
+    st["rotMat"]["right"] = (-sy, cy, 0, 0)
+    st["rotMat"]["up"] = (0, 0, 1, 0)
+    st["vel"]["x"], st["vel"]["y"], st["vel"]["z"] = vel
+    st["angVel"]["x"] = st["angVel"]["y"] = st["angVel"]["z"] = 0.0
+    if supersonic is not None:
+        st["isSupersonic"] = supersonic
+    if boost is not None:
+        st["boost"] = boost
+    ref.set_car_state(cid, st)
+
+
+def supersonic_ram(ref, teams):
+    """Car 0 (blue) comes up the field at 2,150 uu/s under boost -- it crosses the supersonic threshold on the way -- and rams
+    a parked orange car with its bumper: a demo (Arena.cpp:323-405), 360 demoed ticks, and a respawn that draws from the arena
+    RNG (Car.cpp:43-87).  The other cars are spread out of the way; the ball is parked in a corner."""
+    ids = list(ref.car_ids)
+    victim = ids[[i for i, t in enumerate(teams) if t != teams[0]][0]]
+    _place_car(ref, ids[0], 0.0, -2300.0, np.pi / 2, vel=(0.0, 2150.0, 0.0), boost=100.0)
+    _place_car(ref, victim, 0.0, -300.0, 0.0)
+    k = 0
+    for cid in ids:
+        if cid in (ids[0], victim):
+            continue
+        _place_car(ref, cid, -2500.0 + 1700.0 * k, 2600.0, -np.pi / 2)
+        k += 1
+    bs = ref.ball_state()
+    bs["pos"]["x"], bs["pos"]["y"], bs["pos"]["z"] = 2800.0, -3800.0, 93.15
+    bs["vel"]["x"] = bs["vel"]["y"] = bs["vel"]["z"] = 0.0
+    ref.set_ball_state(bs)
+    return ids[0], victim
+
+
+def ball_at_goal(ref, mode):
+    """Ball fired at the orange goal while the cars play on: a goal with cars in play (Arena.cpp:748-752, 893-927)."""
+    bs = ref.ball_state()
+    if mode == T.MODE_HOOPS:
+        bs["pos"]["x"], bs["pos"]["y"], bs["pos"]["z"] = 0.0, 2650.0, 900.0
+        bs["vel"]["x"], bs["vel"]["y"], bs["vel"]["z"] = 0.0, 250.0, -300.0
+    else:
+        bs["pos"]["x"], bs["pos"]["y"], bs["pos"]["z"] = 150.0, 3600.0, 250.0
+        bs["vel"]["x"], bs["vel"]["y"], bs["vel"]["z"] = -60.0, 2600.0, 120.0
+    ref.set_ball_state(bs)
+
+
+def apply_scenario(ref, mode, teams, aim):
+    """aim: False (kickoff) | True (cars on a 900 uu circle around the ball) | "walls" | "aim700" (tight circle: bumps and,
+    once a car is supersonic, demos) | "ram" (scripted supersonic demo) | "goal".  Returns the per-car control override used
+    during the forced-drive ticks: {car index: "drive" | "park"} (default "drive" for every car)."""
+    roles = {}
+    if aim == "walls":
+        cars_at_walls(ref, mode)
+    elif aim == "aim700":
+        aim_cars_at_ball(ref, radius=700.0)
+    elif aim == "charge":
+        # cars on a wide circle, already at 2,000 uu/s towards the ball with full boost: they turn supersonic on the way in and
+        # meet around the ball -- demos between opponents, bumps between team mates, car-ball hits at top speed
+        aim_cars_at_ball(ref, radius=1500.0)
+        for cid in ref.car_ids:
+            st = ref.car_state(cid)
+            f = st["rotMat"]["forward"]
+            st["vel"]["x"], st["vel"]["y"] = 2000.0 * float(f["x"]), 2000.0 * float(f["y"])
+            st["boost"] = 100.0
+            ref.set_car_state(cid, st)
+    elif aim == "ram":
+        a, v = supersonic_ram(ref, teams)
+        roles = {i: "park" for i in range(len(teams))}
+        roles[ref.car_ids.index(a)] = "drive"
+    elif aim == "goal":
+        aim_cars_at_ball(ref, radius=1500.0)
+        ball_at_goal(ref, mode)
+    elif aim:
+        aim_cars_at_ball(ref)
+    return roles
+
+
+def force_controls(c, roles):
+    for i in range(len(c)):
+        role = roles.get(i, "drive")
+        for f in ("steer", "pitch", "yaw", "roll"):
+            c[f][i] = 0
+        c["jump"][i] = 0; c["handbrake"][i] = 0
+        c["throttle"][i] = 1 if role == "drive" else 0
+        c["boost"][i] = 1 if role == "drive" else 0
+    return c
+
+
 def record_rollout(refsim, mode, teams, seed, ticks, drive=0, aim=False):
     ref = make_ref_arena(refsim, mode, teams)
     n = len(teams)
     ref.seed_rng(seed)
     ref.reset_kickoff(seed)
-    if aim == "walls":
-        cars_at_walls(ref, mode)
-    elif aim:
-        aim_cars_at_ball(ref)
+    canonical_kickoff(ref, teams)
+    roles = apply_scenario(ref, mode, teams, aim)
     sched = ControlSchedule(n, seed)
     npads = ref.num_pads
     rec = dict(mode=np.int32(mode), teams=np.asarray(teams, np.int32), seed=np.int32(seed),
@@ -209,13 +306,16 @@ def record_rollout(refsim, mode, teams, seed, ticks, drive=0, aim=False):
                # ticks in which a suspension ray rests on a DYNAMIC body (another car / the ball): the reference
                # resolves those with a sub-simplex cast that stops at dist^2 < 1e-4 and normalises with rsqrtss,
                # so the hit is only defined to ~1e-2 bt (see DESIGN.md "ill-conditioned events")
-               wheel_on_dynamic=np.zeros(ticks, np.uint8))
+               wheel_on_dynamic=np.zeros(ticks, np.uint8),
+               # the respawn RNG (thread-local in the reference) is re-seeded with seed + t before every tick, so that a tick
+               # with a respawn is an independent single-step case like every other
+               rng_per_tick=np.int32(1))
     events = []
     for t in range(ticks):
+        ref.seed_rng(seed + t)
         c = sched.at(t)
         if t < drive:
-            c["throttle"] = 1; c["boost"] = 1; c["steer"] = 0; c["jump"] = 0; c["handbrake"] = 0
-            c["pitch"] = 0; c["yaw"] = 0; c["roll"] = 0
+            c = force_controls(c, roles)
         rec["controls"][t] = c
         for i, cid in enumerate(ref.car_ids):
             rec["car_pre"][t, i] = ref.car_state(cid)
@@ -238,6 +338,19 @@ def record_rollout(refsim, mode, teams, seed, ticks, drive=0, aim=False):
             events.append((t, int(e["type"]), int(e["a"]), int(e["b"])))
     rec["events"] = np.asarray(events, np.int32).reshape(-1, 4)
     ref.close()
+    return rec
+
+
+def upgrade_record(rec):
+    """Records written before RsbCarInternal grew `rbBasis` carry the older 160-byte layout: copy the named fields over
+    (hasRigidBody keeps bit 1 clear, so the basis is not applied)."""
+    ci = rec["carint_pre"]
+    if ci.dtype != T.CarInternal:
+        out = np.zeros(ci.shape, T.CarInternal)
+        for name in ci.dtype.names:
+            if name in T.CarInternal.names:
+                out[name] = ci[name]
+        rec["carint_pre"] = out
     return rec
 
 
@@ -268,7 +381,7 @@ def replay_record(rec, lib, n_arenas=1, ticks=None, tol=1e-4):
     for t in range(T_):
         for a in check_arenas:
             load_pre_state(batch, rec, t, a)
-            batch.seed_rng(a, int(rec["seed"]))
+            batch.seed_rng(a, int(rec["seed"]) + (t if int(rec.get("rng_per_tick", 0)) else 0))
         ctrl = np.broadcast_to(rec["controls"][t], (n_arenas, len(teams)))
         batch.set_controls(ctrl)
         batch.step(1)
@@ -333,3 +446,47 @@ def canonical_kickoff(ref, teams):
         states.sort(key=lambda st: (round(float(st["pos"]["x"]), 3), round(float(st["pos"]["y"]), 3)))
         for cid, st in zip(members, states):
             ref.set_car_state(cid, st)
+
+
+def free_rollout_compare(lib, refsim, mode, teams, seed, ticks, aim=False, drive=0, n_arenas=2):
+    """FREE-RUNNING parity: both sides start from the same complete state and are then only fed the same controls (no
+    re-synchronisation).  Returns per-tick worst relative float error, the discrete mismatches, and event lists of both sides."""
+    ref = make_ref_arena(refsim, mode, teams)
+    ref.seed_rng(seed)
+    ref.reset_kickoff(seed)
+    canonical_kickoff(ref, teams)
+    roles = apply_scenario(ref, mode, teams, aim)
+    batch = ArenaBatch(mode, n_arenas, teams, lib=lib)
+    for a in range(n_arenas):
+        sync_from_ref(batch, ref, a)
+        batch.seed_rng(a, seed)
+    ref.seed_rng(seed)
+    sched = ControlSchedule(len(teams), seed)
+    worst = np.zeros(ticks)
+    mism, ev_ref, ev_mine = [], [], []
+    ref.drain_events(); batch.get_events()
+    for t in range(ticks):
+        c = sched.at(t)
+        if t < drive:
+            c = force_controls(c, roles)
+        for i, cid in enumerate(ref.car_ids):
+            ref.set_controls(cid, c[i])
+        batch.set_controls(np.broadcast_to(c, (n_arenas, len(teams))))
+        ref.step(1)
+        batch.step(1)
+        cs, bs = batch.get_car_states(), batch.get_ball_states()
+        for a in (0, n_arenas - 1):
+            for i, cid in enumerate(ref.car_ids):
+                bad, errs = compare_car(cs[a, i], ref.car_state(cid))
+                if bad:
+                    mism.append((t, a, i, bad))
+                worst[t] = max(worst[t], max(errs.values()))
+            worst[t] = max(worst[t], max(compare_ball(bs[a], ref.ball_state()).values()))
+        for e in ref.drain_events():
+            ev_ref.append((t, int(e["type"]), int(e["a"]), int(e["b"])))
+        for e in batch.get_events():
+            if int(e["arena"]) == 0:
+                ev_mine.append((t, int(e["type"]), int(e["a"]), int(e["b"])))
+    err = int(batch.get_error_flags().max())
+    batch.close(); ref.close()
+    return dict(worst=worst, mismatches=mism, events_ref=ev_ref, events_mine=ev_mine, error_flags=err)

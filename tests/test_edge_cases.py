@@ -86,10 +86,15 @@ def test_event_buffer_cap(hostlib):
     b.set_ball_states(np.arange(4), bs)
     b.step(30)
     # Without a reset the goal fires on EVERY tick the ball stays in the goal, as in the reference (Arena.cpp:744-752 calls the
-    # goal callback whenever IsBallScored()).  Fewer slots than events: truncated to cap, sorted by (arena, tick).
-    ev = b.get_events(cap=2)
-    assert len(ev) == 2 and list(ev["arena"]) == [0, 0] and np.all(ev["type"] == T.EVENT_GOAL)
-    assert ev["tick"][1] == ev["tick"][0] + 1
+    # goal callback whenever IsBallScored()).  Fewer slots than events: the C call hands out `cap` at a time and reports that more
+    # are pending (rc 1) -- nothing is dropped; the Python front end loops.  Sorted by (arena, tick).
+    import ctypes as C
+    out = np.zeros(2, T.Event); n = C.c_int()
+    assert hostlib.rsb_get_events(b.h, rlib.ptr(out), 2, C.byref(n)) == 1 and n.value == 2 and b"pending" in hostlib.rsb_last_error()
+    assert list(out["arena"]) == [0, 0] and np.all(out["type"] == T.EVENT_GOAL) and out["tick"][1] == out["tick"][0] + 1
+    ev = b.get_events(cap=7)
+    assert len(ev) > 7 and np.all(ev["type"] == T.EVENT_GOAL) and ev["tick"][0] == out["tick"][1] + 1
+    assert np.all(np.diff(ev["arena"].astype(np.int64)) >= 0) and sorted(set(ev["arena"])) == [0, 1, 2, 3]
     assert len(b.get_events()) == 0    # the buffer is drained by the call
     assert np.all(b.is_ball_scored())  # no auto reset: the ball stays in the goal (the reference leaves resets to the caller)
     b.close()

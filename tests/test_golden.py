@@ -27,7 +27,7 @@ TOL_ILLCOND = 2e-2
 
 def load(path):
     with np.load(path) as z:
-        return {k: z[k] for k in z.files}
+        return pu.upgrade_record({k: z[k] for k in z.files})
 
 
 def check(res, name):
@@ -41,7 +41,30 @@ def check(res, name):
 
 
 def test_golden_files_present():
-    assert len(GOLDEN) >= 10
+    assert len(GOLDEN) >= 17
+
+
+def test_golden_records_cover_demos_goals_supersonic():
+    """The records must actually contain the events they are meant to pin (no committed record held a demo)."""
+    tot = dict(demo_events=0, bump_events=0, goal_events=0, demoed=0, supersonic=0, scored=0, respawns=0, demo_ticks_with_rot_change=0)
+    for path in GOLDEN:
+        rec = load(path)
+        ev = rec["events"]
+        if len(ev):
+            tot["goal_events"] += int((ev[:, 1] == 1).sum()); tot["bump_events"] += int((ev[:, 1] == 2).sum()); tot["demo_events"] += int((ev[:, 1] == 3).sum())
+        pre, post = rec["car_pre"], rec["car_post"]
+        tot["demoed"] += int(post["isDemoed"].sum()); tot["supersonic"] += int(post["isSupersonic"].sum()); tot["scored"] += int(rec["scored"].sum())
+        tot["respawns"] += int(((pre["isDemoed"] != 0) & (post["isDemoed"] == 0)).sum())   # the record spans the respawn tick (Car.cpp:69-87)
+        # the tick of the demo itself: the victim's body still integrates, CarState.rotMat must stay at its pre-tick value (Car.cpp:133-138)
+        hit = (pre["isDemoed"] == 0) & (post["isDemoed"] != 0)
+        for t, i in zip(*np.nonzero(hit)):
+            assert pre["rotMat"][t, i].tobytes() == post["rotMat"][t, i].tobytes()
+            tot["demo_ticks_with_rot_change"] += 1
+        if "demo" in os.path.basename(path):
+            assert post["isDemoed"].any() and post["isSupersonic"].any(), path
+    assert tot["demo_events"] >= 8 and tot["bump_events"] >= 10 and tot["goal_events"] >= 2, tot
+    assert tot["demoed"] >= 360 * 8 and tot["respawns"] >= 8 and tot["supersonic"] >= 500 and tot["scored"] >= 50, tot
+    assert tot["demo_ticks_with_rot_change"] >= 8, tot
 
 
 @pytest.mark.parametrize("path", GOLDEN, ids=NAMES)

@@ -74,3 +74,27 @@ def test_two_rank_gloo_job_equals_single_process(hostlib, tmp_path):
     assert pu.struct_equal(np.load(out + ".cars.npy"), cars)
     assert pu.struct_equal(np.load(out + ".ball.npy"), ball)
     assert len({cars[a].tobytes() for a in range(N_TOTAL)}) == N_TOTAL  # distinct arenas really ran
+
+
+def test_auto_reset_and_events_use_global_arena_index(hostlib):
+    """Device-side auto reset seeds and event arena ids are functions of the GLOBAL arena index (rsb_set_arena_offset): a
+    shard gives the same per-arena results and the same event records as the corresponding arenas of the whole job."""
+    def run(rank, world):
+        sh = ShardedArenaBatch(T.MODE_SOCCAR, 6, TEAMS, seed=SEED, rank=rank, world_size=world, device=0, lib=hostlib)
+        sh.reset_to_random_kickoff(SEED)
+        sh.set_auto_reset(True, 4242)
+        b = sh.batch
+        bs = b.get_ball_states()
+        bs["pos"]["y"] = 4700; bs["pos"]["z"] = 200; bs["vel"]["y"] = 3000 + 100 * sh.global_ids   # every arena scores, at its own tick
+        b.set_ball_states(np.arange(b.n_arenas), bs)
+        b.step(60)
+        out = sh.batch.get_car_states(), sh.batch.get_ball_states(), sh.get_events()
+        sh.close()
+        return out
+    cars, ball, ev = run(0, 1)
+    assert len(ev) == 6 and sorted(ev["arena"]) == list(range(6))
+    for rank in (0, 1):
+        c, bl, e = run(rank, 2)
+        lo, hi = shard_bounds(6, 2, rank)
+        assert pu.struct_equal(c, cars[lo:hi]) and pu.struct_equal(bl, ball[lo:hi])
+        assert pu.struct_equal(e, ev[(ev["arena"] >= lo) & (ev["arena"] < hi)])
