@@ -162,7 +162,7 @@ def run_cuda(args):
     from rocketsim_b200 import lib as rlib, synthetic_meshes as sm, types as T
     from rocketsim_b200.arena_batch import ArenaBatch
 
-    L = rlib.load(os.environ.get("RSB_BENCH_LIB") or None)  # developer override: A/B another CUDA build of the same library
+    L = rlib.load()  # rocketsim_b200/librsb.so, nothing else (developer A/B runs of other builds: scripts/ab_bench.py)
     rlib.init_from_mem(sm.mesh_sets(), L)
     n_cars = 2 * args.cars_per_team
     teams = [0] * args.cars_per_team + [1] * args.cars_per_team

@@ -31,13 +31,16 @@ def _newest_source() -> float:
     return newest
 
 
-def build_cuda(force: bool = False, verbose: bool = False, profile: bool = False) -> str:
-    """profile=True builds the developer variant librsb_prof.so with per-phase cycle counters (-DRSB_PROFILE)."""
+def build_cuda(force: bool = False, verbose: bool = False, profile: bool = False, defines=(), suffix: str = "") -> str:
+    """profile=True builds the developer variant librsb_prof.so with per-phase cycle counters (-DRSB_PROFILE).
+    defines / suffix: developer A/B builds (librsb<suffix>.so with extra -D switches); the package only ever loads librsb.so."""
     out = OUT.replace("librsb.so", "librsb_prof.so") if profile else OUT
+    if suffix:
+        out = out.replace(".so", suffix + ".so")
     if not force and os.path.exists(out) and os.path.getmtime(out) >= _newest_source():
         return out
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-DRSB_PROFILE"] if profile else []) + ["-I" + os.path.join(HERE, "csrc"), SRC, "-o", out]
+    cmd = [nvcc] + NVCC_FLAGS + (["-DRSB_PROFILE"] if profile else []) + ["-D" + d for d in defines] + ["-I" + os.path.join(HERE, "csrc"), SRC, "-o", out]
     if verbose:
         cmd += ["-Xptxas", "-v"]
     r = subprocess.run(cmd, capture_output=True, text=True)

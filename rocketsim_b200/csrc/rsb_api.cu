@@ -87,6 +87,7 @@ static SceneDev* get_scene_dev(int device, int mode) {
 		const MeshHost& m = h.meshes[i];
 		MeshD& d = sc.meshes[i];
 		d.nodes = (const BvhNode*)up(m.nodes.data(), m.nodes.size() * sizeof(BvhNode)); d.nNodes = (int)m.nodes.size();
+		d.nodeBounds = (const float*)up(m.nodeBounds.data(), m.nodeBounds.size() * 4);
 		d.hdrs = (const SubtreeHdr*)up(m.hdrs.data(), m.hdrs.size() * sizeof(SubtreeHdr)); d.nHdrs = (int)m.hdrs.size();
 		d.tris = (const int32_t*)up(m.tris.data(), m.tris.size() * 4);
 		d.verts = (const float*)up(m.verts.data(), m.verts.size() * 4);
@@ -266,6 +267,7 @@ constexpr int BLOCKS_PER_SM = RSB_BLOCKS_PER_SM;
 static_assert(offsetof(ArenaS, cars) % 8 == 0 && sizeof(CarS) % 8 == 0 && sizeof(BodyW) % 8 == 0 && sizeof(WheelW) % 8 == 0 && sizeof(Manifold) % 8 == 0, "records are staged in 8-byte words");
 constexpr size_t SMEM_P_BYTES = (sizeof(BatchParams) + 15) & ~(size_t)15;
 constexpr size_t SMEM_SC_BYTES = (sizeof(Scene) + 15) & ~(size_t)15;
+constexpr size_t SMEM_Q_BYTES = 16 + 512 * 2;  // detector queue of the block: counter + entries (DETECT_QUEUE_CAP)
 constexpr size_t SMEM_MAX = (228 * 1024) / BLOCKS_PER_SM - 1024;  // 228 KB per SM, 1 KB reserved per resident block
 
 // Shared-memory layout of one resident arena: [ArenaS prefix (header, ball, pads, nCars cars) | BodyW x nb |
@@ -304,21 +306,25 @@ struct StepArgs {
 // developer builds: per phase [0..15] block wall cycles, [16..31] sum of busy-thread cycles, [32..47] busy-thread count,
 // [48..63] sum over blocks of the slowest thread's cycles
 __device__ unsigned long long g_prof[64];
+__device__ unsigned long long g_blockCycles[1024];  // elapsed cycles of each block of the last launch (imbalance between SMs)
 
 // [phase NS=0 / DYN=1][bucket: min(7, detector calls of the slowest item) + 8 if it ran EPA][0 = sum of its cycles, 1 = count]
 __device__ unsigned long long g_prof2[2][16][2];
 #define PHASE_PROF_BEGIN() long long _pt0 = clock64()
 #define PHASE_PROF_ITEMS(i, had) do { if (had) { unsigned long long _d = (unsigned long long)(clock64() - _pt0); atomicAdd(&g_prof[16 + i], _d); atomicAdd(&g_prof[32 + i], 1ull); atomicMax(&s_profMax, _d); } } while (0)
 #define PHASE_PROF_END(i) do { if (threadIdx.x == 0) { atomicAdd(&g_prof[i], (unsigned long long)(clock64() - _pt0)); atomicAdd(&g_prof[48 + i], s_profMax); s_profMax = 0; \
-	if (i == PH_NARROW_STATIC || i == PH_DYN_SOLVE) { int c = (int)(s_profMax2 & 0xfffff); int bk = min(7, c & 255) + ((c >> 8) ? 8 : 0); int ph = (i == PH_DYN_SOLVE); atomicAdd(&g_prof2[ph][bk][0], s_profMax2 >> 20); atomicAdd(&g_prof2[ph][bk][1], 1ull); s_profMax2 = 0; } } __syncthreads(); } while (0)
+	if (i == PH_NARROW_DETECT || i == PH_DYN_SOLVE) { int c = (int)(s_profMax2 & 0xfffff); int bk = min(7, c & 255) + ((c >> 8) ? 8 : 0); int ph = (i == PH_DYN_SOLVE); atomicAdd(&g_prof2[ph][bk][0], s_profMax2 >> 20); atomicAdd(&g_prof2[ph][bk][1], 1ull); s_profMax2 = 0; } } __syncthreads(); } while (0)
 #else
 #define PHASE_PROF_BEGIN() ((void)0)
 #define PHASE_PROF_ITEMS(i, had) ((void)0)
 #define PHASE_PROF_END(i) ((void)0)
 #endif
 
+constexpr int DETECT_QUEUE_CAP = 512;
 __device__ __forceinline__ Ctx make_ctx(const StepArgs& a, const BatchParams* sP, const Scene* sSc, unsigned char* sS, int a0, int ar) {
+	extern __shared__ __align__(16) unsigned char smem[];
 	Ctx cx;
+	cx.nq = (unsigned*)(smem + SMEM_P_BYTES + SMEM_SC_BYTES); cx.q = (uint16_t*)(cx.nq + 4); cx.qcap = DETECT_QUEUE_CAP; cx.arLocal = ar;
 	unsigned char* base = sS + (size_t)ar * a.lay.stride;
 	cx.s = (ArenaS*)base; cx.g = a.S + (a0 + ar); cx.body = (BodyW*)(base + a.lay.bodyOff); cx.wheels = (WheelW*)(base + a.lay.wheelOff);
 	cx.padLocked = (int*)(base + a.lay.padOff); cx.misc = (int*)(base + a.lay.miscOff);
@@ -401,6 +407,20 @@ __device__ __forceinline__ void run_phase_block(const StepArgs& a, const BatchPa
 	__shared__ unsigned long long s_profMax;
 #endif
 	PHASE_PROF_BEGIN();
+	if (PH == PH_NARROW_DETECT) {
+		// the block's detector queue: entry i goes to thread ptid == i, i.e. consecutive entries to different warps -- a GJK / EPA
+		// call is a long data-dependent loop, two of them in one warp would run one after the other
+		extern __shared__ __align__(16) unsigned char smem[];
+		const unsigned* nqp = (const unsigned*)(smem + SMEM_P_BYTES + SMEM_SC_BYTES);
+		const uint16_t* q = (const uint16_t*)(nqp + 4);
+		const int nq = min((int)*nqp, DETECT_QUEUE_CAP);
+		for (int i = ptid; i < nq; i += STEP_THREADS) {
+			const int e = q[i];
+			const Ctx cx = make_ctx(a, sP, sSc, sS, a0, e >> 7);
+			phase_run(cx, PH, e & 127);
+		}
+		PHASE_PROF_ITEMS(PH, ptid < nq);
+	} else {
 	const int n = phase_items(*sP, PH) * nA;
 	const int nRounds = (n + STEP_THREADS - 1) / STEP_THREADS + 1;
 	for (int k = 0; k < nRounds; k++) {
@@ -410,9 +430,10 @@ __device__ __forceinline__ void run_phase_block(const StepArgs& a, const BatchPa
 		phase_run(cx, PH, item);
 	}
 	PHASE_PROF_ITEMS(PH, phase_thread_busy<PH>(threadIdx.x, ptid, nA, *sP));
+	}
 #if defined(RSB_PROFILE)
 	__shared__ unsigned long long s_profMax2;
-	if (PH == PH_NARROW_STATIC || PH == PH_DYN_SOLVE) {
+	if (PH == PH_NARROW_DETECT || PH == PH_DYN_SOLVE) {
 		EpaScratch* es = a.E + ((size_t)blockIdx.x * STEP_THREADS + threadIdx.x);
 		if (phase_thread_busy<PH>(threadIdx.x, ptid, nA, *sP)) { unsigned long long d = (unsigned long long)(clock64() - _pt0); int c = es->profCalls; atomicMax(&s_profMax2, (d << 20) | (unsigned long long)(c & 0xfffff)); }
 		es->profCalls = 0;
@@ -433,12 +454,16 @@ __device__ __forceinline__ void run_phase_block(const StepArgs& a, const BatchPa
 	PHASE_PROF_END(PH);
 }
 
+
 __global__ void __launch_bounds__(STEP_THREADS, BLOCKS_PER_SM) arena_step_kernel(const StepArgs a) {
 	extern __shared__ __align__(16) unsigned char smem[];
 	BatchParams* sP = (BatchParams*)smem;
 	Scene* sSc = (Scene*)(smem + SMEM_P_BYTES);
-	unsigned char* sS = smem + SMEM_P_BYTES + SMEM_SC_BYTES;
+	unsigned char* sS = smem + SMEM_P_BYTES + SMEM_SC_BYTES + SMEM_Q_BYTES;
 	const int tid = threadIdx.x;
+#if defined(RSB_PROFILE)
+	const long long _kt0 = clock64();
+#endif
 	for (int i = tid; i < (int)(sizeof(BatchParams) / 4); i += STEP_THREADS) ((uint32_t*)sP)[i] = ((const uint32_t*)a.P)[i];
 	for (int i = tid; i < (int)(sizeof(Scene) / 4); i += STEP_THREADS) ((uint32_t*)sSc)[i] = ((const uint32_t*)a.sc)[i];
 	// item -> thread permutation: consecutive items go to different warps, so that a phase with few
@@ -471,8 +496,11 @@ __global__ void __launch_bounds__(STEP_THREADS, BLOCKS_PER_SM) arena_step_kernel
 			run_phase_block<PH_WHEELS>(a, sP, sSc, sS, a0, nA, ptid);
 			run_phase_block<PH_CAR_LOGIC>(a, sP, sSc, sS, a0, nA, ptid);
 			run_phase_block<PH_PREDICT>(a, sP, sSc, sS, a0, nA, ptid);
+			if (tid == 0) *(unsigned*)(smem + SMEM_P_BYTES + SMEM_SC_BYTES) = 0u;  // detector queue; the next write to it is two barriers away
 			run_phase_block<PH_PAIRS>(a, sP, sSc, sS, a0, nA, ptid);
 			run_phase_block<PH_NARROW_STATIC>(a, sP, sSc, sS, a0, nA, ptid);
+			run_phase_block<PH_NARROW_DETECT>(a, sP, sSc, sS, a0, nA, ptid);
+			run_phase_block<PH_NARROW_COMMIT>(a, sP, sSc, sS, a0, nA, ptid);
 			run_phase_block<PH_DYN_SOLVE>(a, sP, sSc, sS, a0, nA, ptid);
 			run_phase_block<PH_FINISH_BODY>(a, sP, sSc, sS, a0, nA, ptid);
 			run_phase_block<PH_CAR_POST>(a, sP, sSc, sS, a0, nA, ptid);
@@ -505,13 +533,18 @@ __global__ void __launch_bounds__(STEP_THREADS, BLOCKS_PER_SM) arena_step_kernel
 			}
 		}
 	}
+#if defined(RSB_PROFILE)
+	if (tid == 0 && blockIdx.x < 1024) g_blockCycles[blockIdx.x] = (unsigned long long)(clock64() - _kt0);
+#endif
 }
 #else
 // host check build (tests only): the same phases, one thread, state in place
 static void arena_step_host(const StepArgs& a) {
 	const int nCars = a.P->nCars;
 	for (int arena = 0; arena < a.nArenas; arena++) {
-		Ctx cx; cx.s = a.S + arena; cx.g = cx.s; cx.w = a.W + arena; cx.epa = a.E; cx.p = a.P; cx.sc = a.sc; cx.ev = a.ev; cx.arena = arena;
+		uint16_t hq[512]; unsigned hnq = 0;
+		Ctx cx; cx.q = hq; cx.nq = &hnq; cx.qcap = 512; cx.arLocal = 0;
+		cx.s = a.S + arena; cx.g = cx.s; cx.w = a.W + arena; cx.epa = a.E; cx.p = a.P; cx.sc = a.sc; cx.ev = a.ev; cx.arena = arena;
 		cx.body = a.H[arena].body; cx.wheels = a.H[arena].wheels; cx.padLocked = a.H[arena].padLocked; cx.misc = a.H[arena].misc;
 		cx.pl = &a.H[arena].pairs; cx.mf = a.H[arena].mf; cx.solv = a.H[arena].solv;
 		for (int t = 0; t < a.nTicks; t++) {
@@ -932,6 +965,11 @@ int rsb_batch_create(int device, int game_mode, int n_arenas, int n_cars, const 
 		P.team[i] = teams ? teams[i] : (i < (n_cars + 1) / 2 ? 0 : 1);
 	}
 	fill_pads(game_mode, P);
+	for (int team = 0; team < 2; team++) {
+		auto yaw_of = [&](float yaw) { return team == 0 ? yaw : (float)((double)yaw + 3.14159265358979323846); };
+		for (int i = 0; i < 5; i++) P.kickBasis[team][i] = basis_from_ypr(yaw_of(kickoff_slot(game_mode, i).yaw), 0.f, 0.f);
+		for (int i = 0; i < 4; i++) P.respBasis[team][i] = basis_from_ypr(yaw_of(respawn_slot(game_mode == HOOPS, i).yaw), 0.f, 0.f);
+	}
 	{
 		ArenaS tmpS; memset(&tmpS, 0, sizeof(tmpS));
 		Ctx cx; cx.s = &tmpS; cx.w = nullptr; cx.epa = nullptr; cx.body = nullptr; cx.wheels = nullptr; cx.padLocked = nullptr; cx.misc = nullptr; cx.pl = nullptr; cx.mf = nullptr; cx.solv = nullptr; cx.p = &P; cx.sc = nullptr; cx.arena = 0; cx.ev.buf = nullptr;
@@ -1043,7 +1081,7 @@ static void launch_step(RsbBatch* b, int n_ticks, const CtrlS* seq, int nCtrl) {
 #ifndef RSB_HOSTCHECK
 	// chunk size: fill every SM once if the batch fits (one wave), else the fewest equal waves
 	const int sms = b->numSMs * BLOCKS_PER_SM;  // resident block slots
-	const int APB_MAX = (int)((b->smemBudget - SMEM_P_BYTES - SMEM_SC_BYTES) / a.lay.stride);
+	const int APB_MAX = (int)((b->smemBudget - SMEM_P_BYTES - SMEM_SC_BYTES - SMEM_Q_BYTES) / a.lay.stride);
 	const int chunksMin = (P.nArenas + APB_MAX - 1) / APB_MAX;
 	const int waves = (chunksMin + sms - 1) / sms;
 	a.apb = (P.nArenas + waves * sms - 1) / (waves * sms);
@@ -1051,7 +1089,7 @@ static void launch_step(RsbBatch* b, int n_ticks, const CtrlS* seq, int nCtrl) {
 	if (a.apb > APB_MAX) a.apb = APB_MAX;
 	const int nChunks = (P.nArenas + a.apb - 1) / a.apb;
 	const int grid = nChunks < sms ? nChunks : sms;
-	const size_t smem = SMEM_P_BYTES + SMEM_SC_BYTES + (size_t)a.apb * a.lay.stride;
+	const size_t smem = SMEM_P_BYTES + SMEM_SC_BYTES + SMEM_Q_BYTES + (size_t)a.apb * a.lay.stride;
 	arena_step_kernel<<<grid, STEP_THREADS, smem, b->stream>>>(a);
 	CUDA_OK(cudaGetLastError());
 #else
@@ -1592,7 +1630,7 @@ int rsb_debug_profile(uint64_t* out64, int reset) {
 	CUDA_OK(cudaDeviceSynchronize());
 	CUDA_OK(cudaMemcpyFromSymbol(out64, g_prof, sizeof(unsigned long long) * 64));
 	{ static unsigned long long h2[2][16][2]; CUDA_OK(cudaMemcpyFromSymbol(h2, g_prof2, sizeof(h2)));
-	  if (getenv("RSB_PROF2")) for (int ph = 0; ph < 2; ph++) for (int k = 0; k < 16; k++) if (h2[ph][k][1]) printf("prof2 %s slowest-item detector calls %d%s epa %d: n %llu mean cycles %llu\n", ph ? "DYN_SOLVE" : "NARROW_STATIC", k & 7, (k & 7) == 7 ? "+" : "", k >> 3, h2[ph][k][1], h2[ph][k][0] / h2[ph][k][1]);
+	  if (getenv("RSB_PROF2")) for (int ph = 0; ph < 2; ph++) for (int k = 0; k < 16; k++) if (h2[ph][k][1]) printf("prof2 %s slowest-item detector calls %d%s epa %d: n %llu mean cycles %llu\n", ph ? "DYN_SOLVE" : "NARROW_DETECT", k & 7, (k & 7) == 7 ? "+" : "", k >> 3, h2[ph][k][1], h2[ph][k][0] / h2[ph][k][1]);
 	  if (reset) { memset(h2, 0, sizeof(h2)); CUDA_OK(cudaMemcpyToSymbol(g_prof2, h2, sizeof(h2))); } }
 	{ unsigned long long h3[64]; CUDA_OK(cudaMemcpyFromSymbol(h3, g_subprof, sizeof(h3)));
 	  const char* nm[32] = {"DYN dyn pairs", "DYN islands (+has_rows)", "DYN solver: bodies", "DYN solver: rows", "DYN solver: split sweeps", "DYN solver: velocity sweeps", "DYN solver: writeback", "DYN solver: whole",
@@ -1600,6 +1638,12 @@ int rsb_debug_profile(uint64_t* out64, int reset) {
 	                        "CAR friction", "CAR update_wheels", "CAR air/jump/flip", "CAR vehicle_second", "CAR boost", "PAIRS cells", "PAIRS statics", "PAIRS dynamics", "24", "25", "26", "27", "28", "29", "30", "31"};
 	  if (getenv("RSB_PROF2")) for (int k = 0; k < 32; k++) if (h3[32 + k]) printf("subprof %-28s n %llu mean cycles %llu total Mcycles %llu\n", nm[k], h3[32 + k], h3[k] / h3[32 + k], h3[k] / 1000000);
 	  if (reset) { memset(h3, 0, sizeof(h3)); CUDA_OK(cudaMemcpyToSymbol(g_subprof, h3, sizeof(h3))); } }
+	if (getenv("RSB_PROF2")) {
+		static unsigned long long bc[1024]; CUDA_OK(cudaMemcpyFromSymbol(bc, g_blockCycles, sizeof(bc)));
+		unsigned long long mn = ~0ull, mx = 0, sum = 0; int n = 0;
+		for (int i = 0; i < 1024; i++) if (bc[i]) { mn = std::min(mn, bc[i]); mx = std::max(mx, bc[i]); sum += bc[i]; n++; }
+		if (n) printf("blocks of the last launch: %d, cycles min %llu mean %llu max %llu (max/mean %.3f)\n", n, mn, sum / n, mx, (double)mx * n / (double)sum);
+	}
 	if (reset) { unsigned long long z[64] = {0}; CUDA_OK(cudaMemcpyToSymbol(g_prof, z, sizeof(z))); }
 #else
 	(void)reset;

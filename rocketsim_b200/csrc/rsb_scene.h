@@ -27,6 +27,7 @@ struct MeshHost {
 	std::vector<int32_t> tris;     // 3 per triangle
 	std::vector<float> verts;      // 4 per vertex
 	std::vector<BvhNode> nodes;
+	std::vector<float> nodeBounds;  // 8 floats per node: unquantize(qmin), 0, unquantize(qmax), 0 (the ray walk's box, rsb_ray.h)
 	std::vector<SubtreeHdr> hdrs;
 	std::vector<TriInfo> info;
 	V3 bvhMin, bvhMax, bvhQuant;
@@ -355,6 +356,13 @@ inline MeshHost build_mesh(const uint8_t* data, size_t size) {
 		V3 amin(kLargeFloat, kLargeFloat, kLargeFloat), amax(-kLargeFloat, -kLargeFloat, -kLargeFloat);
 		for (int j = 0; j < 3; j++) { amin = vmin(amin, A[j]); amax = vmax(amax, A[j]); }
 		bvh_query(m, amin, amax, [&](int tb) { connect(m, t, A, tb); });
+	}
+	// unquantized node boxes for the ray walk (btQuantizedBvh::unQuantize: (float)q / quantization + bvhAabbMin, IEEE division)
+	m.nodeBounds.resize(m.nodes.size() * 8);
+	for (size_t n = 0; n < m.nodes.size(); n++) {
+		const V3 lo = scene_detail::unquantize(m, m.nodes[n].qmin), hi = scene_detail::unquantize(m, m.nodes[n].qmax);
+		float* o = &m.nodeBounds[n * 8];
+		o[0] = lo.x; o[1] = lo.y; o[2] = lo.z; o[3] = 0.f; o[4] = hi.x; o[5] = hi.y; o[6] = hi.z; o[7] = 0.f;
 	}
 	return m;
 }

@@ -113,8 +113,9 @@ RSB_HD void cull_points2(int n, float p[], int m, int i0, int iret[]) {
 	}
 }
 
-// boxes 1/2 = (shape, world transform); manifold mi has body0 = owner of box 1.
-RSB_HD void box_box(const Ctx& cx, int mi, const Convex& box1, const Xform& xf1, const Convex& box2, const Xform& xf2) {
+// boxes 1/2 = (shape, world transform); the manifold's body0 = owner of box 1.  Pure detector: returns the number of contacts
+// (<= 4) and writes the common normal on B, the points and the signed depths; the commit phase adds them in order.
+RSB_HD int box_box_detect(const Ctx& cx, const Convex& box1, const Xform& xf1, const Convex& box2, const Xform& xf2, V3& outNormalOnB, V3 outPts[4], float outDep[4]) {
 	const float fudge_factor = 1.05f;
 #if defined(RSB_PROFILE)
 	if (cx.epa) cx.epa->profCalls += 1;
@@ -145,7 +146,7 @@ RSB_HD void box_box(const Ctx& cx, int mi, const Convex& box1, const Xform& xf1,
 
 #define RSB_TST(expr1, expr2, norm, cc) \
 	s2 = fabsf(expr1) - (expr2); \
-	if (s2 > 0) return; \
+	if (s2 > 0) return 0; \
 	if (s2 > s) { s = s2; nsel0 = (norm)[0]; nsel1 = (norm)[4]; nsel2 = (norm)[8]; haveR = 1; invert_normal = ((expr1) < 0); code = (cc); }
 	s = -3.402823466e+38f;
 	invert_normal = 0;
@@ -159,7 +160,7 @@ RSB_HD void box_box(const Ctx& cx, int mi, const Convex& box1, const Xform& xf1,
 #undef RSB_TST
 #define RSB_TST(expr1, expr2, n1, n2, n3, cc) \
 	s2 = fabsf(expr1) - (expr2); \
-	if (s2 > kEps) return; \
+	if (s2 > kEps) return 0; \
 	l = sqrtf((n1) * (n1) + (n2) * (n2) + (n3) * (n3)); \
 	if (l > kEps) { \
 		s2 /= l; \
@@ -183,14 +184,14 @@ RSB_HD void box_box(const Ctx& cx, int mi, const Convex& box1, const Xform& xf1,
 	RSB_TST(pp[1] * R12 - pp[0] * R22, (A[0] * Q22 + A[1] * Q12 + B[0] * Q33 + B[2] * Q31), -R22, R12, 0, 14);
 	RSB_TST(pp[1] * R13 - pp[0] * R23, (A[0] * Q23 + A[1] * Q13 + B[0] * Q32 + B[1] * Q31), -R23, R13, 0, 15);
 #undef RSB_TST
-	if (!code) return;
+	if (!code) return 0;
 
 	if (haveR) { normal[0] = nsel0; normal[1] = nsel1; normal[2] = nsel2; }
 	else { normal[0] = ddot_pq(R1, normalC, 1, 1); normal[1] = ddot_pq(R1 + 4, normalC, 1, 1); normal[2] = ddot_pq(R1 + 8, normalC, 1, 1); }
 	if (invert_normal) { normal[0] = -normal[0]; normal[1] = -normal[1]; normal[2] = -normal[2]; }
 	depth = -s;
-	const V3 negNormal(-normal[0], -normal[1], -normal[2]);
-	V3 outPts[4]; float outDep[4]; int nOut = 0;  // <= maxc = 4 contacts
+	outNormalOnB = V3(-normal[0], -normal[1], -normal[2]);
+	int nOut = 0;  // <= maxc = 4 contacts
 
 	if (code > 6) {
 		float pa[3], pb[3], sign;
@@ -261,7 +262,7 @@ RSB_HD void box_box(const Ctx& cx, int mi, const Convex& box1, const Xform& xf1,
 	float rect[2] = {Sa[code1], Sa[code2]};
 	float ret[16];
 	int n = intersect_rect_quad2(rect, quad, ret);
-	if (n < 1) return;
+	if (n < 1) return 0;
 	float point[3 * 8], dep[8];
 	float det1 = 1.f / (m11 * m22 - m12 * m21);
 	m11 *= det1; m12 *= det1; m21 *= det1; m22 *= det1;
@@ -277,7 +278,7 @@ RSB_HD void box_box(const Ctx& cx, int mi, const Convex& box1, const Xform& xf1,
 			cnum++;
 		}
 	}
-	if (cnum < 1) return;
+	if (cnum < 1) return 0;
 	int maxc = 4;
 	if (maxc > cnum) maxc = cnum;
 	if (maxc < 1) maxc = 1;
@@ -304,8 +305,7 @@ RSB_HD void box_box(const Ctx& cx, int mi, const Convex& box1, const Xform& xf1,
 	}
 	}
 emit:
-	// one call site: the contact hook (Arena::_BulletContactAddedCallback and all it pulls in) is inlined here once
-	for (int k = 0; k < nOut; k++) add_contact_point(cx, mi, negNormal, outPts[k], outDep[k], -1, -1, true);
+	return nOut;
 }
 
 }  // namespace rsb

@@ -56,10 +56,9 @@ RSB_HD void car_respawn(const Ctx& cx, int ci) {
 	K::SpawnPos sp = respawn_slot(P.mode == HOOPS, slot);
 	bool blue = (P.team[ci] == 0);
 	V3 posUU(sp.x, sp.y * (blue ? 1.f : -1.f), K::CAR_RESPAWN_Z);
-	float yaw = (float)((double)sp.yaw + (blue ? 0.0 : 3.14159265358979323846));
 	car_reset_state(c, P.mut.carSpawnBoostAmount);
 	c.rb.pos = posUU * UU_TO_BT;
-	c.rb.basis = basis_from_ypr(yaw, 0.f, 0.f);
+	c.rb.basis = P.respBasis[blue ? 0 : 1][slot];  // Angle(yaw + (blue ? 0 : pi), 0, 0).ToRotMat(), host-computed (BatchParams)
 	c.rb.vel = v3zero();
 	c.rb.angvel = v3zero();
 	cx.body[ci + 1].invInertiaW = world_inv_inertia(c.rb.basis, cx.body[ci + 1].invInertiaLocal);
@@ -107,7 +106,11 @@ RSB_HD void wheel_trace(const Ctx& cx, int ci, int wi) {
 		V3 up = -w.wheelDirWS;
 		V3 right = w.wheelAxleWS;
 		V3 fwd = normalized(cross(up, right));
-		Q4 steeringOrn = q_axis_angle(up, c.wSteer[wi]);
+		// btQuaternion(up, steer): sin(0) = 0 and cos(0) = 1 exactly, so the libm calls are skipped for an unsteered wheel
+		const float steer = c.wSteer[wi];
+		Q4 steeringOrn;
+		if (steer == 0.f) { const float s0 = (steer * 0.5f) / len(up);  /* sinf(+-0) = +-0 */ steeringOrn = q4(up.x * s0, up.y * s0, up.z * s0, 1.f); }
+		else steeringOrn = q_axis_angle(up, steer);
 		M3 steeringMat = m3_from_quat(steeringOrn);
 		// basis2 columns: [forward=0] fwd, [right=1] -right, [up=2] up
 		M3 basis2(V3(fwd.x, -right.x, up.x), V3(fwd.y, -right.y, up.y), V3(fwd.z, -right.z, up.z));

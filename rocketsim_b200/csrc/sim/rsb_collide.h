@@ -168,15 +168,17 @@ RSB_HD void body_filter(const Ctx& cx, int obj, int& group, int& mask) {
 }
 
 RSB_HD void add_pair(const Ctx& cx, int a, int b, int entry = 0) {
-	int ga, ma, gb, mb;
-	body_filter(cx, a, ga, ma); body_filter(cx, b, gb, mb);
-	if (!((ga & mb) && (gb & ma))) return;  // needsBroadphaseCollision
 	if (cx.pl->nPairs >= MAX_MANIFOLDS) { set_error(cx, ERR_MANIFOLD_OVERFLOW); return; }
 	cx.pl->a[cx.pl->nPairs] = a; cx.pl->b[cx.pl->nPairs] = b; cx.pl->entry[cx.pl->nPairs] = (uint16_t)entry; cx.pl->nPairs++;
 }
 
 // calculateOverlappingPairs: pair list in creation order; (proxy0, proxy1) sorted by handle id
 // (statics first; ball before cars; lower car index first).
+// The collision filter (needsBroadphaseCollision) of a (static, body) pair was applied when the body's candidate list was
+// built (update_aabb); two dynamic bodies always pass it (ball: group DEFAULT|..., mask ALL; cars likewise).  A dynamic pair
+// (lo, hi) is created when the LOWER body is visited -- adjacency and AABB overlap are symmetric, so by the time the higher
+// body meets the lower one the pair exists already (the reference's pair-cache lookup) -- in the order of the cell's
+// dynamic-handle list.
 RSB_HD void compute_pairs(const Ctx& cx) {
 	const Scene& sc = *cx.sc;
 	const int nb = n_bodies(cx);
@@ -184,28 +186,27 @@ RSB_HD void compute_pairs(const Ctx& cx) {
 	for (int b = 0; b < nb; b++) {
 		const BodyW& bw = cx.body[b];
 		if (bw.nCand >= 0) {
-			for (int q = 0; q < bw.nCand; q++) { add_pair(cx, STATIC_BASE + bw.candObj[q], b, bw.cand[q]); }
+			for (int q = 0; q < bw.nCand; q++) add_pair(cx, STATIC_BASE + bw.candObj[q], b, bw.cand[q]);
 		} else {  // candidate list overflowed: full scan
+			int gb, mb; body_filter(cx, b, gb, mb);
 			int cell = cx.s->cellIdx[b];
 			for (int s = sc.cellStart[cell]; s < sc.cellStart[cell + 1]; s++) {
 				int obj = STATIC_BASE + sc.cellStatics[s];
 				V3 mn, mx; static_proxy_aabb(cx, obj, mn, mx);
-				if (aabb_overlap(bw.aabbMin, bw.aabbMax, mn, mx)) add_pair(cx, obj, b, s);
+				int ga, ma; body_filter(cx, obj, ga, ma);
+				if (aabb_overlap(bw.aabbMin, bw.aabbMax, mn, mx) && (ga & mb) && (gb & ma)) add_pair(cx, obj, b, s);
 			}
 		}
-		if (nb > 1) {
+		if (b + 1 < nb) {
 			// dynamic proxies registered in b's cell, in the cell list's order (ascending stamp)
 			const int ci = cx.s->cellI[b], cj = cx.s->cellJ[b], ck = cx.s->cellK[b];
 			for (int q = 0; q < nb; q++) {
 				const int o = cx.s->dynOrder[q];
-				if (o == b) continue;
+				if (o <= b) continue;
 				if (abs((int)cx.s->cellI[o] - ci) > 1 || abs((int)cx.s->cellJ[o] - cj) > 1 || abs((int)cx.s->cellK[o] - ck) > 1) continue;
 				const BodyW& ow = cx.body[o];
 				if (!aabb_overlap(bw.aabbMin, bw.aabbMax, ow.aabbMin, ow.aabbMax)) continue;
-				int lo = b < o ? b : o, hi = b < o ? o : b;
-				bool exists = false;
-				for (int k = 0; k < cx.pl->nPairs; k++) if (cx.pl->a[k] == lo && cx.pl->b[k] == hi) { exists = true; break; }
-				if (!exists) add_pair(cx, lo, hi);
+				add_pair(cx, b, o);
 			}
 		}
 	}
@@ -228,6 +229,11 @@ RSB_HD float body_angular_motion_disc(const Ctx& cx, int obj) {
 RSB_HD int new_manifold(const Ctx& cx, int slot, int body0, int body1) {
 	Manifold& m = cx.mf[slot];
 	m.body0 = body0; m.body1 = body1; m.nPts = 0; m.pts = cx.w->points + slot * 4;
+#if defined(__CUDA_ARCH__)
+	atomicOr(&cx.pl->mfMask, 1u << slot);
+#else
+	cx.pl->mfMask |= 1u << slot;
+#endif
 	float t0 = (body0 >= STATIC_BASE ? kLargeFloat : cx.p->motionDisc[body0]) * kContactBreaking;
 	float t1 = (body1 >= STATIC_BASE ? kLargeFloat : cx.p->motionDisc[body1]) * kContactBreaking;
 	m.breakingThresh = t0 < t1 ? t0 : t1;
@@ -582,22 +588,57 @@ RSB_HD bool triangle_vs_aabb(const V3 t[3], const V3& mn, const V3& mx) {  // Te
 	return true;
 }
 
+// ------------------------------------------------------------------ staged narrowphase: candidate records + detector queue
+RSB_HD int cand_alloc(const Ctx& cx, int n) {
+#if defined(__CUDA_ARCH__)
+	const int i = atomicAdd(&cx.misc[3], n);
+#else
+	const int i = cx.misc[3]; cx.misc[3] += n;
+#endif
+	if (i + n > MAX_CANDS) { set_error(cx, ERR_TRI_OVERFLOW); return -1; }
+	return i;
+}
+RSB_HD void detect_queue_push(const Ctx& cx, int idx) {
+#if defined(__CUDA_ARCH__)
+	const unsigned q = atomicAdd(cx.nq, 1u);
+#else
+	const unsigned q = (*cx.nq)++;
+#endif
+	if (q < (unsigned)cx.qcap) cx.q[q] = (uint16_t)(cx.arLocal * 128 + idx);
+	else set_error(cx, ERR_TRI_OVERFLOW);
+}
+RSB_HD void cand_emit(const Ctx& cx, int pair, int mesh, int tri, int state, const V3& normal, const V3& point, float depth) {
+	const int i = cand_alloc(cx, 1);
+	if (i < 0) return;
+	CandRec r; r.pair = (int16_t)pair; r.mesh = (int16_t)mesh; r.tri = tri; r.state = state; r.depth = depth; r.normal = normal; r.point = point;
+	cx.w->cand[i] = r;
+	if (state == CAND_PENDING) detect_queue_push(cx, i);
+}
+
+RSB_HD void convex_local_aabb(const Ctx& cx, const Convex& shape, const Xform& xf, V3& amin, V3& amax) {
+	if (shape.kind == SH_SPHERE) { float mg = shape.margin + 0.08f; V3 e(mg, mg, mg); amin = xf.origin - e; amax = xf.origin + e; }
+	else if (shape.kind == SH_BOX) transform_aabb_he(shape.he, shape.margin, xf.basis, xf.origin, amin, amax);
+	else transform_aabb_mm(cx.p->puckLocalAabbMin, cx.p->puckLocalAabbMax, shape.margin, xf.basis, xf.origin, amin, amax);
+}
+
 // Convex (ball sphere / puck hull / car box) vs an arena mesh:
 // btConvexConcaveCollisionAlgorithm::processCollision + btConvexTriangleCallback::processTriangle
 // (btConvexConcaveCollisionAlgorithm.cpp:71-250) over the BVH's AABB query
 // (btQuantizedBvh.cpp:655-729: subtree headers in order, stackless walk inside each).
-RSB_HD void convex_vs_mesh(const Ctx& cx, int mi, int body, const Convex& shape, const Xform& xf, int meshIdx, int entry) {
+// The walk finds the triangles whose box overlaps the convex and that pass the supporting-plane early-out.  A sphere is
+// resolved on the spot (closed form); any other shape gets one candidate record per triangle (DEFER), in leaf order.
+template <bool DEFER>
+RSB_HD void convex_vs_mesh(const Ctx& cx, int mi, const Convex& shape, const Xform& xf, int meshIdx, int entry) {
 	const MeshD& mesh = cx.sc->meshes[meshIdx];
 	Manifold& mf = cx.mf[mi];
 	// convex AABB in triangle space (mesh at origin, identity): shape->getAabb(convexInTriangleSpace)
 	V3 amin, amax;
-	if (shape.kind == SH_SPHERE) { float mg = shape.margin + 0.08f; V3 e(mg, mg, mg); amin = xf.origin - e; amax = xf.origin + e; }
-	else if (shape.kind == SH_BOX) transform_aabb_he(shape.he, shape.margin, xf.basis, xf.origin, amin, amax);
-	else transform_aabb_mm(cx.p->puckLocalAabbMin, cx.p->puckLocalAabbMax, shape.margin, xf.basis, xf.origin, amin, amax);
+	convex_local_aabb(cx, shape, xf, amin, amax);
 	// extraMargin = mesh margin (0) + closestPointDistanceThreshold (0)
 	uint16_t qmin[3], qmax[3];
 	bvh_quantize_clamped(mesh, amin, 0, qmin);
 	bvh_quantize_clamped(mesh, amax, 1, qmax);
+	const M3 invB = inverse(xf.basis);
 	// only the headers that can overlap a query from this broadphase cell (same order as the full header loop)
 	const int hEnd = cx.sc->cellHdrStart[entry + 1];
 	for (int hi = cx.sc->cellHdrStart[entry]; hi < hEnd; hi++) {
@@ -618,7 +659,6 @@ RSB_HD void convex_vs_mesh(const Ctx& cx, int mi, int body, const Convex& shape,
 					bool skip = false;
 					{
 						V3 tn = normalized(cross(t[1] - t[0], t[2] - t[0]));
-						M3 invB = inverse(xf.basis);
 						for (int side = 0; side < 2 && !skip; side++) {
 							V3 localPt = support_with_margin(shape, invB * tn);
 							V3 worldPt = xf_apply(xf, localPt);
@@ -630,17 +670,14 @@ RSB_HD void convex_vs_mesh(const Ctx& cx, int mi, int body, const Convex& shape,
 						}
 					}
 					if (!skip) {
-						if (shape.kind == SH_SPHERE) {
+						if (!DEFER) {
 							V3 point, normal; float depth;
 							// sphereInTr origin = (center - 0) * I
 							V3 c = vmul(xf.origin - v3zero(), m3identity());
 							if (sphere_triangle(c, shape.margin, t, mf.breakingThresh, point, normal, depth))
 								add_contact_point(cx, mi, m3identity() * normal, m3identity() * point + v3zero(), depth, meshIdx, tri, false);
 						} else {
-							Convex triShape; triShape.kind = SH_TRI; triShape.margin = 0.f; triShape.he = v3zero();
-							triShape.tri[0] = t[0]; triShape.tri[1] = t[1]; triShape.tri[2] = t[2]; triShape.pts = nullptr; triShape.npts = 0;
-							Xform xfT; xfT.basis = m3identity(); xfT.origin = v3zero();
-							convex_convex(cx, mi, shape, xf, triShape, xfT, meshIdx, tri);
+							cand_emit(cx, mi, meshIdx, tri, CAND_PENDING, v3zero(), v3zero(), 0.f);
 						}
 					}
 				}
@@ -649,11 +686,11 @@ RSB_HD void convex_vs_mesh(const Ctx& cx, int mi, int body, const Convex& shape,
 			else cur += -nd.idx;
 		}
 	}
-	refresh_contact_points(cx, mi);
-	(void)body;
+	if (!DEFER) refresh_contact_points(cx, mi);
 }
 
 // btConvexPlaneCollisionAlgorithm::processCollision (btConvexPlaneCollisionAlgorithm.cpp:92-161)
+template <bool DEFER>
 RSB_HD void convex_vs_plane(const Ctx& cx, int mi, const Convex& shape, const Xform& xf, const PlaneD& pl) {
 	Manifold& mf = cx.mf[mi];
 	const V3 planeNormal = pl.n;
@@ -668,9 +705,10 @@ RSB_HD void convex_vs_plane(const Ctx& cx, int mi, const Convex& shape, const Xf
 		V3 vtxInPlaneProjected = vtxInPlane - distance * planeNormal;
 		V3 vtxInPlaneWorld = m3identity() * vtxInPlaneProjected + pl.pos;
 		V3 normalOnSurfaceB = m3identity() * planeNormal;
-		add_contact_point(cx, mi, normalOnSurfaceB, vtxInPlaneWorld, distance, -1, -1, false);
+		if (!DEFER) add_contact_point(cx, mi, normalOnSurfaceB, vtxInPlaneWorld, distance, -1, -1, false);
+		else cand_emit(cx, mi, -1, -1, CAND_CONTACT, normalOnSurfaceB, vtxInPlaneWorld, distance);
 	}
-	if (mf.nPts) refresh_contact_points(cx, mi);
+	if (!DEFER && mf.nPts) refresh_contact_points(cx, mi);
 }
 
 RSB_HD Convex car_box(const CarCfgD& cfg) {
@@ -681,17 +719,19 @@ RSB_HD Xform car_child_xform(const RigidS& rb, const CarCfgD& cfg) {
 	Xform t; t.basis = rb.basis * m3identity(); t.origin = rb.basis * cfg.hitboxOffset + rb.pos;
 	return t;
 }
-RSB_HD void convex_world_aabb(const Ctx& cx, const Convex& s, const Xform& t, V3& mn, V3& mx) {
-	if (s.kind == SH_SPHERE) { float mg = s.margin + 0.08f; V3 e(mg, mg, mg); mn = t.origin - e; mx = t.origin + e; }
-	else if (s.kind == SH_BOX) transform_aabb_he(s.he, s.margin, t.basis, t.origin, mn, mx);
-	else transform_aabb_mm(cx.p->puckLocalAabbMin, cx.p->puckLocalAabbMax, s.margin, t.basis, t.origin, mn, mx);
-}
+RSB_HD void convex_world_aabb(const Ctx& cx, const Convex& s, const Xform& t, V3& mn, V3& mx) { convex_local_aabb(cx, s, t, mn, mx); }
 
-// performDiscreteCollisionDetection, split so that the per-body work runs on one thread per body:
-//   collide_pairs         (arena)  cell bookkeeping + broadphase pair list; manifold slot k <-> pair k
-//   collide_static_pairs  (body b) narrowphase + contact hooks of b's pairs with static objects
-//   collide_dynamic_pairs (arena)  ball-car and car-car pairs, in pair order (their hooks touch two bodies)
-// Manifold order (= solver row order) is the pair order whatever the execution order.
+// performDiscreteCollisionDetection in four phases (rsb_tick.h):
+//   collide_pairs            PH_PAIRS           (arena)   cell bookkeeping + broadphase pair list; manifold slot k <-> pair k
+//   collide_static_pairs     PH_NARROW_STATIC   (body b)  b's pairs with static objects: the sphere ball is resolved on the spot
+//                                                         (closed-form detectors + contact hooks); a car box / the puck hull only
+//                                                         records candidates
+//   enqueue_dynamic_pairs    PH_NARROW_STATIC   (arena)   ball-car and car-car pairs that pass the AABB checks -> candidates
+//   detect_candidate         PH_NARROW_DETECT   (record)  GJK(+EPA) / box-box for one pending record
+//   commit_static_candidates PH_NARROW_COMMIT   (body b)  b's records -> manifolds + contact hooks, in record order
+//   commit_dynamic_candidates PH_DYN_SOLVE      (arena)   same for ball-car / car-car (their hooks touch two bodies)
+// Manifold order (= solver row order) is the pair order whatever the execution order; within a manifold the
+// points arrive in BVH leaf order / detector order, as in the reference.
 RSB_HD void collide_pairs(const Ctx& cx) {
 	RSB_SUBPROF_BEGIN();
 	apply_cell_changes(cx);
@@ -699,6 +739,8 @@ RSB_HD void collide_pairs(const Ctx& cx) {
 	compute_pairs(cx);
 	RSB_SUBPROF_MARK(22);
 	cx.pl->nManifolds = cx.pl->nPairs;
+	cx.pl->deferMask = 0u; cx.pl->mfMask = 0u;
+	cx.misc[3] = 0;
 	for (int k = 0; k < cx.pl->nPairs; k++) { cx.mf[k].body0 = -1; cx.mf[k].nPts = 0; }
 }
 
@@ -709,10 +751,19 @@ RSB_HD bool pair_needs_collision(const Ctx& cx, int a, int b) {
 	return actA || actB;
 }
 
+RSB_HD void mark_deferred(const Ctx& cx, int k) {
+#if defined(__CUDA_ARCH__)
+	atomicOr(&cx.pl->deferMask, 1u << k);
+#else
+	cx.pl->deferMask |= 1u << k;
+#endif
+}
+
 RSB_HD void collide_static_pairs(const Ctx& cx, int b) {
 	const BatchParams& P = *cx.p;
 	const Scene& sc = *cx.sc;
 	const int nPairs = cx.pl->nPairs;
+	const bool inlineBody = (b == 0) && P.ballIsSphere;
 	RSB_SUBPROF_BEGIN();
 	for (int k = 0; k < nPairs; k++) {
 		if (cx.pl->b[k] != b) continue;
@@ -722,30 +773,35 @@ RSB_HD void collide_static_pairs(const Ctx& cx, int b) {
 		const int sk = a - STATIC_BASE;
 		const bool isMesh = sk < sc.nMeshes;
 		const RigidS& rb = rigid_of(cx, b);
-		if (b == 0) {
+		if (inlineBody) {
 			Convex shape = ball_convex(P);
 			Xform xf; xf.basis = rb.basis; xf.origin = rb.pos;
 			int mi = new_manifold(cx, k, 0, a);
-			if (isMesh) convex_vs_mesh(cx, mi, 0, shape, xf, sk, cx.pl->entry[k]);
-			else convex_vs_plane(cx, mi, shape, xf, sc.planes[sk - sc.nMeshes]);
-		} else {
-			const CarCfgD& cfg = P.carCfg[b - 1];
+			if (isMesh) convex_vs_mesh<false>(cx, mi, shape, xf, sk, cx.pl->entry[k]);
+			else convex_vs_plane<false>(cx, mi, shape, xf, sc.planes[sk - sc.nMeshes]);
+			continue;
+		}
+		Convex shape; Xform xf;
+		if (b == 0) { shape = ball_convex(P); xf.basis = rb.basis; xf.origin = rb.pos; }
+		else {
 			// btCompoundLeafCallback::ProcessChildShape: child AABB vs the other shape's AABB
 			V3 omn, omx;
 			static_aabb(cx, a, omn, omx);
 			if (!aabb_overlap(cx.body[b].childMin, cx.body[b].childMax, omn, omx)) continue;
-			Convex shape = car_box(cfg);
-			const Xform xf = cx.body[b].childXf;
-			int mi = new_manifold(cx, k, b, a);
-			RSB_SUBPROF_MARK(12);
-			if (isMesh) convex_vs_mesh(cx, mi, b, shape, xf, sk, cx.pl->entry[k]);
-			else convex_vs_plane(cx, mi, shape, xf, sc.planes[sk - sc.nMeshes]);
-			RSB_SUBPROF_MARK(isMesh ? 14 : 13);
+			shape = car_box(P.carCfg[b - 1]);
+			xf = cx.body[b].childXf;
 		}
+		int mi = new_manifold(cx, k, b, a);
+		mark_deferred(cx, k);
+		RSB_SUBPROF_MARK(12);
+		if (isMesh) convex_vs_mesh<true>(cx, mi, shape, xf, sk, cx.pl->entry[k]);
+		else convex_vs_plane<true>(cx, mi, shape, xf, sc.planes[sk - sc.nMeshes]);
+		RSB_SUBPROF_MARK(isMesh ? 14 : 13);
 	}
 }
 
-RSB_HD void collide_dynamic_pairs(const Ctx& cx) {
+// ball-car and car-car pairs, in pair order: the compound / child AABB gates of the reference, a manifold, and a pending record
+RSB_HD void enqueue_dynamic_pairs(const Ctx& cx) {
 	const BatchParams& P = *cx.p;
 	for (int k = 0; k < cx.pl->nPairs; k++) {
 		const int a = cx.pl->a[k], b = cx.pl->b[k];
@@ -753,33 +809,94 @@ RSB_HD void collide_dynamic_pairs(const Ctx& cx) {
 		if (!pair_needs_collision(cx, a, b)) continue;
 		if (a == 0) {
 			// (ball, car): swapped compound -> convex-convex(box of the car, ball shape); manifold (car, ball)
-			const CarCfgD& cfg = P.carCfg[b - 1];
 			const RigidS& rball = rigid_of(cx, 0);
 			Convex ball = ball_convex(P); Xform xfb; xfb.basis = rball.basis; xfb.origin = rball.pos;
 			V3 omn, omx;
 			convex_world_aabb(cx, ball, xfb, omn, omx);
 			if (!aabb_overlap(cx.body[b].childMin, cx.body[b].childMax, omn, omx)) continue;
-			Convex box = car_box(cfg); const Xform xfc = cx.body[b].childXf;
-			int mi = new_manifold(cx, k, b, 0);
-			convex_convex(cx, mi, box, xfc, ball, xfb, -1, -1);
-			refresh_contact_points(cx, mi);
+			new_manifold(cx, k, b, 0);
+			mark_deferred(cx, k);
+			cand_emit(cx, k, -1, -1, CAND_PENDING, v3zero(), v3zero(), 0.f);
 		} else {
 			// (carLo=a, carHi=b): compound-compound -> ... -> box-box(body0 = box of b, body1 = box of a); manifold (b, a)
-			const CarCfgD& cfgA = P.carCfg[a - 1]; const CarCfgD& cfgB = P.carCfg[b - 1];
-			const RigidS& ra = rigid_of(cx, a); const RigidS& rbb = rigid_of(cx, b);
+			const CarCfgD& cfgB = P.carCfg[b - 1];
+			const RigidS& rbb = rigid_of(cx, b);
 			const V3 amn = cx.body[a].childMin, amx = cx.body[a].childMax;   // child of A
 			V3 cmn, cmx;
 			compound_aabb(cfgB, rbb.basis, rbb.pos, cmn, cmx);  // whole compound B
 			if (!aabb_overlap(amn, amx, cmn, cmx)) continue;
 			if (!aabb_overlap(cx.body[b].childMin, cx.body[b].childMax, amn, amx)) continue;   // child of B vs box A
-			Convex boxA = car_box(cfgA), boxB = car_box(cfgB);
-			const Xform xfA = cx.body[a].childXf, xfB = cx.body[b].childXf;
-			(void)ra;
-			int mi = new_manifold(cx, k, b, a);
-			box_box(cx, mi, boxB, xfB, boxA, xfA);
-			refresh_contact_points(cx, mi);
+			new_manifold(cx, k, b, a);
+			mark_deferred(cx, k);
+			// the box-box detector reports up to 4 points: 4 consecutive records, the first one carries the request
+			const int i = cand_alloc(cx, 4);
+			if (i < 0) continue;
+			for (int j = 0; j < 4; j++) {
+				CandRec r; r.pair = (int16_t)k; r.mesh = -1; r.tri = -1; r.state = j == 0 ? CAND_PENDING : CAND_NONE; r.depth = 0.f; r.normal = v3zero(); r.point = v3zero();
+				cx.w->cand[i + j] = r;
+			}
+			detect_queue_push(cx, i);
 		}
 	}
+}
+
+// PH_NARROW_DETECT: the detector of one pending record, on its own thread
+RSB_HD void detect_candidate(const Ctx& cx, int idx) {
+	const BatchParams& P = *cx.p;
+	CandRec* rec = &cx.w->cand[idx];
+	const int k = rec->pair;
+	const int a = cx.pl->a[k], b = cx.pl->b[k];
+	V3 n, pt; float d;
+	if (a >= STATIC_BASE) {
+		// (body b, triangle of an arena mesh)
+		const RigidS& rb = rigid_of(cx, b);
+		Convex shape; Xform xf;
+		if (b == 0) { shape = ball_convex(P); xf.basis = rb.basis; xf.origin = rb.pos; }
+		else { shape = car_box(P.carCfg[b - 1]); xf = cx.body[b].childXf; }
+		Convex triShape; triShape.kind = SH_TRI; triShape.margin = 0.f; triShape.he = v3zero(); triShape.pts = nullptr; triShape.npts = 0;
+		mesh_triangle(cx.sc->meshes[rec->mesh], rec->tri, triShape.tri[0], triShape.tri[1], triShape.tri[2]);
+		Xform xfT; xfT.basis = m3identity(); xfT.origin = v3zero();
+		const bool hit = convex_convex_detect(cx, cx.mf[k].breakingThresh, shape, xf, triShape, xfT, n, pt, d);
+		if (hit) { rec->normal = n; rec->point = pt; rec->depth = d; }
+		rec->state = hit ? CAND_CONTACT : CAND_NONE;
+	} else if (a == 0) {
+		const RigidS& rball = rigid_of(cx, 0);
+		Convex ball = ball_convex(P); Xform xfb; xfb.basis = rball.basis; xfb.origin = rball.pos;
+		Convex box = car_box(P.carCfg[b - 1]); const Xform xfc = cx.body[b].childXf;
+		const bool hit = convex_convex_detect(cx, cx.mf[k].breakingThresh, box, xfc, ball, xfb, n, pt, d);
+		if (hit) { rec->normal = n; rec->point = pt; rec->depth = d; }
+		rec->state = hit ? CAND_CONTACT : CAND_NONE;
+	} else {
+		Convex boxA = car_box(P.carCfg[a - 1]), boxB = car_box(P.carCfg[b - 1]);
+		const Xform xfA = cx.body[a].childXf, xfB = cx.body[b].childXf;
+		V3 pts[4]; float dep[4];
+		const int nOut = box_box_detect(cx, boxB, xfB, boxA, xfA, n, pts, dep);
+		for (int j = 0; j < 4; j++) {
+			if (j < nOut) { rec[j].normal = n; rec[j].point = pts[j]; rec[j].depth = dep[j]; }
+			rec[j].state = j < nOut ? CAND_CONTACT : CAND_NONE;
+		}
+	}
+}
+
+// PH_NARROW_COMMIT (body b) / PH_DYN_SOLVE (dynamic pairs, b = -1): records -> manifolds + contact hooks, in record order.
+// The records of one thread's walk carry ascending indices, so one pass in index order filtered by owner restores the order
+// in which the reference's detectors add their points.
+RSB_HD void commit_candidates(const Ctx& cx, int b) {
+	const int n = cx.misc[3] < MAX_CANDS ? cx.misc[3] : MAX_CANDS;
+	const uint32_t deferred = cx.pl->deferMask;
+	int curPair = -1;
+	for (int i = 0; i < n; i++) {
+		const CandRec r = cx.w->cand[i];
+		const int k = r.pair;
+		const bool dyn = cx.pl->a[k] < STATIC_BASE;
+		if (b < 0 ? !dyn : (dyn || cx.pl->b[k] != b)) continue;
+		if (k != curPair) { if (curPair >= 0) refresh_contact_points(cx, curPair); curPair = k; }
+		if (r.state != CAND_CONTACT) continue;
+		if (b < 0) add_contact_point(cx, k, r.normal, r.point, r.depth, -1, -1, true);
+		else add_contact_point(cx, k, r.normal, r.point, r.depth, r.mesh, r.tri, false);
+	}
+	if (curPair >= 0) refresh_contact_points(cx, curPair);
+	(void)deferred;
 }
 
 }  // namespace rsb

@@ -44,12 +44,14 @@ RSB_HD V3 convex_aabb_center(const Ctx& cx, const Convex& s, const Xform& t) {
 // is being passed by reference to a __noinline__ callee can share its stack slot with the callee's own locals)
 RSB_HD_NOINLINE bool epa_penetration(const Ctx& cx, Convex A, Xform tA, Convex B, Xform tB, V3& v, V3& wa, V3& wb);
 
-// GJK closest points + addContactPoint.  A/B with world transforms; triMesh/triIndex forwarded.
-RSB_CC_ATTR void convex_convex(const Ctx& cx, int mi, const Convex& A, const Xform& xfA, const Convex& B, const Xform& xfB, int triMesh, int triIndex) {
+// GJK closest points (+ EPA when the cores overlap) of A/B at their world transforms.  Pure detector: reports the contact
+// (normal on B, point on B in world space, signed distance) and leaves the manifold alone -- PH_NARROW_DETECT runs it on one
+// thread per candidate, the commit phases add the results in order.
+RSB_CC_ATTR bool convex_convex_detect(const Ctx& cx, float breaking, const Convex& A, const Xform& xfA, const Convex& B, const Xform& xfB,
+                                      V3& outNormal, V3& outPoint, float& outDist) {
 #if defined(RSB_PROFILE)
 	if (cx.epa) cx.epa->profCalls += 1;
 #endif
-	const float breaking = cx.mf[mi].breakingThresh;
 	float maxDist2 = A.margin + B.margin + breaking;
 	maxDist2 *= maxDist2;
 
@@ -146,8 +148,10 @@ RSB_CC_ATTR void convex_convex(const Ctx& cx, int mi, const Convex& A, const Xfo
 		V3 posB = convex_aabb_center(cx, B, localB);
 		V3 diff = posA - posB;
 		if (dot(diff, normalInB) < 0.f) normalInB *= -1.f;
-		add_contact_point(cx, mi, normalInB, pointOnB + positionOffset, distance, triMesh, triIndex, triMesh < 0 && cx.mf[mi].body1 < STATIC_BASE);
+		outNormal = normalInB; outPoint = pointOnB + positionOffset; outDist = distance;
+		return true;
 	}
+	return false;
 }
 
 }  // namespace rsb

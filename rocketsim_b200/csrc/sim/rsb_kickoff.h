@@ -63,11 +63,14 @@ RSB_HD void kickoff_reset(ArenaS& A, const BatchParams& P, int seed) {
 	int amount = nBlue > nOrange ? nBlue : nOrange;
 	for (int k = 0; k < amount; k++) {
 		K::SpawnPos sp;
+		int kickIdx = -1, respIdx = -1;
 		if (k < L) {
 			int idx = order[k] < L - 1 ? order[k] : L - 1;
 			sp = kickoff_slot(P.mode, idx);
+			kickIdx = idx;
 		} else {
 			int ridx = (k - L) % L;
+			respIdx = ridx;
 			sp = respawn_slot(P.mode == HOOPS, ridx);
 			sp.y += 250.f * numAtRespawn[ridx];
 			numAtRespawn[ridx]++;
@@ -79,10 +82,10 @@ RSB_HD void kickoff_reset(ArenaS& A, const BatchParams& P, int seed) {
 			CarS& c = A.cars[isBlue ? blue[k] : orange[k]];
 			car_reset_state(c, P.mut.carSpawnBoostAmount);
 			V3 pos(sp.x, sp.y, K::CAR_SPAWN_REST_Z);
-			float yaw = sp.yaw;
-			if (!isBlue) { pos = pos * V3(-1.f, -1.f, 1.f); yaw = (float)((double)yaw + 3.14159265358979323846); }
+			if (!isBlue) pos = pos * V3(-1.f, -1.f, 1.f);
 			c.rb.pos = pos * UU_TO_BT;
-			c.rb.basis = basis_from_ypr(yaw, 0.f, 0.f);
+			// Angle(yaw + (blue ? 0 : pi), 0, 0).ToRotMat(), host-computed (BatchParams)
+			c.rb.basis = kickIdx >= 0 ? P.kickBasis[isBlue ? 0 : 1][kickIdx] : P.respBasis[isBlue ? 0 : 1][respIdx];
 			c.rb.vel = v3zero(); c.rb.angvel = v3zero();
 			c.isOnGround = 1;
 		}

@@ -134,9 +134,11 @@ RSB_HD bool ray_mesh(const Scene& sc, const MeshD& m, int entry, const V3& from,
 		bool boxBoxOverlap = quant_overlap(qmin, qmax, nd.qmin, nd.qmax);
 		bool isLeaf = nd.idx >= 0;
 		if (boxBoxOverlap) {
+			// unQuantize(node corners): six IEEE divisions per node in the reference, tabulated at scene build (MeshD::nodeBounds)
+			const float* nb = m.nodeBounds + 8 * (size_t)cur;
 			V3 bounds[2];
-			bounds[0] = bvh_unquantize(m, nd.qmin);
-			bounds[1] = bvh_unquantize(m, nd.qmax);
+			bounds[0] = V3(nb[0], nb[1], nb[2]);
+			bounds[1] = V3(nb[4], nb[5], nb[6]);
 			rayBoxOverlap = ray_aabb2(from, inv, sign, bounds, 0.0f, lambda_max);
 		}
 		if (isLeaf && rayBoxOverlap) {

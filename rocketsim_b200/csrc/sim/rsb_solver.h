@@ -41,56 +41,78 @@ RSB_HD void quicksort_keys(int* key, int* val, int lo, int hi) {
 
 // calculateSimulationIslands + buildIslands: island tags, wake-ups, and the manifold order
 // handed to the solver.  Returns the number of manifolds to solve (order in pl->manifoldOrder).
-// <= 7 bodies: the union-find forest lives in one register (4 bits per body) and the per-island predicates are bit masks
-// indexed by root; the unite sequence, the roots it produces and the (non-stable) manifold sort are the reference's.
+// <= 7 bodies: the union-find forest lives in one register (4 bits per body), activation states and response flags are
+// gathered into bit fields once, and only the manifolds that exist this tick (PairList::mfMask) are visited; the unite
+// sequence, the roots it produces and the (non-stable) manifold sort are the reference's.
 RSB_HD int build_islands(const Ctx& cx) {
 	const int nb = n_bodies(cx);
 	uint32_t par = 0x76543210u;  // par[b] = b
-	// findUnions over ALL broadphase pairs whose bodies both merge islands
+	uint32_t noResp = 0, acts = 0;  // bit b / 4 bits per body
+	for (int b = 0; b < nb; b++) {
+		noResp |= (cx.body[b].noResponse ? 1u : 0u) << b;
+		acts |= (uint32_t)cx.body[b].activation << (4 * b);
+	}
+	// findUnions over ALL broadphase pairs whose bodies both merge islands (dynamic pairs sit behind each body's static pairs)
 	const int nPairs = cx.pl->nPairs;
 	for (int k = 0; k < nPairs; k++) {
-		const int a = cx.pl->a[k], b = cx.pl->b[k];
-		if (a >= STATIC_BASE || b >= STATIC_BASE) continue;
-		if (cx.body[a].noResponse || cx.body[b].noResponse) continue;
+		const int a = cx.pl->a[k];
+		if (a >= STATIC_BASE) continue;
+		const int b = cx.pl->b[k];
+		if (((noResp >> a) | (noResp >> b)) & 1u) continue;
 		int i = a, j = b;
 		for (;;) { const int q = (par >> (4 * i)) & 15; if (q == i) break; i = q; }
 		for (;;) { const int q = (par >> (4 * j)) & 15; if (q == j) break; j = q; }
 		if (i != j) par = (par & ~(15u << (4 * i))) | ((uint32_t)j << (4 * i));  // id[root(a)] = root(b)
 	}
 	uint32_t tags = 0, rootsActive = 0;
-	for (int b = 0; b < nb; b++) {
-		int r = b;
-		for (;;) { const int q = (par >> (4 * r)) & 15; if (q == r) break; r = q; }
-		cx.body[b].islandTag = r;
-		tags |= (uint32_t)r << (4 * b);
-		const int act = cx.body[b].activation;
-		if (act == ACT_ACTIVE || act == ACT_DISABLE_DEACT) rootsActive |= 1u << r;
+	if (par == 0x76543210u) {  // no union: every body is its own island
+		tags = par;
+		for (int b = 0; b < nb; b++) {
+			const int act = (acts >> (4 * b)) & 15;
+			if (act == ACT_ACTIVE || act == ACT_DISABLE_DEACT) rootsActive |= 1u << b;
+		}
+	} else {
+		for (int b = 0; b < nb; b++) {
+			int r = b;
+			for (;;) { const int q = (par >> (4 * r)) & 15; if (q == r) break; r = q; }
+			tags |= (uint32_t)r << (4 * b);
+			const int act = (acts >> (4 * b)) & 15;
+			if (act == ACT_ACTIVE || act == ACT_DISABLE_DEACT) rootsActive |= 1u << r;
+		}
 	}
 	// per island: all sleeping? else wake sleepers (ISLAND_SLEEPING -> WANTS_DEACTIVATION)
 	uint32_t rootsAwake = 0, notSleeping = 0;
 	for (int b = 0; b < nb; b++) {
 		const int r = (tags >> (4 * b)) & 15;
-		int act = cx.body[b].activation;
-		if ((rootsActive >> r) & 1) { if (act == ACT_SLEEPING) { act = ACT_WANTS_DEACT; cx.body[b].activation = act; } }
-		else if (act != ACT_DISABLE_DEACT && act != ACT_DISABLE_SIM && act != ACT_SLEEPING) { act = ACT_SLEEPING; cx.body[b].activation = act; }
+		const int act0 = (acts >> (4 * b)) & 15;
+		int act = act0;
+		if ((rootsActive >> r) & 1) { if (act == ACT_SLEEPING) act = ACT_WANTS_DEACT; }
+		else if (act != ACT_DISABLE_DEACT && act != ACT_DISABLE_SIM && act != ACT_SLEEPING) act = ACT_SLEEPING;
+		if (act != act0) cx.body[b].activation = act;
+		cx.body[b].islandTag = r;
 		if (act != ACT_SLEEPING) notSleeping |= 1u << b;
 		if (act != ACT_SLEEPING && act != ACT_DISABLE_SIM) rootsAwake |= 1u << r;  // body_active
 	}
 	// m_islandmanifold: manifolds with an awake body and needsResponse, then quickSort by island id
 	int keys[MAX_MANIFOLDS], order[MAX_MANIFOLDS];
 	int n = 0;
-	const int nMf = cx.pl->nManifolds;
-	for (int m = 0; m < nMf; m++) {
-		const Manifold& mf = cx.mf[m];
-		const int b0 = mf.body0, b1 = mf.body1;
-		if (b0 < 0) continue;  // pair without a manifold
-		const bool s0 = b0 >= STATIC_BASE, s1 = b1 >= STATIC_BASE;
-		const bool awake0 = !s0 && ((notSleeping >> b0) & 1);
+	uint32_t mm = cx.pl->mfMask;
+	while (mm) {
+#if defined(__CUDA_ARCH__)
+		const int m = __ffs((int)mm) - 1;
+#else
+		const int m = __builtin_ctz(mm);
+#endif
+		mm &= mm - 1;
+		// manifold of pair m: body0 is always dynamic (= pl->b[m]); body1 = pl->a[m], static for a static pair
+		const int b0 = cx.pl->b[m], b1 = cx.pl->a[m];
+		const bool s1 = b1 >= STATIC_BASE;
+		const bool awake0 = (notSleeping >> b0) & 1;
 		const bool awake1 = !s1 && ((notSleeping >> b1) & 1);
 		if (!(awake0 || awake1)) continue;
-		const bool resp = (s0 || !cx.body[b0].noResponse) && (s1 || !cx.body[b1].noResponse) && (!s0 || !s1);
+		const bool resp = !((noResp >> b0) & 1) && (s1 || !((noResp >> b1) & 1));
 		if (!resp) continue;
-		keys[n] = !s0 ? (int)((tags >> (4 * b0)) & 15) : (int)((tags >> (4 * b1)) & 15);
+		keys[n] = (int)((tags >> (4 * b0)) & 15);
 		order[n] = m;
 		n++;
 	}

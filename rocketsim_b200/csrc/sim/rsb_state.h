@@ -168,6 +168,9 @@ struct BatchParams {
 	int padGrid[8 * 10];  // BoostPadGrid (BoostPadGrid.h:10-29): pad index or -1
 	// README bench loop on device: when set, a goal is followed by ResetToRandomKickoff(autoResetSeed + arena + tick)
 	int autoReset; uint32_t autoResetSeed;
+	// spawn orientations [team][slot], computed on the HOST at batch creation: the reference builds them with glibc's sinf / cosf
+	// (Angle::ToRotMat), which the device libm only matches to 1 ulp -- a kickoff or respawn must start bit-identical
+	M3 kickBasis[2][5], respBasis[2][4];
 	int arenaOffset;  // global index of the batch's arena 0 in a sharded job (auto-reset seeds and event arena ids are global)
 	int trackerEnabled; TrackerCfgD tracker;  // device-side GameEventTracker (rsb_set_event_tracker)
 	float boundRadius[MAX_BODIES]; // radius of a sphere around the shape centre that contains the shape incl. margins
@@ -181,6 +184,7 @@ struct TriInfo { int32_t flags; float a01, a12, a20; };  // btTriangleInfo, flag
 
 struct MeshD {
 	const BvhNode* nodes; int nNodes;
+	const float* nodeBounds;  // per node: unquantized box, min xyz_ max xyz_ (8 floats), = btQuantizedBvh::unQuantize of the node's corners, precomputed at scene build
 	const SubtreeHdr* hdrs; int nHdrs;
 	const int32_t* tris;   // 3 indices per triangle
 	const float* verts;    // 4 floats per vertex (16-byte stride like btVector3)

@@ -47,8 +47,11 @@ enum Phase : int {
 	PH_CAR_LOGIC,      // T1  friction, game logic, suspension/boost forces; T2 pads+ball  item = car | pad | ball
 	PH_PREDICT,        // T3  gravity, damping, predicted transform, swept AABB            item = body
 	PH_PAIRS,          // T3  broadphase cell bookkeeping + pair list                      item = arena
-	PH_NARROW_STATIC,  // T3  narrowphase + contact hooks vs static objects                item = body
-	PH_DYN_SOLVE,      // T3  ball-car / car-car narrowphase, islands, solver (if rows)    item = arena
+	PH_NARROW_STATIC,  // T3  pair walk vs static objects (sphere ball: contacts on the spot;   item = body | arena
+	                   //     box / hull: candidate records) + dynamic-pair candidates
+	PH_NARROW_DETECT,  // T3  GJK(+EPA) / box-box of one pending candidate record           item = queue entry
+	PH_NARROW_COMMIT,  // T3  candidate records of static pairs -> manifolds + hooks        item = body
+	PH_DYN_SOLVE,      // T3  ball-car / car-car records -> manifolds + hooks, islands, solver item = arena
 	PH_FINISH_BODY,    // T3  contact-free solver write-back, integrateTransforms          item = body
 	PH_CAR_POST,       // T4  Car::_PostTickUpdate / _FinishPhysicsTick, pad grid check    item = car
 	PH_PADS_POST,      // T5  pads give boost / start cooldown                             item = pad
@@ -60,7 +63,9 @@ RSB_HD int phase_items(const BatchParams& P, int phase) {
 	const int nCars = P.nCars, nb = nCars + 1;
 	const int nPadItems = (P.mode != THE_VOID && nCars != 0) ? P.nPads : 0;
 	switch (phase) {
-	case PH_INIT: case PH_PREDICT: case PH_NARROW_STATIC: case PH_FINISH_BODY: return nb;
+	case PH_INIT: case PH_PREDICT: case PH_NARROW_COMMIT: case PH_FINISH_BODY: return nb;
+	case PH_NARROW_STATIC: return nb + (nCars > 0 ? 1 : 0);  // + the arena's dynamic pairs
+	case PH_NARROW_DETECT: return 0;                         // variable: the block's detector queue (dealt by the caller)
 	case PH_WHEELS: return nCars * 4;
 	case PH_CAR_LOGIC: return nCars + nPadItems + 1;
 	case PH_CAR_POST: return nCars;
@@ -109,10 +114,17 @@ RSB_HD void phase_run(const Ctx& cx, int phase, int item) {
 		break;
 	}
 	case PH_PAIRS: collide_pairs(cx); break;
-	case PH_NARROW_STATIC: collide_static_pairs(cx, item); break;
+	case PH_NARROW_STATIC:
+		if (item <= nCars) collide_static_pairs(cx, item);
+		else enqueue_dynamic_pairs(cx);
+		break;
+	case PH_NARROW_DETECT: detect_candidate(cx, item); break;
+	case PH_NARROW_COMMIT:
+		if (!(item == 0 && P.ballIsSphere)) commit_candidates(cx, item);  // the sphere ball committed its contacts on the spot
+		break;
 	case PH_DYN_SOLVE: {
 		RSB_SUBPROF_BEGIN();
-		collide_dynamic_pairs(cx);
+		commit_candidates(cx, -1);
 		RSB_SUBPROF_MARK(0);
 		const int nSolve = build_islands(cx);  // calculateSimulationIslands + buildIslands
 		RSB_SUBPROF_MARK(1);
@@ -164,7 +176,13 @@ RSB_HD void phase_run(const Ctx& cx, int phase, int item) {
 
 // One whole tick of one arena on one thread (host check build, single-arena helpers).
 RSB_HD void arena_tick(const Ctx& cx) {
+	*cx.nq = 0;
 	for (int ph = 0; ph < PH_COUNT; ph++) {
+		if (ph == PH_NARROW_DETECT) {
+			const unsigned nq = *cx.nq < (unsigned)cx.qcap ? *cx.nq : (unsigned)cx.qcap;
+			for (unsigned i = 0; i < nq; i++) phase_run(cx, ph, cx.q[i] & 127);
+			continue;
+		}
 		const int n = phase_items(*cx.p, ph);
 		for (int i = 0; i < n; i++) phase_run(cx, ph, i);
 	}

@@ -67,9 +67,28 @@ struct Manifold {  // btPersistentManifold subset; slot k belongs to broadphase 
 // broadphase pair list in creation order (btHashedOverlappingPairCache array) + solver manifold order
 struct PairList {
 	int nPairs, nManifolds;
+	uint32_t mfMask;     // bit k: pair k has a manifold (new_manifold was called for it this tick)
+	uint32_t deferMask;  // bit k: the contacts of pair k go through candidate records (committed in PH_NARROW_COMMIT / PH_DYN_SOLVE)
 	uint8_t a[MAX_MANIFOLDS], b[MAX_MANIFOLDS];
 	uint8_t manifoldOrder[MAX_MANIFOLDS];
 	uint16_t entry[MAX_MANIFOLDS];  // static pairs: position of the static object in the cell list (Scene::cellStatics)
+};
+
+// Contact candidate of the staged narrowphase (rsb_collide.h).  Bodies whose shape needs an iterative detector (car box, puck
+// hull) do not run it inside the per-body pair walk: the walk only RECORDS what has to be tested -- one record per
+// (pair, triangle), per plane contact, per dynamic pair -- in pair order / BVH leaf order; PH_NARROW_DETECT then runs one
+// detector per pending record on its own thread (so the triangles of one car-mesh pair, and GJK / EPA calls of different
+// arenas, proceed in parallel instead of one after the other on the body's thread), and the records are committed to the
+// manifolds in index order, which is the order the reference adds them in.
+constexpr int MAX_CANDS = 96;
+enum CandState : int { CAND_PENDING = 0, CAND_CONTACT = 1, CAND_NONE = 2 };
+struct CandRec {
+	int16_t pair;   // manifold slot = broadphase pair index
+	int16_t mesh;   // arena mesh of the triangle, -1 none
+	int32_t tri;    // triangle index, -1 none
+	int32_t state;  // CandState
+	float depth;
+	V3 normal, point;  // normalOnB / pointInWorld as the detector reports them
 };
 
 struct SolverBody {
@@ -123,7 +142,7 @@ struct ArenaH {
 	BodyW body[MAX_BODIES];
 	WheelW wheels[MAX_WHEELS];
 	int padLocked[MAX_PADS];  // BoostPadState::curLockedCar as car index, -1 none
-	int misc[4];              // [0] = this tick needs the general solver, [1] = #manifolds handed to it
+	int misc[4];              // [0] = this tick needs the general solver, [1] = #manifolds handed to it, [2] = bodies written back by the solver, [3] = #contact candidates
 	PairList pairs;
 	Manifold mf[MAX_MANIFOLDS];
 	alignas(8) unsigned char solv[SOLV_BYTES_MAX];
@@ -131,6 +150,7 @@ struct ArenaH {
 
 // Cold per-tick scratch (global memory): only touched when there are contacts.
 struct ArenaW {
+	CandRec cand[MAX_CANDS];
 	ContactPt points[MAX_POINTS];
 	SolverRow rows[MAX_ROWS];    // overflow beyond SOLVER_ROWS_FAST (indexed like the full pool)
 	SolverRow frows[MAX_ROWS];
@@ -173,6 +193,8 @@ struct Ctx {
 	const Scene* sc;
 	EventSink ev;
 	int arena;  // global arena index inside the batch
+	// detector work queue of the executing block (PH_NARROW_DETECT): entries = arLocal * 128 + candidate index
+	uint16_t* q; unsigned* nq; int qcap; int arLocal;
 };
 
 struct SolverView {

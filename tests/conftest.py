@@ -56,7 +56,6 @@ def cudalib(mesh_sets):
     if not torch.cuda.is_available():
         pytest.fail("gpu test selected but no CUDA device is visible")
     from rocketsim_b200 import lib
-    # RSB_TEST_LIB: developer override to A/B another CUDA build of the same library (never a host build)
-    L = lib.load(os.environ.get("RSB_TEST_LIB") or None)  # raises if librsb.so was not built: no fallback
+    L = lib.load()  # rocketsim_b200/librsb.so; raises if it was not built: no fallback
     lib.init_from_mem(mesh_sets, L)
     return L
