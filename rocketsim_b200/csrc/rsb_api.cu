@@ -104,6 +104,9 @@ static SceneDev* get_scene_dev(int device, int mode) {
 	sc.cellHdrStart = (const int32_t*)up(h.cellHdrStart.data(), h.cellHdrStart.size() * 4);
 	sc.cellHdrs = (const uint16_t*)up(h.cellHdrs.data(), h.cellHdrs.size() * 2);
 	sc.cellHdrsRay = (const uint16_t*)up(h.cellHdrsRay.data(), h.cellHdrsRay.size() * 2);
+	sc.cellRayLeafStart = (const int32_t*)up(h.cellRayLeafStart.data(), h.cellRayLeafStart.size() * 4);
+	sc.cellRayLeaves = (const int32_t*)up(h.cellRayLeaves.data(), h.cellRayLeaves.size() * 4);
+	sc.rayLeafReach = h.rayLeafReach;
 	sd->dScene = (Scene*)up(&sc, sizeof(sc));
 #ifndef RSB_HOSTCHECK
 	CUDA_OK(cudaDeviceSynchronize());
@@ -306,13 +309,14 @@ struct StepArgs {
 // developer builds: per phase [0..15] block wall cycles, [16..31] sum of busy-thread cycles, [32..47] busy-thread count,
 // [48..63] sum over blocks of the slowest thread's cycles
 __device__ unsigned long long g_prof[64];
-__device__ unsigned long long g_blockCycles[1024];  // elapsed cycles of each block of the last launch (imbalance between SMs)
+__device__ unsigned long long g_blockCycles[1024];
+__device__ unsigned long long g_blockPhase[256][16];  // per block: wall cycles per phase, accumulated over the launch  // elapsed cycles of each block of the last launch (imbalance between SMs)
 
 // [phase NS=0 / DYN=1][bucket: min(7, detector calls of the slowest item) + 8 if it ran EPA][0 = sum of its cycles, 1 = count]
 __device__ unsigned long long g_prof2[2][16][2];
 #define PHASE_PROF_BEGIN() long long _pt0 = clock64()
 #define PHASE_PROF_ITEMS(i, had) do { if (had) { unsigned long long _d = (unsigned long long)(clock64() - _pt0); atomicAdd(&g_prof[16 + i], _d); atomicAdd(&g_prof[32 + i], 1ull); atomicMax(&s_profMax, _d); } } while (0)
-#define PHASE_PROF_END(i) do { if (threadIdx.x == 0) { atomicAdd(&g_prof[i], (unsigned long long)(clock64() - _pt0)); atomicAdd(&g_prof[48 + i], s_profMax); s_profMax = 0; \
+#define PHASE_PROF_END(i) do { if (threadIdx.x == 0) { atomicAdd(&g_prof[i], (unsigned long long)(clock64() - _pt0)); if (blockIdx.x < 256) g_blockPhase[blockIdx.x][i] += (unsigned long long)(clock64() - _pt0); atomicAdd(&g_prof[48 + i], s_profMax); s_profMax = 0; \
 	if (i == PH_NARROW_DETECT || i == PH_DYN_SOLVE) { int c = (int)(s_profMax2 & 0xfffff); int bk = min(7, c & 255) + ((c >> 8) ? 8 : 0); int ph = (i == PH_DYN_SOLVE); atomicAdd(&g_prof2[ph][bk][0], s_profMax2 >> 20); atomicAdd(&g_prof2[ph][bk][1], 1ull); s_profMax2 = 0; } } __syncthreads(); } while (0)
 #else
 #define PHASE_PROF_BEGIN() ((void)0)
@@ -1643,6 +1647,16 @@ int rsb_debug_profile(uint64_t* out64, int reset) {
 		unsigned long long mn = ~0ull, mx = 0, sum = 0; int n = 0;
 		for (int i = 0; i < 1024; i++) if (bc[i]) { mn = std::min(mn, bc[i]); mx = std::max(mx, bc[i]); sum += bc[i]; n++; }
 		if (n) printf("blocks of the last launch: %d, cycles min %llu mean %llu max %llu (max/mean %.3f)\n", n, mn, sum / n, mx, (double)mx * n / (double)sum);
+		static unsigned long long bp[256][16]; CUDA_OK(cudaMemcpyFromSymbol(bp, g_blockPhase, sizeof(bp)));
+		if (n) {
+			std::vector<int> idx; for (int i = 0; i < 256; i++) if (bc[i]) idx.push_back(i);
+			std::sort(idx.begin(), idx.end(), [&](int x, int y) { return bc[x] < bc[y]; });
+			const int pick[5] = {idx.front(), idx[idx.size() / 4], idx[idx.size() / 2], idx[idx.size() * 3 / 4], idx.back()};
+			printf("per-block phase walls (Mcycles since reset) for the fastest / q1 / median / q3 / slowest block of the last launch:\n");
+			for (int ph = 0; ph < 16; ph++) { bool any = false; for (int q = 0; q < 5; q++) any |= bp[pick[q]][ph] != 0; if (!any) continue;
+				printf("  phase %2d:", ph); for (int q = 0; q < 5; q++) printf(" %8.1f", bp[pick[q]][ph] / 1e6); printf("\n"); }
+		}
+		if (reset) { memset(bp, 0, sizeof(bp)); CUDA_OK(cudaMemcpyToSymbol(g_blockPhase, bp, sizeof(bp))); }
 	}
 	if (reset) { unsigned long long z[64] = {0}; CUDA_OK(cudaMemcpyToSymbol(g_prof, z, sizeof(z))); }
 #else

@@ -51,6 +51,9 @@ struct SceneHost {
 	// root node (ray queries).  Pure culling: skipped headers cannot overlap the quantised query box.
 	std::vector<int32_t> cellHdrStart;
 	std::vector<uint16_t> cellHdrs, cellHdrsRay;
+	// per cell-list entry of a mesh: leaf nodes reachable by a short ray cast from inside the cell (Scene::cellRayLeaves)
+	std::vector<int32_t> cellRayLeafStart, cellRayLeaves;
+	float rayLeafReach = 0.f;
 };
 
 namespace scene_detail {
@@ -532,6 +535,31 @@ inline SceneHost build_scene(int mode, std::vector<MeshHost> meshes) {
 				s.cellHdrsRay.insert(s.cellHdrsRay.end(), list.begin(), list.end());
 			}
 			s.cellHdrStart.push_back((int32_t)s.cellHdrs.size());
+		}
+	}
+	// leaf candidates of short rays (suspension rays are ~1 bt long; 3 bt of reach + 0.1 bt of slack for the conservative
+	// quantised boxes).  Border cells also serve every position outside the grid (grid_cell_of clamps).
+	s.rayLeafReach = 3.0f;
+	s.cellRayLeafStart.assign(1, 0);
+	for (int c = 0; c < total; c++) {
+		const int ci = c / (s.cellsY * s.cellsZ), cj = (c / s.cellsZ) % s.cellsY, ck = c % s.cellsZ;
+		const float grow = s.rayLeafReach + 0.1f;
+		V3 lo = s.gridMin + V3((float)ci, (float)cj, (float)ck) * s.cellSize - V3(grow, grow, grow);
+		V3 hi = s.gridMin + V3((float)(ci + 1), (float)(cj + 1), (float)(ck + 1)) * s.cellSize + V3(grow, grow, grow);
+		if (ci == 0) lo.x = -INF; if (cj == 0) lo.y = -INF; if (ck == 0) lo.z = -INF;
+		if (ci == s.cellsX - 1) hi.x = INF; if (cj == s.cellsY - 1) hi.y = INF; if (ck == s.cellsZ - 1) hi.z = INF;
+		for (int e = s.cellStart[c]; e < s.cellStart[c + 1]; e++) {
+			const int o = s.cellStatics[e];
+			if (o < (int)s.meshes.size()) {
+				const MeshHost& m = s.meshes[o];
+				for (size_t n = 0; n < m.nodes.size(); n++) {
+					if (m.nodes[n].idx < 0) continue;  // internal node
+					const float* b = &m.nodeBounds[n * 8];
+					if (b[0] > hi.x || b[4] < lo.x || b[1] > hi.y || b[5] < lo.y || b[2] > hi.z || b[6] < lo.z) continue;
+					s.cellRayLeaves.push_back((int32_t)n);
+				}
+			}
+			s.cellRayLeafStart.push_back((int32_t)s.cellRayLeaves.size());
 		}
 	}
 	return s;

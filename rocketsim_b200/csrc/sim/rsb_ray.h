@@ -122,6 +122,25 @@ RSB_HD bool ray_mesh(const Scene& sc, const MeshD& m, int entry, const V3& from,
 	bvh_quantize_clamped(m, rayAabbMin, 0, qmin);
 	bvh_quantize_clamped(m, rayAabbMax, 1, qmax);
 	bool any = false;
+	if (lambda_max <= sc.rayLeafReach) {
+		// short ray (every suspension ray): the leaves this cell's rays can reach, in leaf order, each gated by its OWN box tests
+		// -- the same leaves the hierarchical walk reports (see Scene::cellRayLeaves), without the dependent node-to-node loads
+		const int lEnd = sc.cellRayLeafStart[entry + 1];
+		for (int li = sc.cellRayLeafStart[entry]; li < lEnd; li++) {
+			const int cur = sc.cellRayLeaves[li];
+			const BvhNode nd = m.nodes[cur];
+			if (!quant_overlap(qmin, qmax, nd.qmin, nd.qmax)) continue;
+			const float* nb = m.nodeBounds + 8 * (size_t)cur;
+			V3 bounds[2];
+			bounds[0] = V3(nb[0], nb[1], nb[2]);
+			bounds[1] = V3(nb[4], nb[5], nb[6]);
+			if (!ray_aabb2(from, inv, sign, bounds, 0.0f, lambda_max)) continue;
+			V3 a, b, c;
+			mesh_triangle(m, nd.idx & 0x1fffff, a, b, c);
+			if (ray_triangle(from, to, a, b, c, hitFraction, outNormal)) any = true;
+		}
+		return any;
+	}
 	const int hEnd = sc.cellHdrStart[entry + 1];
 	for (int hi = sc.cellHdrStart[entry]; hi < hEnd; hi++) {
 	const SubtreeHdr hd = m.hdrs[sc.cellHdrsRay[hi]];
@@ -257,7 +276,12 @@ RSB_HD bool cast_vehicle_ray(const Ctx& cx, int self, const V3& from, const V3& 
 				}
 				if (ray_mesh(sc, m, s, from, to, closest, normal)) obj = STATIC_BASE + k;
 			} else {
-				if (ray_plane(sc.planes[k - sc.nMeshes], from, to, closest, normal)) obj = STATIC_BASE + k;
+				const PlaneD& pl = sc.planes[k - sc.nMeshes];
+				// conservative cull (ours): the triangle test only reports a hit when the end points lie on opposite sides of the
+				// triangle's plane, which is the static plane up to rounding (< 1e-4 bt at arena scale); 1e-2 bt of slack
+				const float da = dot(pl.n, from - pl.pos), db = dot(pl.n, to - pl.pos);
+				if ((da > 1e-2f && db > 1e-2f) || (da < -1e-2f && db < -1e-2f)) continue;
+				if (ray_plane(pl, from, to, closest, normal)) obj = STATIC_BASE + k;
 			}
 		}
 	}

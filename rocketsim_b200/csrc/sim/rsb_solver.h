@@ -66,6 +66,37 @@ RSB_HD int build_islands(const Ctx& cx) {
 	}
 	uint32_t tags = 0, rootsActive = 0;
 	if (par == 0x76543210u) {  // no union: every body is its own island
+		// Common case, short cut.  A one-body island changes no activation state (WANTS_DEACTIVATION only arises from a union
+		// with a sleeper), islandTag[b] = b was set by init_body_work, and when at most ONE eligible manifold carries contact
+		// points the order the sort would produce is irrelevant: the solver skips point-less manifolds.
+		uint32_t notSl = 0, awake = 0;
+		for (int b = 0; b < nb; b++) {
+			const int act = (acts >> (4 * b)) & 15;
+			if (act != ACT_SLEEPING) notSl |= 1u << b;
+			if (act != ACT_SLEEPING && act != ACT_DISABLE_SIM) awake |= 1u << b;
+		}
+		int withPts = 0, last = -1;
+		uint32_t mm = cx.pl->mfMask;
+		while (mm) {
+#if defined(__CUDA_ARCH__)
+			const int m = __ffs((int)mm) - 1;
+#else
+			const int m = __builtin_ctz(mm);
+#endif
+			mm &= mm - 1;
+			if (cx.mf[m].nPts <= 0) continue;
+			const int b0 = cx.pl->b[m], b1 = cx.pl->a[m];
+			const bool s1 = b1 >= STATIC_BASE;
+			if (!(((notSl >> b0) & 1) || (!s1 && ((notSl >> b1) & 1)))) continue;
+			if (((noResp >> b0) & 1) || (!s1 && ((noResp >> b1) & 1))) continue;
+			withPts++; last = m;
+		}
+		if (withPts == 0) return 0;
+		if (withPts == 1) {
+			if (!((awake >> cx.pl->b[last]) & 1)) return 0;
+			cx.pl->manifoldOrder[0] = (uint8_t)last;
+			return 1;
+		}
 		tags = par;
 		for (int b = 0; b < nb; b++) {
 			const int act = (acts >> (4 * b)) & 15;

@@ -216,6 +216,13 @@ struct Scene {
 	const int32_t* cellHdrStart;
 	const uint16_t* cellHdrs;
 	const uint16_t* cellHdrsRay;
+	// per cellStatics entry of a mesh: the LEAF nodes (ascending = BVH leaf order) that a ray of length <= rayLeafReach starting
+	// inside the cell can reach (node box vs the cell box grown by the reach).  A leaf is reported by the reference's walk
+	// exactly when the leaf's own quantised-box and ray-box tests pass (both tests are monotone under box containment, and
+	// every ancestor box contains the leaf box), so testing the listed leaves in order reproduces the walk (rsb_ray.h).
+	const int32_t* cellRayLeafStart;
+	const int32_t* cellRayLeaves;
+	float rayLeafReach;
 };
 
 }  // namespace rsb

@@ -82,6 +82,12 @@ for r in rows[2:]:
         if v:
             stall_kind[src][hdr[i]] += v
 print(f"total samples {tot}, warp instructions {tot_inst}")
+_st = collections.Counter()
+for k, c in stall_kind.items():
+    for name, v in c.items():
+        _st[name] += v
+_stt = sum(_st.values())
+print("== stall reasons (share of samples): " + ", ".join(f"{k[6:]} {100 * v / max(_stt, 1):.1f}%" for k, v in _st.most_common(12)))
 print("== by file"); [print(f"  {100*n/tot:5.1f} %  {f}") for f, n in by_file.most_common(12)]
 by_fn, inst_fn = collections.Counter(), collections.Counter()
 for (f, l), n in by_line.items():
