@@ -17,15 +17,18 @@
 // errors surface as std::runtime_error like the reference's RS_ERR_CLOSE (src/Framework.h:67-72).
 //
 // Differences from the reference, by construction of the batched design:
-//   * cars are fixed at the first Step/GetState/SetState of an arena (the device record is sized then): AddCar after
-//     that throws, and RemoveCar is not offered;
+//   * cars are fixed at the first Step/GetState/SetState of an arena (the device record is sized then): AddCar / RemoveCar
+//     after that throw;
 //   * callbacks run on the calling thread right after Step() returns the events of the stepped ticks (the reference
 //     calls them from inside the tick); with Step(n > 1) they arrive in tick order after the n ticks;
-//   * ArenaConfig is the default one only.
+//   * ArenaConfig: noBallRot and custom boost pads are honoured; fields that would change the broadphase grid
+//     (memWeightMode, minPos, maxPos, maxAABBLen, useCustomBroadphase) must keep their defaults, other values throw.
 #pragma once
 
 #include <cstdint>
 #include <cstring>
+#include <algorithm>
+#include <filesystem>
 #include <fstream>
 #include <functional>
 #include <map>
@@ -49,6 +52,21 @@ using CarConfig = RsbCarConfig;
 using BoostPadState = RsbBoostPadState;
 
 enum class GameMode : uint8_t { SOCCAR = 0, HOOPS = 1, HEATSEEKER = 2, SNOWDAY = 3, DROPSHOT = 4, THE_VOID = 5 };
+constexpr const char* GAMEMODE_STRS[] = {"soccar", "hoops", "heatseeker", "snowday", "dropshot", "void"};  // src/Sim/GameMode.h:19-26
+
+// ArenaConfig (src/Sim/Arena/ArenaConfig/ArenaConfig.h:11-50), same fields and defaults
+enum class ArenaMemWeightMode : uint8_t { HEAVY, LIGHT };
+struct BoostPadConfig { Vec pos = {}; bool isBig = false; };
+struct ArenaConfig {
+	ArenaMemWeightMode memWeightMode = ArenaMemWeightMode::HEAVY;
+	Vec minPos = Vec{-5600, -6000, 0, 0}, maxPos = Vec{5600, 6000, 2200, 0};
+	float maxAABBLen = 370;
+	bool noBallRot = true;
+	bool useCustomBroadphase = true;
+	int maxObjects = 512;
+	bool useCustomBoostPads = false;
+	std::vector<BoostPadConfig> customBoostPads = {};
+};
 enum class Team : uint8_t { BLUE = 0, ORANGE = 1 };
 
 inline void Check(int rc) { if (rc != 0) throw std::runtime_error(std::string("RocketSimB200: ") + rsb_last_error()); }
@@ -75,11 +93,18 @@ inline void InitFromMem(const std::map<GameMode, std::vector<std::vector<uint8_t
 class ArenaBatch {
 public:
 	ArenaBatch(GameMode mode, int numArenas, const std::vector<Team>& teams, const std::vector<CarConfig>& configs = {},
-	           const MutatorConfig* mutator = nullptr, float tickRate = 120.f, uint32_t seed = 0, int device = 0)
+	           const MutatorConfig* mutator = nullptr, float tickRate = 120.f, uint32_t seed = 0, int device = 0, const ArenaConfig& arenaConfig = {})
 		: gameMode(mode), numArenas(numArenas), numCars((int)teams.size()) {
 		std::vector<int> t; for (Team x : teams) t.push_back((int)x);
 		if (!configs.empty() && configs.size() != teams.size()) throw std::runtime_error("RocketSimB200: one CarConfig per car slot expected");
-		Check(rsb_batch_create(device, (int)mode, numArenas, numCars, t.data(), configs.empty() ? nullptr : configs.data(), mutator, tickRate, seed, &h_));
+		RsbArenaConfig ac; rsb_default_arena_config(&ac);
+		ac.memWeightMode = (uint8_t)arenaConfig.memWeightMode; ac.minPos = arenaConfig.minPos; ac.maxPos = arenaConfig.maxPos; ac.maxAABBLen = arenaConfig.maxAABBLen;
+		ac.noBallRot = arenaConfig.noBallRot; ac.useCustomBroadphase = arenaConfig.useCustomBroadphase; ac.maxObjects = arenaConfig.maxObjects;
+		ac.useCustomBoostPads = arenaConfig.useCustomBoostPads;
+		std::vector<RsbBoostPadConfig> pads;
+		for (const BoostPadConfig& pc : arenaConfig.customBoostPads) { RsbBoostPadConfig r; std::memset(&r, 0, sizeof(r)); r.pos = pc.pos; r.isBig = pc.isBig; pads.push_back(r); }
+		ac.customBoostPads = pads.empty() ? nullptr : pads.data(); ac.numCustomBoostPads = (uint32_t)pads.size();
+		Check(rsb_batch_create_ex(device, (int)mode, &ac, numArenas, numCars, t.data(), configs.empty() ? nullptr : configs.data(), mutator, tickRate, seed, &h_));
 		Check(rsb_batch_info(h_, nullptr, nullptr, &numPads, nullptr));
 	}
 	~ArenaBatch() { if (h_) rsb_batch_destroy(h_); }
@@ -159,6 +184,7 @@ public:
 private:
 	friend class Arena;
 	Arena* arena_ = nullptr;
+	uint32_t slot_ = 0;                 // car slot in the device record (differs from id - 1 after a RemoveCar)
 };
 
 class Ball {
@@ -185,22 +211,35 @@ public:
 	uint64_t tickCount = 0;
 	float GetTickRate() const { return 1 / tickTime; }
 
-	// Arena::Create (Arena.h:111).  The caller deletes the arena, as in the reference.
-	static Arena* Create(GameMode gameMode, float tickRate = 120, int device = 0, uint32_t rngSeed = 0) {
+	// Arena::Create(gameMode, arenaConfig = {}, tickRate = 120) (Arena.h:111); `device` / `rngSeed` are ours (which GPU, seed of
+	// the respawn RNG that the reference takes from a thread-local engine).  The caller deletes the arena, as in the reference.
+	static Arena* Create(GameMode gameMode, const ArenaConfig& arenaConfig = {}, float tickRate = 120, int device = 0, uint32_t rngSeed = 0) {
 		if (!(tickRate >= 15 && tickRate <= 120)) throw std::runtime_error("RocketSimB200: Tickrate must be from 15 to 120tps");
-		return new Arena(gameMode, tickRate, device, rngSeed);
+		Arena* a = new Arena(gameMode, tickRate, device, rngSeed);
+		a->config_ = arenaConfig;
+		return a;
 	}
+	const ArenaConfig& GetArenaConfig() const { return config_; }
 	~Arena() { delete ball; for (Car* c : cars_) delete c; }
 	Arena(const Arena&) = delete;
 	Arena& operator=(const Arena&) = delete;
 
 	Car* AddCar(Team team, const CarConfig& config = CAR_CONFIG_OCTANE()) {
 		if (batch_) throw std::runtime_error("RocketSimB200: AddCar after the arena's first Step/GetState/SetState is not supported by the batched back end");
-		Car* c = new Car(); c->id = (uint32_t)cars_.size() + 1; c->team = team; c->config = config; c->arena_ = this;
+		Car* c = new Car(); c->id = ++lastCarID_; c->team = team; c->config = config; c->arena_ = this;  // ids keep counting up (Arena.cpp:64-78)
 		cars_.push_back(c);
 		return c;
 	}
-	Car* GetCar(uint32_t id) { return (id >= 1 && id <= cars_.size()) ? cars_[id - 1] : nullptr; }
+	// Arena::RemoveCar (Arena.h:74, Arena.cpp:80-94): false if the id is unknown.  Only before the arena's first Step.
+	bool RemoveCar(uint32_t id) {
+		auto it = std::find_if(cars_.begin(), cars_.end(), [&](Car* c) { return c->id == id; });
+		if (it == cars_.end()) return false;
+		if (batch_) throw std::runtime_error("RocketSimB200: RemoveCar after the arena's first Step/GetState/SetState is not supported by the batched back end");
+		delete *it; cars_.erase(it);
+		return true;
+	}
+	bool RemoveCar(Car* car) { return RemoveCar(car->id); }
+	Car* GetCar(uint32_t id) { for (Car* c : cars_) if (c->id == id) return c; return nullptr; }
 	const std::vector<Car*>& GetCars() const { return cars_; }
 
 	const MutatorConfig& GetMutatorConfig() { return mutator_; }
@@ -230,10 +269,10 @@ public:
 		tickCount += (uint64_t)ticksToSimulate;
 		for (const RsbEvent& e : batch_->GetEvents(4096)) {
 			if (e.type == RSB_EVENT_GOAL) { if (goalFn_) goalFn_(this, (Team)e.a, goalInfo_); }
-			else if (e.type == RSB_EVENT_SHOT) { if (shotFn_) shotFn_(this, GetCar(e.a), GetCar(e.b), shotInfo_); }
-			else if (e.type == RSB_EVENT_GOAL_CREDIT) { if (goalCreditFn_) goalCreditFn_(this, GetCar(e.a), GetCar(e.b), goalCreditInfo_); }
-			else if (e.type == RSB_EVENT_SAVE) { if (saveFn_) saveFn_(this, GetCar(e.a), saveInfo_); }
-			else if (bumpFn_) bumpFn_(this, GetCar(e.a), GetCar(e.b), e.type == RSB_EVENT_DEMO, bumpInfo_);
+			else if (e.type == RSB_EVENT_SHOT) { if (shotFn_) shotFn_(this, CarOfSlotId(e.a), CarOfSlotId(e.b), shotInfo_); }
+			else if (e.type == RSB_EVENT_GOAL_CREDIT) { if (goalCreditFn_) goalCreditFn_(this, CarOfSlotId(e.a), CarOfSlotId(e.b), goalCreditInfo_); }
+			else if (e.type == RSB_EVENT_SAVE) { if (saveFn_) saveFn_(this, CarOfSlotId(e.a), saveInfo_); }
+			else if (bumpFn_) bumpFn_(this, CarOfSlotId(e.a), CarOfSlotId(e.b), e.type == RSB_EVENT_DEMO, bumpInfo_);
 		}
 	}
 	void ResetToRandomKickoff(int seed = -1) { Realize(); batch_->ResetToRandomKickoff({(int32_t)seed}); }
@@ -249,8 +288,12 @@ private:
 		if (batch_) return;
 		std::vector<Team> teams; std::vector<CarConfig> cfgs;
 		for (Car* c : cars_) { teams.push_back(c->team); cfgs.push_back(c->config); }
-		batch_.reset(new ArenaBatch(gameMode, 1, teams, cfgs, &mutator_, 1 / tickTime, seed_, device_));
+		batch_.reset(new ArenaBatch(gameMode, 1, teams, cfgs, &mutator_, 1 / tickTime, seed_, device_, config_));
+		for (size_t i = 0; i < cars_.size(); i++) cars_[i]->slot_ = (uint32_t)i;  // device car slot = position in AddCar order
 	}
+	Car* CarOfSlotId(uint32_t slotId) { return (slotId >= 1 && slotId <= cars_.size()) ? cars_[slotId - 1] : nullptr; }  // event ids are slot + 1
+	ArenaConfig config_;
+	uint32_t lastCarID_ = 0;
 	std::vector<Car*> cars_;
 	std::unique_ptr<ArenaBatch> batch_;
 	MutatorConfig mutator_;
@@ -262,8 +305,8 @@ private:
 	int device_; uint32_t seed_;
 };
 
-inline CarState Car::GetState() { return arena_->Batch().GetCarStates()[id - 1]; }
-inline void Car::SetState(const CarState& s) { arena_->Batch().SetCarState(0, id - 1, s); }
+inline CarState Car::GetState() { ArenaBatch& b = arena_->Batch(); return b.GetCarStates()[slot_]; }
+inline void Car::SetState(const CarState& s) { ArenaBatch& b = arena_->Batch(); b.SetCarState(0, slot_, s); }
 inline BallState Ball::GetState() { return arena_->Batch().GetBallStates()[0]; }
 inline void Ball::SetState(const BallState& s) { arena_->Batch().SetBallState(0, s); }
 
@@ -277,6 +320,21 @@ inline std::vector<uint8_t> ReadFile(const std::string& path) {
 inline void Init(const std::map<GameMode, std::vector<std::string>>& meshPaths, bool silent = false) {
 	std::map<GameMode, std::vector<std::vector<uint8_t>>> files;
 	for (auto& kv : meshPaths) for (auto& p : kv.second) files[kv.first].push_back(ReadFile(p));
+	InitFromMem(files, silent);
+}
+// RocketSim::Init(collisionMeshesFolder) (src/RocketSim.h:27, RocketSim.cpp:55-90): every *.cmf under <folder>/soccar, /hoops,
+// /dropshot (the game modes with meshes of their own); missing sub-folders are skipped, as in the reference.
+inline void Init(const std::filesystem::path& collisionMeshesFolder, bool silent = false) {
+	std::map<GameMode, std::vector<std::vector<uint8_t>>> files;
+	for (GameMode gm : {GameMode::SOCCAR, GameMode::HOOPS, GameMode::DROPSHOT}) {
+		const std::filesystem::path dir = collisionMeshesFolder / GAMEMODE_STRS[(int)gm];
+		if (!std::filesystem::exists(dir)) continue;
+		std::vector<std::filesystem::path> paths;
+		for (auto& entry : std::filesystem::directory_iterator(dir))
+			if (entry.path().has_extension() && entry.path().extension() == ".cmf") paths.push_back(entry.path());
+		std::sort(paths.begin(), paths.end());  // directory order is unspecified; mesh order fixes the static-object order
+		for (auto& p : paths) files[gm].push_back(ReadFile(p.string()));
+	}
 	InitFromMem(files, silent);
 }
 

@@ -49,6 +49,12 @@ int rsb_default_mutator_config(int game_mode, RsbMutatorConfig* out);
 int rsb_batch_create(int device, int game_mode, int n_arenas, int n_cars, const int* teams,
                      const RsbCarConfig* car_configs, const RsbMutatorConfig* mutator, float tick_rate,
                      uint32_t seed, RsbBatch** out);
+/* Arena::Create(gameMode, arenaConfig, tickRate) (src/Sim/Arena/Arena.h:111, Arena.cpp:416-545) for every arena of the batch:
+ * rsb_batch_create with an explicit ArenaConfig (NULL = the default one).  Unsupported values fail with an error naming the
+ * field (see RsbArenaConfig). */
+void rsb_default_arena_config(RsbArenaConfig* out);
+int rsb_batch_create_ex(int device, int game_mode, const RsbArenaConfig* arena_config, int n_arenas, int n_cars, const int* teams,
+                        const RsbCarConfig* car_configs, const RsbMutatorConfig* mutator, float tick_rate, uint32_t seed, RsbBatch** out);
 int rsb_batch_destroy(RsbBatch* b);
 int rsb_batch_info(RsbBatch* b, int* n_arenas, int* n_cars, int* n_pads, int* game_mode);
 /* CUDA stream (cudaStream_t) on which all batch work is enqueued; 0 = legacy default stream */

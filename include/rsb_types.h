@@ -193,6 +193,35 @@ typedef struct RsbBallInternal {
 	float rbVel[4];
 } RsbBallInternal;
 
+/* BoostPadConfig (src/Sim/BoostPad/BoostPad.h:12-18): same layout (Vec pos; bool isBig; padded to 32 bytes). */
+typedef struct RsbBoostPadConfig {
+	RsbVec pos;
+	uint8_t isBig;
+	uint8_t _pad[15];
+} RsbBoostPadConfig;
+
+/* ArenaConfig (src/Sim/Arena/ArenaConfig/ArenaConfig.h:18-50) as a POD: same fields, the std::vector of custom pads as
+ * pointer + count.  rsb_default_arena_config() fills in the reference's defaults.  What the batched back end supports:
+ *   noBallRot            both values (ignored in Snowday, as in the reference)
+ *   useCustomBoostPads   up to 40 pads; like the reference this replaces the pad grid by an all-pads check per car
+ *   maxObjects           accepted, unused (capacity of the reference's proxy array)
+ *   memWeightMode, minPos, maxPos, maxAABBLen, useCustomBroadphase   must keep their default values: the broadphase grid is
+ *                        part of the static scene built once per game mode (rsb_init_from_mem); other values are rejected
+ *                        with an error that names the field. */
+enum { RSB_ARENA_MEM_HEAVY = 0, RSB_ARENA_MEM_LIGHT = 1 };
+typedef struct RsbArenaConfig {
+	uint8_t memWeightMode;
+	uint8_t noBallRot;
+	uint8_t useCustomBroadphase;
+	uint8_t useCustomBoostPads;
+	float maxAABBLen;
+	int32_t maxObjects;
+	uint32_t numCustomBoostPads;
+	RsbVec minPos, maxPos;
+	const RsbBoostPadConfig* customBoostPads;
+	uint64_t _reserved;
+} RsbArenaConfig;
+
 /* Events produced by a step (goal callback Arena.cpp:748-752, bump callback :399-400). */
 enum { RSB_EVENT_GOAL = 1, RSB_EVENT_BUMP = 2, RSB_EVENT_DEMO = 3,
        /* GameEventTracker events (src/Sim/GameEventTracker/GameEventTracker.h:6-8), produced when the tracker is enabled:

@@ -73,10 +73,19 @@ int ref_init_from_mem(int n_meshes, const int* mesh_modes, const uint8_t* const*
 	} catch (std::exception& e) { g_err = e.what(); return -1; }
 }
 
-RefArena* ref_arena_create(int game_mode, float tick_rate) {
+RefArena* ref_arena_create(int game_mode, float tick_rate) { return ref_arena_create_cfg(game_mode, tick_rate, 1, -1, nullptr); }
+
+// ArenaConfig with noBallRot and (n_pads >= 0) custom boost pads: pads = n_pads x (x, y, z, isBig)
+RefArena* ref_arena_create_cfg(int game_mode, float tick_rate, int no_ball_rot, int n_pads, const float* pads) {
 	try {
 		RefArena* r = new RefArena();
-		r->arena = Arena::Create((GameMode)game_mode, ArenaConfig(), tick_rate);
+		ArenaConfig cfg;
+		cfg.noBallRot = no_ball_rot != 0;
+		if (n_pads >= 0) {
+			cfg.useCustomBoostPads = true;
+			for (int i = 0; i < n_pads; i++) { BoostPadConfig pc; pc.pos = Vec(pads[4 * i], pads[4 * i + 1], pads[4 * i + 2]); pc.isBig = pads[4 * i + 3] != 0.f; cfg.customBoostPads.push_back(pc); }
+		}
+		r->arena = Arena::Create((GameMode)game_mode, cfg, tick_rate);
 		if ((GameMode)game_mode != GameMode::THE_VOID) {
 			r->arena->SetGoalScoreCallback([](Arena* a, Team t, void* u) {
 				RefArena* ra = (RefArena*)u;

@@ -27,7 +27,8 @@ typedef struct RefArena RefArena;
 int ref_init_from_mem(int n_meshes, const int* mesh_modes, const uint8_t* const* mesh_ptrs, const size_t* mesh_sizes);
 const char* ref_last_error(void);
 
-RefArena* ref_arena_create(int game_mode, float tick_rate);          /* Arena::Create, Arena.cpp:542 */
+RefArena* ref_arena_create(int game_mode, float tick_rate);
+RefArena* ref_arena_create_cfg(int game_mode, float tick_rate, int no_ball_rot, int n_pads, const float* pads /* n_pads x (x, y, z, isBig) */);          /* Arena::Create, Arena.cpp:542 */
 void ref_arena_destroy(RefArena*);
 uint32_t ref_add_car(RefArena*, int team, int car_preset);           /* Arena::AddCar, Arena.cpp:50 */
 int ref_num_cars(RefArena*);

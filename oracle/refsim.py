@@ -47,6 +47,7 @@ def lib():
         L.ref_init_from_mem.argtypes = [i32, vp, vp, vp]; L.ref_init_from_mem.restype = i32
         L.ref_last_error.restype = C.c_char_p
         L.ref_arena_create.argtypes = [i32, f32]; L.ref_arena_create.restype = vp
+        L.ref_arena_create_cfg.argtypes = [i32, f32, i32, i32, vp]; L.ref_arena_create_cfg.restype = vp
         L.ref_arena_destroy.argtypes = [vp]
         L.ref_add_car.argtypes = [vp, i32, i32]; L.ref_add_car.restype = u32
         L.ref_num_cars.argtypes = [vp]; L.ref_num_pads.argtypes = [vp]
@@ -105,9 +106,14 @@ def init_from_mem(mesh_sets: dict) -> None:
 
 
 class RefArena:
-    def __init__(self, mode: int, tick_rate: float = 120.0):
+    def __init__(self, mode: int, tick_rate: float = 120.0, no_ball_rot: bool = True, custom_pads=None):
+        """custom_pads: None (default pads) or an array n x (x, y, z, isBig) -> ArenaConfig::customBoostPads"""
         self.L = lib()
-        self.h = self.L.ref_arena_create(mode, tick_rate)
+        if no_ball_rot and custom_pads is None:
+            self.h = self.L.ref_arena_create(mode, tick_rate)
+        else:
+            pads = None if custom_pads is None else np.ascontiguousarray(custom_pads, dtype=np.float32).reshape(-1, 4)
+            self.h = self.L.ref_arena_create_cfg(mode, tick_rate, int(no_ball_rot), -1 if pads is None else len(pads), None if pads is None else _ptr(pads))
         if not self.h:
             raise RuntimeError(self.L.ref_last_error().decode())
         self.mode = mode

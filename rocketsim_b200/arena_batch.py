@@ -18,12 +18,22 @@ from . import lib as _lib
 from . import types as T
 
 
+def default_arena_config(lib=None) -> np.ndarray:
+    """``ArenaConfig()`` of the reference as a ``types.ArenaConfig`` record."""
+    L = lib or _lib.load()
+    out = np.zeros(1, dtype=T.ArenaConfig)
+    L.rsb_default_arena_config(_lib.ptr(out))
+    return out[0]
+
+
 class ArenaBatch:
     def __init__(self, game_mode: int, n_arenas: int, teams: Sequence[int], car_configs: Optional[np.ndarray] = None,
                  mutator_config: Optional[np.ndarray] = None, tick_rate: float = 120.0, seed: int = 0, device: int = 0,
-                 lib=None):
-        """``Arena::Create(game_mode, ArenaConfig(), tick_rate)`` x n_arenas, then
-        ``AddCar(team, config)`` for every entry of ``teams`` (car ids 1..n in that order)."""
+                 lib=None, arena_config: Optional[np.ndarray] = None, custom_boost_pads: Optional[np.ndarray] = None):
+        """``Arena::Create(game_mode, arena_config, tick_rate)`` x n_arenas, then ``AddCar(team, config)`` for every entry of
+        ``teams`` (car ids 1..n in that order).  ``arena_config``: a ``types.ArenaConfig`` record (default: the reference's
+        defaults, see ``default_arena_config``); ``custom_boost_pads``: ``types.BoostPadConfig`` array, implies
+        ``useCustomBoostPads`` (``ArenaConfig::customBoostPads``, ArenaConfig.h:43-46)."""
         self.L = lib or _lib.load()
         self.n_arenas = int(n_arenas)
         self.n_cars = len(teams)
@@ -34,8 +44,15 @@ class ArenaBatch:
             raise ValueError("one CarConfig per car slot expected")
         mut = None if mutator_config is None else np.array([mutator_config], dtype=T.MutatorConfig)
         h = C.c_void_p()
-        _lib.check(self.L, self.L.rsb_batch_create(device, game_mode, n_arenas, self.n_cars, _lib.ptr(t) if self.n_cars else None,
-                                                   _lib.ptr(cfg), _lib.ptr(mut), tick_rate, seed, C.byref(h)))
+        ac = None
+        if arena_config is not None or custom_boost_pads is not None:
+            ac = np.array([arena_config], dtype=T.ArenaConfig) if arena_config is not None else np.array([default_arena_config(self.L)], dtype=T.ArenaConfig)
+            if custom_boost_pads is not None:
+                self._pads = np.ascontiguousarray(custom_boost_pads, dtype=T.BoostPadConfig)
+                ac["useCustomBoostPads"] = 1; ac["numCustomBoostPads"] = len(self._pads)
+                ac["customBoostPads"] = self._pads.ctypes.data if len(self._pads) else 0
+        _lib.check(self.L, self.L.rsb_batch_create_ex(device, game_mode, _lib.ptr(ac), n_arenas, self.n_cars, _lib.ptr(t) if self.n_cars else None,
+                                                      _lib.ptr(cfg), _lib.ptr(mut), tick_rate, seed, C.byref(h)))
         self.h = h
         np_ = C.c_int()
         _lib.check(self.L, self.L.rsb_batch_info(self.h, None, None, C.byref(np_), None))

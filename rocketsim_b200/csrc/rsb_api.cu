@@ -126,6 +126,8 @@ struct RsbBatch {
 	EpaScratch* dE = nullptr;      // EPA working sets, one per thread of the step grid
 	RsbBallState* traceOut = nullptr;  // consumed by the next launch (rsb_predict_ball)
 	RsbBatch* pred = nullptr;      // ball-only sibling batch used by rsb_predict_ball (created on first use)
+	RsbArenaConfig acfg;           // the ArenaConfig the batch was created with (customBoostPads points into acfgPads)
+	std::vector<RsbBoostPadConfig> acfgPads;
 	RsbMutatorConfig mutApi;       // the mutator config the batch was created with
 	std::vector<RsbCarConfig> carCfgApi;  // the car configs the batch was created with (wire format, rsb_serialize_arena)
 	float tickRate = 120.f;
@@ -763,16 +765,23 @@ static const float LOCS_SMALL_HOOPS[14][3] = {{1536, -1024, 64}, {-1280, -2304, 
 static const float LOCS_BIG_HOOPS[6][3] = {{-2176, 2944, 72}, {2176, -2944, 72}, {-2176, -2944, 72}, {-2432, 0, 72}, {2432, 0, 72}, {2175.99f, 2944, 72}};
 
 // Arena ctor pad setup (Arena.cpp:498-534), BoostPad::_Setup (BoostPad.cpp:37-49), BoostPadGrid::Add
-static void fill_pads(int mode, BatchParams& P) {
+static void fill_pads(int mode, BatchParams& P, const RsbArenaConfig& ac) {
 	for (int i = 0; i < 80; i++) P.padGrid[i] = -1;
-	P.nPads = 0;
+	P.nPads = 0; P.customPads = 0;
 	if (mode == THE_VOID || mode == DROPSHOT) return;
 	bool hoops = mode == HOOPS;
 	int nSmall = hoops ? 14 : 28;
 	P.nPads = 6 + nSmall;
+	if (ac.useCustomBoostPads) {
+		if (ac.numCustomBoostPads > (uint32_t)MAX_PADS) throw std::runtime_error("ArenaConfig::customBoostPads: at most " + std::to_string(MAX_PADS) + " pads are supported by the batched back end");
+		if (ac.numCustomBoostPads && !ac.customBoostPads) throw std::runtime_error("ArenaConfig::customBoostPads is NULL");
+		P.nPads = (int)ac.numCustomBoostPads; P.customPads = 1;
+	}
 	for (int i = 0; i < P.nPads; i++) {
 		bool big = i < 6;
 		const float* p = hoops ? (big ? LOCS_BIG_HOOPS[i] : LOCS_SMALL_HOOPS[i - 6]) : (big ? LOCS_BIG_SOCCAR[i] : LOCS_SMALL_SOCCAR[i - 6]);
+		float cp[3];
+		if (P.customPads) { big = ac.customBoostPads[i].isBig != 0; cp[0] = ac.customBoostPads[i].pos.x; cp[1] = ac.customBoostPads[i].pos.y; cp[2] = ac.customBoostPads[i].pos.z; p = cp; }
 		PadCfgD& d = P.pads[i];
 		V3 posUU(p[0], p[1], p[2]);
 		d.posBT = posUU * UU_TO_BT;
@@ -781,6 +790,7 @@ static void fill_pads(int mode, BatchParams& P) {
 		d.boxMin = d.posBT - V3(boxRad, boxRad, 0.f);
 		d.boxMax = d.posBT + V3(boxRad, boxRad, K::PAD_BOX_HEIGHT * UU_TO_BT);
 		d.cylRadBT = (big ? K::PAD_CYL_RAD_BIG : K::PAD_CYL_RAD_SMALL) * UU_TO_BT;
+		if (P.customPads) continue;  // no BoostPadGrid::Add for custom pads (Arena.cpp:505-512)
 		int ix = (int)(posUU.x / 1024 + 4), iy = (int)(posUU.y / 1024 + 5);
 		if (ix < 0 || ix >= 8 || iy < 0 || iy >= 10 || P.padGrid[ix * 10 + iy] != -1) throw std::runtime_error("BoostPadGrid::Add(): pad cell collision");
 		P.padGrid[ix * 10 + iy] = i;
@@ -788,12 +798,12 @@ static void fill_pads(int mode, BatchParams& P) {
 }
 
 // Ball::_BulletSetup / MakeBallCollisionShape (Ball.cpp:53-115)
-static void fill_ball(int mode, BatchParams& P) {
+static void fill_ball(int mode, BatchParams& P, bool noBallRot) {
 	const MutD& m = P.mut;
 	P.ballInvMass = 1.0f / m.ballMass;
 	P.ballMass = 1.0f / P.ballInvMass;  // btRigidBody::getMass()
 	P.ballIsSphere = mode != SNOWDAY;
-	P.ballNoRot = P.ballIsSphere ? 1 : 0;  // ArenaConfig::noBallRot default true, spheres only
+	P.ballNoRot = (P.ballIsSphere && noBallRot) ? 1 : 0;  // ArenaConfig::noBallRot, spheres only (Ball.cpp:53-115)
 	P.ballRadiusBT = m.ballRadius * UU_TO_BT;
 	V3 inertia;
 	if (P.ballIsSphere) {
@@ -889,6 +899,7 @@ int rsb_sizeof(const char* n) {
 	if (s == "RsbMutatorConfig") return sizeof(RsbMutatorConfig); if (s == "RsbCarConfig") return sizeof(RsbCarConfig);
 	if (s == "RsbBoostPadState") return sizeof(RsbBoostPadState); if (s == "RsbCarInternal") return sizeof(RsbCarInternal);
 	if (s == "RsbBallInternal") return sizeof(RsbBallInternal); if (s == "RsbEvent") return sizeof(RsbEvent);
+	if (s == "RsbBoostPadConfig") return sizeof(RsbBoostPadConfig); if (s == "RsbArenaConfig") return sizeof(RsbArenaConfig);
 	if (s == "ArenaS") return sizeof(ArenaS); if (s == "ArenaW") return sizeof(ArenaW);
 	return -1;
 }
@@ -916,11 +927,34 @@ int rsb_init_from_mem(int n_meshes, const int* mesh_modes, const uint8_t* const*
 	API_END
 }
 
+void rsb_default_arena_config(RsbArenaConfig* o) {
+	if (!o) return;
+	memset(o, 0, sizeof(*o));
+	o->memWeightMode = RSB_ARENA_MEM_HEAVY; o->noBallRot = 1; o->useCustomBroadphase = 1; o->useCustomBoostPads = 0;
+	o->maxAABBLen = 370.f; o->maxObjects = 512;
+	o->minPos = RsbVec{-5600, -6000, 0, 0}; o->maxPos = RsbVec{5600, 6000, 2200, 0};
+}
+
 int rsb_batch_create(int device, int game_mode, int n_arenas, int n_cars, const int* teams, const RsbCarConfig* car_configs,
                      const RsbMutatorConfig* mutator, float tick_rate, uint32_t seed, RsbBatch** out) {
+	return rsb_batch_create_ex(device, game_mode, nullptr, n_arenas, n_cars, teams, car_configs, mutator, tick_rate, seed, out);
+}
+
+int rsb_batch_create_ex(int device, int game_mode, const RsbArenaConfig* arena_config, int n_arenas, int n_cars, const int* teams,
+                        const RsbCarConfig* car_configs, const RsbMutatorConfig* mutator, float tick_rate, uint32_t seed, RsbBatch** out) {
 	API_BEGIN
 	if (!out) throw std::runtime_error("out is NULL");
 	*out = nullptr;
+	RsbArenaConfig ac; rsb_default_arena_config(&ac);
+	if (arena_config) {
+		ac = *arena_config;
+		RsbArenaConfig d; rsb_default_arena_config(&d);
+		// the broadphase grid is part of the static scene built per game mode: only the default ArenaConfig geometry is available
+		if (ac.memWeightMode != d.memWeightMode) throw std::runtime_error("ArenaConfig::memWeightMode = LIGHT is not supported by the batched back end (the broadphase grid is built once per game mode with the HEAVY cell size)");
+		if (memcmp(&ac.minPos, &d.minPos, 12) || memcmp(&ac.maxPos, &d.maxPos, 12)) throw std::runtime_error("ArenaConfig::minPos / maxPos other than the defaults are not supported by the batched back end");
+		if (ac.maxAABBLen != d.maxAABBLen) throw std::runtime_error("ArenaConfig::maxAABBLen other than 370 is not supported by the batched back end");
+		if (!ac.useCustomBroadphase) throw std::runtime_error("ArenaConfig::useCustomBroadphase = false (btDbvtBroadphase) is not supported by the batched back end");
+	}
 	if (n_arenas <= 0) throw std::runtime_error("n_arenas must be positive");
 	if (n_cars < 0 || n_cars > MAX_CARS) throw std::runtime_error("n_cars must be in [0, " + std::to_string(MAX_CARS) + "]");
 	if (!(tick_rate >= 15 && tick_rate <= 120)) throw std::runtime_error("Tickrate must be from 15 to 120tps");  // Arena.cpp:419
@@ -940,6 +974,9 @@ int rsb_batch_create(int device, int game_mode, int n_arenas, int n_cars, const 
 #endif
 	RsbBatch* b = new RsbBatch();
 	b->device = device;
+	b->acfg = ac;
+	if (ac.useCustomBoostPads && ac.numCustomBoostPads <= (uint32_t)MAX_PADS && ac.customBoostPads) b->acfgPads.assign(ac.customBoostPads, ac.customBoostPads + ac.numCustomBoostPads);
+	b->acfg.customBoostPads = b->acfgPads.empty() ? nullptr : b->acfgPads.data();
 #ifndef RSB_HOSTCHECK
 	{
 		cudaDeviceProp prop;
@@ -962,13 +999,13 @@ int rsb_batch_create(int device, int game_mode, int n_arenas, int n_cars, const 
 	b->mutApi = mc; b->tickRate = tick_rate;
 	fill_mut(mc, P.mut);
 	P.gravityBT = P.mut.gravity * UU_TO_BT;
-	fill_ball(game_mode, P);
+	fill_ball(game_mode, P, ac.noBallRot != 0);
 	for (int i = 0; i < n_cars; i++) {
 		fill_car_cfg(car_configs ? car_configs[i] : preset_octane(), P.carCfg[i]);
 		b->carCfgApi.push_back(car_configs ? car_configs[i] : preset_octane());
 		P.team[i] = teams ? teams[i] : (i < (n_cars + 1) / 2 ? 0 : 1);
 	}
-	fill_pads(game_mode, P);
+	fill_pads(game_mode, P, ac);
 	for (int team = 0; team < 2; team++) {
 		auto yaw_of = [&](float yaw) { return team == 0 ? yaw : (float)((double)yaw + 3.14159265358979323846); };
 		for (int i = 0; i < 5; i++) P.kickBasis[team][i] = basis_from_ypr(yaw_of(kickoff_slot(game_mode, i).yaw), 0.f, 0.f);
@@ -1242,7 +1279,7 @@ int rsb_predict_ball(RsbBatch* b, int n_ticks, RsbBallState* out) {
 	if (n_ticks < 1) throw std::runtime_error("n_ticks must be >= 1");
 	if (!b->pred) {
 		RsbBatch* p = nullptr;
-		if (rsb_batch_create(b->device, b->hp.mode, b->hp.nArenas, 0, nullptr, nullptr, &b->mutApi, b->tickRate, 0, &p) != 0) throw std::runtime_error(g_err);
+		if (rsb_batch_create_ex(b->device, b->hp.mode, &b->acfg, b->hp.nArenas, 0, nullptr, nullptr, &b->mutApi, b->tickRate, 0, &p) != 0) throw std::runtime_error(g_err);
 		b->pred = p;
 	}
 	RsbBatch* p = b->pred;
@@ -1333,6 +1370,7 @@ int rsb_serialize_arena(RsbBatch* b, uint32_t arena, uint8_t* out, size_t cap, s
 	if (arena >= (uint32_t)P.nArenas) throw std::runtime_error("arena index out of range");
 	rsbser::ArenaImage img;
 	img.gameMode = (uint8_t)P.mode; img.tickTime = P.dt; img.lastCarID = (uint32_t)P.nCars; img.mut = b->mutApi;
+	img.noBallRot = b->acfg.noBallRot != 0;
 	const size_t need = (size_t)std::max(1, P.nCars) * (sizeof(RsbCarState) + sizeof(RsbCarControls)) + sizeof(RsbBallState) + (size_t)MAX_PADS * sizeof(RsbBoostPadState) + 64;
 	b->ensure_scratch(need);
 	char* base = (char*)b->dScratch;
@@ -1370,6 +1408,7 @@ int rsb_deserialize_arena(RsbBatch* b, uint32_t arena, const uint8_t* data, size
 	rsbser::ArenaImage img = rsbser::read_arena(data, n, [](int mode) { return mode == HOOPS ? 20 : ((mode == THE_VOID || mode == DROPSHOT) ? 0 : 34); });
 	if (img.gameMode != P.mode) throw std::runtime_error("Arena::Deserialize(): the stream's game mode differs from the batch's");
 	if (img.tickTime != P.dt) throw std::runtime_error("Arena::Deserialize(): the stream's tick rate differs from the batch's");
+	if (img.noBallRot != (b->acfg.noBallRot != 0)) throw std::runtime_error("Arena::Deserialize(): the stream's ArenaConfig::noBallRot differs from the batch's");
 	if ((int)img.cars.size() != P.nCars) throw std::runtime_error("Arena::Deserialize(): the stream has " + std::to_string(img.cars.size()) + " cars, the batch has " + std::to_string(P.nCars) + " car slots");
 	if (memcmp(&img.mut, &b->mutApi, offsetof(RsbMutatorConfig, _pad2)) != 0) {
 		RsbMutatorConfig x = img.mut, y = b->mutApi; x._pad0 = y._pad0 = 0; x._pad1[0] = x._pad1[1] = y._pad1[0] = y._pad1[1] = 0;

@@ -253,6 +253,10 @@ RSB_HD void pad_check_collide(const Ctx& cx, int pi, int ci) {
 // BoostPadGrid::CheckCollision
 RSB_HD void pad_grid_check(const Ctx& cx, int ci) {
 	const CarS& c = cx.s->cars[ci];
+	if (cx.p->customPads) {  // ArenaConfig::useCustomBoostPads: BoostPad::_CheckCollide for every pad, without the grid's early-outs
+		for (int pad = 0; pad < cx.p->nPads; pad++) pad_check_collide(cx, pad, ci);
+		return;
+	}
 	if (c.isDemoed || c.boost >= K::BOOST_MAX) return;
 	V3 carPos = c.rb.pos * BT_TO_UU;
 	const float EXTENT_Z = K::PAD_CYL_HEIGHT + 250.f;

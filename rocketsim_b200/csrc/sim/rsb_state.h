@@ -166,6 +166,7 @@ struct BatchParams {
 	int team[MAX_CARS];
 	PadCfgD pads[MAX_PADS];
 	int padGrid[8 * 10];  // BoostPadGrid (BoostPadGrid.h:10-29): pad index or -1
+	int customPads;       // ArenaConfig::useCustomBoostPads: no grid, every pad is checked against every car (Arena.cpp:724-730)
 	// README bench loop on device: when set, a goal is followed by ResetToRandomKickoff(autoResetSeed + arena + tick)
 	int autoReset; uint32_t autoResetSeed;
 	// spawn orientations [team][slot], computed on the HOST at batch creation: the reference builds them with glibc's sinf / cosf

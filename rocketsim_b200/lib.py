@@ -28,7 +28,7 @@ EXPORTS = [
     "rsb_get_error_flags", "rsb_seed_rng", "rsb_get_observations", "rsb_observation_floats",
     "rsb_get_car_internals", "rsb_set_car_internals", "rsb_get_ball_internals", "rsb_set_ball_internals",
     "rsb_reset_to_random_kickoff", "rsb_scene_counts", "rsb_scene_dump", "rsb_scene_num_meshes", "rsb_scene_cells",
-    "rsb_bench_fill_controls_device", "rsb_debug_get_wheels", "rsb_step_with_controls", "rsb_set_auto_reset", "rsb_debug_get_manifolds", "rsb_debug_get_solver_rows", "rsb_debug_profile", "rsb_debug_get_solver_bodies", "rsb_debug_get_misc", "rsb_car_config_preset", "rsb_default_mutator_config", "rsb_set_event_tracker", "rsb_is_ball_probably_going_in", "rsb_predict_ball", "rsb_serialize_arena", "rsb_deserialize_arena", "rsb_clone_arena", "rsb_set_arena_offset",
+    "rsb_bench_fill_controls_device", "rsb_debug_get_wheels", "rsb_step_with_controls", "rsb_set_auto_reset", "rsb_debug_get_manifolds", "rsb_debug_get_solver_rows", "rsb_debug_profile", "rsb_debug_get_solver_bodies", "rsb_debug_get_misc", "rsb_car_config_preset", "rsb_default_mutator_config", "rsb_set_event_tracker", "rsb_is_ball_probably_going_in", "rsb_predict_ball", "rsb_serialize_arena", "rsb_deserialize_arena", "rsb_clone_arena", "rsb_set_arena_offset", "rsb_batch_create_ex", "rsb_default_arena_config",
 ]
 
 
@@ -42,6 +42,9 @@ def _declare(L):
     L.rsb_sizeof.argtypes = [C.c_char_p]
     L.rsb_init_from_mem.argtypes = [i32, vp, vp, vp]
     L.rsb_batch_create.argtypes = [i32, i32, i32, i32, vp, vp, vp, f32, u32, vp]
+    L.rsb_batch_create_ex.argtypes = [i32, i32, vp, i32, i32, vp, vp, vp, f32, u32, vp]
+    L.rsb_default_arena_config.argtypes = [vp]
+    L.rsb_default_arena_config.restype = None
     L.rsb_batch_destroy.argtypes = [vp]
     L.rsb_batch_info.argtypes = [vp, vp, vp, vp, vp]
     L.rsb_set_stream.argtypes = [vp, vp]

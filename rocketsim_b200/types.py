@@ -86,6 +86,13 @@ CarConfig = np.dtype({
 BoostPadState = np.dtype({"names": ["isActive", "cooldown", "prevLockedCarID"], "formats": ["u1", "<f4", "<u4"],
                           "offsets": [0, 4, 8], "itemsize": 12})
 
+BoostPadConfig = np.dtype({"names": ["pos", "isBig"], "formats": [Vec, "u1"], "offsets": [0, 16], "itemsize": 32})
+# RsbArenaConfig (include/rsb_types.h); customBoostPads is a raw pointer filled in by ArenaBatch
+ArenaConfig = np.dtype({"names": ["memWeightMode", "noBallRot", "useCustomBroadphase", "useCustomBoostPads", "maxAABBLen", "maxObjects",
+                                  "numCustomBoostPads", "minPos", "maxPos", "customBoostPads", "_reserved"],
+                        "formats": ["u1", "u1", "u1", "u1", "<f4", "<i4", "<u4", Vec, Vec, "<u8", "<u8"],
+                        "offsets": [0, 1, 2, 3, 4, 8, 12, 16, 32, 48, 56], "itemsize": 64})
+
 CarInternal = np.dtype({
     "names": ["steerAngle", "engineForce", "brake", "latFriction", "longFriction", "extraPushback",
               "velocityImpulseCache", "rbPos", "rbVel", "tickCountSinceUpdate", "hasRigidBody", "rbBasis"],
@@ -112,5 +119,5 @@ CAR_OCTANE, CAR_DOMINUS, CAR_PLANK, CAR_BREAKOUT, CAR_HYBRID, CAR_MERC, CAR_PSYC
 SIZES = {
     "RsbVec": 16, "RsbRotMat": 48, "RsbCarControls": 24, "RsbBallHitInfo": 80, "RsbCarState": 352,
     "RsbBallState": 144, "RsbMutatorConfig": 128, "RsbCarConfig": 112, "RsbBoostPadState": 12,
-    "RsbCarInternal": 208, "RsbBallInternal": 64, "RsbEvent": 24,
+    "RsbCarInternal": 208, "RsbBoostPadConfig": 32, "RsbArenaConfig": 64, "RsbBallInternal": 64, "RsbEvent": 24,
 }

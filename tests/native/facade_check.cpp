@@ -23,7 +23,8 @@ int main(int argc, char** argv) {
 		Init(paths, true);
 
 		int goals = 0, bumps = 0; Team lastScorer = Team::BLUE;
-		Arena* arena = Arena::Create(mode, 120);
+		Arena* arena = Arena::Create(mode, ArenaConfig(), 120);  // the reference's signature (Arena.h:111)
+		{ Car* tmp = arena->AddCar(Team::ORANGE); if (!arena->RemoveCar(tmp->id) || arena->RemoveCar(77)) throw std::runtime_error("RemoveCar"); }
 		Car* a = arena->AddCar(Team::BLUE);
 		Car* b = arena->AddCar(Team::ORANGE, CAR_CONFIG_DOMINUS());
 		arena->SetGoalScoreCallback([&](Arena*, Team t, void*) { goals++; lastScorer = t; });
@@ -51,7 +52,8 @@ int main(int argc, char** argv) {
 		// error behaviour: AddCar after the first Step throws, bad tick rate throws (Arena.cpp:419)
 		int errs = 0;
 		try { arena->AddCar(Team::BLUE); } catch (const std::runtime_error&) { errs++; }
-		try { Arena::Create(mode, 10); } catch (const std::runtime_error&) { errs++; }
+		try { Arena::Create(mode, ArenaConfig(), 10); } catch (const std::runtime_error&) { errs++; }
+		try { ArenaConfig bad; bad.maxAABBLen = 500; Arena* x = Arena::Create(mode, bad); x->Step(1); } catch (const std::runtime_error&) { errs++; }
 		printf("errors %d\n", errs);
 		delete arena;
 	} catch (const std::exception& e) {

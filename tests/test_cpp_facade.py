@@ -66,7 +66,7 @@ def check(out, oracle):
     assert out["ticks"].split() == [str(TICKS), "scored", "0"]
     g = out["goals"].split()
     assert int(g[0]) == 1 and int(g[2]) == T.TEAM_BLUE  # ball crossed +y: blue scores, exactly one callback
-    assert out["errors"] == "2"
+    assert out["errors"] == "3"
 
 
 def test_cpp_facade_hostcheck(hostlib, oracle, mesh_sets, tmp_path):
