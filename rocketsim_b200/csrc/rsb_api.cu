@@ -398,7 +398,10 @@ __device__ __forceinline__ bool map_item(int k, int tid, int ptid, int nA, const
 			return true;
 		}
 	}
-	const int i = ptid + k * STEP_THREADS;
+#ifndef RSB_NARROW_NATURAL
+#define RSB_NARROW_NATURAL 0  // developer A/B: deal the default-mapped phases in thread order (few warps, dense lanes) instead of across warps
+#endif
+	const int i = (RSB_NARROW_NATURAL ? tid : ptid) + k * STEP_THREADS;
 	if (i >= phase_items(P, PH) * nA) return false;
 	ar = i % nA; item = i / nA;
 	return true;
@@ -407,7 +410,7 @@ __device__ __forceinline__ bool map_item(int k, int tid, int ptid, int nA, const
 template <int PH>
 __device__ __forceinline__ bool phase_thread_busy(int tid, int ptid, int nA, const BatchParams& P) { int ar, item; return map_item<PH>(0, tid, ptid, nA, P, ar, item); }
 
-template <int PH>
+template <int PH, int SLOT = PH>
 __device__ __forceinline__ void run_phase_block(const StepArgs& a, const BatchParams* sP, const Scene* sSc, unsigned char* sS, int a0, int nA, int ptid) {
 #if defined(RSB_PROFILE)
 	__shared__ unsigned long long s_profMax;
@@ -425,7 +428,7 @@ __device__ __forceinline__ void run_phase_block(const StepArgs& a, const BatchPa
 			const Ctx cx = make_ctx(a, sP, sSc, sS, a0, e >> 7);
 			phase_run(cx, PH, e & 127);
 		}
-		PHASE_PROF_ITEMS(PH, ptid < nq);
+		PHASE_PROF_ITEMS(SLOT, ptid < nq);
 	} else {
 	const int n = phase_items(*sP, PH) * nA;
 	const int nRounds = (n + STEP_THREADS - 1) / STEP_THREADS + 1;
@@ -435,7 +438,7 @@ __device__ __forceinline__ void run_phase_block(const StepArgs& a, const BatchPa
 		const Ctx cx = make_ctx(a, sP, sSc, sS, a0, ar);
 		phase_run(cx, PH, item);
 	}
-	PHASE_PROF_ITEMS(PH, phase_thread_busy<PH>(threadIdx.x, ptid, nA, *sP));
+	PHASE_PROF_ITEMS(SLOT, phase_thread_busy<PH>(threadIdx.x, ptid, nA, *sP));
 	}
 #if defined(RSB_PROFILE)
 	__shared__ unsigned long long s_profMax2;
@@ -457,7 +460,7 @@ __device__ __forceinline__ void run_phase_block(const StepArgs& a, const BatchPa
 		}
 		__syncthreads();
 	}
-	PHASE_PROF_END(PH);
+	PHASE_PROF_END(SLOT);
 }
 
 
@@ -498,8 +501,14 @@ __global__ void __launch_bounds__(STEP_THREADS, BLOCKS_PER_SM) arena_step_kernel
 				__syncthreads();
 			}
 			run_phase_block<PH_INIT>(a, sP, sSc, sS, a0, nA, ptid);
+#if defined(RSB_EXP_TWICE)
+			run_phase_block<PH_INIT, 15>(a, sP, sSc, sS, a0, nA, ptid);
+#endif
 			run_phase_block<PH_PRE_BEGIN>(a, sP, sSc, sS, a0, nA, ptid);
 			run_phase_block<PH_WHEELS>(a, sP, sSc, sS, a0, nA, ptid);
+#if defined(RSB_EXP_TWICE)  // developer experiment: the wheel phase is idempotent; its second run measures the same code WARM in the instruction cache
+			run_phase_block<PH_WHEELS, 14>(a, sP, sSc, sS, a0, nA, ptid);
+#endif
 			run_phase_block<PH_CAR_LOGIC>(a, sP, sSc, sS, a0, nA, ptid);
 			run_phase_block<PH_PREDICT>(a, sP, sSc, sS, a0, nA, ptid);
 			if (tid == 0) *(unsigned*)(smem + SMEM_P_BYTES + SMEM_SC_BYTES) = 0u;  // detector queue; the next write to it is two barriers away

@@ -370,33 +370,10 @@ inline MeshHost build_mesh(const uint8_t* data, size_t size) {
 	return m;
 }
 
-// btVector3::normalize() as compiled for x86-64 (bt/LinearMath/btVector3.h:304-340): rsqrtss estimate + one Newton step.
-// btStaticPlaneShape stores planeNormal.normalized() (btStaticPlaneShape.cpp:19-25), so the reference's arena planes carry
-// e.g. (0, 0, 0.99999994) rather than (0, 0, 1); that value reaches every plane contact normal and friction direction.
-// Scene building is host code, so we run the same instruction sequence on the same CPU.
-inline V3 bullet_normalized_host(const V3& v) {
-#if defined(__SSE__) && !defined(__CUDA_ARCH__)
-	__m128 vec = _mm_set_ps(0.f, v.z, v.y, v.x);
-	__m128 vd = _mm_mul_ps(vec, vec);
-	__m128 z = _mm_movehl_ps(vd, vd);
-	__m128 y = _mm_shuffle_ps(vd, vd, 0x55);
-	vd = _mm_add_ss(vd, y);
-	vd = _mm_add_ss(vd, z);
-	y = _mm_rsqrt_ss(vd);
-	z = _mm_set_ss(1.5f);
-	vd = _mm_mul_ss(vd, _mm_set_ss(0.5f));
-	vd = _mm_mul_ss(vd, y);
-	vd = _mm_mul_ss(vd, y);
-	z = _mm_sub_ss(z, vd);
-	y = _mm_mul_ss(y, z);
-	y = _mm_shuffle_ps(y, y, 0x80);
-	vec = _mm_mul_ps(vec, y);
-	float o[4]; _mm_storeu_ps(o, vec);
-	return V3(o[0], o[1], o[2]);
-#else
-	return v * (1.0f / sqrtf(dot(v, v)));
-#endif
-}
+// btStaticPlaneShape stores planeNormal.normalized() (btStaticPlaneShape.cpp:19-25): with the reference's rsqrtss-based
+// btVector3::normalize() the arena planes carry e.g. (0, 0, 0.99999994) rather than (0, 0, 1); that value reaches every plane
+// contact normal and friction direction.  normalized() (rsb_math.h) reproduces that instruction sequence on any host.
+inline V3 bullet_normalized_host(const V3& v) { return normalized(v); }
 
 inline PlaneD make_plane(const V3& posUU, const V3& nIn) {
 	PlaneD p;

@@ -11,6 +11,7 @@
 
 #include <math.h>
 #include <stdint.h>
+#include <string.h>
 
 #if defined(__CUDACC__)
 #define RSB_HD __host__ __device__ __forceinline__
@@ -76,7 +77,54 @@ RSB_HD float len2(const V3& a) { return dot(a, a); }
 RSB_HD float len(const V3& a) { return sqrtf(dot(a, a)); }
 RSB_HD bool is_zero(const V3& a) { return a.x == 0.f && a.y == 0.f && a.z == 0.f; }
 RSB_HD bool fuzzy_zero(const V3& a) { return len2(a) < kEps * kEps; }
-RSB_HD V3 normalized(const V3& a) { return a * (1.0f / sqrtf(len2(a))); }  // btVector3::normalize (reference: rsqrtss + 1 NR step)
+// btVector3::normalize() (bt/LinearMath/btVector3.h:304-340).  The reference's x86-64 build takes the SSE branch: the 12-bit
+// rsqrtss ESTIMATE of x.x followed by one Newton-Raphson step, y = y0 * (1.5 - ((x * 0.5) * y0) * y0), and the vector times y.
+// The estimate is a pure function of (exponent parity, top 10 mantissa bits) on Intel CPUs; kRsqrtTab holds it (generated and
+// verified against the instruction by scripts/gen_rsqrt_table.c), so the normalised vectors match the reference bit for bit.
+#if defined(__CUDACC__)
+static __device__ const uint16_t kRsqrtTabDev[2048] = {
+#include "rsb_rsqrt_tab.inc"
+};
+#endif
+static const uint16_t kRsqrtTabHost[2048] = {
+#include "rsb_rsqrt_tab.inc"
+};
+RSB_HD float rsqrtss_estimate(float x) {
+#if defined(__CUDA_ARCH__)
+	const uint32_t b = __float_as_uint(x);
+#else
+	uint32_t b; memcpy(&b, &x, 4);
+#endif
+	const uint32_t e = (b >> 23) & 0xffu, m = b & 0x7fffffu;
+	uint32_t r;
+	if (b >> 31) r = (e == 0) ? 0xff800000u : 0xffc00000u;  // -0 / negative denormal -> -inf, negative -> NaN
+	else if (e == 0) r = 0x7f800000u;                       // +0 and denormals -> +inf
+	else if (e == 255) r = m ? b : 0u;                      // NaN -> NaN, +inf -> 0
+	else {
+		const uint32_t idx = ((e & 1u) << 10) | (m >> 13);
+		const int k = ((int)e - ((e & 1u) ? 127 : 128)) / 2;
+#if defined(__CUDA_ARCH__)
+		const uint32_t t = kRsqrtTabDev[idx];
+#else
+		const uint32_t t = kRsqrtTabHost[idx];
+#endif
+		r = (t << 11) + (126u << 23) - ((uint32_t)k << 23);    // entry 0x1000 carries into the exponent: exactly 1.0
+	}
+#if defined(__CUDA_ARCH__)
+	return __uint_as_float(r);
+#else
+	float f; memcpy(&f, &r, 4); return f;
+#endif
+}
+RSB_HD V3 normalized(const V3& a) {
+	float vd = len2(a);
+	const float y0 = rsqrtss_estimate(vd);
+	vd = vd * 0.5f;
+	vd = vd * y0;
+	vd = vd * y0;
+	const float y = y0 * (1.5f - vd);
+	return V3(a.x * y, a.y * y, a.z * y);
+}
 // btVector3::safeNormalize (btVector3.h:292-305)
 RSB_HD V3 safe_normalized(const V3& a) {
 	float l2 = len2(a);

@@ -200,6 +200,7 @@ RSB_HD_NOINLINE bool ray_convex(Convex shapeB, Xform xfB, V3 from, V3 to, float&
 	Simplex sx;
 	sx.reset();
 	V3 linVelA = to - from;
+	const V3 originB0 = xfB.origin;
 	float lambda = 0.f;
 	V3 originA = from;
 	V3 r = linVelA;  // linVelB = 0
@@ -221,6 +222,9 @@ RSB_HD_NOINLINE bool ray_convex(Convex shapeB, Xform xfB, V3 from, V3 to, float&
 			if (VdotR >= -(kEps * kEps)) return false;
 			lambda = lambda - VdotW / VdotR;
 			originA = lerp(from, to, lambda);
+			// interpolatedTransB is re-interpolated too, between two IDENTICAL origins (fromB == toB): (1 - l) * o + l * o is not
+			// always o in fp32, and the reference casts against that rounded origin from here on (btSubSimplexConvexCast.cpp:97-98)
+			xfB.origin = lerp(originB0, originB0, lambda);
 			w = supA - supB;
 			n = v;
 		}

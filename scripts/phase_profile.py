@@ -14,7 +14,7 @@ L = rlib.load(path); rlib.init_from_mem(sm.mesh_sets(), L)
 b = ArenaBatch(mode, A, [0] * cpt + [1] * cpt, seed=1234, lib=L)
 b.reset_to_random_kickoff((1234 + np.arange(A)).astype(np.int32)); b.set_auto_reset(True, 1234)
 seq = torch.empty(TICKS * A * 2 * cpt * 24, dtype=torch.uint8, device="cuda")
-names = ["INIT", "PRE_BEGIN", "WHEELS", "CAR_LOGIC", "PREDICT", "PAIRS", "NARROW_STATIC", "NARROW_DETECT", "NARROW_COMMIT", "DYN_SOLVE", "FINISH_BODY", "CAR_POST", "PADS_POST", "TAIL"]
+names = ["INIT", "PRE_BEGIN", "WHEELS", "CAR_LOGIC", "PREDICT", "PAIRS", "NARROW_STATIC", "NARROW_DETECT", "NARROW_COMMIT", "DYN_SOLVE", "FINISH_BODY", "CAR_POST", "PADS_POST", "TAIL", "EXP14", "EXP15"]
 out = (C.c_uint64 * 64)()
 for rep in range(3):
     rlib.check(L, L.rsb_bench_fill_controls_device(b.h, C.c_void_p(seq.data_ptr()), TICKS, rep * TICKS, 1234))

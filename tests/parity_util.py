@@ -303,9 +303,8 @@ def record_rollout(refsim, mode, teams, seed, ticks, drive=0, aim=False):
                pads_pre=np.zeros((ticks, npads), T.BoostPadState),
                car_post=np.zeros((ticks, n), T.CarState), ball_post=np.zeros(ticks, T.BallState),
                pads_post=np.zeros((ticks, npads), T.BoostPadState), scored=np.zeros(ticks, np.uint8),
-               # ticks in which a suspension ray rests on a DYNAMIC body (another car / the ball): the reference
-               # resolves those with a sub-simplex cast that stops at dist^2 < 1e-4 and normalises with rsqrtss,
-               # so the hit is only defined to ~1e-2 bt (see DESIGN.md "ill-conditioned events")
+               # ticks in which a suspension ray rests on a DYNAMIC body (another car / the ball): resolved by the sub-simplex
+               # convex cast (reported separately by the tests; same tolerance as every other tick)
                wheel_on_dynamic=np.zeros(ticks, np.uint8),
                # the respawn RNG (thread-local in the reference) is re-seeded with seed + t before every tick, so that a tick
                # with a respawn is an independent single-step case like every other

@@ -18,11 +18,10 @@ NAMES = [os.path.basename(p)[:-4] for p in GOLDEN]
 
 # float tolerance (relative, see parity_util.rel_err), every field, every well-conditioned tick
 TOL = 1e-4
-# Ticks in which a suspension ray rests on another car / the ball ("wheel_on_dynamic" in the records): the reference
-# resolves that hit with btSubsimplexConvexCast, which stops at dist^2 < 1e-4 (1 cm) and normalises with the SSE
-# rsqrtss estimate (bt/LinearMath/btVector3.h:304-340) -- the result is only defined to ~1e-2 and is not reproducible
-# across CPU vendors either.  Those ticks carry a looser, documented bound (DESIGN.md "ill-conditioned events").
-TOL_ILLCOND = 2e-2
+# Ticks in which a suspension ray rests on another car / the ball ("wheel_on_dynamic" in the records) go through
+# btSubsimplexConvexCast.  Round 1 gave them a 2e-2 carve-out; the cast is now bit-exact against Bullet's
+# (tests/test_native_units.py), so they are held to the same bar and only reported separately.
+TOL_ILLCOND = TOL
 
 
 def load(path):
@@ -37,7 +36,6 @@ def check(res, name):
         assert v <= TOL, f"{name}: {k} rel err {v:.3g} > {TOL}"
     for k, v in res["worst_illcond"].items():
         assert v <= TOL_ILLCOND, f"{name}: {k} rel err {v:.3g} > {TOL_ILLCOND} (ill-conditioned tick)"
-    assert res["n_illcond"] <= 0.05 * res["ticks"], "too many ill-conditioned ticks for the record to be a useful pin"
 
 
 def test_golden_files_present():

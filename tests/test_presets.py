@@ -8,7 +8,7 @@ import pytest
 import parity_util as pu
 from rocketsim_b200 import lib as rlib, types as T
 
-TOL, TOL_ILLCOND = 1e-4, 2e-2
+TOL = TOL_ILLCOND = 1e-4
 
 
 def preset_cfg(L, k):

@@ -17,7 +17,7 @@ import parity_util as pu
 from rocketsim_b200 import types as T
 
 TOL = 1e-4          # single-step float tolerance (relative, parity_util.rel_err)
-TOL_ILLCOND = 2e-2  # ticks with a suspension ray resting on a dynamic body
+TOL_ILLCOND = TOL  # ticks with a suspension ray resting on a dynamic body: same bar as every other tick (the cast is bit-exact)
 
 # BASELINE.json configs: VOID 1v1, Soccar 2v2, Soccar 3v3 (demos/bumps), Hoops 2v2, Heatseeker 1v1, Snowday 3v3
 CONFIGS = [("void_1v1", T.MODE_THE_VOID, 1), ("soccar_2v2", T.MODE_SOCCAR, 2), ("soccar_3v3", T.MODE_SOCCAR, 3),
@@ -111,9 +111,6 @@ def test_cuda_single_step_vs_live_oracle(cudalib, oracle, name, mode, cpt):
         assert v <= TOL, f"{name}: {k} rel err {v:.3g} > {TOL}"
     for k, v in worst_ill.items():
         assert v <= TOL_ILLCOND, f"{name}: {k} rel err {v:.3g} > {TOL_ILLCOND} (ill-conditioned tick)"
-    # The scripted drive-at-the-ball opening piles cars up, so up to 10 % of ill-conditioned ticks is normal here.  The bound only
-    # guards against the looser tolerance becoming the rule.  (Kickoffs are re-dealt canonically: parity_util.canonical_kickoff.)
-    assert n_ill <= 0.10 * ticks
 
 
 DEMO_CASES = [("soccar_3v3_ram", T.MODE_SOCCAR, 3, "ram"), ("soccar_3v3_charge", T.MODE_SOCCAR, 3, "charge"),
