@@ -202,11 +202,12 @@ RSB_HD M3 inverse(const M3& m) {
 
 struct Q4 { float x, y, z, w; };
 RSB_HD Q4 q4(float x, float y, float z, float w) { Q4 q; q.x = x; q.y = y; q.z = z; q.w = w; return q; }
+// operator*(btQuaternion, btQuaternion), SSE variant (btQuaternion.h:619-650): (A0 - A3) + (A1 + A2) per lane
 RSB_HD Q4 qmul(const Q4& a, const Q4& b) {
-	return q4(a.w * b.x + a.x * b.w + a.y * b.z - a.z * b.y,
-	          a.w * b.y + a.y * b.w + a.z * b.x - a.x * b.z,
-	          a.w * b.z + a.z * b.w + a.x * b.y - a.y * b.x,
-	          a.w * b.w - a.x * b.x - a.y * b.y - a.z * b.z);
+	return q4((a.w * b.x - a.z * b.y) + (a.x * b.w + a.y * b.z),
+	          (a.w * b.y - a.x * b.z) + (a.y * b.w + a.z * b.x),
+	          (a.w * b.z - a.y * b.x) + (a.z * b.w + a.x * b.y),
+	          (a.w * b.w - a.z * b.z) + (-(a.x * b.x + a.y * b.y)));
 }
 RSB_HD float qlen2(const Q4& q) { return (q.x * q.x + q.z * q.z) + (q.y * q.y + q.w * q.w); }
 // btQuaternion(axis, angle) (btQuaternion.h:108-115)
@@ -215,17 +216,17 @@ RSB_HD Q4 q_axis_angle(const V3& axis, float angle) {
 	float s = sinf(angle * 0.5f) / d;
 	return q4(axis.x * s, axis.y * s, axis.z * s, cosf(angle * 0.5f));
 }
-// btMatrix3x3::setRotation (btMatrix3x3.h:216-288)
+// btMatrix3x3::setRotation, SSE variant (btMatrix3x3.h:222-274): products of the raw components, pairwise sums, THEN the
+// scale s = 2 / |q|^2, then + identity -- not the scalar branch's x * (y * s) form, which rounds differently
 RSB_HD M3 m3_from_quat(const Q4& q) {
-	float d = qlen2(q);
-	float s = 2.0f / d;
-	float xs = q.x * s, ys = q.y * s, zs = q.z * s;
-	float wx = q.w * xs, wy = q.w * ys, wz = q.w * zs;
-	float xx = q.x * xs, xy = q.x * ys, xz = q.x * zs;
-	float yy = q.y * ys, yz = q.y * zs, zz = q.z * zs;
-	return M3(V3(1.0f - (yy + zz), xy - wz, xz + wy),
-	          V3(xy + wz, 1.0f - (xx + zz), yz - wx),
-	          V3(xz - wy, yz + wx, 1.0f - (xx + yy)));
+	const float d = qlen2(q);
+	const float s = 2.0f / d;
+	const float xx = q.x * q.x, yy = q.y * q.y, zz = q.z * q.z;
+	const float xy = q.x * q.y, xz = q.x * q.z, yz = q.y * q.z;
+	const float wx = q.w * q.x, wy = q.w * q.y, wz = q.w * q.z;
+	return M3(V3(((-yy) + (-zz)) * s + 1.0f, (xy + (-wz)) * s + 0.0f, (xz + wy) * s + 0.0f),
+	          V3((xy + wz) * s + 0.0f, ((-xx) + (-zz)) * s + 1.0f, (yz + (-wx)) * s + 0.0f),
+	          V3((xz + (-wy)) * s + 0.0f, (yz + wx) * s + 0.0f, ((-xx) + (-yy)) * s + 1.0f));
 }
 // btMatrix3x3::getRotation, SIMD variant (btMatrix3x3.h:421-499)
 RSB_HD Q4 quat_from_m3(const M3& m) {

