@@ -1007,6 +1007,8 @@ int rsb_batch_create_ex(int device, int game_mode, const RsbArenaConfig* arena_c
 	if (mutator) mc = *mutator; else default_mutator(game_mode, mc);
 	b->mutApi = mc; b->tickRate = tick_rate;
 	fill_mut(mc, P.mut);
+	P.ballLinDampFactor = powf(1.f - P.mut.ballDrag, P.dt);
+	P.flipZDampFactor = powf(1.f - K::FLIP_Z_DAMP_120, P.dt / (1 / 120.f));
 	P.gravityBT = P.mut.gravity * UU_TO_BT;
 	fill_ball(game_mode, P, ac.noBallRot != 0);
 	for (int i = 0; i < n_cars; i++) {

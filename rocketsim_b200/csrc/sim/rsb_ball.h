@@ -39,7 +39,7 @@ RSB_HD Ang ang_from_vec(const V3& f) {
 	return a;
 }
 RSB_HD V3 ang_forward(const Ang& a) {
-	float cp = cosf(-a.pitch), cy = cosf(a.yaw), sy = sinf(a.yaw), sp = sinf(-a.pitch);
+	float cp = rs_cosf(-a.pitch), cy = rs_cosf(a.yaw), sy = rs_sinf(a.yaw), sp = rs_sinf(-a.pitch);
 	return V3(cp * cy, cp * sy, -sp);
 }
 RSB_HD Ang round_angle_ue3(Ang ang) {

@@ -23,8 +23,8 @@ RSB_HD uint32_t minstd_seed_int(int seed) { uint32_t x = (uint32_t)((uint64_t)(i
 // Angle(yaw,0,0).ToRotMat() -> btMatrix3x3::setEulerYPR(yaw,-0,-0) (MathTypes.cpp:72-77, btMatrix3x3.h:290-328)
 RSB_HD M3 basis_from_ypr(float yaw, float pitch, float roll) {
 	float eulerX = -roll, eulerY = -pitch, eulerZ = yaw;
-	float ci = cosf(eulerX), cj = cosf(eulerY), ch = cosf(eulerZ);
-	float si = sinf(eulerX), sj = sinf(eulerY), sh = sinf(eulerZ);
+	float ci = rs_cosf(eulerX), cj = rs_cosf(eulerY), ch = rs_cosf(eulerZ);
+	float si = rs_sinf(eulerX), sj = rs_sinf(eulerY), sh = rs_sinf(eulerZ);
 	float cc = ci * ch, cs = ci * sh, sc = si * ch, ss = si * sh;
 	return M3(V3(cj * ch, sj * sc - cs, sj * cc + ss), V3(cj * sh, sj * ss + cc, sj * cs - sc), V3(-sj, cj * si, cj * ci));
 }
@@ -568,7 +568,7 @@ RSB_HD void car_update_double_jump_or_flip(const Ctx& cx, int ci, bool jumpPress
 		c.flipTime += dt;
 		if (c.flipTime <= K::FLIP_TORQUE_TIME) {
 			if (c.flipTime >= K::FLIP_Z_DAMP_START && (c.rb.vel.z < 0.f || c.flipTime < K::FLIP_Z_DAMP_END))
-				c.rb.vel.z *= powf(1.f - K::FLIP_Z_DAMP_120, dt / (1 / 120.f));
+				c.rb.vel.z *= cx.p->flipZDampFactor;  // powf(1 - FLIP_Z_DAMP_120, dt / (1 / 120)), a batch constant
 		}
 	} else if (c.hasFlipped) {
 		c.flipTime += dt;

@@ -166,6 +166,9 @@ struct BatchParams {
 	int team[MAX_CARS];
 	PadCfgD pads[MAX_PADS];
 	int padGrid[8 * 10];  // BoostPadGrid (BoostPadGrid.h:10-29): pad index or -1
+	// powf results whose arguments are batch constants, computed on the HOST (glibc, like the reference): the ball's linear damping
+	// factor powf(1 - ballDrag, dt) (btRigidBody::applyDamping) and the flip z-damp factor powf(1 - FLIP_Z_DAMP_120, dt * 120)
+	float ballLinDampFactor, flipZDampFactor;
 	int customPads;       // ArenaConfig::useCustomBoostPads: no grid, every pad is checked against every car (Arena.cpp:724-730)
 	// README bench loop on device: when set, a goal is followed by ResetToRandomKickoff(autoResetSeed + arena + tick)
 	int autoReset; uint32_t autoResetSeed;

@@ -105,9 +105,9 @@ RSB_HD void phase_run(const Ctx& cx, int phase, int item) {
 		BodyW& bw = cx.body[b];
 		RigidS& rb = rigid_of(cx, b);
 		if (body_active(bw)) apply_central_force(bw, P.gravityBT * (1.f / bw.invMass));
-		float linDamp = (b == 0) ? P.mut.ballDrag : 0.f;
-		rb.vel *= powf(1.f - linDamp, dt);
-		rb.angvel *= powf(1.f - 0.f, dt);
+		// applyDamping: vel *= powf(1 - linDamping, dt), angvel *= powf(1 - 0, dt) = 1 (btRigidBody.cpp:143-147); cars have no damping
+		rb.vel *= (b == 0) ? P.ballLinDampFactor : 1.f;
+		rb.angvel *= 1.f;
 		Xform cur; cur.basis = rb.basis; cur.origin = rb.pos;
 		integrate_transform(cur, rb.vel, rb.angvel, dt, (b == 0) && P.ballNoRot, bw.interp);
 		update_aabb(cx, b);
