@@ -27,9 +27,9 @@ RSB_HD void ang_normalize_fix(Ang& a) {
 RSB_HD Ang ang_from_vec(const V3& f) {
 	Ang a; a.roll = 0.f;
 	if (fabsf(f.y) > kEps || fabsf(f.x) > kEps) {
-		a.yaw = atan2f(f.y, f.x);
+		a.yaw = rs_atan2f(f.y, f.x);
 		float dist2D = sqrtf(f.x * f.x + f.y * f.y);
-		a.pitch = -atan2f(-f.z, dist2D);
+		a.pitch = -rs_atan2f(-f.z, dist2D);
 	} else {
 		a.yaw = 0.f;
 		if (f.z > kEps) a.pitch = (float)(3.14159265358979323846 / 2);

@@ -470,9 +470,9 @@ RSB_HD void car_update_jump(const Ctx& cx, int ci, bool jumpPressed) {
 
 // Angle::FromRotMat roll component (MathTypes.cpp:62-70; btMatrix3x3::getEulerYPR :527-552)
 RSB_HD float roll_from_basis(const M3& m) {
-	float yaw = atan2f(m.r[1].x, m.r[0].x);
+	float yaw = rs_atan2f(m.r[1].x, m.r[0].x);
 	float pitch = asinf(-m.r[2].x);
-	float roll = atan2f(m.r[2].y, m.r[2].z);
+	float roll = rs_atan2f(m.r[2].y, m.r[2].z);
 	if (fabsf(pitch) == kHalfPi) {
 		if (roll > 0.f) roll -= kPi; else roll += kPi;
 	}

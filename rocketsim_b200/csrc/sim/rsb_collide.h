@@ -265,7 +265,7 @@ RSB_HD int sort_cached_points(const Manifold& m, const ContactPt& pt) {
 	return maxIndex;
 }
 
-RSB_HD float get_angle(const V3& edgeA, const V3& normalA, const V3& normalB) { return atan2f(dot(normalB, edgeA), dot(normalB, normalA)); }
+RSB_HD float get_angle(const V3& edgeA, const V3& normalA, const V3& normalB) { return rs_atan2f(dot(normalB, edgeA), dot(normalB, normalA)); }
 RSB_HD V3 quat_rotate(const Q4& q, const V3& v) {  // quatRotate (btQuaternion.h): q * v * q^-1
 	// q * v (quaternion times vector)
 	Q4 t = q4(q.w * v.x + q.y * v.z - q.z * v.y, q.w * v.y + q.z * v.x - q.x * v.z, q.w * v.z + q.x * v.y - q.y * v.x, -q.x * v.x - q.y * v.y - q.z * v.z);

@@ -63,7 +63,7 @@ def test_rsqrt_table_matches_the_instruction():
     assert "0 mismatches" in r.stderr
 
 
-def test_sinf_cosf_restatement_matches_host_libm():
+def test_libm_restatements_match_host_libm():
     """rs_sinf / rs_cosf (rsb_math.h: glibc's double-precision algorithm, FMA variant) vs the host libm the reference calls, on every
     61st float with |x| < 120 (36.8 M values; the full 2.2e9 sweep is `sincos_check 1`).  Hosts without FMA run glibc's non-FMA
     variant, which differs in 34 of 2.2e9 results: tolerate a handful there."""
@@ -75,3 +75,7 @@ def test_sinf_cosf_restatement_matches_host_libm():
     assert n > 30_000_000
     has_fma = " fma " in open("/proc/cpuinfo").read()
     assert (bs, bc) == (0, 0) if has_fma else (bs + bc) <= 4, out
+    m = re.search(r"atanf checked (\d+) mismatch (\d+) atan2f checked (\d+) mismatch (\d+)", out)
+    assert m, out
+    na, ba, n2, b2 = map(int, m.groups())
+    assert na > 60_000_000 and n2 > 60_000_000 and (ba, b2) == (0, 0), out  # fdlibm atanf / atan2f restatement (rs_atanf, rs_atan2f)
