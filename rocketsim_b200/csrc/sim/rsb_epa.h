@@ -49,87 +49,81 @@ RSB_HD void mink_init(Mink& m, const Convex& A, const Xform& tA, const Convex& B
 	m.margins = margins;
 }
 
-RSB_HD float det3(const V3& a, const V3& b, const V3& c) {
+// ---- closest point of a simplex to the origin, with the barycentric weights of the supporting sub-simplex -------------------
+// Same decisions and arithmetic as the reference's sub-determinant projection (gjkepa2_impl::GJK::projectorigin,
+// btGjkEpa2.cpp:430-560), arranged as value-returning routines: an OriginFit carries the squared distance (< 0: degenerate
+// simplex), the weights and the bit mask of the vertices that support the closest point.  A k-simplex first asks its
+// (k-1)-faces that can see the origin; only when none does is the origin's projection interior to the simplex itself.
+struct OriginFit { float d2; float w[4]; unsigned mask; };
+
+RSB_HD float triple3(const V3& a, const V3& b, const V3& c) {  // signed volume, the reference's term order
 	return (a.y * b.z * c.x + a.z * b.x * c.y - a.x * b.z * c.y - a.y * b.x * c.z + a.x * b.y * c.z - a.z * b.y * c.x);
 }
-RSB_HD float project_origin2(const V3& a, const V3& b, float* w, unsigned& m) {
-	const V3 d = b - a;
-	const float l = len2(d);
-	if (l > 0.f) {
-		const float t = (l > 0.f) ? -dot(a, d) / l : 0.f;
-		if (t >= 1.f) { w[0] = 0; w[1] = 1; m = 2; return len2(b); }
-		else if (t <= 0.f) { w[0] = 1; w[1] = 0; m = 1; return len2(a); }
-		else { w[0] = 1 - (w[1] = t); m = 3; return len2(a + d * t); }
-	}
-	return -1.f;
+RSB_HD OriginFit fit_segment(const V3& a, const V3& b) {
+	OriginFit f; f.d2 = -1.f; f.w[0] = f.w[1] = f.w[2] = f.w[3] = 0.f; f.mask = 0;
+	const V3 ab = b - a;
+	const float l2 = len2(ab);
+	if (!(l2 > 0.f)) return f;
+	const float t = -dot(a, ab) / l2;
+	if (t >= 1.f) { f.w[1] = 1.f; f.mask = 2; f.d2 = len2(b); }
+	else if (t <= 0.f) { f.w[0] = 1.f; f.mask = 1; f.d2 = len2(a); }
+	else { f.w[1] = t; f.w[0] = 1 - t; f.mask = 3; f.d2 = len2(a + ab * t); }
+	return f;
 }
-RSB_HD float project_origin3(const V3& a, const V3& b, const V3& c, float* w, unsigned& m) {
-	const unsigned imd3[3] = {1, 2, 0};
+RSB_HD OriginFit fit_triangle(const V3& a, const V3& b, const V3& c) {
+	OriginFit f; f.d2 = -1.f; f.w[0] = f.w[1] = f.w[2] = f.w[3] = 0.f; f.mask = 0;
 	const V3 vt[3] = {a, b, c};
-	const V3 dl[3] = {a - b, b - c, c - a};
-	const V3 n = cross(dl[0], dl[1]);
-	const float l = len2(n);
-	if (l > 0.f) {
-		float mindist = -1.f;
-		float subw[2] = {0.f, 0.f};
-		unsigned subm = 0;
-		for (unsigned i = 0; i < 3; ++i) {
-			if (dot(vt[i], cross(dl[i], n)) > 0.f) {
-				const unsigned j = imd3[i];
-				const float subd = project_origin2(vt[i], vt[j], subw, subm);
-				if ((mindist < 0.f) || (subd < mindist)) {
-					mindist = subd;
-					m = ((subm & 1) ? 1u << i : 0u) + ((subm & 2) ? 1u << j : 0u);
-					w[i] = subw[0]; w[j] = subw[1]; w[imd3[j]] = 0.f;
-				}
-			}
+	const V3 edge[3] = {a - b, b - c, c - a};
+	const V3 n = cross(edge[0], edge[1]);
+	const float l2 = len2(n);
+	if (!(l2 > 0.f)) return f;
+	for (unsigned i = 0; i < 3; ++i) {
+		if (!(dot(vt[i], cross(edge[i], n)) > 0.f)) continue;   // the origin is not outside edge (i, i+1)
+		const unsigned j = (i + 1) % 3, k = (j + 1) % 3;
+		const OriginFit e = fit_segment(vt[i], vt[j]);
+		if (f.d2 < 0.f || e.d2 < f.d2) {
+			f.d2 = e.d2;
+			f.mask = ((e.mask & 1) ? 1u << i : 0u) + ((e.mask & 2) ? 1u << j : 0u);
+			f.w[i] = e.w[0]; f.w[j] = e.w[1]; f.w[k] = 0.f;
 		}
-		if (mindist < 0.f) {
-			const float d = dot(a, n);
-			const float s = sqrtf(l);
-			const V3 p = n * (d / l);
-			mindist = len2(p);
-			m = 7;
-			w[0] = len(cross(dl[1], b - p)) / s;
-			w[1] = len(cross(dl[2], c - p)) / s;
-			w[2] = 1 - (w[0] + w[1]);
-		}
-		return mindist;
 	}
-	return -1.f;
+	if (f.d2 < 0.f) {  // interior: foot of the perpendicular, weights from the sub-triangle areas
+		const float d = dot(a, n);
+		const float s = sqrtf(l2);
+		const V3 p = n * (d / l2);
+		f.d2 = len2(p);
+		f.mask = 7;
+		f.w[0] = len(cross(edge[1], b - p)) / s;
+		f.w[1] = len(cross(edge[2], c - p)) / s;
+		f.w[2] = 1 - (f.w[0] + f.w[1]);
+	}
+	return f;
 }
-RSB_HD float project_origin4(const V3& a, const V3& b, const V3& c, const V3& d, float* w, unsigned& m) {
-	const unsigned imd3[3] = {1, 2, 0};
-	const V3 vt[4] = {a, b, c, d};
-	const V3 dl[3] = {a - d, b - d, c - d};
-	const float vl = det3(dl[0], dl[1], dl[2]);
-	const bool ng = (vl * dot(a, cross(b - c, a - b))) <= 0.f;
-	if (ng && (fabsf(vl) > 0.f)) {
-		float mindist = -1.f;
-		float subw[3] = {0.f, 0.f, 0.f};
-		unsigned subm = 0;
-		for (unsigned i = 0; i < 3; ++i) {
-			const unsigned j = imd3[i];
-			const float s = vl * dot(d, cross(dl[i], dl[j]));
-			if (s > 0.f) {
-				const float subd = project_origin3(vt[i], vt[j], d, subw, subm);
-				if ((mindist < 0.f) || (subd < mindist)) {
-					mindist = subd;
-					m = ((subm & 1) ? 1u << i : 0u) + ((subm & 2) ? 1u << j : 0u) + ((subm & 4) ? 8u : 0u);
-					w[i] = subw[0]; w[j] = subw[1]; w[imd3[j]] = 0.f; w[3] = subw[2];
-				}
-			}
+RSB_HD OriginFit fit_tetra(const V3& a, const V3& b, const V3& c, const V3& d) {
+	OriginFit f; f.d2 = -1.f; f.w[0] = f.w[1] = f.w[2] = f.w[3] = 0.f; f.mask = 0;
+	const V3 vt[3] = {a, b, c};
+	const V3 apex[3] = {a - d, b - d, c - d};
+	const float vol = triple3(apex[0], apex[1], apex[2]);
+	const bool wellOriented = (vol * dot(a, cross(b - c, a - b))) <= 0.f;
+	if (!(wellOriented && fabsf(vol) > 0.f)) return f;
+	for (unsigned i = 0; i < 3; ++i) {
+		const unsigned j = (i + 1) % 3, k = (j + 1) % 3;
+		if (!(vol * dot(d, cross(apex[i], apex[j])) > 0.f)) continue;   // the origin is not outside face (i, j, d)
+		const OriginFit t = fit_triangle(vt[i], vt[j], d);
+		if (f.d2 < 0.f || t.d2 < f.d2) {
+			f.d2 = t.d2;
+			f.mask = ((t.mask & 1) ? 1u << i : 0u) + ((t.mask & 2) ? 1u << j : 0u) + ((t.mask & 4) ? 8u : 0u);
+			f.w[i] = t.w[0]; f.w[j] = t.w[1]; f.w[k] = 0.f; f.w[3] = t.w[2];
 		}
-		if (mindist < 0.f) {
-			mindist = 0.f; m = 15;
-			w[0] = det3(c, b, d) / vl;
-			w[1] = det3(a, c, d) / vl;
-			w[2] = det3(b, a, d) / vl;
-			w[3] = 1 - (w[0] + w[1] + w[2]);
-		}
-		return mindist;
 	}
-	return -1.f;
+	if (f.d2 < 0.f) {  // the origin is inside the tetrahedron
+		f.d2 = 0.f; f.mask = 15;
+		f.w[0] = triple3(c, b, d) / vol;
+		f.w[1] = triple3(a, c, d) / vol;
+		f.w[2] = triple3(b, a, d) / vol;
+		f.w[3] = 1 - (f.w[0] + f.w[1] + f.w[2]);
+	}
+	return f;
 }
 
 enum Gjk2Status { G2_VALID = 0, G2_INSIDE = 1, G2_FAILED = 2 };
@@ -178,13 +172,15 @@ RSB_HD_NOINLINE int gjk2_evaluate(Gjk2& g, V3 guess) {
 		const float omega = dot(g.ray, w) / rl;
 		alpha = omega > alpha ? omega : alpha;
 		if (((rl - alpha) - (GJK2_ACCURACY * rl)) <= 0.f) { cs.rank--; break; }
-		float weights[4];
-		unsigned mask = 0;
+		OriginFit fit; fit.d2 = sqdist; fit.mask = 0; fit.w[0] = fit.w[1] = fit.w[2] = fit.w[3] = 0.f;
 		switch (cs.rank) {
-		case 2: sqdist = project_origin2(cs.c[0].w, cs.c[1].w, weights, mask); break;
-		case 3: sqdist = project_origin3(cs.c[0].w, cs.c[1].w, cs.c[2].w, weights, mask); break;
-		case 4: sqdist = project_origin4(cs.c[0].w, cs.c[1].w, cs.c[2].w, cs.c[3].w, weights, mask); break;
+		case 2: fit = fit_segment(cs.c[0].w, cs.c[1].w); break;
+		case 3: fit = fit_triangle(cs.c[0].w, cs.c[1].w, cs.c[2].w); break;
+		case 4: fit = fit_tetra(cs.c[0].w, cs.c[1].w, cs.c[2].w, cs.c[3].w); break;
 		}
+		sqdist = fit.d2;
+		const float* weights = fit.w;
+		const unsigned mask = fit.mask;
 		if (sqdist >= 0.f) {
 			ns.rank = 0;
 			g.ray = v3zero();
@@ -217,7 +213,7 @@ RSB_HD_NOINLINE bool gjk2_enclose_origin(Gjk2& g) {
 	for (int guard = 0; guard < 4096; guard++) {
 		const int r = s.rank;
 		if (r == 4) {
-			if (fabsf(det3(s.c[0].w - s.c[3].w, s.c[1].w - s.c[3].w, s.c[2].w - s.c[3].w)) > 0.f) return true;
+			if (fabsf(triple3(s.c[0].w - s.c[3].w, s.c[1].w - s.c[3].w, s.c[2].w - s.c[3].w)) > 0.f) return true;
 			if (r == base) return false;
 			s.rank--;
 			continue;
@@ -395,7 +391,7 @@ RSB_HD_NOINLINE int epa_evaluate(Epa& e, Gjk2& gjk, V3 guess) {
 	if ((simplex.rank > 1) && gjk2_enclose_origin(gjk)) {
 		e.status = EPA_VALID;
 		e.nextsv = 0;
-		if (det3(simplex.c[0].w - simplex.c[3].w, simplex.c[1].w - simplex.c[3].w, simplex.c[2].w - simplex.c[3].w) < 0.f) {
+		if (triple3(simplex.c[0].w - simplex.c[3].w, simplex.c[1].w - simplex.c[3].w, simplex.c[2].w - simplex.c[3].w) < 0.f) {
 			SV t = simplex.c[0]; simplex.c[0] = simplex.c[1]; simplex.c[1] = t;
 			float tp = simplex.p[0]; simplex.p[0] = simplex.p[1]; simplex.p[1] = tp;
 		}

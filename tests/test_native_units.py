@@ -79,3 +79,16 @@ def test_libm_restatements_match_host_libm():
     assert m, out
     na, ba, n2, b2 = map(int, m.groups())
     assert na > 60_000_000 and n2 > 60_000_000 and (ba, b2) == (0, 0), out  # fdlibm atanf / atan2f restatement (rs_atanf, rs_atan2f)
+
+
+def test_box_box_detector_matches_bullet(oracle):
+    """box_box_detect (rsb_boxbox.h, our own organisation of the 15-axis SAT + face clipping) vs btBoxBoxDetector on 200k random
+    near-contact box pairs (flat-on-the-ground, nearly aligned and arbitrary orientations): identical contact count, order, normal,
+    points and depths, bit for bit."""
+    exe = build("boxbox_check")
+    out = subprocess.run([exe, "200000"], capture_output=True, text=True).stdout
+    m = re.search(r"cases (\d+) with_contact (\d+) single (\d+) multi (\d+) four (\d+) mismatches (\d+)", out)
+    assert m, out
+    n, hits, single, multi, four, bad = map(int, m.groups())
+    assert hits > 20000 and single > 2000 and multi > 10000 and four > 5000, out  # edge-edge, clipped-face and culled-to-4 cases all occur
+    assert bad == 0, out
