@@ -108,41 +108,59 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(self.sm)}
 
 
-def run_reference(args):
-    """The reference's own CPU implementation (oracle/_ref) on the host cores, same workload/metric."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
+def workload_config(args, world):
+    """`config` of the JSON line: identical for both arms (the driver compares them)."""
+    n_cars = 2 * args.cars_per_team
+    return {"workload": f"{MODE_NAMES[args.mode]} {args.cars_per_team}v{args.cars_per_team}, README bench inputs (redrawn every 2-60 ticks/car), "
+                        f"{args.arenas} arenas/GPU, kickoff reset on goal", "arenas_per_gpu": args.arenas, "ticks_per_step": args.ticks_per_step,
+            "n_cars": n_cars, "meshes": "synthetic .cmf (SURVEY F4)", "l2": "256 MiB flush write between timed steps",
+            "parallelism": f"replicas x{world} (independent arena shards, no collective)"}
+
+
+def cpu_reference_sample(args, steps, warmup):
+    """The reference's CPU Arena::Step on all host cores, one arena per thread (README style, its fastest configuration): a short
+    untimed warm-up, then a bounded sample of 512 x ticks_per_step ticks per step.  Used by BOTH the reference arm and the CUDA
+    arm's cpu_baseline leg, so the two numbers of one box agree."""
     from oracle import refsim
     from rocketsim_b200 import synthetic_meshes as sm
     if not refsim.available():
         refsim.build()
     refsim.init_from_mem(sm.mesh_sets())
-    cores = os.cpu_count() or 1
-    threads = cores
-    # README style (README.md:10-11): one arena per thread is the reference's fastest configuration (more arenas per
-    # thread only add cache pressure: measured 375k -> 28k arena-ticks/s from 1 to 64 arenas/thread on 8 cores).
-    # Bounded sample: a reference "step" = 512 x ticks_per_step ticks of `threads` arenas (about half a second of CPU work
-    # per step at the default 120 ticks); construction is untimed.
+    threads = os.cpu_count() or 1
     apt = 1
     ticks = 512 * args.ticks_per_step
-    if args.warmup > 0:
-        refsim.bench(args.mode, args.cars_per_team, threads, apt, max(1, ticks * args.warmup // 8), SEED)
-    v, wall = refsim.bench(args.mode, args.cars_per_team, threads, apt, ticks * max(1, args.steps), SEED)
-    value = v
+    if warmup > 0:
+        refsim.bench(args.mode, args.cars_per_team, threads, apt, max(1, ticks * warmup // 8), SEED)
+    v, wall = refsim.bench(args.mode, args.cars_per_team, threads, apt, ticks * max(1, steps), SEED)
+    sample = f"{threads} threads x {apt} arena x {ticks * max(1, steps)} ticks ({wall:.1f} s), oracle/_ref"
+    return v, wall, threads, sample
+
+
+def run_reference(args):
+    """The reference's own CPU implementation (oracle/_ref) on the host cores, same workload/metric."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    # README style (README.md:10-11): one arena per thread is the reference's fastest configuration (more arenas per
+    # thread only add cache pressure: measured 375k -> 28k arena-ticks/s from 1 to 64 arenas/thread on 8 cores).
+    value, wall, threads, sample = cpu_reference_sample(args, args.steps, args.warmup)
     n_cars = 2 * args.cars_per_team
-    sample = f"{threads} threads x {apt} arena x {ticks * max(1, args.steps)} ticks ({wall:.1f} s), oracle/_ref"
     line = {
         "impl": "reference", "metric": "arena_ticks_per_s", "value": value, "unit": "arena-ticks/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": wall * 1e3 / max(1, args.steps), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{MODE_NAMES[args.mode]} {args.cars_per_team}v{args.cars_per_team}, README bench inputs, "
-                               f"{args.arenas} arenas/GPU on the CUDA arm; CPU arm: bounded sample", "ticks_per_step": args.ticks_per_step,
-                   "n_cars": n_cars, "meshes": "synthetic .cmf (SURVEY F4)"},
+        "config": workload_config(args, args.gpus),
         "cpu_baseline": {"value": value, "unit": "arena-ticks/s", "cores": threads, "kind": "reference", "sample": sample},
         "e2e": {"value": value, "unit": "arena-ticks/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    # BASELINE.md §3.3: the many-arenas-per-thread variant next to the README-style one (reported, never the headline)
+    try:
+        from oracle import refsim
+        v64, w64 = refsim.bench(args.mode, args.cars_per_team, threads, 64, max(200, int(2.0 * value / (threads * 64))), SEED)
+        line["cpu_baseline_64_arenas_per_thread"] = {"value": v64, "unit": "arena-ticks/s", "cores": threads, "wall_s": w64}
+    except Exception as e:
+        line["cpu_baseline_64_arenas_per_thread"] = {"value": None, "error": str(e)}
     print(json.dumps(line), flush=True)
 
 
@@ -257,10 +275,28 @@ def run_cuda(args):
     e2e_ms = max(e0.elapsed_time(e1), (t_host1 - t_host0) * 1e3)  # the slower of the device clock and the host wall clock
     checksum = float(np.abs(car_out["pos"]["x"]).sum())
 
-    t = torch.tensor([total_ms, e2e_ms, float(np.mean(kern_ms))], dtype=torch.float64, device="cuda")
+    # ---- long window: the e2e batch simply keeps playing, device resident, for --long-window-ticks more ticks
+    long_ms = None
+    if args.long_window_ticks > 0:
+        nst = max(1, args.long_window_ticks // TPS)
+        args.long_window_ticks = nst * TPS
+        barrier()
+        l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0.record(stream)
+        for k in range(nst):
+            buf = d_seq[k & 1]
+            rlib.check(L, L.rsb_bench_fill_controls_device(batch.h, C.c_void_p(buf.data_ptr()), TPS, (n_steps_total + k) * TPS, SEED + rank))
+            rlib.check(L, L.rsb_step_with_controls_device(batch.h, C.c_void_p(buf.data_ptr()), TPS))
+        l1.record(stream)
+        barrier()
+        long_ms = l0.elapsed_time(l1)
+        err = np.maximum(err, batch.get_error_flags())
+
+    t = torch.tensor([total_ms, e2e_ms, float(np.mean(kern_ms)), long_ms if long_ms is not None else 0.0], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, e2e_ms, kern_ms_mean = [float(x) for x in t.cpu()]
+    total_ms, e2e_ms, kern_ms_mean, long_max = [float(x) for x in t.cpu()]
+    long_ms = long_max if long_ms is not None else None
     errs = torch.tensor([int(err.max())], device="cuda")
     if world > 1:
         dist.all_reduce(errs, op=dist.ReduceOp.MAX)
@@ -277,10 +313,7 @@ def run_cuda(args):
             "metric": "arena_ticks_per_s", "value": value, "unit": "arena-ticks/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{MODE_NAMES[args.mode]} {args.cars_per_team}v{args.cars_per_team}, README bench inputs (redrawn every 2-60 ticks/car), "
-                                   f"{A} arenas/GPU, kickoff reset on goal", "arenas_per_gpu": A, "ticks_per_step": TPS,
-                       "n_cars": n_cars, "meshes": "synthetic .cmf (SURVEY F4)", "l2": "256 MiB flush write between timed steps",
-                       "parallelism": f"replicas x{world} (independent arena shards, no collective)"},
+            "config": workload_config(args, world),
             "e2e": {"value": e2e, "unit": "arena-ticks/s", "h2d_bytes_per_step": ctrl_bytes, "d2h_bytes_per_step": d2h_bytes,
                     "ms_per_step": e2e_ms / args.steps, "launches_per_step": 3 + 2,
                     "path": "rsb_step_with_controls (host control sequence, pinned) + rsb_get_car_states + rsb_get_ball_states (pinned)"},
@@ -292,21 +325,14 @@ def run_cuda(args):
             "clocks": sampler.result(),
             "device_error_flags": int(errs.item()), "checksum": checksum,
         }
+        if long_ms is not None:
+            line["long_window"] = {"ticks": args.long_window_ticks, "value": world * A * args.long_window_ticks / (long_ms * 1e-3), "unit": "arena-ticks/s",
+                                   "note": "device-resident arm continued for a long window (games fully developed); control sequences "
+                                           "generated on the device per step inside the timed region"}
         if world == 1 and not args.no_cpu_baseline:
             try:
-                from oracle import refsim
-                if refsim.available() or os.path.isdir(refsim.REFERENCE_ROOT):
-                    refsim.init_from_mem(sm.mesh_sets())
-                    cores = os.cpu_count() or 1
-                    apt = 1  # README style: the reference's fastest configuration
-                    v, wall = refsim.bench(args.mode, args.cars_per_team, cores, apt, 2000, SEED)  # calibrate
-                    ticks = int(max(2000, min(5_000_000, 12.0 * v / (cores * apt))))
-                    v, wall = refsim.bench(args.mode, args.cars_per_team, cores, apt, ticks, SEED)
-                    line["cpu_baseline"] = {"value": v, "unit": "arena-ticks/s", "cores": cores, "kind": "reference",
-                                            "sample": f"{cores} threads x {apt} arena x {ticks} ticks ({wall:.1f} s), oracle/_ref"}
-                else:
-                    line["cpu_baseline"] = {"value": None, "unit": "arena-ticks/s", "cores": 0, "kind": "reference",
-                                            "sample": "oracle/_ref not built"}
+                v, wall, cores, sample = cpu_reference_sample(args, 5, 1)
+                line["cpu_baseline"] = {"value": v, "unit": "arena-ticks/s", "cores": cores, "kind": "reference", "sample": sample}
             except Exception as e:  # the checker must never break the measurement
                 line["cpu_baseline"] = {"value": None, "unit": "arena-ticks/s", "cores": 0, "kind": "reference", "sample": f"failed: {e}"}
         print(json.dumps(line), flush=True)
@@ -326,6 +352,7 @@ def main():
     ap.add_argument("--arenas", type=int, default=4096, help="arenas per GPU")
     ap.add_argument("--ticks-per-step", type=int, default=120)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--long-window-ticks", type=int, default=36000, help="extra device-resident window after the timed steps (0 = off)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "cuda" else args.warmup
     if args.impl == "reference":

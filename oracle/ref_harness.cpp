@@ -397,6 +397,29 @@ void ref_get_solver_bodies(RefArena* r, int n, float* out) {
 	}
 }
 
+/* Steps an EXISTING arena `ticks` ticks with the pinned README-bench input stream of global arena id `gid` (include/rsb_bench_inputs.h),
+ * starting at stream tick `tick0`, entirely in C (no per-tick FFI); no kickoff reset.  Returns the stepping wall time in seconds.
+ * Used for BASELINE config 1 (THE_VOID 1v1, 1 M ticks): the CPU number and the state the GPU rollout is compared with. */
+double ref_run_bench_inputs(RefArena* r, int ticks, uint64_t seed, int gid, int tick0) {
+	const int ncars = (int)r->cars.size();
+	std::vector<RsbInputSched> ss(ncars);
+	for (auto& s : ss) rsb_inp_init(&s);
+	// replay the schedule up to tick0 so that a rollout can be continued in several calls
+	for (int k = 0; k < tick0; k++) for (int i = 0; i < ncars; i++) rsb_inp_update(&ss[i], seed, gid, i, k);
+	auto t0 = std::chrono::steady_clock::now();
+	for (int k = tick0; k < tick0 + ticks; k++) {
+		for (int i = 0; i < ncars; i++) {
+			RsbInputSched& s = ss[i];
+			rsb_inp_update(&s, seed, gid, i, k);
+			CarControls& c = r->cars[i]->controls;
+			c.throttle = s.throttle; c.steer = s.steer; c.pitch = s.pitch; c.yaw = s.yaw; c.roll = s.roll;
+			c.jump = s.jump; c.boost = s.boost; c.handbrake = s.handbrake;
+		}
+		r->arena->Step(1);
+	}
+	return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+
 double ref_bench(int mode, int cars_per_team, int n_threads, int arenas_per_thread, int ticks, uint64_t seed, double* wall_s) {
 	std::atomic<int> ready(0);
 	std::atomic<bool> go(false);

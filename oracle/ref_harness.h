@@ -92,6 +92,7 @@ void ref_get_solver_bodies(RefArena*, int n, float* out); /* 12 floats each: lin
 
 /* ---- CPU throughput harness: T threads x A arenas, README input schedule ---- */
 /* returns arena-ticks/s; writes wall seconds to *wall_s.  mesh data must be initialised first. */
+double ref_run_bench_inputs(RefArena*, int ticks, uint64_t seed, int gid, int tick0);  /* Arena::Step x ticks with the pinned bench input stream, in C */
 double ref_bench(int game_mode, int cars_per_team, int n_threads, int arenas_per_thread,
                  int ticks, uint64_t seed, double* wall_s);
 

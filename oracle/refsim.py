@@ -50,6 +50,7 @@ def lib():
         L.ref_arena_create_cfg.argtypes = [i32, f32, i32, i32, vp]; L.ref_arena_create_cfg.restype = vp
         L.ref_arena_destroy.argtypes = [vp]
         L.ref_add_car.argtypes = [vp, i32, i32]; L.ref_add_car.restype = u32
+        L.ref_run_bench_inputs.argtypes = [vp, i32, C.c_uint64, i32, i32]; L.ref_run_bench_inputs.restype = C.c_double
         L.ref_num_cars.argtypes = [vp]; L.ref_num_pads.argtypes = [vp]
         L.ref_seed_thread_rng.argtypes = [u32]
         L.ref_reset_kickoff.argtypes = [vp, i32]
@@ -174,6 +175,10 @@ class RefArena:
 
     def step(self, n: int = 1):
         self.L.ref_step(self.h, n)
+
+    def run_bench_inputs(self, ticks: int, seed: int, gid: int, tick0: int = 0) -> float:
+        """`ticks` x Arena::Step with the pinned README-bench input stream of global arena `gid`, in C; returns the wall seconds"""
+        return float(self.L.ref_run_bench_inputs(self.h, ticks, seed, gid, tick0))
 
     @property
     def tick_count(self):

@@ -124,6 +124,7 @@ struct RsbBatch {
 	ArenaW* dW = nullptr;
 	ArenaH* dH = nullptr;          // global mirror of the hot per-tick scratch
 	EpaScratch* dE = nullptr;      // EPA working sets, one per thread of the step grid
+	int* dChunkNext = nullptr;     // work counter of a multi-wave launch (chunks beyond the resident grid are fetched dynamically)
 	RsbBallState* traceOut = nullptr;  // consumed by the next launch (rsb_predict_ball)
 	RsbBatch* pred = nullptr;      // ball-only sibling batch used by rsb_predict_ball (created on first use)
 	RsbArenaConfig acfg;           // the ArenaConfig the batch was created with (customBoostPads points into acfgPads)
@@ -261,7 +262,7 @@ static thread_local int g_hostIdx = 0;
 // (one instruction-cache working set), suspension rays / car logic / body integration use one
 // thread per wheel / car / body, and HBM sees each arena record once per launch in and once out.
 #ifndef RSB_STEP_THREADS
-#define RSB_STEP_THREADS 256
+#define RSB_STEP_THREADS 448  // 14 warps, 144 registers: the 448 wheel rays of 28 resident 2v2 arenas take one round (A/B on B200: +6..9 % over 256 threads, 512 threads / 128 registers lose it again to spills)
 #endif
 constexpr int STEP_THREADS = RSB_STEP_THREADS;
 // resident blocks per SM: each block keeps its own chunk of arenas; blocks drift through the tick phases independently
@@ -272,7 +273,21 @@ constexpr int BLOCKS_PER_SM = RSB_BLOCKS_PER_SM;
 static_assert(offsetof(ArenaS, cars) % 8 == 0 && sizeof(CarS) % 8 == 0 && sizeof(BodyW) % 8 == 0 && sizeof(WheelW) % 8 == 0 && sizeof(Manifold) % 8 == 0, "records are staged in 8-byte words");
 constexpr size_t SMEM_P_BYTES = (sizeof(BatchParams) + 15) & ~(size_t)15;
 constexpr size_t SMEM_SC_BYTES = (sizeof(Scene) + 15) & ~(size_t)15;
-constexpr size_t SMEM_Q_BYTES = 16 + 512 * 2;  // detector queue of the block: counter + entries (DETECT_QUEUE_CAP)
+// Scheduling of the tick phases inside a block (see arena_step_kernel):
+//   0 (default)  block-synchronous: all warps run one phase at a time, items dealt over the whole block, __syncthreads() in
+//                between.  Every warp of the SM is in the same few KB of code at the same time.
+//   1            warp-autonomous (developer A/B, -DRSB_WARP_SCHED=1): every warp owns a fixed subset of the block's arenas and
+//                runs the whole tick for them on its own, phases separated by __syncwarp() only, so that no warp waits for the
+//                slowest arena of the block.  MEASURED ON B200: 4.7x SLOWER (4.4 M vs 20.8 M arena-ticks/s, bit-identical
+//                results) -- 14 warps in 14 different places of a 1.2 MB kernel thrash the 32 KB instruction cache.  The tick
+//                is instruction-fetch bound as soon as the warps of an SM stop sharing their instruction stream; this is what
+//                keeps the block-synchronous design (and its barrier stalls) in place.
+#ifndef RSB_WARP_SCHED
+#define RSB_WARP_SCHED 0
+#endif
+constexpr int WARP_QUEUE_CAP = 96;  // detector queue entries per warp (warp-autonomous scheduling)
+constexpr size_t SMEM_Q_BYTES = RSB_WARP_SCHED ? (size_t)(RSB_STEP_THREADS / 32) * (16 + WARP_QUEUE_CAP * 2)
+                                               : (size_t)(16 + 512 * 2);  // detector queue(s): counter + entries
 constexpr size_t SMEM_MAX = (228 * 1024) / BLOCKS_PER_SM - 1024;  // 228 KB per SM, 1 KB reserved per resident block
 
 // Shared-memory layout of one resident arena: [ArenaS prefix (header, ball, pads, nCars cars) | BodyW x nb |
@@ -301,6 +316,7 @@ struct ArenaLayout {
 struct StepArgs {
 	ArenaS* S; ArenaH* H; ArenaW* W; EpaScratch* E; const BatchParams* P; const Scene* sc; EventSink ev;
 	int nArenas, nTicks; const CtrlS* ctrlSeq; int nCtrl; int apb;
+	int* chunkNext;  // device counter (starts at 0): a block that has finished its chunk fetches chunk gridDim.x + counter++
 	int mirror;  // keep the full debug mirror (ArenaH) up to date: single-tick launches only
 	RsbBallState* ballTrace;  // optional [nTicks + 1][nArenas]: Ball::GetState() after every tick (row t + 1), see rsb_predict_ball
 	ArenaLayout lay;
@@ -330,7 +346,11 @@ constexpr int DETECT_QUEUE_CAP = 512;
 __device__ __forceinline__ Ctx make_ctx(const StepArgs& a, const BatchParams* sP, const Scene* sSc, unsigned char* sS, int a0, int ar) {
 	extern __shared__ __align__(16) unsigned char smem[];
 	Ctx cx;
+#if RSB_WARP_SCHED
+	cx.nq = (unsigned*)(smem + SMEM_P_BYTES + SMEM_SC_BYTES + (size_t)(threadIdx.x >> 5) * (16 + WARP_QUEUE_CAP * 2)); cx.q = (uint16_t*)(cx.nq + 4); cx.qcap = WARP_QUEUE_CAP; cx.arLocal = ar;
+#else
 	cx.nq = (unsigned*)(smem + SMEM_P_BYTES + SMEM_SC_BYTES); cx.q = (uint16_t*)(cx.nq + 4); cx.qcap = DETECT_QUEUE_CAP; cx.arLocal = ar;
+#endif
 	unsigned char* base = sS + (size_t)ar * a.lay.stride;
 	cx.s = (ArenaS*)base; cx.g = a.S + (a0 + ar); cx.body = (BodyW*)(base + a.lay.bodyOff); cx.wheels = (WheelW*)(base + a.lay.wheelOff);
 	cx.padLocked = (int*)(base + a.lay.padOff); cx.misc = (int*)(base + a.lay.miscOff);
@@ -464,6 +484,51 @@ __device__ __forceinline__ void run_phase_block(const StepArgs& a, const BatchPa
 }
 
 
+#if RSB_WARP_SCHED
+// One phase of the tick for the arenas owned by the calling warp (block-local indices warp, warp + NW, ...): its items go to the
+// warp's lanes in rounds of 32, and the warp alone synchronises.  Items of a phase only touch their own arena, so nothing here
+// depends on what the other warps of the block are doing.
+template <int PH>
+__device__ __forceinline__ void run_phase_warp(const StepArgs& a, const BatchParams* sP, const Scene* sSc, unsigned char* sS, int a0, int nA, int warp, int lane) {
+	constexpr int NW = STEP_THREADS / 32;
+	const int nMine = warp < nA ? (nA - warp + NW - 1) / NW : 0;
+	if (PH == PH_NARROW_DETECT) {
+		extern __shared__ __align__(16) unsigned char smem[];
+		const unsigned* nqp = (const unsigned*)(smem + SMEM_P_BYTES + SMEM_SC_BYTES + (size_t)warp * (16 + WARP_QUEUE_CAP * 2));
+		const uint16_t* q = (const uint16_t*)(nqp + 4);
+		const int nq = min((int)*nqp, WARP_QUEUE_CAP);
+		for (int i = lane; i < nq; i += 32) {
+			const int e = q[i];
+			const Ctx cx = make_ctx(a, sP, sSc, sS, a0, e >> 7);
+			phase_run(cx, PH, e & 127);
+		}
+	} else {
+		const int per = phase_items(*sP, PH), n = per * nMine;
+		for (int i = lane; i < n; i += 32) {
+			int k, item;
+			if (PH == PH_WHEELS) { k = i / per; item = i - k * per; }  // the wheels of a car sit in neighbouring lanes
+			else { item = i / nMine; k = i - item * nMine; }           // same item kind in neighbouring lanes
+			const Ctx cx = make_ctx(a, sP, sSc, sS, a0, warp + k * NW);
+			phase_run(cx, PH, item);
+		}
+	}
+	__syncwarp();
+	if (a.mirror && (PH == PH_CAR_LOGIC || PH == PH_DYN_SOLVE)) {
+		// single-tick launches keep the debug mirror complete: the wheel scratch and the solver scratch alias each other
+		const int words = (PH == PH_CAR_LOGIC ? a.lay.wheelBytes : a.lay.solvBytes) / 4;
+		for (int k = 0; k < nMine; k++) {
+			const int ar = warp + k * NW;
+			ArenaH* dst = a.H + a0 + ar;
+			for (int w = lane; w < words; w += 32) {
+				const uint32_t v = ((const uint32_t*)(sS + (size_t)ar * a.lay.stride + a.lay.wheelOff))[w];
+				if (PH == PH_CAR_LOGIC) ((uint32_t*)dst->wheels)[w] = v; else ((uint32_t*)dst->solv)[w] = v;
+			}
+		}
+		__syncwarp();
+	}
+}
+#endif
+
 __global__ void __launch_bounds__(STEP_THREADS, BLOCKS_PER_SM) arena_step_kernel(const StepArgs a) {
 	extern __shared__ __align__(16) unsigned char smem[];
 	BatchParams* sP = (BatchParams*)smem;
@@ -481,7 +546,10 @@ __global__ void __launch_bounds__(STEP_THREADS, BLOCKS_PER_SM) arena_step_kernel
 	const int nCars = a.P->nCars, nPads = a.P->nPads, nb = nCars + 1;
 	const int sWords = a.lay.sBytes / 8, strideWords = a.lay.stride / 8;
 	const int nChunks = (a.nArenas + a.apb - 1) / a.apb;
-	for (int chunk = blockIdx.x; chunk < nChunks; chunk += gridDim.x) {
+	// A block starts with chunk blockIdx.x; when the batch has more chunks than resident blocks the remaining ones are handed out
+	// first come, first served: chunks differ in cost (contact-heavy games), a fixed round-robin would wait for the unluckiest block.
+	__shared__ int s_nextChunk;
+	for (int chunk = blockIdx.x; chunk < nChunks;) {
 		const int a0 = chunk * a.apb;
 		const int nA = min(a.apb, a.nArenas - a0);
 		__syncthreads();
@@ -493,6 +561,44 @@ __global__ void __launch_bounds__(STEP_THREADS, BLOCKS_PER_SM) arena_step_kernel
 			((uint2*)(sS + (size_t)ar * a.lay.stride))[w] = v;
 		}
 		__syncthreads();
+#if RSB_WARP_SCHED
+		{
+			constexpr int NW = STEP_THREADS / 32;
+			const int warp = tid >> 5, lane = tid & 31;
+			const int nMine = warp < nA ? (nA - warp + NW - 1) / NW : 0;
+			unsigned* myq = (unsigned*)(smem + SMEM_P_BYTES + SMEM_SC_BYTES + (size_t)warp * (16 + WARP_QUEUE_CAP * 2));
+			for (int t = 0; t < a.nTicks; t++) {
+				if (a.ctrlSeq) {
+					const int ct = t < a.nCtrl ? t : a.nCtrl - 1;
+					for (int i = lane; i < nMine * nCars; i += 32) {
+						const int k = i / nCars, ci = i - k * nCars, ar = warp + k * NW;
+						((ArenaS*)(sS + (size_t)ar * a.lay.stride))->cars[ci].controls = a.ctrlSeq[((size_t)ct * a.nArenas + a0 + ar) * nCars + ci];
+					}
+				}
+				if (lane == 0) *myq = 0u;  // this warp's detector queue
+				__syncwarp();
+				run_phase_warp<PH_INIT>(a, sP, sSc, sS, a0, nA, warp, lane);
+				run_phase_warp<PH_PRE_BEGIN>(a, sP, sSc, sS, a0, nA, warp, lane);
+				run_phase_warp<PH_WHEELS>(a, sP, sSc, sS, a0, nA, warp, lane);
+				run_phase_warp<PH_CAR_LOGIC>(a, sP, sSc, sS, a0, nA, warp, lane);
+				run_phase_warp<PH_PREDICT>(a, sP, sSc, sS, a0, nA, warp, lane);
+				run_phase_warp<PH_PAIRS>(a, sP, sSc, sS, a0, nA, warp, lane);
+				run_phase_warp<PH_NARROW_STATIC>(a, sP, sSc, sS, a0, nA, warp, lane);
+				run_phase_warp<PH_NARROW_DETECT>(a, sP, sSc, sS, a0, nA, warp, lane);
+				run_phase_warp<PH_NARROW_COMMIT>(a, sP, sSc, sS, a0, nA, warp, lane);
+				run_phase_warp<PH_DYN_SOLVE>(a, sP, sSc, sS, a0, nA, warp, lane);
+				run_phase_warp<PH_FINISH_BODY>(a, sP, sSc, sS, a0, nA, warp, lane);
+				run_phase_warp<PH_CAR_POST>(a, sP, sSc, sS, a0, nA, warp, lane);
+				run_phase_warp<PH_PADS_POST>(a, sP, sSc, sS, a0, nA, warp, lane);
+				run_phase_warp<PH_TAIL>(a, sP, sSc, sS, a0, nA, warp, lane);
+				if (a.ballTrace && lane < nMine) {
+					const int ar = warp + lane * NW;
+					ball_to_api(((const ArenaS*)(sS + (size_t)ar * a.lay.stride))->ball, a.ballTrace[(size_t)(t + 1) * a.nArenas + a0 + ar]);
+				}
+			}
+			__syncthreads();
+		}
+#else
 		for (int t = 0; t < a.nTicks; t++) {
 			if (a.ctrlSeq) {
 				const int ct = t < a.nCtrl ? t : a.nCtrl - 1;
@@ -524,6 +630,7 @@ __global__ void __launch_bounds__(STEP_THREADS, BLOCKS_PER_SM) arena_step_kernel
 			if (a.ballTrace)  // the ball is next written in PH_CAR_LOGIC, several barriers from here
 				for (int i = tid; i < nA; i += STEP_THREADS) ball_to_api(((const ArenaS*)(sS + (size_t)i * a.lay.stride))->ball, a.ballTrace[(size_t)(t + 1) * a.nArenas + a0 + i]);
 		}
+#endif
 		// records back to HBM; the last tick's hot scratch goes to its global mirror (debug probes)
 		for (int i = tid; i < nA * sWords; i += STEP_THREADS) {
 			const int ar = i / sWords, w = i - ar * sWords;
@@ -547,6 +654,9 @@ __global__ void __launch_bounds__(STEP_THREADS, BLOCKS_PER_SM) arena_step_kernel
 				else if (off - a.lay.mfOff < MAX_MANIFOLDS * (int)sizeof(Manifold)) ((uint32_t*)dst->mf)[(off - a.lay.mfOff) / 4] = v;
 			}
 		}
+		if (tid == 0) s_nextChunk = (int)gridDim.x + atomicAdd(a.chunkNext, 1);
+		__syncthreads();
+		chunk = s_nextChunk;
 	}
 #if defined(RSB_PROFILE)
 	if (tid == 0 && blockIdx.x < 1024) g_blockCycles[blockIdx.x] = (unsigned long long)(clock64() - _kt0);
@@ -1043,6 +1153,7 @@ int rsb_batch_create_ex(int device, int game_mode, const RsbArenaConfig* arena_c
 	b->dE = (EpaScratch*)dev_alloc(sizeof(EpaScratch));
 #endif
 	b->eventCap = (uint32_t)std::max(4096, n_arenas * 4);
+	b->dChunkNext = (int*)dev_alloc(sizeof(int));
 	b->dEvents = (EventSink::Ev*)dev_alloc(sizeof(EventSink::Ev) * b->eventCap);
 	b->dEventCount = (uint32_t*)dev_alloc(sizeof(uint32_t));
 	b->dCtrl = (CtrlS*)dev_alloc(sizeof(CtrlS) * (size_t)n_arenas * std::max(1, n_cars));
@@ -1101,7 +1212,7 @@ int rsb_batch_destroy(RsbBatch* b) {
 	if (b->copyStream) { cudaStreamDestroy(b->copyStream); for (auto& e : b->chunkReady) cudaEventDestroy(e); cudaEventDestroy(b->seqFree); }
 #endif
 	if (b->pred) { rsb_batch_destroy(b->pred); b->pred = nullptr; }
-	dev_free(b->dP); dev_free(b->dS); dev_free(b->dW); dev_free(b->dH); dev_free(b->dE); dev_free(b->dEvents); dev_free(b->dEventCount); dev_free(b->dCtrl); dev_free(b->dCtrlSeq); dev_free(b->dScratch);
+	dev_free(b->dP); dev_free(b->dS); dev_free(b->dW); dev_free(b->dH); dev_free(b->dE); dev_free(b->dChunkNext); dev_free(b->dEvents); dev_free(b->dEventCount); dev_free(b->dCtrl); dev_free(b->dCtrlSeq); dev_free(b->dScratch);
 	delete b;
 	API_END
 }
@@ -1142,6 +1253,8 @@ static void launch_step(RsbBatch* b, int n_ticks, const CtrlS* seq, int nCtrl) {
 	const int nChunks = (P.nArenas + a.apb - 1) / a.apb;
 	const int grid = nChunks < sms ? nChunks : sms;
 	const size_t smem = SMEM_P_BYTES + SMEM_SC_BYTES + SMEM_Q_BYTES + (size_t)a.apb * a.lay.stride;
+	a.chunkNext = b->dChunkNext;
+	CUDA_OK(cudaMemsetAsync(b->dChunkNext, 0, sizeof(int), b->stream));
 	arena_step_kernel<<<grid, STEP_THREADS, smem, b->stream>>>(a);
 	CUDA_OK(cudaGetLastError());
 #else

@@ -212,7 +212,10 @@ RSB_HD bool fuzzy_zero(const V3& a) { return len2(a) < kEps * kEps; }
 // The estimate is a pure function of (exponent parity, top 10 mantissa bits) on Intel CPUs; kRsqrtTab holds it (generated and
 // verified against the instruction by scripts/gen_rsqrt_table.c), so the normalised vectors match the reference bit for bit.
 #if defined(__CUDACC__)
-static __device__ const uint16_t kRsqrtTabDev[2048] = {
+#ifndef RSB_RSQRT_TAB_SPACE
+#define RSB_RSQRT_TAB_SPACE __device__  // developer A/B: __constant__
+#endif
+static RSB_RSQRT_TAB_SPACE const uint16_t kRsqrtTabDev[2048] = {
 #include "rsb_rsqrt_tab.inc"
 };
 #endif
@@ -248,6 +251,9 @@ RSB_HD float rsqrtss_estimate(float x) {
 }
 RSB_HD V3 normalized(const V3& a) {
 	float vd = len2(a);
+#if defined(RSB_EXP_PLAIN_NORMALIZE)  // developer A/B only (breaks bit-exactness): cost of the table lookup
+	{ const float r = 1.0f / sqrtf(vd); return V3(a.x * r, a.y * r, a.z * r); }
+#endif
 	const float y0 = rsqrtss_estimate(vd);
 	vd = vd * 0.5f;
 	vd = vd * y0;

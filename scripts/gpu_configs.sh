@@ -5,14 +5,16 @@ TAG=${1:-cfg}; OUT=gpurun_out/${TAG}_configs.jsonl; : > $OUT
 run() {  # name mode cars_per_team arenas
   echo "== $1"
   timeout 300 python bench.py --impl reference --mode $2 --cars-per-team $3 --arenas $4 --steps 3 --warmup 1 2>&1 | tail -1 | sed "s/^{/{\"case\": \"$1\", /" >> $OUT
-  timeout 600 python bench.py --mode $2 --cars-per-team $3 --arenas $4 --steps 5 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 | sed "s/^{/{\"case\": \"$1\", /" >> $OUT
+  timeout 600 python bench.py --mode $2 --cars-per-team $3 --arenas $4 --steps 5 --warmup 3 --no-cpu-baseline --long-window-ticks 0 2>&1 | tail -1 | sed "s/^{/{\"case\": \"$1\", /" >> $OUT
 }
-run soccar_3v3_8192 0 3 8192
-run hoops_2v2_16384 1 2 16384
-run heatseeker_1v1_16384 2 1 16384
-run snowday_3v3_4096 3 3 4096
-run snowday_3v3_32768 3 3 32768
-run soccar_2v2_65536 0 2 65536
+run soccar_2v2_8192 0 2 8192       # per-GPU share of the north-star size (65,536 arenas on 8 GPUs)
+run soccar_3v3_8192 0 3 8192       # per-GPU share of config 3 (65,536 on 8 GPUs)
+run hoops_2v2_16384 1 2 16384      # config 4
+run heatseeker_1v1_16384 2 1 16384 # config 4
+run snowday_3v3_4096 3 3 4096      # config 5 at 8 GPUs (per-GPU share of 32,768)
+run snowday_3v3_32768 3 3 32768    # config 5 on one GPU
+echo "== config 1 (THE_VOID 1v1, 1 M ticks)"
+timeout 900 python scripts/config1_void.py 1000000 4 2>&1 | tail -1 > gpurun_out/${TAG}_config1_void.json; cut -c1-400 gpurun_out/${TAG}_config1_void.json
 python - <<PY
 import json
 for l in open("$OUT"):
