@@ -529,7 +529,12 @@ __device__ __forceinline__ void run_phase_warp(const StepArgs& a, const BatchPar
 }
 #endif
 
+// ptxas derives 128 registers from __launch_bounds__(448); the register file holds 144 per thread at this block size
+#if defined(RSB_MAXNREG)
+__global__ void __maxnreg__(RSB_MAXNREG) arena_step_kernel(const StepArgs a) {
+#else
 __global__ void __launch_bounds__(STEP_THREADS, BLOCKS_PER_SM) arena_step_kernel(const StepArgs a) {
+#endif
 	extern __shared__ __align__(16) unsigned char smem[];
 	BatchParams* sP = (BatchParams*)smem;
 	Scene* sSc = (Scene*)(smem + SMEM_P_BYTES);

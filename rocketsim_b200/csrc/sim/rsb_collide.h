@@ -763,7 +763,13 @@ RSB_HD void collide_static_pairs(const Ctx& cx, int b) {
 	const BatchParams& P = *cx.p;
 	const Scene& sc = *cx.sc;
 	const int nPairs = cx.pl->nPairs;
-	const bool inlineBody = (b == 0) && P.ballIsSphere;
+#ifndef RSB_SPHERE_INLINE
+#define RSB_SPHERE_INLINE 0  // developer A/B: 1 = round-1 behaviour, the sphere ball resolves its triangles inside the walk
+#endif
+	// The sphere ball used to run its closed-form sphere-triangle tests inside the walk, one after the other on the ball's thread --
+	// next to a ramp that thread was the slowest of the whole phase.  It now records its triangles like every other shape and
+	// the tests run one per thread in PH_NARROW_DETECT.
+	const bool inlineBody = RSB_SPHERE_INLINE && (b == 0) && P.ballIsSphere;
 	RSB_SUBPROF_BEGIN();
 	for (int k = 0; k < nPairs; k++) {
 		if (cx.pl->b[k] != b) continue;
@@ -850,6 +856,16 @@ RSB_HD void detect_candidate(const Ctx& cx, int idx) {
 	if (a >= STATIC_BASE) {
 		// (body b, triangle of an arena mesh)
 		const RigidS& rb = rigid_of(cx, b);
+		if (b == 0 && P.ballIsSphere) {
+			// sphere vs triangle in closed form (SphereTriangleDetector, the reference's choice for this shape pair)
+			V3 t[3];
+			mesh_triangle(cx.sc->meshes[rec->mesh], rec->tri, t[0], t[1], t[2]);
+			const V3 c = vmul(rb.pos - v3zero(), m3identity());
+			const bool hit = sphere_triangle(c, P.ballRadiusBT, t, cx.mf[k].breakingThresh, pt, n, d);
+			if (hit) { rec->normal = m3identity() * n; rec->point = m3identity() * pt + v3zero(); rec->depth = d; }
+			rec->state = hit ? CAND_CONTACT : CAND_NONE;
+			return;
+		}
 		Convex shape; Xform xf;
 		if (b == 0) { shape = ball_convex(P); xf.basis = rb.basis; xf.origin = rb.pos; }
 		else { shape = car_box(P.carCfg[b - 1]); xf = cx.body[b].childXf; }

@@ -120,7 +120,7 @@ RSB_HD void phase_run(const Ctx& cx, int phase, int item) {
 		break;
 	case PH_NARROW_DETECT: detect_candidate(cx, item); break;
 	case PH_NARROW_COMMIT:
-		if (!(item == 0 && P.ballIsSphere)) commit_candidates(cx, item);  // the sphere ball committed its contacts on the spot
+		if (!(RSB_SPHERE_INLINE && item == 0 && P.ballIsSphere)) commit_candidates(cx, item);
 		break;
 	case PH_DYN_SOLVE: {
 		RSB_SUBPROF_BEGIN();
