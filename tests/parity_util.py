@@ -489,3 +489,39 @@ def free_rollout_compare(lib, refsim, mode, teams, seed, ticks, aim=False, drive
     err = int(batch.get_error_flags().max())
     batch.close(); ref.close()
     return dict(worst=worst, mismatches=mism, events_ref=ev_ref, events_mine=ev_mine, error_flags=err)
+
+
+_PLATFORM = {}
+
+
+def reference_platform(refsim) -> bool:
+    """True when the reference AS BUILT AND RUN ON THIS HOST regenerates the committed golden records bit for bit.  Two inputs of the
+    reference are host properties: the rsqrtss estimate inside btVector3::normalize (an Intel table; AMD parts return different
+    estimates) and libm.  The golden records come from an Intel host with glibc 2.39 and the library reproduces THAT platform
+    (rsb_math.h).  Elsewhere the live oracle differs from it in the last bits -- and, for a suspension ray resting on a dynamic
+    body, by up to ~1e-2 (the convex cast stops at dist^2 < 1e-4) -- so live-oracle tests fall back to the round-1 tolerances."""
+    if "ok" not in _PLATFORM:
+        import glob
+        path = os.path.join(ROOT, "tests", "golden", "soccar_2v2_aim.npz")
+        with np.load(path) as z:
+            rec = upgrade_record({k: z[k] for k in z.files})
+        teams = [int(x) for x in rec["teams"]]
+        ref = make_ref_arena(refsim, int(rec["mode"]), teams)
+        ok = True
+        for t in range(0, 200, 5):
+            for i, cid in enumerate(ref.car_ids):
+                ref.set_car_state(cid, rec["car_pre"][t, i]); ref.set_car_internal(cid, rec["carint_pre"][t, i]); ref.set_controls(cid, rec["controls"][t, i])
+            ref.set_ball_state(rec["ball_pre"][t]); ref.set_ball_internal(rec["ballint_pre"][t]); ref.set_pad_states(rec["pads_pre"][t])
+            ref.step(1)
+            for i, cid in enumerate(ref.car_ids):
+                got = ref.car_state(cid)
+                ok = ok and all(got[f].tobytes() == rec["car_post"][t, i][f].tobytes() for f in ("pos", "vel", "angVel", "rotMat"))
+        ref.close()
+        _PLATFORM["ok"] = bool(ok)
+    return _PLATFORM["ok"]
+
+
+def illcond_tol(refsim, tol=1e-4) -> float:
+    """Tolerance for ticks with a wheel on a dynamic body in LIVE-oracle tests: the normal bar on the reference platform, the
+    round-1 carve-out (2e-2) on a host whose reference computes normalize() differently."""
+    return tol if reference_platform(refsim) else 2e-2

@@ -71,7 +71,7 @@ def run_presets(lib, oracle, presets, ticks, seed, mutate=False):
     batch.close(); ref.close()
     assert err == 0 and not mism, (err, mism[:4])
     assert worst <= TOL, worst
-    assert worst_ill <= TOL_ILLCOND, worst_ill
+    assert worst_ill <= pu.illcond_tol(oracle, TOL_ILLCOND), worst_ill
 
 
 def test_presets_hostcheck(hostlib, oracle):
