@@ -514,9 +514,9 @@ inline SceneHost build_scene(int mode, std::vector<MeshHost> meshes) {
 			s.cellHdrStart.push_back((int32_t)s.cellHdrs.size());
 		}
 	}
-	// leaf candidates of short rays (suspension rays are ~1 bt long; 3 bt of reach + 0.1 bt of slack for the conservative
+	// leaf candidates of short rays (suspension rays are <= 1.28 bt long; 1.4 bt of reach + 0.1 bt of slack for the conservative
 	// quantised boxes).  Border cells also serve every position outside the grid (grid_cell_of clamps).
-	s.rayLeafReach = 3.0f;
+	s.rayLeafReach = 1.4f;  // every car preset casts <= 1.28 bt (rest 39.5 + travel 12 + radius 15 - 2.5 uu); longer rays of custom configs take the hierarchical walk
 	s.cellRayLeafStart.assign(1, 0);
 	for (int c = 0; c < total; c++) {
 		const int ci = c / (s.cellsY * s.cellsZ), cj = (c / s.cellsZ) % s.cellsY, ck = c % s.cellsZ;
