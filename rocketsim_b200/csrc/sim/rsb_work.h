@@ -80,7 +80,7 @@ struct PairList {
 // detector per pending record on its own thread (so the triangles of one car-mesh pair, and GJK / EPA calls of different
 // arenas, proceed in parallel instead of one after the other on the body's thread), and the records are committed to the
 // manifolds in index order, which is the order the reference adds them in.
-constexpr int MAX_CANDS = 96;
+constexpr int MAX_CANDS = 120;
 enum CandState : int { CAND_PENDING = 0, CAND_CONTACT = 1, CAND_NONE = 2 };
 struct CandRec {
 	int16_t pair;   // manifold slot = broadphase pair index
