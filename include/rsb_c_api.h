@@ -120,6 +120,11 @@ int rsb_set_ball_states(RsbBatch* b, const uint32_t* arena_idx, int n, const Rsb
 /* Replace BoostPad::GetState / SetState (src/Sim/BoostPad/BoostPad.h:44-45); [n_arenas][n_pads]. */
 int rsb_get_pad_states(RsbBatch* b, RsbBoostPadState* out);
 int rsb_set_pad_states(RsbBatch* b, const uint32_t* arena_idx, int n, const RsbBoostPadState* states /* [n][n_pads] */);
+/* Replace Arena::GetDropshotTilesState / SetDropshotTilesState (src/Sim/Arena/Arena.h:178-179, Arena.cpp:225-242) of a Dropshot
+ * batch: one DropshotTileState::damageState byte (0 full, 1 damaged, 2 broken) per tile, [n_arenas][2 teams][70 tiles]
+ * (src/Sim/Arena/DropshotTiles/DropshotTiles.h:7-33).  Setting also updates the tiles' contact response, as the reference does. */
+int rsb_get_dropshot_tiles(RsbBatch* b, uint8_t* out /* [n_arenas][140] */);
+int rsb_set_dropshot_tiles(RsbBatch* b, const uint32_t* arena_idx, int n, const uint8_t* states /* [n][140] */);
 /* Arena::tickCount (Arena.h:60) and Arena::IsBallScored (Arena.h:144, Arena.cpp:893-927); [n_arenas]. */
 int rsb_get_tick_counts(RsbBatch* b, uint64_t* out);
 int rsb_is_ball_scored(RsbBatch* b, uint8_t* out);

@@ -226,6 +226,9 @@ void ref_get_ball_state(RefArena* r, RsbBallState* out) {
 	BallState s = r->arena->ball->GetState();
 	memset(out, 0, sizeof(*out));
 	memcpy(out, &s, sizeof(s));
+	/* BallState::DropshotInfo::lastDamageTick has no initialiser and is "only valid if hasDamaged" (Ball.h:44-45): report 0
+	 * instead of the indeterminate value until the first damage */
+	if (!out->dsInfo.hasDamaged) out->dsInfo.lastDamageTick = 0;
 }
 void ref_set_ball_state(RefArena* r, const RsbBallState* in) {
 	BallState s; memcpy(&s, in, sizeof(s));
@@ -264,6 +267,21 @@ void ref_set_pad_states(RefArena* r, const RsbBoostPadState* in) {
 		s.isActive = in[i].isActive; s.cooldown = in[i].cooldown; s.prevLockedCarID = in[i].prevLockedCarID; s.curLockedCar = NULL;
 		pads[i]->SetState(s);
 	}
+}
+/* Arena::GetDropshotTilesState / SetDropshotTilesState (Arena.h:178-179): 140 damage-state bytes, [team][70] */
+void ref_get_dropshot_tiles(RefArena* r, uint8_t* out) {
+	DropshotTilesState s = r->arena->GetDropshotTilesState();
+	for (int t = 0; t < 2; t++) for (int i = 0; i < 70; i++) out[t * 70 + i] = s.states[t][i].damageState;
+}
+void ref_set_dropshot_tiles(RefArena* r, const uint8_t* in) {
+	DropshotTilesState s;
+	for (int t = 0; t < 2; t++) for (int i = 0; i < 70; i++) s.states[t][i].damageState = in[t * 70 + i];
+	r->arena->SetDropshotTilesState(s);
+}
+/* DropshotTiles::GetTilePos (DropshotTiles.cpp:13-20), uu */
+void ref_get_dropshot_tile_pos(int team, int idx, float* xyz) {
+	Vec p = DropshotTiles::GetTilePos(team, idx);
+	xyz[0] = p.x; xyz[1] = p.y; xyz[2] = p.z;
 }
 void ref_get_pad_positions(RefArena* r, float* o) {
 	auto& pads = r->arena->_boostPads;

@@ -57,6 +57,9 @@ void ref_set_ball_internal(RefArena*, const RsbBallInternal* in);
 void ref_get_pad_states(RefArena*, RsbBoostPadState* out);             /* n = ref_num_pads */
 void ref_set_pad_states(RefArena*, const RsbBoostPadState* in);
 void ref_get_pad_positions(RefArena*, float* out_xyz_isbig);           /* 4 floats per pad */
+void ref_get_dropshot_tiles(RefArena*, uint8_t* out140);               /* Arena::GetDropshotTilesState, Arena.h:178 */
+void ref_set_dropshot_tiles(RefArena*, const uint8_t* in140);          /* Arena::SetDropshotTilesState, Arena.cpp:225 */
+void ref_get_dropshot_tile_pos(int team, int idx, float* xyz);         /* DropshotTiles::GetTilePos, DropshotTiles.cpp:13 */
 void ref_get_mutator_config(RefArena*, RsbMutatorConfig* out);
 void ref_set_mutator_config(RefArena*, const RsbMutatorConfig* in);    /* Arena::SetMutatorConfig, Arena.cpp:17 */
 void ref_default_mutator_config(int game_mode, RsbMutatorConfig* out); /* MutatorConfig(GameMode) */

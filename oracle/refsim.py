@@ -71,6 +71,8 @@ def lib():
             getattr(L, "ref_get_" + n).argtypes = [vp, vp]
             getattr(L, "ref_set_" + n).argtypes = [vp, vp]
         L.ref_get_pad_positions.argtypes = [vp, vp]
+        L.ref_get_dropshot_tiles.argtypes = [vp, vp]; L.ref_set_dropshot_tiles.argtypes = [vp, vp]
+        L.ref_get_dropshot_tile_pos.argtypes = [i32, i32, vp]
         L.ref_default_mutator_config.argtypes = [i32, vp]
         L.ref_get_car_config.argtypes = [i32, vp]
         L.ref_drain_events.argtypes = [vp, vp, i32]; L.ref_drain_events.restype = i32
@@ -253,6 +255,15 @@ class RefArena:
         a = np.array([m], dtype=T.MutatorConfig)
         self.L.ref_set_mutator_config(self.h, _ptr(a))
 
+    def dropshot_tiles(self):
+        out = np.zeros(140, dtype=np.uint8)
+        self.L.ref_get_dropshot_tiles(self.h, _ptr(out))
+        return out
+
+    def set_dropshot_tiles(self, states):
+        a = np.ascontiguousarray(states, dtype=np.uint8).reshape(140)
+        self.L.ref_set_dropshot_tiles(self.h, _ptr(a))
+
     def pad_positions(self):
         out = np.zeros((max(self.num_pads, 1), 4), dtype=np.float32)
         self.L.ref_get_pad_positions(self.h, _ptr(out))
@@ -287,6 +298,12 @@ class RefArena:
         out = np.zeros(18, dtype=np.float32)
         self.L.ref_get_car_body(self.h, car_id, _ptr(out))
         return out
+
+
+def dropshot_tile_pos(team: int, idx: int):
+    out = np.zeros(3, dtype=np.float32)
+    lib().ref_get_dropshot_tile_pos(team, idx, _ptr(out))
+    return out
 
 
 def default_mutator_config(mode: int):

@@ -148,6 +148,10 @@ class ArenaBatch:
     def get_pad_states(self):
         return self._get("rsb_get_pad_states", T.BoostPadState, (self.n_arenas, self.n_pads))
 
+    def get_dropshot_tiles(self):
+        """Arena::GetDropshotTilesState of every arena: damage states (0 full, 1 damaged, 2 broken), [n_arenas, 2, 70]."""
+        return self._get("rsb_get_dropshot_tiles", np.uint8, (self.n_arenas, 2, 70))
+
     def get_car_internals(self):
         return self._get("rsb_get_car_internals", T.CarInternal, (self.n_arenas, self.n_cars))
 
@@ -219,6 +223,12 @@ class ArenaBatch:
         s = self._payload(np.ascontiguousarray(states, dtype=T.BoostPadState).ravel(), len(ai), "set_pad_states", self.n_pads)
         if self.n_pads:
             _lib.check(self.L, self.L.rsb_set_pad_states(self.h, _lib.ptr(ai), len(ai), _lib.ptr(s)))
+
+    def set_dropshot_tiles(self, arena_idx, states):
+        """Arena::SetDropshotTilesState for the listed arenas; states [len(arena_idx), 2, 70] of 0 / 1 / 2."""
+        ai, _ = self._idx(arena_idx)
+        s = self._payload(np.ascontiguousarray(states, dtype=np.uint8).ravel(), len(ai), "set_dropshot_tiles", 140)
+        _lib.check(self.L, self.L.rsb_set_dropshot_tiles(self.h, _lib.ptr(ai), len(ai), _lib.ptr(s)))
 
     def seed_rng(self, arena: int, seed: int):
         _lib.check(self.L, self.L.rsb_seed_rng(self.h, arena, seed))

@@ -97,6 +97,8 @@ static SceneDev* get_scene_dev(int device, int mode) {
 		d.aabbMin = m.aabbMin; d.aabbMax = m.aabbMax; d.group = m.group; d.mask = m.mask;
 	}
 	for (int i = 0; i < sc.nPlanes; i++) sc.planes[i] = h.planes[i];
+	sc.nTiles = (int)h.tiles.size();
+	sc.tiles = sc.nTiles ? (const TileD*)up(h.tiles.data(), h.tiles.size() * sizeof(TileD)) : nullptr;
 	sc.gridMin = h.gridMin; sc.gridMax = h.gridMax; sc.cellSize = h.cellSize;
 	sc.cellsX = h.cellsX; sc.cellsY = h.cellsY; sc.cellsZ = h.cellsZ;
 	sc.cellStart = (const int32_t*)up(h.cellStart.data(), h.cellStart.size() * 4);
@@ -242,6 +244,16 @@ RSB_HD void ball_from_api(const RsbBallState& s, BallS& b) {
 	b.hsYTargetDir = s.hsInfo.yTargetDir; b.hsCurTargetSpeed = s.hsInfo.curTargetSpeed; b.hsTimeSinceHit = s.hsInfo.timeSinceHit;
 	b.velImpulseCache = v3zero();
 	b.tickCountSinceUpdate = 0;
+}
+
+// BallState::dsInfo (Ball.h:34-47) lives in the cold tail of the arena record (Dropshot only)
+RSB_HD void ds_to_api(const ArenaS& A, RsbBallState& o) {
+	o.dsInfo.chargeLevel = A.dsChargeLevel; o.dsInfo.accumulatedHitForce = A.dsAccumulatedHitForce; o.dsInfo.yTargetDir = A.dsYTargetDir;
+	o.dsInfo.hasDamaged = A.dsHasDamaged ? 1 : 0; o.dsInfo.lastDamageTick = A.dsLastDamageTick;
+}
+RSB_HD void ds_from_api(const RsbBallState& s, ArenaS& A) {
+	A.dsChargeLevel = s.dsInfo.chargeLevel; A.dsAccumulatedHitForce = s.dsInfo.accumulatedHitForce; A.dsYTargetDir = s.dsInfo.yTargetDir;
+	A.dsHasDamaged = s.dsInfo.hasDamaged ? 1u : 0u; A.dsLastDamageTick = s.dsInfo.lastDamageTick;
 }
 
 // ------------------------------------------------------------------ kernels
@@ -633,7 +645,11 @@ __global__ void __launch_bounds__(STEP_THREADS, BLOCKS_PER_SM) arena_step_kernel
 			run_phase_block<PH_PADS_POST>(a, sP, sSc, sS, a0, nA, ptid);
 			run_phase_block<PH_TAIL>(a, sP, sSc, sS, a0, nA, ptid);
 			if (a.ballTrace)  // the ball is next written in PH_CAR_LOGIC, several barriers from here
-				for (int i = tid; i < nA; i += STEP_THREADS) ball_to_api(((const ArenaS*)(sS + (size_t)i * a.lay.stride))->ball, a.ballTrace[(size_t)(t + 1) * a.nArenas + a0 + i]);
+				for (int i = tid; i < nA; i += STEP_THREADS) {
+					RsbBallState& o = a.ballTrace[(size_t)(t + 1) * a.nArenas + a0 + i];
+					ball_to_api(((const ArenaS*)(sS + (size_t)i * a.lay.stride))->ball, o);
+					if (sP->mode == DROPSHOT) ds_to_api(a.S[a0 + i], o);
+				}
 		}
 #endif
 		// records back to HBM; the last tick's hot scratch goes to its global mirror (debug probes)
@@ -684,7 +700,7 @@ static void arena_step_host(const StepArgs& a) {
 				for (int ci = 0; ci < nCars; ci++) cx.s->cars[ci].controls = src[ci];
 			}
 			arena_tick(cx);
-			if (a.ballTrace) ball_to_api(cx.s->ball, a.ballTrace[(size_t)(t + 1) * a.nArenas + arena]);
+			if (a.ballTrace) { RsbBallState& o = a.ballTrace[(size_t)(t + 1) * a.nArenas + arena]; ball_to_api(cx.s->ball, o); if (a.P->mode == DROPSHOT) ds_to_api(*cx.s, o); }
 		}
 	}
 }
@@ -702,13 +718,26 @@ RSB_GLOBAL void set_car_states_kernel(ArenaS* S, const uint32_t* ai, const uint3
 	KERNEL_1D(i, n);
 	car_from_api(in[i], S[ai[i]], (int)ci[i]);
 }
-RSB_GLOBAL void get_ball_states_kernel(const ArenaS* S, RsbBallState* out, int nArenas) {
+RSB_GLOBAL void get_ball_states_kernel(const ArenaS* S, RsbBallState* out, int nArenas, int dropshot) {
 	KERNEL_1D(i, nArenas);
 	ball_to_api(S[i].ball, out[i]);
+	if (dropshot) ds_to_api(S[i], out[i]);
 }
-RSB_GLOBAL void set_ball_states_kernel(ArenaS* S, const uint32_t* ai, const RsbBallState* in, int n) {
+RSB_GLOBAL void set_ball_states_kernel(ArenaS* S, const uint32_t* ai, const RsbBallState* in, int n, int dropshot) {
 	KERNEL_1D(i, n);
 	ball_from_api(in[i], S[ai[i]].ball);
+	if (dropshot) ds_from_api(in[i], S[ai[i]]);
+}
+// Arena::GetDropshotTilesState / SetDropshotTilesState (Arena.h:178-179, Arena.cpp:225-242): one damage state per tile,
+// [team][70]; setting the states also updates the tile bodies' contact response, as the reference does.
+RSB_GLOBAL void get_tiles_kernel(const ArenaS* S, uint8_t* out, int nArenas) {
+	KERNEL_1D(i, nArenas * MAX_TILES);
+	out[i] = S[i / MAX_TILES].tiles[i % MAX_TILES] & 3u;
+}
+RSB_GLOBAL void set_tiles_kernel(ArenaS* S, const uint32_t* ai, const uint8_t* in, int n) {
+	KERNEL_1D(i, n * MAX_TILES);
+	const uint8_t st = in[i] & 3u;
+	S[ai[i / MAX_TILES]].tiles[i % MAX_TILES] = (uint8_t)(st | (st == 2u ? 4u : 0u));
 }
 RSB_GLOBAL void get_pad_states_kernel(const ArenaS* S, RsbBoostPadState* out, int nArenas, int nPads) {
 	KERNEL_1D(i, nArenas * nPads);
@@ -811,7 +840,7 @@ RSB_GLOBAL void fill_controls_kernel(CtrlS* out, int nArenas, int nCars, int nTi
 RSB_GLOBAL void reset_kickoff_kernel(ArenaS* S, const BatchParams* P, const uint32_t* ai, const int32_t* seeds, int n) {
 	KERNEL_1D(i, n);
 	const int arena = ai ? (int)ai[i] : i;
-	kickoff_reset(S[arena], *P, seeds[i]);
+	kickoff_reset(S[arena], S[arena], *P, seeds[i]);
 }
 
 // ------------------------------------------------------------------ parameter setup (host)
@@ -1082,7 +1111,6 @@ int rsb_batch_create_ex(int device, int game_mode, const RsbArenaConfig* arena_c
 	if (n_arenas <= 0) throw std::runtime_error("n_arenas must be positive");
 	if (n_cars < 0 || n_cars > MAX_CARS) throw std::runtime_error("n_cars must be in [0, " + std::to_string(MAX_CARS) + "]");
 	if (!(tick_rate >= 15 && tick_rate <= 120)) throw std::runtime_error("Tickrate must be from 15 to 120tps");  // Arena.cpp:419
-	if (game_mode == DROPSHOT) throw std::runtime_error("Dropshot is out of scope of the batched path");
 	{
 		std::lock_guard<std::mutex> lk(g_initMutex);
 		if (!g_initialized) throw std::runtime_error("Cannot create Arena, RocketSim has not been initialized, call rsb_init_from_mem() first");
@@ -1176,8 +1204,9 @@ int rsb_batch_create_ex(int device, int game_mode, const RsbArenaConfig* arena_c
 		A.ball.rb.pos = V3(0, 0, K::BALL_REST_Z) * UU_TO_BT;  // ball->SetState(BallState())
 		A.ball.rb.basis = m3identity();
 		A.ball.hsCurTargetSpeed = K::HS_INITIAL_TARGET_SPEED;
+		A.dsChargeLevel = 1;  // BallState::DropshotInfo default; every tile starts intact (state 0)
 		for (int p = 0; p < P.nPads; p++) { A.pads[p].isActive = 1; }
-		Ctx cx; cx.s = &A; cx.w = &tmpW; cx.epa = nullptr; cx.p = &P; cx.sc = &hsc; cx.arena = a; cx.ev.buf = nullptr;
+		Ctx cx; cx.s = &A; cx.g = &A; cx.w = &tmpW; cx.epa = nullptr; cx.p = &P; cx.sc = &hsc; cx.arena = a; cx.ev.buf = nullptr;
 		cx.body = tmpH.body; cx.wheels = tmpH.wheels; cx.padLocked = tmpH.padLocked; cx.misc = tmpH.misc; cx.pl = &tmpH.pairs; cx.mf = tmpH.mf; cx.solv = tmpH.solv;
 		for (int c = 0; c < n_cars; c++) {
 			tmpH.body[c + 1].invInertiaLocal = P.carCfg[c].invInertiaLocal;
@@ -1398,8 +1427,8 @@ int rsb_is_ball_probably_going_in(RsbBatch* b, float max_time, float extra_margi
 // BallState, as the reference does, so the x50 / x0.02 round trip of the position is reproduced
 RSB_GLOBAL void copy_ball_kernel(const ArenaS* src, ArenaS* dst, RsbBallState* row0, int nArenas) {
 	KERNEL_1D(i, nArenas);
-	RsbBallState st; ball_to_api(src[i].ball, st);
-	ball_from_api(st, dst[i].ball);
+	RsbBallState st; ball_to_api(src[i].ball, st); ds_to_api(src[i], st);
+	ball_from_api(st, dst[i].ball); ds_from_api(st, dst[i]);
 	row0[i] = st;
 }
 int rsb_predict_ball(RsbBatch* b, int n_ticks, RsbBallState* out) {
@@ -1461,7 +1490,8 @@ RSB_GLOBAL void clone_arena_kernel(ArenaS* S, const BatchParams* P, const Scene*
 	const ArenaS& A = S[src];
 	ArenaS& B = S[dst];
 	const int nCars = P->nCars;
-	RsbBallState bs; ball_to_api(A.ball, bs); ball_from_api(bs, B.ball);
+	RsbBallState bs; ball_to_api(A.ball, bs); ds_to_api(A, bs); ball_from_api(bs, B.ball); ds_from_api(bs, B);
+	for (int t = 0; t < MAX_TILES; t++) B.tiles[t] = 0;  // a new Arena starts with every tile intact; Clone does not copy tile states
 	B.ball.velImpulseCache = A.ball.velImpulseCache;
 	B.ball.groundStickApplied = 0;
 	for (int c = 0; c < nCars; c++) {
@@ -1513,7 +1543,7 @@ int rsb_serialize_arena(RsbBatch* b, uint32_t arena, uint8_t* out, size_t cap, s
 		LAUNCH_1D(get_controls_kernel, P.nCars, b, S1, dCtl, 1, P.nCars);
 		d2h(cars.data(), dCars, sizeof(RsbCarState) * P.nCars, b->stream); d2h(ctl.data(), dCtl, sizeof(RsbCarControls) * P.nCars, b->stream);
 	}
-	LAUNCH_1D(get_ball_states_kernel, 1, b, S1, dBall, 1);
+	LAUNCH_1D(get_ball_states_kernel, 1, b, S1, dBall, 1, b->hp.mode == DROPSHOT);
 	d2h(&img.ball, dBall, sizeof(RsbBallState), b->stream);
 	if (P.nPads) { LAUNCH_1D(get_pad_states_kernel, P.nPads, b, S1, dPads, 1, P.nPads); d2h(img.pads.data(), dPads, sizeof(RsbBoostPadState) * P.nPads, b->stream); }
 	LAUNCH_1D(get_misc_kernel, 1, b, S1, b->dP, b->dScene, dTick, (uint8_t*)nullptr, (uint32_t*)nullptr, 1);
@@ -1584,7 +1614,11 @@ int rsb_sync(RsbBatch* b) {
 	LAUNCH_1D(kern, (int)_n, b, __VA_ARGS__); d2h(out, b->dScratch, _n * sizeof(T), b->stream); API_END
 
 int rsb_get_car_states(RsbBatch* b, RsbCarState* out) { GET_IMPL(get_car_states_kernel, RsbCarState, (size_t)b->hp.nArenas * b->hp.nCars, b->dS, (RsbCarState*)b->dScratch, b->hp.nArenas, b->hp.nCars) }
-int rsb_get_ball_states(RsbBatch* b, RsbBallState* out) { GET_IMPL(get_ball_states_kernel, RsbBallState, (size_t)b->hp.nArenas, b->dS, (RsbBallState*)b->dScratch, b->hp.nArenas) }
+int rsb_get_ball_states(RsbBatch* b, RsbBallState* out) { GET_IMPL(get_ball_states_kernel, RsbBallState, (size_t)b->hp.nArenas, b->dS, (RsbBallState*)b->dScratch, b->hp.nArenas, b->hp.mode == DROPSHOT) }
+int rsb_get_dropshot_tiles(RsbBatch* b, uint8_t* out) {
+	if (b->hp.mode != DROPSHOT) return fail("rsb_get_dropshot_tiles: the batch is not a Dropshot batch");
+	GET_IMPL(get_tiles_kernel, uint8_t, (size_t)b->hp.nArenas * MAX_TILES, b->dS, (uint8_t*)b->dScratch, b->hp.nArenas)
+}
 int rsb_get_pad_states(RsbBatch* b, RsbBoostPadState* out) { GET_IMPL(get_pad_states_kernel, RsbBoostPadState, (size_t)b->hp.nArenas * b->hp.nPads, b->dS, (RsbBoostPadState*)b->dScratch, b->hp.nArenas, b->hp.nPads) }
 int rsb_get_car_internals(RsbBatch* b, RsbCarInternal* out) { GET_IMPL(get_car_internals_kernel, RsbCarInternal, (size_t)b->hp.nArenas * b->hp.nCars, b->dS, (RsbCarInternal*)b->dScratch, b->hp.nArenas, b->hp.nCars) }
 int rsb_get_ball_internals(RsbBatch* b, RsbBallInternal* out) { GET_IMPL(get_ball_internals_kernel, RsbBallInternal, (size_t)b->hp.nArenas, b->dS, (RsbBallInternal*)b->dScratch, b->hp.nArenas) }
@@ -1623,7 +1657,17 @@ int rsb_set_ball_states(RsbBatch* b, const uint32_t* ai, int n, const RsbBallSta
 	API_BEGIN set_device(b); if (n <= 0) return 0; check_idx(b, ai, nullptr, n);
 	uint32_t *dai, *dci; RsbBallState* dp;
 	stage_set(b, ai, (const uint32_t*)nullptr, n, st, (size_t)n, &dai, &dci, &dp);
-	LAUNCH_1D(set_ball_states_kernel, n, b, b->dS, dai, dp, n);
+	LAUNCH_1D(set_ball_states_kernel, n, b, b->dS, dai, dp, n, b->hp.mode == DROPSHOT);
+	API_END
+}
+int rsb_set_dropshot_tiles(RsbBatch* b, const uint32_t* ai, int n, const uint8_t* st) {
+	API_BEGIN set_device(b);
+	if (b->hp.mode != DROPSHOT) throw std::runtime_error("rsb_set_dropshot_tiles: the batch is not a Dropshot batch");
+	if (n <= 0) return 0; check_idx(b, ai, nullptr, n);
+	for (size_t i = 0; i < (size_t)n * MAX_TILES; i++) if (st[i] > 2) throw std::runtime_error("rsb_set_dropshot_tiles: damage state must be 0 (full), 1 (damaged) or 2 (broken)");
+	uint32_t *dai, *dci; uint8_t* dp;
+	stage_set(b, ai, (const uint32_t*)nullptr, n, st, (size_t)n * MAX_TILES, &dai, &dci, &dp);
+	LAUNCH_1D(set_tiles_kernel, n * MAX_TILES, b, b->dS, dai, dp, n);
 	API_END
 }
 int rsb_set_pad_states(RsbBatch* b, const uint32_t* ai, int n, const RsbBoostPadState* st) {

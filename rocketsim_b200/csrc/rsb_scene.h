@@ -41,6 +41,7 @@ struct SceneHost {
 	int mode = THE_VOID;
 	std::vector<MeshHost> meshes;
 	std::vector<PlaneD> planes;
+	std::vector<TileD> tiles;  // Dropshot floor tiles, team 0 then team 1 (Arena.cpp:1070-1085)
 	V3 gridMin, gridMax;
 	float cellSize = 0.f;
 	int cellsX = 0, cellsY = 0, cellsZ = 0;
@@ -375,8 +376,11 @@ inline MeshHost build_mesh(const uint8_t* data, size_t size) {
 // contact normal and friction direction.  normalized() (rsb_math.h) reproduces that instruction sequence on any host.
 inline V3 bullet_normalized_host(const V3& v) { return normalized(v); }
 
-inline PlaneD make_plane(const V3& posUU, const V3& nIn) {
+inline PlaneD make_plane(const V3& posUU, const V3& nIn, int filter = 0) {
 	PlaneD p;
+	// _AddStaticCollisionShape (Arena.cpp:976-987): group = mask = `filter` when given, else the static defaults of addRigidBody
+	p.group = filter ? filter : FILT_STATIC;
+	p.mask = filter ? filter : (FILT_ALL ^ FILT_STATIC);
 	const V3 n = bullet_normalized_host(nIn);
 	p.n = n; p.pos = posUU * UU_TO_BT;
 	p.d = dot(n, p.pos);
@@ -391,6 +395,80 @@ inline PlaneD make_plane(const V3& posUU, const V3& nIn) {
 	p.aabbMax.set(axis, o + (0.f + OFF));
 	if (backwards) p.aabbMax.set(axis, kLargeFloat); else p.aabbMin.set(axis, -kLargeFloat);
 	return p;
+}
+
+// DropshotTiles::Init + MakeTileShapes (DropshotTiles.cpp:22-112) and the tile bodies of Arena::_SetupArenaCollisionShapes
+// (Arena.cpp:1070-1085), in the reference's float arithmetic.
+inline std::vector<TileD> make_dropshot_tiles() {
+	const float BT_TO_UU_ = 50.f, UU_TO_BT_ = (1.f / 50.f);
+	const V3 HEX[6] = {V3(0.0f, -8.85f, 0.f), V3(7.6643f, -4.425f, 0.f), V3(7.6643f, 4.425f, 0.f), V3(0.0f, 8.85f, 0.f), V3(-7.6643f, 4.425f, 0.f), V3(-7.6643f, -4.425f, 0.f)};
+	const float TILE_WIDTH_X = HEX[1].x * 2 * BT_TO_UU_;
+	const float ROW_OFFSET_Y = (HEX[3].y + HEX[4].y) * BT_TO_UU_;
+	const float TILE_OFFSET_Y = 2.54736f * BT_TO_UU_;
+	const int FIRST_ROW = 13, LAST_ROW = 7, ROWS = FIRST_ROW - LAST_ROW + 1;
+	V3 pos[TILES_PER_TEAM];
+	int cur = 0;
+	float y = TILE_OFFSET_Y;
+	for (int i = 0, numTiles = FIRST_ROW; i < ROWS; i++, numTiles--) {
+		float rowSizeX = TILE_WIDTH_X * numTiles;
+		float rowStartX = -(rowSizeX / 2.f) + (TILE_WIDTH_X / 2);
+		for (int j = 0; j < numTiles; j++, cur++) {
+			if (cur >= TILES_PER_TEAM) throw std::runtime_error("dropshot tile table overflow");
+			float x = rowStartX + TILE_WIDTH_X * j;
+			pos[cur] = V3(x, y, 0.f);
+		}
+		y += ROW_OFFSET_Y;
+	}
+	if (cur != TILES_PER_TEAM) throw std::runtime_error("dropshot tile table incomplete");
+	std::vector<TileD> tiles(MAX_TILES);
+	const float margin = 0.04f;  // btConvexHullShape default (CONVEX_DISTANCE_MARGIN)
+	const float NEIGHBOR_MAX_RADIUS = TILE_WIDTH_X * 1.2f;
+	for (int team = 0; team < 2; team++) {
+		for (int i = 0; i < TILES_PER_TEAM; i++) {
+			TileD& t = tiles[team * TILES_PER_TEAM + i];
+			memset(&t, 0, sizeof(t));
+			const V3 tp = pos[i] * ((team == 0) ? -1.f : 1.f);  // GetTilePos
+			t.posY = tp.y;
+			const float CLAMP_Y = TILE_OFFSET_Y * UU_TO_BT_;
+			for (int j = 0; j < 6; j++) {
+				V3 vert = tp * UU_TO_BT_ + HEX[j];
+				if (team == 0) vert.y = vert.y < -CLAMP_Y ? vert.y : -CLAMP_Y;  // RS_MIN(vert.y, -CLAMP_Y)
+				else vert.y = vert.y > CLAMP_Y ? vert.y : CLAMP_Y;              // RS_MAX(vert.y, CLAMP_Y)
+				t.pts[j] = vert;
+			}
+			// recalcLocalAabb (btPolyhedralConvexShape.cpp:499-529): support points (first maximum of the dot product) along +-axes
+			V3 lmin, lmax;
+			for (int a = 0; a < 3; a++) {
+				V3 dp(0, 0, 0), dn(0, 0, 0); dp.set(a, 1.f); dn.set(a, -1.f);
+				float bp = -3.402823466e+38f, bn = -3.402823466e+38f; int ip = -1, in = -1;
+				for (int j = 0; j < 6; j++) {
+					float d1 = dot(t.pts[j], dp), d2 = dot(t.pts[j], dn);
+					if (d1 > bp) { bp = d1; ip = j; }
+					if (d2 > bn) { bn = d2; in = j; }
+				}
+				lmax.set(a, t.pts[ip][a] + margin);
+				lmin.set(a, t.pts[in][a] - margin);
+			}
+			// getAabb(body transform) = btTransformAabb(localMin, localMax, margin, t) with t = (identity, (0, 0, -margin))
+			const V3 origin(0.f, 0.f, -margin);
+			V3 lh = 0.5f * (lmax - lmin);
+			lh += V3(margin, margin, margin);
+			const V3 lc = 0.5f * (lmax + lmin);
+			const M3 I = m3identity();
+			const V3 center = I * lc + origin;
+			const V3 extent(dot(lh, I.r[0]), dot(lh, I.r[1]), dot(lh, I.r[2]));
+			t.aabbMin = center - extent; t.aabbMax = center + extent;
+			// neighbour lists (team-independent: computed from team 0 positions, DropshotTiles.cpp:92-112)
+			const V3 p0 = pos[i] * -1.f;
+			for (int j = 0; j < TILES_PER_TEAM; j++) {
+				const V3 d = p0 - pos[j] * -1.f;
+				const float dist = sqrtf(d.x * d.x + d.y * d.y + d.z * d.z);
+				if (dist < NEIGHBOR_MAX_RADIUS) { if (t.n1 >= 7) throw std::runtime_error("dropshot neighbour table"); t.nb1[t.n1++] = (uint8_t)j; }
+				if (dist < NEIGHBOR_MAX_RADIUS * 2) { if (t.n2 >= 20) throw std::runtime_error("dropshot neighbour table"); t.nb2[t.n2++] = (uint8_t)j; }
+			}
+		}
+	}
+	return tiles;
 }
 
 inline void grid_indices(const SceneHost& s, const V3& pos, int& i, int& j, int& k) {
@@ -413,14 +491,19 @@ inline SceneHost build_scene(int mode, std::vector<MeshHost> meshes) {
 		m.group = net ? FILT_HOOPS_NET : FILT_STATIC;
 		m.mask = net ? FILT_HOOPS_NET : (FILT_ALL ^ FILT_STATIC);
 	}
+	const bool isDropshot = mode == DROPSHOT;
 	if (mode != THE_VOID) {
 		float extentX = isHoops ? K::ARENA_EXTENT_X_HOOPS : K::ARENA_EXTENT_X;
 		float extentY = isHoops ? K::ARENA_EXTENT_Y_HOOPS : K::ARENA_EXTENT_Y;
-		float height = isHoops ? K::ARENA_HEIGHT_HOOPS : K::ARENA_HEIGHT;
-		s.planes.push_back(make_plane(V3(0, 0, 0), V3(0, 0, 1)));
+		float height = isDropshot ? 2024.f : (isHoops ? K::ARENA_HEIGHT_HOOPS : K::ARENA_HEIGHT);  // ARENA_HEIGHT_DROPSHOT (RLConst.h:22)
+		// Dropshot: the floor plane sits at FLOOR_HEIGHT_DROPSHOT = 1.5 uu and only collides with cars and wheel rays
+		// (DROPSHOT_FLOOR filter); the ball lands on the tiles.  No side walls (Arena.cpp:1051-1061).
+		s.planes.push_back(make_plane(V3(0, 0, isDropshot ? 1.5f : 0.f), V3(0, 0, 1), isDropshot ? FILT_DROPSHOT_FLOOR : 0));
 		s.planes.push_back(make_plane(V3(0, 0, height), V3(0, 0, -1)));
-		s.planes.push_back(make_plane(V3(-extentX, 0, height / 2), V3(1, 0, 0)));
-		s.planes.push_back(make_plane(V3(extentX, 0, height / 2), V3(-1, 0, 0)));
+		if (!isDropshot) {
+			s.planes.push_back(make_plane(V3(-extentX, 0, height / 2), V3(1, 0, 0)));
+			s.planes.push_back(make_plane(V3(extentX, 0, height / 2), V3(-1, 0, 0)));
+		}
 		if (isHoops) {
 			s.planes.push_back(make_plane(V3(0, -extentY, height / 2), V3(0, 1, 0)));
 			s.planes.push_back(make_plane(V3(0, extentY, height / 2), V3(0, -1, 0)));
@@ -435,13 +518,17 @@ inline SceneHost build_scene(int mode, std::vector<MeshHost> meshes) {
 	s.cellsX = cl(range.x / s.cellSize); s.cellsY = cl(range.y / s.cellSize); s.cellsZ = cl(range.z / s.cellSize);
 	const int total = s.cellsX * s.cellsY * s.cellsZ;
 	std::vector<std::vector<uint8_t>> cells(total);
-	const int nStatics = (int)s.meshes.size() + (int)s.planes.size();
+	if (isDropshot) s.tiles = make_dropshot_tiles();
+	const int nStatics = (int)s.meshes.size() + (int)s.planes.size() + (int)s.tiles.size();
+	if (nStatics > 255) throw std::runtime_error("too many static objects");
 	const V3 ct(0.02f, 0.02f, 0.02f);
 	for (int o = 0; o < nStatics; o++) {
 		const bool isMesh = o < (int)s.meshes.size();
+		const int op = o - (int)s.meshes.size(), ot = op - (int)s.planes.size();
 		V3 amin, amax;
 		if (isMesh) { amin = s.meshes[o].aabbMin - ct; amax = s.meshes[o].aabbMax + ct; }
-		else { amin = s.planes[o - s.meshes.size()].aabbMin - ct; amax = s.planes[o - s.meshes.size()].aabbMax + ct; }
+		else if (ot < 0) { amin = s.planes[op].aabbMin - ct; amax = s.planes[op].aabbMax + ct; }
+		else { amin = s.tiles[ot].aabbMin - ct; amax = s.tiles[ot].aabbMax + ct; }
 		V3 cmax = vmin(amax, s.gridMax);
 		int iMin, jMin, kMin, iMax, jMax, kMax;
 		grid_indices(s, amin, iMin, jMin, kMin);

@@ -88,13 +88,14 @@ RSB_HD void ball_pretick(const Ctx& cx) {
 	} else if (mode == SNOWDAY) {
 		b.groundStickApplied = 0;
 	} else if (mode == HOOPS || mode == DROPSHOT) {
-		float launchDelay = K::BALL_HOOPS_LAUNCH_DELAY;
+		const bool isDropshot = (mode == DROPSHOT);
+		float launchDelay = isDropshot ? 0.26f : K::BALL_HOOPS_LAUNCH_DELAY;  // Dropshot::BALL_LAUNCH_DELAY (RLConst.h:209)
 		float curKickoffTime = b.tickCountSinceUpdate * dt;
 		float prevKickoffTime = curKickoffTime - dt;
 		if (prevKickoffTime < launchDelay && curKickoffTime >= launchDelay) {
 			V3 pos = b.rb.pos * BT_TO_UU, vel = b.rb.vel * BT_TO_UU;
 			if (is_zero(vel) && is_zero(b.rb.angvel) && pos.x == 0.f && pos.y == 0.f) {
-				V3 imp = V3(0.f, 0.f, K::BALL_HOOPS_LAUNCH_Z_VEL) * cx.p->ballMass * UU_TO_BT;
+				V3 imp = V3(0.f, 0.f, isDropshot ? 985.f : K::BALL_HOOPS_LAUNCH_Z_VEL) * cx.p->ballMass * UU_TO_BT;  // Dropshot::BALL_LAUNCH_Z_VEL
 				b.rb.vel += imp * bw.invMass;
 				bw.activation = ACT_ACTIVE;
 			}
@@ -145,6 +146,18 @@ RSB_HD_NOINLINE void ball_on_hit(Ctx cx, int ci, V3 relPosUU) {
 			b.hsCurTargetSpeed = (t < K::HS_MAX_SPEED) ? t : K::HS_MAX_SPEED;
 		}
 		b.hsYTargetDir = newTargetDir;
+	} else if (mode == DROPSHOT) {
+		// charge the ball with the speed the car drives into it (Ball.cpp:299-323); dsInfo lives in the record's cold tail
+		ArenaS& G = *cx.g;
+		V3 dirFromCar = rs_normalized(ballPos - carPos);
+		V3 relVelFromCar = carVel - ballVel;
+		float velIntoBall = dot(dirFromCar, relVelFromCar);
+		if (velIntoBall >= 500.f) {  // MIN_CHARGE_HIT_SPEED
+			G.dsAccumulatedHitForce += velIntoBall;
+			if (G.dsAccumulatedHitForce >= 2500.f) G.dsChargeLevel = 2;   // MIN_ABSORBED_FORCE_FOR_CHARGE
+			if (G.dsAccumulatedHitForce >= 11000.f) G.dsChargeLevel = 3;  // MIN_ABSORBED_FORCE_FOR_SUPERCHARGE
+		}
+		if (G.dsChargeLevel > 1) G.dsYTargetDir = (cx.p->team[ci] == 0) ? 1.f : -1.f;
 	}
 }
 
@@ -211,6 +224,8 @@ RSB_HD bool is_ball_scored(const Ctx& cx) {
 		}
 		return false;
 	}
+	case DROPSHOT:  // the ball fell through a broken tile (Arena.cpp:916-923)
+		return (b.rb.pos.z * BT_TO_UU) < -(cx.p->mut.ballRadius * 1.75f);
 	default: return false;
 	}
 }

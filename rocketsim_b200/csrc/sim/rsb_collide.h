@@ -18,15 +18,25 @@ namespace rsb {
 
 constexpr float kContactBreaking = 0.02f;  // gContactBreakingThreshold
 
+// static object index k (= obj - STATIC_BASE): meshes [0, nMeshes), planes [nMeshes, nMeshes + nPlanes), Dropshot tiles behind them
+RSB_HD int static_tile_index(const Scene& sc, int k) { return k - sc.nMeshes - sc.nPlanes; }  // >= 0: a Dropshot tile
 RSB_HD V3 static_origin(const Ctx& cx, int obj) {
 	int k = obj - STATIC_BASE;
 	if (k < cx.sc->nMeshes) return v3zero();
-	return cx.sc->planes[k - cx.sc->nMeshes].pos;
+	if (k < cx.sc->nMeshes + cx.sc->nPlanes) return cx.sc->planes[k - cx.sc->nMeshes].pos;
+	return V3(0.f, 0.f, -0.04f);  // tile bodies sit one collision margin below the floor (Arena.cpp:1078)
 }
 RSB_HD void static_aabb(const Ctx& cx, int obj, V3& mn, V3& mx) {
 	int k = obj - STATIC_BASE;
 	if (k < cx.sc->nMeshes) { mn = cx.sc->meshes[k].aabbMin; mx = cx.sc->meshes[k].aabbMax; }
-	else { mn = cx.sc->planes[k - cx.sc->nMeshes].aabbMin; mx = cx.sc->planes[k - cx.sc->nMeshes].aabbMax; }
+	else if (k < cx.sc->nMeshes + cx.sc->nPlanes) { mn = cx.sc->planes[k - cx.sc->nMeshes].aabbMin; mx = cx.sc->planes[k - cx.sc->nMeshes].aabbMax; }
+	else { const TileD& t = cx.sc->tiles[static_tile_index(*cx.sc, k)]; mn = t.aabbMin; mx = t.aabbMax; }
+}
+// CF_NO_CONTACT_RESPONSE of a static object: only a broken Dropshot tile has it (Arena::SetDropshotTilesState, Arena.cpp:225-242)
+RSB_HD bool static_no_response(const Ctx& cx, int obj) {
+	if (cx.p->mode != DROPSHOT) return false;
+	const int t = static_tile_index(*cx.sc, obj - STATIC_BASE);
+	return t >= 0 && (cx.g->tiles[t] & 4u) != 0;
 }
 // broadphase proxy AABB of a static = shape AABB +- gContactBreakingThreshold (updateSingleAabb)
 RSB_HD void static_proxy_aabb(const Ctx& cx, int obj, V3& mn, V3& mx) {
@@ -162,7 +172,8 @@ RSB_HD void body_filter(const Ctx& cx, int obj, int& group, int& mask) {
 	if (obj >= STATIC_BASE) {
 		int k = obj - STATIC_BASE;
 		if (k < cx.sc->nMeshes) { group = cx.sc->meshes[k].group; mask = cx.sc->meshes[k].mask; }
-		else { group = FILT_STATIC; mask = FILT_ALL ^ FILT_STATIC; }
+		else if (k < cx.sc->nMeshes + cx.sc->nPlanes) { group = cx.sc->planes[k - cx.sc->nMeshes].group; mask = cx.sc->planes[k - cx.sc->nMeshes].mask; }
+		else { group = FILT_DROPSHOT_TILE; mask = FILT_DROPSHOT_TILE; }
 	} else if (obj == 0) { group = FILT_DEFAULT | FILT_HOOPS_NET | FILT_DROPSHOT_TILE; mask = FILT_ALL; }
 	else { group = FILT_DEFAULT | FILT_DROPSHOT_FLOOR; mask = FILT_ALL; }
 }
@@ -482,6 +493,67 @@ RSB_ACP_ATTR void add_contact_point(const Ctx& cx, int mi, const V3& normalOnB, 
 	if (triMesh >= 0) adjust_internal_edge(cx, cp, cx.sc->meshes[triMesh], triIndex);
 }
 
+// Ball::_OnDropshotTileCollision (Ball.cpp:364-409), called from the (ball, tile) branch of the contact callback (Arena.cpp:291-296).
+// Tile states live in the cold tail of the arena record; the tile's rigid-body flag (bit 2) is only synchronised at the end of
+// the tick (tick_tail), so that the ball still bounces off the tile it has just broken.
+RSB_HD_NOINLINE void ball_on_dropshot_tile(Ctx cx, int tile) {
+	ArenaS& G = *cx.g;
+	const int team = tile / TILES_PER_TEAM, idx = tile - team * TILES_PER_TEAM;
+	if ((G.tiles[tile] & 3u) == 2u) return;  // already broken (two tiles hit at once)
+	const uint64_t tickCount = cx.s->tickCount;
+	if (G.dsHasDamaged) {
+		float timeSinceDamage = (tickCount - G.dsLastDamageTick) * cx.p->dt;
+		if (timeSinceDamage <= 0.1f) return;  // MIN_DAMAGE_INTERVAL
+	}
+	const V3 vel = cx.s->ball.rb.vel * BT_TO_UU;
+	if (vel.z > -250.f) return;  // MIN_DOWNWARD_SPEED_TO_DAMAGE
+	const TileD& td = cx.sc->tiles[tile];
+	if (G.dsChargeLevel > 1 && G.dsYTargetDir != 0.f) {
+		const int sgn = (td.posY > 0.f) - (td.posY < 0.f);
+		if ((float)sgn != G.dsYTargetDir) return;  // wrong side of the arena
+	}
+	const int lvl = G.dsChargeLevel;
+	const int n = lvl <= 1 ? 1 : (lvl == 2 ? td.n1 : td.n2);
+	for (int q = 0; q < n; q++) {
+		const int i = lvl <= 1 ? idx : (lvl == 2 ? td.nb1[q] : td.nb2[q]);
+		uint8_t& st = G.tiles[team * TILES_PER_TEAM + i];
+		if ((st & 3u) != 2u) st = (uint8_t)((st & ~3u) | ((st & 3u) + 1u));
+	}
+	G.dsHasDamaged = 1u;
+	G.dsLastDamageTick = tickCount;
+	G.dsAccumulatedHitForce = 0.f;
+	G.dsChargeLevel = 1;
+	G.dsYTargetDir = 0.f;
+}
+
+// addContactPoint for a (tile, ball) manifold: convex-convex keeps the broadphase order, so body0 is the STATIC tile and body1
+// the ball (btConvexConvexAlgorithm.cpp:268-276); combined material as for any static pair; the callback only runs the tile hook.
+RSB_HD void add_contact_point_tile(const Ctx& cx, int mi, const V3& normalOnB, const V3& pointInWorld, float depth) {
+	Manifold& m = cx.mf[mi];
+	if (depth > m.breakingThresh) return;
+	ContactPt pt;
+	V3 pointA = pointInWorld + normalOnB * depth;
+	Xform t0 = obj_xform(cx, m.body0), t1 = obj_xform(cx, m.body1);
+	pt.localA = xf_inv_apply(t0, pointA);
+	pt.localB = xf_inv_apply(t1, pointInWorld);
+	pt.normalB = normalOnB; pt.dist = depth;
+	pt.posA = pointA; pt.posB = pointInWorld;
+	pt.isSpecial = 0;
+	pt.partId0 = -1; pt.index0 = -1; pt.partId1 = -1; pt.index1 = -1;
+	{
+		const float fa = K::ARENA_COLLISION_BASE_FRICTION, fb = cx.body[m.body1].friction;
+		const float ra = K::ARENA_COLLISION_BASE_RESTITUTION, rb = cx.body[m.body1].restitution;
+		pt.friction = (fa < fb) ? fa : fb; pt.restitution = (ra > rb) ? ra : rb;
+	}
+	int insertIndex = m.nPts;
+	if (insertIndex == 4) insertIndex = sort_cached_points(m, pt);
+	else m.nPts++;
+	if (insertIndex < 0) insertIndex = 0;
+	m.pts[insertIndex] = pt;
+	if (static_no_response(cx, m.body0) || cx.body[m.body1].noResponse) return;
+	ball_on_dropshot_tile(cx, static_tile_index(*cx.sc, m.body0 - STATIC_BASE));
+}
+
 // btPersistentManifold::refreshContactPoints (btPersistentManifold.cpp:263-329)
 RSB_HD void refresh_contact_points(const Ctx& cx, int mi) {
 	Manifold& m = cx.mf[mi];
@@ -598,7 +670,7 @@ RSB_HD int cand_alloc(const Ctx& cx, int n) {
 	if (i + n > MAX_CANDS) { set_error(cx, ERR_TRI_OVERFLOW); return -1; }
 	return i;
 }
-RSB_HD void detect_candidate(const Ctx& cx, int idx);
+RSB_HD_NOINLINE void detect_candidate_cold(Ctx cx, int idx);
 RSB_HD void detect_queue_push(const Ctx& cx, int idx) {
 #if defined(__CUDA_ARCH__)
 	const unsigned q = atomicAdd(cx.nq, 1u);
@@ -606,7 +678,7 @@ RSB_HD void detect_queue_push(const Ctx& cx, int idx) {
 	const unsigned q = (*cx.nq)++;
 #endif
 	if (q < (unsigned)cx.qcap) cx.q[q] = (uint16_t)(cx.arLocal * 128 + idx);
-	else detect_candidate(cx, idx);  // the block's queue is full: run the detector right here (same result, only slower)
+	else detect_candidate_cold(cx, idx);  // the block's queue is full: run the detector right here (same result, only slower)
 }
 RSB_HD void cand_emit(const Ctx& cx, int pair, int mesh, int tri, int state, const V3& normal, const V3& point, float depth) {
 	const int i = cand_alloc(cx, 1);
@@ -780,6 +852,13 @@ RSB_HD void collide_static_pairs(const Ctx& cx, int b) {
 		const int sk = a - STATIC_BASE;
 		const bool isMesh = sk < sc.nMeshes;
 		const RigidS& rb = rigid_of(cx, b);
+		if (static_tile_index(sc, sk) >= 0) {
+			// (tile, ball): btConvexConvexAlgorithm on (hull, sphere) in broadphase order -> manifold (tile, ball), one GJK query
+			new_manifold(cx, k, a, b);
+			mark_deferred(cx, k);
+			cand_emit(cx, k, -1, -1, CAND_PENDING, v3zero(), v3zero(), 0.f);
+			continue;
+		}
 		if (inlineBody) {
 			Convex shape = ball_convex(P);
 			Xform xf; xf.basis = rb.basis; xf.origin = rb.pos;
@@ -847,17 +926,25 @@ RSB_HD void enqueue_dynamic_pairs(const Ctx& cx) {
 	}
 }
 
-// PH_NARROW_DETECT: the detector of one pending record, on its own thread
+// PH_NARROW_DETECT: the detector of one pending record, on its own thread.  Every GJK / EPA query -- (body, mesh triangle),
+// (car box, ball), (Dropshot tile hull, ball) -- goes through ONE call site of the (inlined) pair detector: the branches only
+// choose the two shapes and transforms.
 RSB_HD void detect_candidate(const Ctx& cx, int idx) {
 	const BatchParams& P = *cx.p;
 	CandRec* rec = &cx.w->cand[idx];
 	const int k = rec->pair;
 	const int a = cx.pl->a[k], b = cx.pl->b[k];
 	V3 n, pt; float d;
+	Convex shA, shB; Xform xfA, xfB;
 	if (a >= STATIC_BASE) {
-		// (body b, triangle of an arena mesh)
 		const RigidS& rb = rigid_of(cx, b);
-		if (b == 0 && P.ballIsSphere) {
+		const int tile = cx.sc->nTiles ? static_tile_index(*cx.sc, a - STATIC_BASE) : -1;
+		if (tile >= 0) {
+			// (Dropshot tile hull = A, ball = B): convex-convex keeps the broadphase order (btConvexConvexAlgorithm.cpp:268-276)
+			shA.kind = SH_HULL; shA.margin = 0.04f; shA.he = v3zero(); shA.pts = cx.sc->tiles[tile].pts; shA.npts = 6;
+			xfA.basis = m3identity(); xfA.origin = static_origin(cx, a);
+			shB = ball_convex(P); xfB.basis = rb.basis; xfB.origin = rb.pos;
+		} else if (b == 0 && P.ballIsSphere) {
 			// sphere vs triangle in closed form (SphereTriangleDetector, the reference's choice for this shape pair)
 			V3 t[3];
 			mesh_triangle(cx.sc->meshes[rec->mesh], rec->tri, t[0], t[1], t[2]);
@@ -866,34 +953,37 @@ RSB_HD void detect_candidate(const Ctx& cx, int idx) {
 			if (hit) { rec->normal = m3identity() * n; rec->point = m3identity() * pt + v3zero(); rec->depth = d; }
 			rec->state = hit ? CAND_CONTACT : CAND_NONE;
 			return;
+		} else {
+			// (body b = A, triangle of an arena mesh = B)
+			if (b == 0) { shA = ball_convex(P); xfA.basis = rb.basis; xfA.origin = rb.pos; }
+			else { shA = car_box(P.carCfg[b - 1]); xfA = cx.body[b].childXf; }
+			shB.kind = SH_TRI; shB.margin = 0.f; shB.he = v3zero(); shB.pts = nullptr; shB.npts = 0;
+			mesh_triangle(cx.sc->meshes[rec->mesh], rec->tri, shB.tri[0], shB.tri[1], shB.tri[2]);
+			xfB.basis = m3identity(); xfB.origin = v3zero();
 		}
-		Convex shape; Xform xf;
-		if (b == 0) { shape = ball_convex(P); xf.basis = rb.basis; xf.origin = rb.pos; }
-		else { shape = car_box(P.carCfg[b - 1]); xf = cx.body[b].childXf; }
-		Convex triShape; triShape.kind = SH_TRI; triShape.margin = 0.f; triShape.he = v3zero(); triShape.pts = nullptr; triShape.npts = 0;
-		mesh_triangle(cx.sc->meshes[rec->mesh], rec->tri, triShape.tri[0], triShape.tri[1], triShape.tri[2]);
-		Xform xfT; xfT.basis = m3identity(); xfT.origin = v3zero();
-		const bool hit = convex_convex_detect(cx, cx.mf[k].breakingThresh, shape, xf, triShape, xfT, n, pt, d);
-		if (hit) { rec->normal = n; rec->point = pt; rec->depth = d; }
-		rec->state = hit ? CAND_CONTACT : CAND_NONE;
 	} else if (a == 0) {
+		// (car box = A, ball = B)
 		const RigidS& rball = rigid_of(cx, 0);
-		Convex ball = ball_convex(P); Xform xfb; xfb.basis = rball.basis; xfb.origin = rball.pos;
-		Convex box = car_box(P.carCfg[b - 1]); const Xform xfc = cx.body[b].childXf;
-		const bool hit = convex_convex_detect(cx, cx.mf[k].breakingThresh, box, xfc, ball, xfb, n, pt, d);
-		if (hit) { rec->normal = n; rec->point = pt; rec->depth = d; }
-		rec->state = hit ? CAND_CONTACT : CAND_NONE;
+		shA = car_box(P.carCfg[b - 1]); xfA = cx.body[b].childXf;
+		shB = ball_convex(P); xfB.basis = rball.basis; xfB.origin = rball.pos;
 	} else {
 		Convex boxA = car_box(P.carCfg[a - 1]), boxB = car_box(P.carCfg[b - 1]);
-		const Xform xfA = cx.body[a].childXf, xfB = cx.body[b].childXf;
+		const Xform xfa = cx.body[a].childXf, xfb = cx.body[b].childXf;
 		V3 pts[4]; float dep[4];
-		const int nOut = box_box_detect(cx, boxB, xfB, boxA, xfA, n, pts, dep);
+		const int nOut = box_box_detect(cx, boxB, xfb, boxA, xfa, n, pts, dep);
 		for (int j = 0; j < 4; j++) {
 			if (j < nOut) { rec[j].normal = n; rec[j].point = pts[j]; rec[j].depth = dep[j]; }
 			rec[j].state = j < nOut ? CAND_CONTACT : CAND_NONE;
 		}
+		return;
 	}
+	const bool hit = convex_convex_detect(cx, cx.mf[k].breakingThresh, shA, xfA, shB, xfB, n, pt, d);
+	if (hit) { rec->normal = n; rec->point = pt; rec->depth = d; }
+	rec->state = hit ? CAND_CONTACT : CAND_NONE;
 }
+// the same detector out of line: the cold path of a full detector queue (detect_queue_push).  By-value context: see the
+// toolchain note in DESIGN.md (caller-local aggregates passed by reference to __noinline__ device functions).
+RSB_HD_NOINLINE void detect_candidate_cold(Ctx cx, int idx) { detect_candidate(cx, idx); }
 
 // PH_NARROW_COMMIT (body b) / PH_DYN_SOLVE (dynamic pairs, b = -1): records -> manifolds + contact hooks, in record order.
 // The records of one thread's walk carry ascending indices, so one pass in index order filtered by owner restores the order
@@ -910,6 +1000,7 @@ RSB_HD void commit_candidates(const Ctx& cx, int b) {
 		if (k != curPair) { if (curPair >= 0) refresh_contact_points(cx, curPair); curPair = k; }
 		if (r.state != CAND_CONTACT) continue;
 		if (b < 0) add_contact_point(cx, k, r.normal, r.point, r.depth, -1, -1, true);
+		else if (cx.sc->nTiles && cx.mf[k].body0 >= STATIC_BASE) add_contact_point_tile(cx, k, r.normal, r.point, r.depth);
 		else add_contact_point(cx, k, r.normal, r.point, r.depth, r.mesh, r.tri, false);
 	}
 	if (curPair >= 0) refresh_contact_points(cx, curPair);

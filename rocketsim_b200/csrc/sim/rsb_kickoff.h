@@ -29,11 +29,24 @@ RSB_HD K::SpawnPos kickoff_slot(int mode, int i) {
 		const K::SpawnPos t[5] = {{-1000, -4620, P2}, {1000, -4620, P2}, {-2000, -4620, P2}, {2000, -4620, P2}, {0, 0, 0}};
 		return t[i];
 	}
+	if (mode == DROPSHOT) {  // CAR_SPAWN_LOCATIONS_DROPSHOT (RLConst.h:381-388)
+		const K::SpawnPos t[5] = {{-1867, -2380, P4 * 1}, {1867, -2380, P4 * 3}, {-256, -3576, P4 * 2}, {256, -3576, P4 * 2}, {0, -4088, P4 * 2}};
+		return t[i];
+	}
 	const K::SpawnPos t[5] = {{-2048, -2560, P4 * 1}, {2048, -2560, P4 * 3}, {-256, -3840, P4 * 2}, {256, -3840, P4 * 2}, {0, -4608, P4 * 2}};
 	return t[i];
 }
 
-RSB_HD void kickoff_reset(ArenaS& A, const BatchParams& P, int seed) {
+RSB_HD void dropshot_reset(ArenaS& G) {
+	G.dsChargeLevel = 1; G.dsAccumulatedHitForce = 0.f; G.dsYTargetDir = 0.f; G.dsHasDamaged = 0u; G.dsLastDamageTick = 0ull;
+	for (int t = 0; t < MAX_TILES; t++) G.tiles[t] = 0;
+}
+// Arena::SetDropshotTilesState(_dropshotTilesState): tile bodies take their no-contact-response flag from the damage states
+RSB_HD void dropshot_sync_tiles(ArenaS& G) {
+	for (int t = 0; t < MAX_TILES; t++) G.tiles[t] = (uint8_t)((G.tiles[t] & 3u) | (((G.tiles[t] & 3u) == 2u) ? 4u : 0u));
+}
+
+RSB_HD void kickoff_reset(ArenaS& A, ArenaS& G, const BatchParams& P, int seed) {
 	uint32_t localRng = minstd_seed_int(seed);
 	uint32_t& rng = (seed == -1) ? A.rng : localRng;
 	int order[5] = {0, 1, 2, 3, 4};
@@ -71,7 +84,12 @@ RSB_HD void kickoff_reset(ArenaS& A, const BatchParams& P, int seed) {
 		} else {
 			int ridx = (k - L) % L;
 			respIdx = ridx;
-			sp = respawn_slot(P.mode == HOOPS, ridx);
+			// CAR_RESPAWN_LOCATIONS_DROPSHOT (RLConst.h:407-413) is only used here; Car::Respawn takes the Soccar table in Dropshot
+			if (P.mode == DROPSHOT) {
+				const float H = (float)(3.14159265358979323846 / 2);
+				const K::SpawnPos t[4] = {{-2176, -3410, H}, {-1152, -3100, H}, {2176, -3410, H}, {1152, -3100, H}};
+				sp = t[ridx];
+			} else sp = respawn_slot(P.mode == HOOPS, ridx);
 			sp.y += 250.f * numAtRespawn[ridx];
 			numAtRespawn[ridx]++;
 		}
@@ -105,6 +123,9 @@ RSB_HD void kickoff_reset(ArenaS& A, const BatchParams& P, int seed) {
 	b.rb.pos = bpos * UU_TO_BT; b.rb.vel = bvel * UU_TO_BT;
 	b.velImpulseCache = v3zero(); b.tickCountSinceUpdate = 0;
 	for (int p = 0; p < P.nPads; p++) { A.pads[p].isActive = 1; A.pads[p].cooldown = 0.f; A.pads[p].prevLockedCarID = 0; }
+	// ball->SetState(BallState()) resets dsInfo; SetDropshotTilesState({}) restores every tile (Arena.cpp:205-217).  G = the arena's
+	// record in HBM (== A outside the step kernel)
+	if (P.mode == DROPSHOT) dropshot_reset(G);
 }
 
 }  // namespace rsb

@@ -279,8 +279,9 @@ RSB_HD bool cast_vehicle_ray(const Ctx& cx, int self, const V3& from, const V3& 
 					    smn.z > m.aabbMax.z + slack || smx.z < m.aabbMin.z - slack) continue;
 				}
 				if (ray_mesh(sc, m, s, from, to, closest, normal)) obj = STATIC_BASE + k;
-			} else {
+			} else if (k < sc.nMeshes + sc.nPlanes) {
 				const PlaneD& pl = sc.planes[k - sc.nMeshes];
+				if (!((pl.group & FILT_ALL) != 0 && (rayGroup & pl.mask))) continue;
 				// conservative cull (ours): the triangle test only reports a hit when the end points lie on opposite sides of the
 				// triangle's plane, which is the static plane up to rounding (< 1e-4 bt at arena scale); 1e-2 bt of slack
 				const float da = dot(pl.n, from - pl.pos), db = dot(pl.n, to - pl.pos);

@@ -89,6 +89,7 @@ RSB_HD int build_islands(const Ctx& cx) {
 			const bool s1 = b1 >= STATIC_BASE;
 			if (!(((notSl >> b0) & 1) || (!s1 && ((notSl >> b1) & 1)))) continue;
 			if (((noResp >> b0) & 1) || (!s1 && ((noResp >> b1) & 1))) continue;
+			if (s1 && static_no_response(cx, b1)) continue;  // broken Dropshot tile
 			withPts++; last = m;
 		}
 		if (withPts == 0) return 0;
@@ -143,6 +144,7 @@ RSB_HD int build_islands(const Ctx& cx) {
 		if (!(awake0 || awake1)) continue;
 		const bool resp = !((noResp >> b0) & 1) && (s1 || !((noResp >> b1) & 1));
 		if (!resp) continue;
+		if (s1 && static_no_response(cx, b1)) continue;  // broken Dropshot tile
 		keys[n] = (int)((tags >> (4 * b0)) & 15);
 		order[n] = m;
 		n++;

@@ -24,6 +24,7 @@ constexpr int MAX_MANIFOLDS = 32;    // broadphase pairs per arena and tick (= m
 constexpr int MAX_POINTS = MAX_MANIFOLDS * 4;
 constexpr int MAX_ROWS = MAX_POINTS + MAX_BODIES;
 constexpr int MAX_EVENTS_PER_ARENA = 8;
+constexpr int TILES_PER_TEAM = 70, MAX_TILES = 2 * TILES_PER_TEAM;  // RLConst::Dropshot (RLConst.h:223-225)
 
 enum GameMode : int { SOCCAR = 0, HOOPS = 1, HEATSEEKER = 2, SNOWDAY = 3, DROPSHOT = 4, THE_VOID = 5 };
 
@@ -108,6 +109,15 @@ struct ArenaS {
 	// top of Car::_PostTickUpdate, which returns early for a demoed car (Car.cpp:133-138), while the victim's rigid body still
 	// goes through the solve + integration of the tick it was demoed in.  Captured at the moment of the demo.
 	M3 demoRotMat[MAX_CARS];
+	// Dropshot (mode DROPSHOT only): BallState::dsInfo (Ball.h:34-47) and the tile field.  tiles[team * 70 + i]: bits 0-1 =
+	// DropshotTileState::damageState (Arena::_dropshotTilesState), bit 2 = the tile's rigid body currently has
+	// CF_NO_CONTACT_RESPONSE.  The two differ between the tick a tile breaks and the end of that tick (Arena.cpp:741-746).
+	int32_t dsChargeLevel;
+	float dsAccumulatedHitForce, dsYTargetDir;
+	uint32_t dsHasDamaged;
+	uint64_t dsLastDamageTick;
+	uint8_t tiles[MAX_TILES];
+	uint8_t _padTiles[4];
 };
 
 enum ErrorFlags : uint32_t {
@@ -199,14 +209,25 @@ struct MeshD {
 	int group, mask;              // collision filter (HOOPS_NET for the 505-vertex mesh)
 };
 
-struct PlaneD { V3 n; float d; V3 pos; V3 aabbMin, aabbMax; };  // world plane n.x = d ; body origin pos
+struct PlaneD { V3 n; float d; V3 pos; V3 aabbMin, aabbMax; int group, mask; };  // world plane n.x = d ; body origin pos ; collision filter
+// Dropshot floor tile (DropshotTiles.cpp:22-62, Arena.cpp:1070-1085): a btConvexHullShape of 6 coplanar points given in WORLD
+// coordinates (Bullet units), on a static body at (0, 0, -margin); nb1 / nb2 = the tiles damaged by a charge-level 2 / 3 hit
+// (indices within the tile's team, ascending, incl. the tile itself; DropshotTiles.cpp:92-112)
+struct TileD {
+	V3 pts[6];
+	V3 aabbMin, aabbMax;  // world AABB of the shape (getAabb of the body's transform)
+	float posY;           // GetTilePos(team, idx).y (uu)
+	uint8_t n1, n2, nb1[7], nb2[20];
+	uint8_t _pad[3];
+};
 
 constexpr int MAX_MESHES = 20;
 constexpr int MAX_PLANES = 6;
-constexpr int MAX_STATICS = MAX_MESHES + MAX_PLANES;
+constexpr int MAX_STATICS = MAX_MESHES + MAX_PLANES + MAX_TILES;  // static object index: meshes, then planes, then tiles (world order)
 
 struct Scene {
 	int nMeshes, nPlanes;
+	int nTiles; const TileD* tiles;  // Dropshot only
 	MeshD meshes[MAX_MESHES];
 	PlaneD planes[MAX_PLANES];
 	// btRSBroadphase grid (btRSBroadphase.cpp:43-84): static object lists per cell, CSR

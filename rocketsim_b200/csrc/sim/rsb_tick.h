@@ -155,6 +155,9 @@ RSB_HD void phase_run(const Ctx& cx, int phase, int item) {
 	case PH_PADS_POST: pad_posttick(cx, item); break;
 	case PH_TAIL:
 		ball_finish_tick(cx);
+		// Dropshot: the rigid bodies of tiles broken this tick lose their contact response now (Arena.cpp:741-746; a damage on
+		// tick 0 is never synchronised there -- `lastDamageTick &&` -- and therefore not here either)
+		if (P.mode == DROPSHOT && cx.g->dsLastDamageTick && cx.g->dsLastDamageTick == S.tickCount) dropshot_sync_tiles(*cx.g);
 		// ---- T6: goal event, tick counter
 		{
 			const bool scored = P.mode != THE_VOID && is_ball_scored(cx);
@@ -165,7 +168,7 @@ RSB_HD void phase_run(const Ctx& cx, int phase, int item) {
 			// the caller's loop is Step(); tracker.Update(); if (scored) Reset -- same order here
 			if (P.trackerEnabled) tracker_update(cx, scored, S.tickCount + 1);
 			// seed = f(global arena index, tick), masked to 31 bits: never negative, never the -1 that selects the arena RNG
-			if (scored && P.autoReset) kickoff_reset(S, P, (int)((P.autoResetSeed + (uint32_t)(P.arenaOffset + cx.arena) + (uint32_t)S.tickCount) & 0x7fffffffu));
+			if (scored && P.autoReset) kickoff_reset(S, *cx.g, P, (int)((P.autoResetSeed + (uint32_t)(P.arenaOffset + cx.arena) + (uint32_t)S.tickCount) & 0x7fffffffu));
 		}
 		S.tickCount++;
 		S.worldFresh = 0;

@@ -29,6 +29,7 @@ EXPORTS = [
     "rsb_get_car_internals", "rsb_set_car_internals", "rsb_get_ball_internals", "rsb_set_ball_internals",
     "rsb_reset_to_random_kickoff", "rsb_scene_counts", "rsb_scene_dump", "rsb_scene_num_meshes", "rsb_scene_cells",
     "rsb_bench_fill_controls_device", "rsb_debug_get_wheels", "rsb_step_with_controls", "rsb_set_auto_reset", "rsb_debug_get_manifolds", "rsb_debug_get_solver_rows", "rsb_debug_profile", "rsb_debug_get_solver_bodies", "rsb_debug_get_misc", "rsb_car_config_preset", "rsb_default_mutator_config", "rsb_set_event_tracker", "rsb_is_ball_probably_going_in", "rsb_predict_ball", "rsb_serialize_arena", "rsb_deserialize_arena", "rsb_clone_arena", "rsb_set_arena_offset", "rsb_batch_create_ex", "rsb_default_arena_config",
+    "rsb_get_dropshot_tiles", "rsb_set_dropshot_tiles",
 ]
 
 
@@ -65,6 +66,8 @@ def _declare(L):
     L.rsb_set_ball_states.argtypes = [vp, vp, i32, vp]
     L.rsb_set_ball_internals.argtypes = [vp, vp, i32, vp]
     L.rsb_set_pad_states.argtypes = [vp, vp, i32, vp]
+    L.rsb_get_dropshot_tiles.argtypes = [vp, vp]
+    L.rsb_set_dropshot_tiles.argtypes = [vp, vp, i32, vp]
     L.rsb_get_events.argtypes = [vp, vp, i32, vp]
     L.rsb_seed_rng.argtypes = [vp, u32, u32]
     L.rsb_observation_floats.argtypes = [vp]

@@ -173,6 +173,39 @@ def hoops_meshes() -> List[bytes]:
     return [ramps.to_cmf(), rims.to_cmf()] + nets
 
 
+def dropshot_meshes() -> List[bytes]:
+    """Dropshot shell: the arena has no side planes (reference ``Arena.cpp:1056-1061``), so the mesh carries all six walls of
+    the hexagonal field (circumradius 5400 uu: encloses the 13..7-tile rows of ``DropshotTiles.cpp``) -- a 45-degree skirt from
+    the floor up to 250 uu, then a vertical wall up to the 2024 uu ceiling -- plus the solid floor strip between the two tile fields,
+    in three meshes (walls / skirts / centre strip)."""
+    RC, H, SK = 5400.0, 2024.0, 250.0
+    ang = np.deg2rad(np.arange(7) * 60.0)
+    cx, cy = RC * np.cos(ang), RC * np.sin(ang)
+    walls, skirts = _Mesh(), _Mesh()
+    for k in range(6):
+        a = np.array([cx[k], cy[k]]); b = np.array([cx[k + 1], cy[k + 1]])
+        mid = 0.5 * (a + b)
+        inward = -mid / np.linalg.norm(mid)
+        ts = np.linspace(0.0, 1.0, 7)
+        edge = a[None, :] + ts[:, None] * (b - a)[None, :]
+        # vertical part
+        zs = np.linspace(SK, H, 4)
+        pts = np.zeros((7, 4, 3))
+        pts[:, :, 0] = edge[:, 0][:, None]; pts[:, :, 1] = edge[:, 1][:, None]; pts[:, :, 2] = zs[None, :]
+        walls.add_grid(pts, np.array([inward[0], inward[1], 0.0]))
+        # skirt: from (edge moved inward by SK) at z = 0 up to the wall foot at z = SK
+        pts = np.zeros((7, 3, 3))
+        for j, f in enumerate((1.0, 0.5, 0.0)):
+            pts[:, j, 0] = edge[:, 0] + inward[0] * SK * f
+            pts[:, j, 1] = edge[:, 1] + inward[1] * SK * f
+            pts[:, j, 2] = SK * (1.0 - f)
+        skirts.add_grid(pts, np.array([inward[0], inward[1], 1.0]))
+    # the tile fields of the two teams start at |y| = 127.4 uu (TILE_OFFSET_Y): the strip between them is solid floor
+    strip = _Mesh()
+    _wall_xy(strip, 0.0, -RC, RC, -130.0, 130.0, 12, 2, 1.0)
+    return [walls.to_cmf(), skirts.to_cmf(), strip.to_cmf()]
+
+
 def far_triangle_mesh() -> bytes:
     """A single far-away triangle: turns any arena into a planes-only arena for staged bring-up."""
     m = _Mesh()
@@ -196,7 +229,9 @@ def mesh_sets(planes_only: bool = False) -> Dict[int, List[bytes]]:
     if planes_only:
         s = [far_triangle_mesh()]
         h = [far_triangle_mesh()]
+        d = [far_triangle_mesh()]
     else:
         s = soccar_meshes()
         h = hoops_meshes()
-    return {MODE_SOCCAR: s, MODE_HOOPS: h, MODE_HEATSEEKER: s, MODE_SNOWDAY: s}
+        d = dropshot_meshes()
+    return {MODE_SOCCAR: s, MODE_HOOPS: h, MODE_HEATSEEKER: s, MODE_SNOWDAY: s, MODE_DROPSHOT: d}

@@ -47,6 +47,12 @@ CASES = {
     "snowday_3v3_demo_charge": (T.MODE_SNOWDAY, 3, 14, 500, 150, "charge"),
     "soccar_2v2_goal": (T.MODE_SOCCAR, 2, 41, 180, 30, "goal"),
     "hoops_2v2_goal": (T.MODE_HOOPS, 2, 43, 240, 30, "goal"),
+    # Dropshot (tile hulls, DROPSHOT_FLOOR plane, ball launch, tile damage, charge levels, the ball falling through = goal)
+    "dropshot_2v2_kickoff": (T.MODE_DROPSHOT, 2, 51, 300, 150, False),
+    "dropshot_2v2_charge": (T.MODE_DROPSHOT, 2, 53, 500, 150, "ds_charge"),
+    "dropshot_2v2_drop": (T.MODE_DROPSHOT, 2, 59, 340, 60, "ds_drop"),
+    "dropshot_3v3_slam": (T.MODE_DROPSHOT, 3, 55, 420, 90, "ds_slam"),
+    "dropshot_2v2_walls": (T.MODE_DROPSHOT, 2, 57, 300, 150, "walls"),
 }
 
 
@@ -62,7 +68,7 @@ def main():
         ev = rec["events"]
         print(f"{name}: {ticks} ticks, {len(ev)} events (goal/bump/demo = {[int((ev[:, 1] == k).sum()) for k in (1, 2, 3)] if len(ev) else 0}), "
               f"demoed car-ticks {int(rec['car_post']['isDemoed'].sum())}, supersonic car-ticks {int(rec['car_post']['isSupersonic'].sum())}, "
-              f"scored ticks {int(rec['scored'].sum())}, wheel-on-dynamic ticks {int(rec['wheel_on_dynamic'].sum())}, {os.path.getsize(path) / 1024:.0f} KiB")
+              f"scored ticks {int(rec['scored'].sum())}, " + (f"tile changes {int((rec['tiles_pre'] != rec['tiles_post']).sum())}, broken at end {int((rec['tiles_post'][-1] == 2).sum())}, max charge {int(rec['ball_post']['dsInfo']['chargeLevel'].max())}, " if 'tiles_pre' in rec else "") + f" wheel-on-dynamic ticks {int(rec['wheel_on_dynamic'].sum())}, {os.path.getsize(path) / 1024:.0f} KiB")
 
 
 if __name__ == "__main__":

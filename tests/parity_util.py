@@ -140,6 +140,8 @@ def sync_from_ref(batch: ArenaBatch, ref, arena=0):
     batch.set_ball_internals([arena], np.array([ref.ball_internal()], dtype=T.BallInternal))
     if batch.n_pads:
         batch.set_pad_states([arena], ref.pad_states())
+    if batch.game_mode == T.MODE_DROPSHOT:
+        batch.set_dropshot_tiles([arena], ref.dropshot_tiles())
 
 
 # ---------------------------------------------------------------------------------------------
@@ -178,6 +180,19 @@ def cars_at_walls(ref, mode):
     """Cars next to the side walls / back walls heading into them, ball launched at a ramp: exercises the arena
     mesh BVH (ramps, back walls, goal boxes) for suspension rays, car-mesh and ball-mesh contacts."""
     ex, ey = (2966.0, 3581.0) if mode == T.MODE_HOOPS else (4096.0, 5120.0)
+    if mode == T.MODE_DROPSHOT:
+        # hexagonal shell of synthetic_meshes.dropshot_meshes (apothem 4,676 uu along y, corners at x = +-5,400): cars head into
+        # the two y walls, two slanted walls and the skirts; the ball is fired into a slanted wall's skirt
+        spots = [(600.0, 4676.0 - 700.0, np.pi / 2), (-1500.0, -(4676.0 - 700.0), -np.pi / 2), (3500.0, 1500.0, np.pi / 6),
+                 (-3500.0, -1500.0, np.pi + np.pi / 6), (3300.0, -1700.0, -np.pi / 6), (-3300.0, 1700.0, np.pi - np.pi / 6)]
+        for i, cid in enumerate(ref.car_ids):
+            x, y, yaw = spots[i % len(spots)]
+            _place_car(ref, cid, x, y, yaw, vel=(1400.0 * float(np.float32(np.cos(yaw))), 1400.0 * float(np.float32(np.sin(yaw))), 0.0))
+        bs = ref.ball_state()
+        bs["pos"]["x"], bs["pos"]["y"], bs["pos"]["z"] = 3000.0, 1200.0, 300.0
+        bs["vel"]["x"], bs["vel"]["y"], bs["vel"]["z"] = 1900.0, 1100.0, -200.0
+        ref.set_ball_state(bs)
+        return
     spots = [(ex - 420.0, -900.0, 0.0), (-(ex - 420.0), 700.0, np.pi), (600.0, ey - 450.0, np.pi / 2),
              (-1500.0, -(ey - 450.0), -np.pi / 2), (ex - 500.0, ey - 700.0, np.pi / 4), (-(ex - 500.0), -(ey - 700.0), -3 * np.pi / 4)]
     for i, cid in enumerate(ref.car_ids):
@@ -271,6 +286,43 @@ def apply_scenario(ref, mode, teams, aim):
     elif aim == "goal":
         aim_cars_at_ball(ref, radius=1500.0)
         ball_at_goal(ref, mode)
+    elif aim == "ds_drop":
+        # Dropshot: the ball drops onto a blue tile field whose tiles are all damaged already and keeps bouncing on one tile: the
+        # first impact breaks it, the second one goes through the hole: a goal
+        aim_cars_at_ball(ref, radius=1500.0)
+        tiles = np.zeros(140, np.uint8); tiles[:70] = 1
+        ref.set_dropshot_tiles(tiles)
+        bs = ref.ball_state()
+        bs["pos"]["x"], bs["pos"]["y"], bs["pos"]["z"] = 900.0, -1250.0, 400.0
+        bs["vel"]["x"], bs["vel"]["y"], bs["vel"]["z"] = 0.0, 0.0, -900.0
+        ref.set_ball_state(bs)
+    elif aim == "ds_charge":
+        # Dropshot: cars arrive at 2,000 uu/s at a ball resting on the orange tiles, off the kickoff spot (so it is not launched,
+        # Ball.cpp:222-224): every hit above 500 uu/s charges it (Ball.cpp:299-323)
+        apply_scenario(ref, mode, teams, "charge")
+        for cid in ref.car_ids:
+            st = ref.car_state(cid)
+            st["pos"]["y"] = float(st["pos"]["y"]) + 400.0
+            ref.set_car_state(cid, st)
+        bs = ref.ball_state()
+        bs["pos"]["y"] = 400.0
+        bs["dsInfo"]["accumulatedHitForce"] = 1500.0  # the first hard hit takes it past MIN_ABSORBED_FORCE_FOR_CHARGE
+        ref.set_ball_state(bs)
+    elif aim == "ds_slam":
+        # Dropshot: a super-charged ball (charge level 3, blue hit it last -> it damages the orange half, y > 0) comes down on
+        # tiles of which some are already damaged / broken: 19-tile damage pattern, tiles breaking, the ball falling through
+        # the hole a few bounces later = a goal (Ball.cpp:364-409, Arena.cpp:741-746, 916-923)
+        aim_cars_at_ball(ref, radius=1500.0)
+        tiles = np.zeros(140, np.uint8)
+        tiles[70 + np.arange(0, 70, 3)] = 1
+        tiles[70 + np.arange(1, 70, 7)] = 2
+        tiles[np.arange(2, 70, 5)] = 1
+        ref.set_dropshot_tiles(tiles)
+        bs = ref.ball_state()
+        bs["pos"]["x"], bs["pos"]["y"], bs["pos"]["z"] = 700.0, 1500.0, 700.0
+        bs["vel"]["x"], bs["vel"]["y"], bs["vel"]["z"] = -300.0, 250.0, -1600.0
+        bs["dsInfo"]["chargeLevel"] = 3; bs["dsInfo"]["yTargetDir"] = 1.0; bs["dsInfo"]["accumulatedHitForce"] = 11500.0
+        ref.set_ball_state(bs)
     elif aim:
         aim_cars_at_ball(ref)
     return roles
@@ -309,6 +361,8 @@ def record_rollout(refsim, mode, teams, seed, ticks, drive=0, aim=False):
                # the respawn RNG (thread-local in the reference) is re-seeded with seed + t before every tick, so that a tick
                # with a respawn is an independent single-step case like every other
                rng_per_tick=np.int32(1))
+    if mode == T.MODE_DROPSHOT:
+        rec["tiles_pre"] = np.zeros((ticks, 140), np.uint8); rec["tiles_post"] = np.zeros((ticks, 140), np.uint8)
     events = []
     for t in range(ticks):
         ref.seed_rng(seed + t)
@@ -323,7 +377,11 @@ def record_rollout(refsim, mode, teams, seed, ticks, drive=0, aim=False):
         rec["ball_pre"][t] = ref.ball_state()
         rec["ballint_pre"][t] = ref.ball_internal()
         rec["pads_pre"][t] = ref.pad_states()
+        if mode == T.MODE_DROPSHOT:
+            rec["tiles_pre"][t] = ref.dropshot_tiles()
         ref.step(1)
+        if mode == T.MODE_DROPSHOT:
+            rec["tiles_post"][t] = ref.dropshot_tiles()
         for i, cid in enumerate(ref.car_ids):
             rec["car_post"][t, i] = ref.car_state(cid)
         rec["ball_post"][t] = ref.ball_state()
@@ -364,6 +422,8 @@ def load_pre_state(batch, rec, t, arena=0):
     batch.set_ball_internals([arena], rec["ballint_pre"][t:t + 1])
     if batch.n_pads:
         batch.set_pad_states([arena], rec["pads_pre"][t])
+    if "tiles_pre" in rec:
+        batch.set_dropshot_tiles([arena], rec["tiles_pre"][t])
 
 
 def replay_record(rec, lib, n_arenas=1, ticks=None, tol=1e-4):
@@ -408,6 +468,11 @@ def replay_record(rec, lib, n_arenas=1, ticks=None, tol=1e-4):
                                                          / np.maximum(np.abs(rec["pads_post"][t]["cooldown"]), 1e-2), initial=0.0)))
             if bool(sc[a]) != bool(rec["scored"][t]):
                 mism.append((t, a, -1, ["scored"]))
+            if "tiles_post" in rec:  # Dropshot: tile damage states and BallState::dsInfo are discrete state
+                if not np.array_equal(batch.get_dropshot_tiles()[a].ravel(), rec["tiles_post"][t]):
+                    mism.append((t, a, -1, ["tiles"]))
+                if not struct_equal(bs[a]["dsInfo"], rec["ball_post"][t]["dsInfo"]):
+                    mism.append((t, a, -1, ["dsInfo"]))
         for e in batch.get_events():
             if int(e["arena"]) == 0:
                 my_events.append((t, int(e["type"]), int(e["a"]), int(e["b"])))

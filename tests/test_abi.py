@@ -66,8 +66,6 @@ def test_batch_create_argument_errors(hostlib):
         ArenaBatch(T.MODE_THE_VOID, 0, [0, 1], lib=hostlib)
     with pytest.raises(lib.RsbError):
         ArenaBatch(T.MODE_THE_VOID, 1, [0] * 7, lib=hostlib)
-    with pytest.raises(lib.RsbError):
-        ArenaBatch(T.MODE_DROPSHOT, 1, [0, 1], lib=hostlib)
     b = ArenaBatch(T.MODE_THE_VOID, 2, [0, 1], lib=hostlib)
     with pytest.raises(lib.RsbError):
         b.set_ball_states([5], np.zeros(1, T.BallState))

@@ -80,8 +80,8 @@ def test_full_size_replicas_and_slot_independence(cudalib):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("mode,cpt", [(T.MODE_SOCCAR, 3), (T.MODE_HOOPS, 2), (T.MODE_HEATSEEKER, 1), (T.MODE_SNOWDAY, 3), (T.MODE_THE_VOID, 1)],
-                         ids=["soccar_3v3", "hoops_2v2", "heatseeker_1v1", "snowday_3v3", "void_1v1"])
+@pytest.mark.parametrize("mode,cpt", [(T.MODE_SOCCAR, 3), (T.MODE_HOOPS, 2), (T.MODE_HEATSEEKER, 1), (T.MODE_SNOWDAY, 3), (T.MODE_THE_VOID, 1), (T.MODE_DROPSHOT, 3)],
+                         ids=["soccar_3v3", "hoops_2v2", "heatseeker_1v1", "snowday_3v3", "void_1v1", "dropshot_3v3"])
 def test_launch_granularity_and_determinism(cudalib, mode, cpt):
     teams = [0] * cpt + [1] * cpt
     n_arenas, n_ticks = 300, 120

@@ -12,7 +12,8 @@ import parity_util as pu
 from rocketsim_b200 import types as T
 from rocketsim_b200.arena_batch import ArenaBatch
 
-MODES = [("soccar", T.MODE_SOCCAR), ("hoops", T.MODE_HOOPS), ("heatseeker", T.MODE_HEATSEEKER), ("snowday", T.MODE_SNOWDAY), ("void", T.MODE_THE_VOID)]
+MODES = [("soccar", T.MODE_SOCCAR), ("hoops", T.MODE_HOOPS), ("heatseeker", T.MODE_HEATSEEKER), ("snowday", T.MODE_SNOWDAY), ("void", T.MODE_THE_VOID),
+         ("dropshot", T.MODE_DROPSHOT)]
 SEEDS = list(range(1, 17)) + [1234, 99991, 2 ** 31 - 1, -7, -123456, -2147483648]   # negative seeds: 64-bit sign extension in libstdc++
 
 
@@ -44,6 +45,7 @@ def _check_kickoffs(lib, oracle, mode, cpt):
         for f in ("pos", "vel", "angVel", "rotMat"):
             assert bs[k][f].tobytes() == rb[f].tobytes(), f"mode {mode} seed {seed} ball {f}"
         assert bs[k]["hsInfo"].tobytes() == rb["hsInfo"].tobytes()
+        assert pu.struct_equal(bs[k]["dsInfo"], rb["dsInfo"])
         if ps is not None:
             rp = ref.pad_states()
             assert np.array_equal(ps[k]["isActive"], rp["isActive"]) and np.array_equal(ps[k]["cooldown"], rp["cooldown"])

@@ -20,7 +20,7 @@ def preset_cfg(L, k):
 def test_constant_tables_match_reference(hostlib, oracle):
     for k in range(7):
         assert pu.struct_equal(preset_cfg(hostlib, k), oracle.car_config(k)), f"preset {k}"
-    for mode in (T.MODE_SOCCAR, T.MODE_HOOPS, T.MODE_HEATSEEKER, T.MODE_SNOWDAY, T.MODE_THE_VOID):
+    for mode in (T.MODE_SOCCAR, T.MODE_HOOPS, T.MODE_HEATSEEKER, T.MODE_SNOWDAY, T.MODE_DROPSHOT, T.MODE_THE_VOID):
         m = np.zeros(1, T.MutatorConfig)
         rlib.check(hostlib, hostlib.rsb_default_mutator_config(mode, rlib.ptr(m)))
         assert pu.struct_equal(m[0], oracle.default_mutator_config(mode)), f"mutator of mode {mode}"
