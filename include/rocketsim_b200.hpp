@@ -69,6 +69,17 @@ struct ArenaConfig {
 };
 enum class Team : uint8_t { BLUE = 0, ORANGE = 1 };
 
+// DropshotTileState / DropshotTilesState (src/Sim/Arena/DropshotTiles/DropshotTiles.h:7-33): same layout, one byte per tile
+struct DropshotTileState {
+	enum { STATE_FULL = 0, STATE_DAMAGED, STATE_BROKEN };
+	uint8_t damageState = STATE_FULL;
+};
+struct DropshotTilesState {
+	enum { STATE_FULL = 0, STATE_DAMAGED, STATE_BROKEN };
+	DropshotTileState states[2][70];  // [RLConst::Dropshot::TEAM_AMOUNT][NUM_TILES_PER_TEAM]
+};
+static_assert(sizeof(DropshotTilesState) == 140, "DropshotTilesState is 140 damage-state bytes");
+
 inline void Check(int rc) { if (rc != 0) throw std::runtime_error(std::string("RocketSimB200: ") + rsb_last_error()); }
 
 inline CarConfig CarConfigPreset(int preset) { CarConfig c; Check(rsb_car_config_preset(preset, &c)); return c; }
@@ -124,6 +135,9 @@ public:
 	std::vector<BoostPadState> GetPadStates() { std::vector<BoostPadState> v((size_t)numArenas * numPads); if (!v.empty()) Check(rsb_get_pad_states(h_, v.data())); return v; }
 	void SetCarState(uint32_t arena, uint32_t carSlot, const CarState& s) { Check(rsb_set_car_states(h_, &arena, &carSlot, 1, &s)); }
 	void SetBallState(uint32_t arena, const BallState& s) { Check(rsb_set_ball_states(h_, &arena, 1, &s)); }
+	// Arena::GetDropshotTilesState / SetDropshotTilesState (Arena.h:178-179) of a Dropshot batch
+	std::vector<DropshotTilesState> GetDropshotTilesStates() { std::vector<DropshotTilesState> v(numArenas); Check(rsb_get_dropshot_tiles(h_, (uint8_t*)v.data())); return v; }
+	void SetDropshotTilesState(uint32_t arena, const DropshotTilesState& s) { Check(rsb_set_dropshot_tiles(h_, &arena, 1, (const uint8_t*)&s)); }
 	std::vector<uint64_t> GetTickCounts() { std::vector<uint64_t> v(numArenas); Check(rsb_get_tick_counts(h_, v.data())); return v; }
 	std::vector<uint8_t> IsBallScored() { std::vector<uint8_t> v(numArenas); Check(rsb_is_ball_scored(h_, v.data())); return v; }
 	std::vector<RsbEvent> GetEvents(int cap = 65536) {
@@ -277,6 +291,9 @@ public:
 	}
 	void ResetToRandomKickoff(int seed = -1) { Realize(); batch_->ResetToRandomKickoff({(int32_t)seed}); }
 	bool IsBallScored() { Realize(); return batch_->IsBallScored()[0] != 0; }
+	// Arena::GetDropshotTilesState / SetDropshotTilesState (Arena.h:178-179, Arena.cpp:225-242); Dropshot arenas only
+	DropshotTilesState GetDropshotTilesState() { Realize(); return batch_->GetDropshotTilesStates()[0]; }
+	void SetDropshotTilesState(const DropshotTilesState& tilesState) { Realize(); batch_->SetDropshotTilesState(0, tilesState); }
 	ArenaBatch& Batch() { Realize(); return *batch_; }
 
 private:

@@ -1477,6 +1477,7 @@ RSB_GLOBAL void fresh_world_kernel(ArenaS* S, const BatchParams* P, const Scene*
 	}
 	A.stampCounter = (uint32_t)nCars + 2;
 	A.ball.groundStickApplied = 0;
+	for (int t = 0; t < MAX_TILES; t++) A.tiles[t] = 0;  // a new Arena has every Dropshot tile intact (tile states are not serialised)
 	for (int c = 0; c < nCars; c++) {
 		CarS& car = A.cars[c];
 		for (int k = 0; k < 4; k++) { car.wSteer[k] = car.wEngine[k] = car.wBrake[k] = car.wLatFriction[k] = car.wLongFriction[k] = car.wExtraPushback[k] = 0.f; }

@@ -670,7 +670,7 @@ RSB_HD int cand_alloc(const Ctx& cx, int n) {
 	if (i + n > MAX_CANDS) { set_error(cx, ERR_TRI_OVERFLOW); return -1; }
 	return i;
 }
-RSB_HD_NOINLINE void detect_candidate_cold(Ctx cx, int idx);
+RSB_HD void detect_candidate(const Ctx& cx, int idx);
 RSB_HD void detect_queue_push(const Ctx& cx, int idx) {
 #if defined(__CUDA_ARCH__)
 	const unsigned q = atomicAdd(cx.nq, 1u);
@@ -678,7 +678,7 @@ RSB_HD void detect_queue_push(const Ctx& cx, int idx) {
 	const unsigned q = (*cx.nq)++;
 #endif
 	if (q < (unsigned)cx.qcap) cx.q[q] = (uint16_t)(cx.arLocal * 128 + idx);
-	else detect_candidate_cold(cx, idx);  // the block's queue is full: run the detector right here (same result, only slower)
+	else detect_candidate(cx, idx);  // the block's queue is full: run the detector right here (same result, only slower)
 }
 RSB_HD void cand_emit(const Ctx& cx, int pair, int mesh, int tri, int state, const V3& normal, const V3& point, float depth) {
 	const int i = cand_alloc(cx, 1);
@@ -852,13 +852,7 @@ RSB_HD void collide_static_pairs(const Ctx& cx, int b) {
 		const int sk = a - STATIC_BASE;
 		const bool isMesh = sk < sc.nMeshes;
 		const RigidS& rb = rigid_of(cx, b);
-		if (static_tile_index(sc, sk) >= 0) {
-			// (tile, ball): btConvexConvexAlgorithm on (hull, sphere) in broadphase order -> manifold (tile, ball), one GJK query
-			new_manifold(cx, k, a, b);
-			mark_deferred(cx, k);
-			cand_emit(cx, k, -1, -1, CAND_PENDING, v3zero(), v3zero(), 0.f);
-			continue;
-		}
+		if (sc.nTiles && static_tile_index(sc, sk) >= 0) continue;  // (tile, ball): a pending record of the arena item (enqueue_dynamic_pairs)
 		if (inlineBody) {
 			Convex shape = ball_convex(P);
 			Xform xf; xf.basis = rb.basis; xf.origin = rb.pos;
@@ -886,21 +880,29 @@ RSB_HD void collide_static_pairs(const Ctx& cx, int b) {
 	}
 }
 
-// ball-car and car-car pairs, in pair order: the compound / child AABB gates of the reference, a manifold, and a pending record
+// ball-car and car-car pairs, in pair order: the compound / child AABB gates of the reference, a manifold, and a pending record.
+// Dropshot (tile, ball) pairs travel the same way -- one GJK query per pair, committed with the dynamic pairs in PH_DYN_SOLVE, in
+// pair order: the ball's tile pairs precede its car pairs, as in the reference's pair array, so a tile hit sees the charge level
+// from before this tick's car hits.  (Sharing the ball-car emit site also keeps the queue-full fallback at one inlined detector.)
 RSB_HD void enqueue_dynamic_pairs(const Ctx& cx) {
 	const BatchParams& P = *cx.p;
+	const bool hasTiles = cx.sc->nTiles != 0;
 	for (int k = 0; k < cx.pl->nPairs; k++) {
 		const int a = cx.pl->a[k], b = cx.pl->b[k];
-		if (a >= STATIC_BASE) continue;
+		const bool tilePair = hasTiles && a >= STATIC_BASE && static_tile_index(*cx.sc, a - STATIC_BASE) >= 0;
+		if (a >= STATIC_BASE && !tilePair) continue;
 		if (!pair_needs_collision(cx, a, b)) continue;
-		if (a == 0) {
-			// (ball, car): swapped compound -> convex-convex(box of the car, ball shape); manifold (car, ball)
-			const RigidS& rball = rigid_of(cx, 0);
-			Convex ball = ball_convex(P); Xform xfb; xfb.basis = rball.basis; xfb.origin = rball.pos;
-			V3 omn, omx;
-			convex_world_aabb(cx, ball, xfb, omn, omx);
-			if (!aabb_overlap(cx.body[b].childMin, cx.body[b].childMax, omn, omx)) continue;
-			new_manifold(cx, k, b, 0);
+		if (a == 0 || tilePair) {
+			if (!tilePair) {
+				// (ball, car): swapped compound -> convex-convex(box of the car, ball shape); manifold (car, ball)
+				const RigidS& rball = rigid_of(cx, 0);
+				Convex ball = ball_convex(P); Xform xfb; xfb.basis = rball.basis; xfb.origin = rball.pos;
+				V3 omn, omx;
+				convex_world_aabb(cx, ball, xfb, omn, omx);
+				if (!aabb_overlap(cx.body[b].childMin, cx.body[b].childMax, omn, omx)) continue;
+			}
+			// (tile, ball): btConvexConvexAlgorithm on (hull, sphere) in broadphase order -> manifold (tile, ball)
+			new_manifold(cx, k, tilePair ? a : b, tilePair ? b : 0);
 			mark_deferred(cx, k);
 			cand_emit(cx, k, -1, -1, CAND_PENDING, v3zero(), v3zero(), 0.f);
 		} else {
@@ -926,25 +928,45 @@ RSB_HD void enqueue_dynamic_pairs(const Ctx& cx) {
 	}
 }
 
-// PH_NARROW_DETECT: the detector of one pending record, on its own thread.  Every GJK / EPA query -- (body, mesh triangle),
-// (car box, ball), (Dropshot tile hull, ball) -- goes through ONE call site of the (inlined) pair detector: the branches only
-// choose the two shapes and transforms.
+// (Dropshot tile hull = A, ball = B): convex-convex keeps the broadphase order (btConvexConvexAlgorithm.cpp:268-276).  Out of line
+// on the device: the two pair-detector call sites of detect_candidate are specialised for their shape kinds by inlining; a third
+// inlined copy would add 22k instructions to every mode's kernel for a pair that only exists in Dropshot.
+#ifndef RSB_TILE_INLINE
+#define RSB_TILE_INLINE 0
+#endif
+#if RSB_TILE_INLINE
+RSB_HD
+#else
+RSB_HD_NOINLINE
+#endif
+void detect_tile_ball(Ctx cx, int idx) {
+	const BatchParams& P = *cx.p;
+	CandRec* rec = &cx.w->cand[idx];
+	const int k = rec->pair;
+	const int a = cx.pl->a[k], b = cx.pl->b[k];
+	const TileD& td = cx.sc->tiles[static_tile_index(*cx.sc, a - STATIC_BASE)];
+	Convex hull; hull.kind = SH_HULL; hull.margin = 0.04f; hull.he = v3zero(); hull.pts = td.pts; hull.npts = 6;
+	Xform xfT; xfT.basis = m3identity(); xfT.origin = static_origin(cx, a);
+	const RigidS& rball = rigid_of(cx, b);
+	Convex ball = ball_convex(P); Xform xfb; xfb.basis = rball.basis; xfb.origin = rball.pos;
+	V3 n, pt; float d;
+	const bool hit = convex_convex_detect(cx, cx.mf[k].breakingThresh, hull, xfT, ball, xfb, n, pt, d);
+	if (hit) { rec->normal = n; rec->point = pt; rec->depth = d; }
+	rec->state = hit ? CAND_CONTACT : CAND_NONE;
+}
+
+// PH_NARROW_DETECT: the detector of one pending record, on its own thread
 RSB_HD void detect_candidate(const Ctx& cx, int idx) {
 	const BatchParams& P = *cx.p;
 	CandRec* rec = &cx.w->cand[idx];
 	const int k = rec->pair;
 	const int a = cx.pl->a[k], b = cx.pl->b[k];
 	V3 n, pt; float d;
-	Convex shA, shB; Xform xfA, xfB;
 	if (a >= STATIC_BASE) {
+		if (cx.sc->nTiles && static_tile_index(*cx.sc, a - STATIC_BASE) >= 0) { detect_tile_ball(cx, idx); return; }
+		// (body b, triangle of an arena mesh)
 		const RigidS& rb = rigid_of(cx, b);
-		const int tile = cx.sc->nTiles ? static_tile_index(*cx.sc, a - STATIC_BASE) : -1;
-		if (tile >= 0) {
-			// (Dropshot tile hull = A, ball = B): convex-convex keeps the broadphase order (btConvexConvexAlgorithm.cpp:268-276)
-			shA.kind = SH_HULL; shA.margin = 0.04f; shA.he = v3zero(); shA.pts = cx.sc->tiles[tile].pts; shA.npts = 6;
-			xfA.basis = m3identity(); xfA.origin = static_origin(cx, a);
-			shB = ball_convex(P); xfB.basis = rb.basis; xfB.origin = rb.pos;
-		} else if (b == 0 && P.ballIsSphere) {
+		if (b == 0 && P.ballIsSphere) {
 			// sphere vs triangle in closed form (SphereTriangleDetector, the reference's choice for this shape pair)
 			V3 t[3];
 			mesh_triangle(cx.sc->meshes[rec->mesh], rec->tri, t[0], t[1], t[2]);
@@ -953,37 +975,34 @@ RSB_HD void detect_candidate(const Ctx& cx, int idx) {
 			if (hit) { rec->normal = m3identity() * n; rec->point = m3identity() * pt + v3zero(); rec->depth = d; }
 			rec->state = hit ? CAND_CONTACT : CAND_NONE;
 			return;
-		} else {
-			// (body b = A, triangle of an arena mesh = B)
-			if (b == 0) { shA = ball_convex(P); xfA.basis = rb.basis; xfA.origin = rb.pos; }
-			else { shA = car_box(P.carCfg[b - 1]); xfA = cx.body[b].childXf; }
-			shB.kind = SH_TRI; shB.margin = 0.f; shB.he = v3zero(); shB.pts = nullptr; shB.npts = 0;
-			mesh_triangle(cx.sc->meshes[rec->mesh], rec->tri, shB.tri[0], shB.tri[1], shB.tri[2]);
-			xfB.basis = m3identity(); xfB.origin = v3zero();
 		}
+		Convex shape; Xform xf;
+		if (b == 0) { shape = ball_convex(P); xf.basis = rb.basis; xf.origin = rb.pos; }
+		else { shape = car_box(P.carCfg[b - 1]); xf = cx.body[b].childXf; }
+		Convex triShape; triShape.kind = SH_TRI; triShape.margin = 0.f; triShape.he = v3zero(); triShape.pts = nullptr; triShape.npts = 0;
+		mesh_triangle(cx.sc->meshes[rec->mesh], rec->tri, triShape.tri[0], triShape.tri[1], triShape.tri[2]);
+		Xform xfT; xfT.basis = m3identity(); xfT.origin = v3zero();
+		const bool hit = convex_convex_detect(cx, cx.mf[k].breakingThresh, shape, xf, triShape, xfT, n, pt, d);
+		if (hit) { rec->normal = n; rec->point = pt; rec->depth = d; }
+		rec->state = hit ? CAND_CONTACT : CAND_NONE;
 	} else if (a == 0) {
-		// (car box = A, ball = B)
 		const RigidS& rball = rigid_of(cx, 0);
-		shA = car_box(P.carCfg[b - 1]); xfA = cx.body[b].childXf;
-		shB = ball_convex(P); xfB.basis = rball.basis; xfB.origin = rball.pos;
+		Convex ball = ball_convex(P); Xform xfb; xfb.basis = rball.basis; xfb.origin = rball.pos;
+		Convex box = car_box(P.carCfg[b - 1]); const Xform xfc = cx.body[b].childXf;
+		const bool hit = convex_convex_detect(cx, cx.mf[k].breakingThresh, box, xfc, ball, xfb, n, pt, d);
+		if (hit) { rec->normal = n; rec->point = pt; rec->depth = d; }
+		rec->state = hit ? CAND_CONTACT : CAND_NONE;
 	} else {
 		Convex boxA = car_box(P.carCfg[a - 1]), boxB = car_box(P.carCfg[b - 1]);
-		const Xform xfa = cx.body[a].childXf, xfb = cx.body[b].childXf;
+		const Xform xfA = cx.body[a].childXf, xfB = cx.body[b].childXf;
 		V3 pts[4]; float dep[4];
-		const int nOut = box_box_detect(cx, boxB, xfb, boxA, xfa, n, pts, dep);
+		const int nOut = box_box_detect(cx, boxB, xfB, boxA, xfA, n, pts, dep);
 		for (int j = 0; j < 4; j++) {
 			if (j < nOut) { rec[j].normal = n; rec[j].point = pts[j]; rec[j].depth = dep[j]; }
 			rec[j].state = j < nOut ? CAND_CONTACT : CAND_NONE;
 		}
-		return;
 	}
-	const bool hit = convex_convex_detect(cx, cx.mf[k].breakingThresh, shA, xfA, shB, xfB, n, pt, d);
-	if (hit) { rec->normal = n; rec->point = pt; rec->depth = d; }
-	rec->state = hit ? CAND_CONTACT : CAND_NONE;
 }
-// the same detector out of line: the cold path of a full detector queue (detect_queue_push).  By-value context: see the
-// toolchain note in DESIGN.md (caller-local aggregates passed by reference to __noinline__ device functions).
-RSB_HD_NOINLINE void detect_candidate_cold(Ctx cx, int idx) { detect_candidate(cx, idx); }
 
 // PH_NARROW_COMMIT (body b) / PH_DYN_SOLVE (dynamic pairs, b = -1): records -> manifolds + contact hooks, in record order.
 // The records of one thread's walk carry ascending indices, so one pass in index order filtered by owner restores the order
@@ -995,12 +1014,12 @@ RSB_HD void commit_candidates(const Ctx& cx, int b) {
 	for (int i = 0; i < n; i++) {
 		const CandRec r = cx.w->cand[i];
 		const int k = r.pair;
-		const bool dyn = cx.pl->a[k] < STATIC_BASE;
+		const bool dyn = cx.pl->a[k] < STATIC_BASE || (cx.sc->nTiles && static_tile_index(*cx.sc, cx.pl->a[k] - STATIC_BASE) >= 0);  // + (tile, ball)
 		if (b < 0 ? !dyn : (dyn || cx.pl->b[k] != b)) continue;
 		if (k != curPair) { if (curPair >= 0) refresh_contact_points(cx, curPair); curPair = k; }
 		if (r.state != CAND_CONTACT) continue;
-		if (b < 0) add_contact_point(cx, k, r.normal, r.point, r.depth, -1, -1, true);
-		else if (cx.sc->nTiles && cx.mf[k].body0 >= STATIC_BASE) add_contact_point_tile(cx, k, r.normal, r.point, r.depth);
+		if (b < 0 && cx.pl->a[k] >= STATIC_BASE) add_contact_point_tile(cx, k, r.normal, r.point, r.depth);
+		else if (b < 0) add_contact_point(cx, k, r.normal, r.point, r.depth, -1, -1, true);
 		else add_contact_point(cx, k, r.normal, r.point, r.depth, r.mesh, r.tri, false);
 	}
 	if (curPair >= 0) refresh_contact_points(cx, curPair);

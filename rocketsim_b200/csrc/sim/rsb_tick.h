@@ -64,7 +64,7 @@ RSB_HD int phase_items(const BatchParams& P, int phase) {
 	const int nPadItems = (P.mode != THE_VOID && nCars != 0) ? P.nPads : 0;
 	switch (phase) {
 	case PH_INIT: case PH_PREDICT: case PH_NARROW_COMMIT: case PH_FINISH_BODY: return nb;
-	case PH_NARROW_STATIC: return nb + (nCars > 0 ? 1 : 0);  // + the arena's dynamic pairs
+	case PH_NARROW_STATIC: return nb + ((nCars > 0 || P.mode == DROPSHOT) ? 1 : 0);  // + the arena's dynamic (and Dropshot tile) pairs
 	case PH_NARROW_DETECT: return 0;                         // variable: the block's detector queue (dealt by the caller)
 	case PH_WHEELS: return nCars * 4;
 	case PH_CAR_LOGIC: return nCars + nPadItems + 1;

@@ -66,8 +66,9 @@ def _declare(L):
     L.rsb_set_ball_states.argtypes = [vp, vp, i32, vp]
     L.rsb_set_ball_internals.argtypes = [vp, vp, i32, vp]
     L.rsb_set_pad_states.argtypes = [vp, vp, i32, vp]
-    L.rsb_get_dropshot_tiles.argtypes = [vp, vp]
-    L.rsb_set_dropshot_tiles.argtypes = [vp, vp, i32, vp]
+    if hasattr(L, "rsb_get_dropshot_tiles"):  # (absent from older developer A/B builds; test_abi checks the product library exports it)
+        L.rsb_get_dropshot_tiles.argtypes = [vp, vp]
+        L.rsb_set_dropshot_tiles.argtypes = [vp, vp, i32, vp]
     L.rsb_get_events.argtypes = [vp, vp, i32, vp]
     L.rsb_seed_rng.argtypes = [vp, u32, u32]
     L.rsb_observation_floats.argtypes = [vp]

@@ -134,6 +134,7 @@ def test_serialize_hostcheck(hostlib, oracle):
     assert run_case(hostlib, oracle, T.MODE_SOCCAR, 2, presets=[0, 1, 3, 5]) <= TOL
     assert run_case(hostlib, oracle, T.MODE_HOOPS, 1) <= TOL
     assert run_case(hostlib, oracle, T.MODE_THE_VOID, 1) <= TOL
+    assert run_case(hostlib, oracle, T.MODE_DROPSHOT, 1) <= TOL   # BallState::dsInfo is in the stream, tile states are not
 
 
 def test_deserialize_rejects_mismatches(hostlib, oracle):
@@ -165,3 +166,4 @@ def test_serialize_cuda(cudalib, oracle):
     assert run_case(cudalib, oracle, T.MODE_SOCCAR, 3, presets=[0, 1, 2, 3, 4, 6]) <= TOL
     assert run_case(cudalib, oracle, T.MODE_SNOWDAY, 2) <= TOL
     assert run_case(cudalib, oracle, T.MODE_HEATSEEKER, 1) <= TOL
+    assert run_case(cudalib, oracle, T.MODE_DROPSHOT, 2) <= TOL
