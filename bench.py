@@ -35,7 +35,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-MODE_NAMES = {0: "soccar", 1: "hoops", 2: "heatseeker", 3: "snowday", 5: "the_void"}
+MODE_NAMES = {0: "soccar", 1: "hoops", 2: "heatseeker", 3: "snowday", 4: "dropshot", 5: "the_void"}
 SEED = 1234
 
 
@@ -44,7 +44,7 @@ def algorithmic_bytes(n_cars: int, n_pads: int) -> int:
 
 
 def n_pads_of(mode: int) -> int:
-    return {0: 34, 1: 20, 2: 34, 3: 34, 5: 0}[mode]
+    return {0: 34, 1: 20, 2: 34, 3: 34, 4: 0, 5: 0}[mode]
 
 
 def ncu_traffic_per_launch(mode, cars_per_team, arenas, ticks):

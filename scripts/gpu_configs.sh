@@ -13,6 +13,7 @@ run hoops_2v2_16384 1 2 16384      # config 4
 run heatseeker_1v1_16384 2 1 16384 # config 4
 run snowday_3v3_4096 3 3 4096      # config 5 at 8 GPUs (per-GPU share of 32,768)
 run snowday_3v3_32768 3 3 32768    # config 5 on one GPU
+run dropshot_2v2_4096 4 2 4096     # Dropshot (not a BASELINE config; same shape as the headline)
 echo "== config 1 (THE_VOID 1v1, 1 M ticks)"
 timeout 900 python scripts/config1_void.py 1000000 4 2>&1 | tail -1 > gpurun_out/${TAG}_config1_void.json; cut -c1-400 gpurun_out/${TAG}_config1_void.json
 python - <<PY
