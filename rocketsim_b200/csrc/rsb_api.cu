@@ -299,7 +299,7 @@ constexpr size_t SMEM_SC_BYTES = (sizeof(Scene) + 15) & ~(size_t)15;
 #endif
 constexpr int WARP_QUEUE_CAP = 96;  // detector queue entries per warp (warp-autonomous scheduling)
 constexpr size_t SMEM_Q_BYTES = RSB_WARP_SCHED ? (size_t)(RSB_STEP_THREADS / 32) * (16 + WARP_QUEUE_CAP * 2)
-                                               : (size_t)(16 + 512 * 2);  // detector queue(s): counter + entries
+                                               : (size_t)(16 + (512 / RSB_BLOCKS_PER_SM) * 2);  // detector queue(s): counter + entries
 constexpr size_t SMEM_MAX = (228 * 1024) / BLOCKS_PER_SM - 1024;  // 228 KB per SM, 1 KB reserved per resident block
 
 // Shared-memory layout of one resident arena: [ArenaS prefix (header, ball, pads, nCars cars) | BodyW x nb |
@@ -354,7 +354,7 @@ __device__ unsigned long long g_prof2[2][16][2];
 #define PHASE_PROF_END(i) ((void)0)
 #endif
 
-constexpr int DETECT_QUEUE_CAP = 512;
+constexpr int DETECT_QUEUE_CAP = 512 / RSB_BLOCKS_PER_SM;
 __device__ __forceinline__ Ctx make_ctx(const StepArgs& a, const BatchParams* sP, const Scene* sSc, unsigned char* sS, int a0, int ar) {
 	extern __shared__ __align__(16) unsigned char smem[];
 	Ctx cx;
