@@ -274,7 +274,7 @@ static thread_local int g_hostIdx = 0;
 // (one instruction-cache working set), suspension rays / car logic / body integration use one
 // thread per wheel / car / body, and HBM sees each arena record once per launch in and once out.
 #ifndef RSB_STEP_THREADS
-#define RSB_STEP_THREADS 448  // 14 warps, 144 registers: the 448 wheel rays of 28 resident 2v2 arenas take one round (A/B on B200: +6..9 % over 256 threads, 512 threads / 128 registers lose it again to spills)
+#define RSB_STEP_THREADS 448  // 14 warps, 128 registers: the 448 wheel rays of 28 resident 2v2 arenas take one round (A/B on B200: +6..9 % over 256 threads, 512 threads / 128 registers lose it again to spills)
 #endif
 constexpr int STEP_THREADS = RSB_STEP_THREADS;
 // resident blocks per SM: each block keeps its own chunk of arenas; blocks drift through the tick phases independently

@@ -21,7 +21,8 @@ TOL_ILLCOND = TOL  # ticks with a suspension ray resting on a dynamic body: same
 
 # BASELINE.json configs: VOID 1v1, Soccar 2v2, Soccar 3v3 (demos/bumps), Hoops 2v2, Heatseeker 1v1, Snowday 3v3
 CONFIGS = [("void_1v1", T.MODE_THE_VOID, 1), ("soccar_2v2", T.MODE_SOCCAR, 2), ("soccar_3v3", T.MODE_SOCCAR, 3),
-           ("hoops_2v2", T.MODE_HOOPS, 2), ("heatseeker_1v1", T.MODE_HEATSEEKER, 1), ("snowday_3v3", T.MODE_SNOWDAY, 3)]
+           ("hoops_2v2", T.MODE_HOOPS, 2), ("heatseeker_1v1", T.MODE_HEATSEEKER, 1), ("snowday_3v3", T.MODE_SNOWDAY, 3),
+           ("dropshot_2v2", T.MODE_DROPSHOT, 2)]
 IDS = [c[0] for c in CONFIGS]
 
 
