@@ -176,7 +176,7 @@ def hoops_meshes() -> List[bytes]:
 def dropshot_meshes() -> List[bytes]:
     """Dropshot shell: the arena has no side planes (reference ``Arena.cpp:1056-1061``), so the mesh carries all six walls of
     the hexagonal field (circumradius 5400 uu: encloses the 13..7-tile rows of ``DropshotTiles.cpp``) -- a 45-degree skirt from
-    the floor up to 250 uu, then a vertical wall up to the 2024 uu ceiling -- plus the solid floor strip between the two tile fields,
+    the floor up to 250 uu in front of a vertical wall from the floor to the 2024 uu ceiling -- plus the solid floor strip between the two tile fields,
     in three meshes (walls / skirts / centre strip)."""
     RC, H, SK = 5400.0, 2024.0, 250.0
     ang = np.deg2rad(np.arange(7) * 60.0)
@@ -188,9 +188,10 @@ def dropshot_meshes() -> List[bytes]:
         inward = -mid / np.linalg.norm(mid)
         ts = np.linspace(0.0, 1.0, 7)
         edge = a[None, :] + ts[:, None] * (b - a)[None, :]
-        # vertical part
-        zs = np.linspace(SK, H, 4)
-        pts = np.zeros((7, 4, 3))
+        # vertical part, down to the floor: the skirts of two neighbouring walls leave a wedge open at every corner, and a
+        # wall that only started at the skirt's top edge would let a car slip out underneath (the reference does let it)
+        zs = np.linspace(0.0, H, 5)
+        pts = np.zeros((7, 5, 3))
         pts[:, :, 0] = edge[:, 0][:, None]; pts[:, :, 1] = edge[:, 1][:, None]; pts[:, :, 2] = zs[None, :]
         walls.add_grid(pts, np.array([inward[0], inward[1], 0.0]))
         # skirt: from (edge moved inward by SK) at z = 0 up to the wall foot at z = SK

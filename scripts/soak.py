@@ -25,7 +25,8 @@ for c in range(TICKS // CH):
 b.sync(); dt = time.perf_counter() - t0
 cs, bs = b.get_car_states(), b.get_ball_states()
 finite = bool(np.isfinite(cs["pos"]["x"]).all() and np.isfinite(cs["vel"]["x"]).all() and np.isfinite(bs["pos"]["z"]).all() and np.isfinite(cs["rotMat"]["up"]["z"]).all())
-inside = bool(np.abs(cs["pos"]["x"]).max() < 4400 and np.abs(cs["pos"]["y"]).max() < 6200 and cs["pos"]["z"].max() < 2200 and cs["pos"]["z"].min() > -50)
+XMAX, YMAX = (5700, 5000) if mode == 4 else (4400, 6200)  # Dropshot: the hexagonal shell of synthetic_meshes.dropshot_meshes
+inside = bool(np.abs(cs["pos"]["x"]).max() < XMAX and np.abs(cs["pos"]["y"]).max() < YMAX and cs["pos"]["z"].max() < 2200 and cs["pos"]["z"].min() > -50)
 err = b.get_error_flags()
 names = {1: "goal", 2: "bump", 3: "demo", 4: "shot", 5: "goal_credit", 6: "save"}
 print(json.dumps({"mode": mode, "cars_per_team": cpt, "arenas": A, "ticks": int(b.get_tick_counts().min()), "arena_ticks_per_s": A * (TICKS // CH) * CH / dt,
