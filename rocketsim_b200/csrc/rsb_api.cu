@@ -334,6 +334,12 @@ struct StepArgs {
 	ArenaLayout lay;
 };
 
+#ifndef RSB_DETECT_QUEUE_CAP
+#define RSB_DETECT_QUEUE_CAP (512 / RSB_BLOCKS_PER_SM)  // developer builds shrink it to exercise the overflow sweep
+#endif
+constexpr int DETECT_QUEUE_CAP = RSB_DETECT_QUEUE_CAP;
+static_assert(DETECT_QUEUE_CAP >= 1 && DETECT_QUEUE_CAP <= 512 / RSB_BLOCKS_PER_SM, "the detector queue's shared-memory slice holds 512 / blocks-per-SM entries");
+
 #ifndef RSB_HOSTCHECK
 #if defined(RSB_PROFILE)
 // developer builds: per phase [0..15] block wall cycles, [16..31] sum of busy-thread cycles, [32..47] busy-thread count,
@@ -354,7 +360,6 @@ __device__ unsigned long long g_prof2[2][16][2];
 #define PHASE_PROF_END(i) ((void)0)
 #endif
 
-constexpr int DETECT_QUEUE_CAP = 512 / RSB_BLOCKS_PER_SM;
 __device__ __forceinline__ Ctx make_ctx(const StepArgs& a, const BatchParams* sP, const Scene* sSc, unsigned char* sS, int a0, int ar) {
 	extern __shared__ __align__(16) unsigned char smem[];
 	Ctx cx;
@@ -454,11 +459,22 @@ __device__ __forceinline__ void run_phase_block(const StepArgs& a, const BatchPa
 		extern __shared__ __align__(16) unsigned char smem[];
 		const unsigned* nqp = (const unsigned*)(smem + SMEM_P_BYTES + SMEM_SC_BYTES);
 		const uint16_t* q = (const uint16_t*)(nqp + 4);
-		const int nq = min((int)*nqp, DETECT_QUEUE_CAP);
-		for (int i = ptid; i < nq; i += STEP_THREADS) {
-			const int e = q[i];
-			const Ctx cx = make_ctx(a, sP, sSc, sS, a0, e >> 7);
-			phase_run(cx, PH, e & 127);
+		const int pushed = (int)*nqp;
+		const int nq = min(pushed, DETECT_QUEUE_CAP);
+		// pass 0: the queued records.  pass 1 (only after a queue overflow, block-uniform): every record of every resident arena
+		// that is still pending -- the ones that did not fit the queue.  One detector call site for both.
+		const int nPass = pushed > DETECT_QUEUE_CAP ? 2 : 1;
+		for (int pass = 0; pass < nPass; pass++) {
+			const int n = pass == 0 ? nq : nA * MAX_CANDS;
+			for (int i = ptid; i < n; i += STEP_THREADS) {
+				int arl, idx;
+				if (pass == 0) { const int e = q[i]; arl = e >> 7; idx = e & 127; }
+				else { arl = i / MAX_CANDS; idx = i - arl * MAX_CANDS; }
+				const Ctx cx = make_ctx(a, sP, sSc, sS, a0, arl);
+				if (pass == 1 && !(idx < cx.misc[3] && cx.w->cand[idx].state == CAND_PENDING)) continue;
+				phase_run(cx, PH, idx);
+			}
+			if (pass + 1 < nPass) __syncthreads();
 		}
 		PHASE_PROF_ITEMS(SLOT, ptid < nq);
 	} else {
@@ -508,11 +524,20 @@ __device__ __forceinline__ void run_phase_warp(const StepArgs& a, const BatchPar
 		extern __shared__ __align__(16) unsigned char smem[];
 		const unsigned* nqp = (const unsigned*)(smem + SMEM_P_BYTES + SMEM_SC_BYTES + (size_t)warp * (16 + WARP_QUEUE_CAP * 2));
 		const uint16_t* q = (const uint16_t*)(nqp + 4);
-		const int nq = min((int)*nqp, WARP_QUEUE_CAP);
-		for (int i = lane; i < nq; i += 32) {
-			const int e = q[i];
-			const Ctx cx = make_ctx(a, sP, sSc, sS, a0, e >> 7);
-			phase_run(cx, PH, e & 127);
+		const int pushed = (int)*nqp;
+		const int nq = min(pushed, WARP_QUEUE_CAP);
+		const int nPass = pushed > WARP_QUEUE_CAP ? 2 : 1;  // pass 1: the records that did not fit the warp's queue (see run_phase_block)
+		for (int pass = 0; pass < nPass; pass++) {
+			const int n = pass == 0 ? nq : nMine * MAX_CANDS;
+			for (int i = lane; i < n; i += 32) {
+				int arl, idx;
+				if (pass == 0) { const int e = q[i]; arl = e >> 7; idx = e & 127; }
+				else { const int k = i / MAX_CANDS; arl = warp + k * NW; idx = i - k * MAX_CANDS; }
+				const Ctx cx = make_ctx(a, sP, sSc, sS, a0, arl);
+				if (pass == 1 && !(idx < cx.misc[3] && cx.w->cand[idx].state == CAND_PENDING)) continue;
+				phase_run(cx, PH, idx);
+			}
+			__syncwarp();
 		}
 	} else {
 		const int per = phase_items(*sP, PH), n = per * nMine;
@@ -689,7 +714,7 @@ static void arena_step_host(const StepArgs& a) {
 	const int nCars = a.P->nCars;
 	for (int arena = 0; arena < a.nArenas; arena++) {
 		uint16_t hq[512]; unsigned hnq = 0;
-		Ctx cx; cx.q = hq; cx.nq = &hnq; cx.qcap = 512; cx.arLocal = 0;
+		Ctx cx; cx.q = hq; cx.nq = &hnq; cx.qcap = DETECT_QUEUE_CAP; cx.arLocal = 0;
 		cx.s = a.S + arena; cx.g = cx.s; cx.w = a.W + arena; cx.epa = a.E; cx.p = a.P; cx.sc = a.sc; cx.ev = a.ev; cx.arena = arena;
 		cx.body = a.H[arena].body; cx.wheels = a.H[arena].wheels; cx.padLocked = a.H[arena].padLocked; cx.misc = a.H[arena].misc;
 		cx.pl = &a.H[arena].pairs; cx.mf = a.H[arena].mf; cx.solv = a.H[arena].solv;

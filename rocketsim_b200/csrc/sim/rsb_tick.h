@@ -184,6 +184,8 @@ RSB_HD void arena_tick(const Ctx& cx) {
 		if (ph == PH_NARROW_DETECT) {
 			const unsigned nq = *cx.nq < (unsigned)cx.qcap ? *cx.nq : (unsigned)cx.qcap;
 			for (unsigned i = 0; i < nq; i++) phase_run(cx, ph, cx.q[i] & 127);
+			if (*cx.nq > (unsigned)cx.qcap)  // queue overflow: the records that are still pending
+				for (int i = 0; i < cx.misc[3] && i < MAX_CANDS; i++) if (cx.w->cand[i].state == CAND_PENDING) phase_run(cx, ph, i);
 			continue;
 		}
 		const int n = phase_items(*cx.p, ph);
