@@ -193,11 +193,18 @@ RSB_HD void add_pair(const Ctx& cx, int a, int b, int entry = 0) {
 RSB_HD void compute_pairs(const Ctx& cx) {
 	const Scene& sc = *cx.sc;
 	const int nb = n_bodies(cx);
-	cx.pl->nPairs = 0;
+	// The pair counter lives in a register (stores to the list are fire-and-forget, a counter in shared memory would be a
+	// dependent load per pair), and the cell coordinates / stamp order of the <= 7 bodies are fetched as four 8-byte words.
+	int nPairs = 0;
+	bool overflow = false;
+	uint32_t dynMask = 0;
+	PairList& pl = *cx.pl;
+	const uint64_t ordW = *(const uint64_t*)cx.s->dynOrder, ciW = *(const uint64_t*)cx.s->cellI, cjW = *(const uint64_t*)cx.s->cellJ, ckW = *(const uint64_t*)cx.s->cellK;
+#define RSB_PAIR_ADD(A_, B_, E_) do { if (nPairs >= MAX_MANIFOLDS) overflow = true; else { pl.a[nPairs] = (uint8_t)(A_); pl.b[nPairs] = (uint8_t)(B_); pl.entry[nPairs] = (uint16_t)(E_); nPairs++; } } while (0)
 	for (int b = 0; b < nb; b++) {
 		const BodyW& bw = cx.body[b];
 		if (bw.nCand >= 0) {
-			for (int q = 0; q < bw.nCand; q++) add_pair(cx, STATIC_BASE + bw.candObj[q], b, bw.cand[q]);
+			for (int q = 0; q < bw.nCand; q++) RSB_PAIR_ADD(STATIC_BASE + bw.candObj[q], b, bw.cand[q]);
 		} else {  // candidate list overflowed: full scan
 			int gb, mb; body_filter(cx, b, gb, mb);
 			int cell = cx.s->cellIdx[b];
@@ -205,22 +212,27 @@ RSB_HD void compute_pairs(const Ctx& cx) {
 				int obj = STATIC_BASE + sc.cellStatics[s];
 				V3 mn, mx; static_proxy_aabb(cx, obj, mn, mx);
 				int ga, ma; body_filter(cx, obj, ga, ma);
-				if (aabb_overlap(bw.aabbMin, bw.aabbMax, mn, mx) && (ga & mb) && (gb & ma)) add_pair(cx, obj, b, s);
+				if (aabb_overlap(bw.aabbMin, bw.aabbMax, mn, mx) && (ga & mb) && (gb & ma)) RSB_PAIR_ADD(obj, b, s);
 			}
 		}
 		if (b + 1 < nb) {
 			// dynamic proxies registered in b's cell, in the cell list's order (ascending stamp)
-			const int ci = cx.s->cellI[b], cj = cx.s->cellJ[b], ck = cx.s->cellK[b];
+			const int ci = (int)((ciW >> (8 * b)) & 255), cj = (int)((cjW >> (8 * b)) & 255), ck = (int)((ckW >> (8 * b)) & 255);
 			for (int q = 0; q < nb; q++) {
-				const int o = cx.s->dynOrder[q];
+				const int o = (int)((ordW >> (8 * q)) & 255);
 				if (o <= b) continue;
-				if (abs((int)cx.s->cellI[o] - ci) > 1 || abs((int)cx.s->cellJ[o] - cj) > 1 || abs((int)cx.s->cellK[o] - ck) > 1) continue;
+				if (abs((int)((ciW >> (8 * o)) & 255) - ci) > 1 || abs((int)((cjW >> (8 * o)) & 255) - cj) > 1 || abs((int)((ckW >> (8 * o)) & 255) - ck) > 1) continue;
 				const BodyW& ow = cx.body[o];
 				if (!aabb_overlap(bw.aabbMin, bw.aabbMax, ow.aabbMin, ow.aabbMax)) continue;
-				add_pair(cx, b, o);
+				if (nPairs < MAX_MANIFOLDS) dynMask |= 1u << nPairs;
+				RSB_PAIR_ADD(b, o, 0);
 			}
 		}
 	}
+#undef RSB_PAIR_ADD
+	if (overflow) set_error(cx, ERR_MANIFOLD_OVERFLOW);
+	pl.nPairs = nPairs;
+	pl.dynMask = dynMask;
 }
 
 // ------------------------------------------------------------------ manifolds + contact hooks

@@ -53,10 +53,13 @@ RSB_HD int build_islands(const Ctx& cx) {
 		acts |= (uint32_t)cx.body[b].activation << (4 * b);
 	}
 	// findUnions over ALL broadphase pairs whose bodies both merge islands (dynamic pairs sit behind each body's static pairs)
-	const int nPairs = cx.pl->nPairs;
-	for (int k = 0; k < nPairs; k++) {
+	for (uint32_t dm = cx.pl->dynMask; dm; dm &= dm - 1) {
+#if defined(__CUDA_ARCH__)
+		const int k = __ffs((int)dm) - 1;
+#else
+		const int k = __builtin_ctz(dm);
+#endif
 		const int a = cx.pl->a[k];
-		if (a >= STATIC_BASE) continue;
 		const int b = cx.pl->b[k];
 		if (((noResp >> a) | (noResp >> b)) & 1u) continue;
 		int i = a, j = b;

@@ -69,6 +69,7 @@ struct PairList {
 	int nPairs, nManifolds;
 	uint32_t mfMask;     // bit k: pair k has a manifold (new_manifold was called for it this tick)
 	uint32_t deferMask;  // bit k: the contacts of pair k go through candidate records (committed in PH_NARROW_COMMIT / PH_DYN_SOLVE)
+	uint32_t dynMask;    // bit k: pair k joins two dynamic bodies (the only pairs that merge islands)
 	uint8_t a[MAX_MANIFOLDS], b[MAX_MANIFOLDS];
 	uint8_t manifoldOrder[MAX_MANIFOLDS];
 	uint16_t entry[MAX_MANIFOLDS];  // static pairs: position of the static object in the cell list (Scene::cellStatics)
