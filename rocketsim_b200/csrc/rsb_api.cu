@@ -360,9 +360,14 @@ __device__ unsigned long long g_prof2[2][16][2];
 #define PHASE_PROF_END(i) ((void)0)
 #endif
 
+// MODE >= 0: the kernel instantiation of one game mode -- the code-path selectors of the context are compile-time constants.
+// MODE < 0: taken from the batch at run time (developer builds with -DRSB_ONE_KERNEL compile only this one).
+template <int MODE>
 __device__ __forceinline__ Ctx make_ctx(const StepArgs& a, const BatchParams* sP, const Scene* sSc, unsigned char* sS, int a0, int ar) {
 	extern __shared__ __align__(16) unsigned char smem[];
 	Ctx cx;
+	if (MODE >= 0) { cx.mode = MODE; cx.ballIsSphere = (MODE != SNOWDAY) ? 1 : 0; cx.nTiles = (MODE == DROPSHOT) ? MAX_TILES : 0; }
+	else { cx.mode = sP->mode; cx.ballIsSphere = sP->ballIsSphere; cx.nTiles = sSc->nTiles; }
 #if RSB_WARP_SCHED
 	cx.nq = (unsigned*)(smem + SMEM_P_BYTES + SMEM_SC_BYTES + (size_t)(threadIdx.x >> 5) * (16 + WARP_QUEUE_CAP * 2)); cx.q = (uint16_t*)(cx.nq + 4); cx.qcap = WARP_QUEUE_CAP; cx.arLocal = ar;
 #else
@@ -447,7 +452,7 @@ __device__ __forceinline__ bool map_item(int k, int tid, int ptid, int nA, const
 template <int PH>
 __device__ __forceinline__ bool phase_thread_busy(int tid, int ptid, int nA, const BatchParams& P) { int ar, item; return map_item<PH>(0, tid, ptid, nA, P, ar, item); }
 
-template <int PH, int SLOT = PH>
+template <int MODE, int PH, int SLOT = PH>
 __device__ __forceinline__ void run_phase_block(const StepArgs& a, const BatchParams* sP, const Scene* sSc, unsigned char* sS, int a0, int nA, int ptid) {
 #if defined(RSB_PROFILE)
 	__shared__ unsigned long long s_profMax;
@@ -470,7 +475,7 @@ __device__ __forceinline__ void run_phase_block(const StepArgs& a, const BatchPa
 				int arl, idx;
 				if (pass == 0) { const int e = q[i]; arl = e >> 7; idx = e & 127; }
 				else { arl = i / MAX_CANDS; idx = i - arl * MAX_CANDS; }
-				const Ctx cx = make_ctx(a, sP, sSc, sS, a0, arl);
+				const Ctx cx = make_ctx<MODE>(a, sP, sSc, sS, a0, arl);
 				if (pass == 1 && !(idx < cx.misc[3] && cx.w->cand[idx].state == CAND_PENDING)) continue;
 				phase_run(cx, PH, idx);
 			}
@@ -483,7 +488,7 @@ __device__ __forceinline__ void run_phase_block(const StepArgs& a, const BatchPa
 	for (int k = 0; k < nRounds; k++) {
 		int ar, item;
 		if (!map_item<PH>(k, threadIdx.x, ptid, nA, *sP, ar, item)) continue;
-		const Ctx cx = make_ctx(a, sP, sSc, sS, a0, ar);
+		const Ctx cx = make_ctx<MODE>(a, sP, sSc, sS, a0, ar);
 		phase_run(cx, PH, item);
 	}
 	PHASE_PROF_ITEMS(SLOT, phase_thread_busy<PH>(threadIdx.x, ptid, nA, *sP));
@@ -516,7 +521,7 @@ __device__ __forceinline__ void run_phase_block(const StepArgs& a, const BatchPa
 // One phase of the tick for the arenas owned by the calling warp (block-local indices warp, warp + NW, ...): its items go to the
 // warp's lanes in rounds of 32, and the warp alone synchronises.  Items of a phase only touch their own arena, so nothing here
 // depends on what the other warps of the block are doing.
-template <int PH>
+template <int MODE, int PH>
 __device__ __forceinline__ void run_phase_warp(const StepArgs& a, const BatchParams* sP, const Scene* sSc, unsigned char* sS, int a0, int nA, int warp, int lane) {
 	constexpr int NW = STEP_THREADS / 32;
 	const int nMine = warp < nA ? (nA - warp + NW - 1) / NW : 0;
@@ -533,7 +538,7 @@ __device__ __forceinline__ void run_phase_warp(const StepArgs& a, const BatchPar
 				int arl, idx;
 				if (pass == 0) { const int e = q[i]; arl = e >> 7; idx = e & 127; }
 				else { const int k = i / MAX_CANDS; arl = warp + k * NW; idx = i - k * MAX_CANDS; }
-				const Ctx cx = make_ctx(a, sP, sSc, sS, a0, arl);
+				const Ctx cx = make_ctx<MODE>(a, sP, sSc, sS, a0, arl);
 				if (pass == 1 && !(idx < cx.misc[3] && cx.w->cand[idx].state == CAND_PENDING)) continue;
 				phase_run(cx, PH, idx);
 			}
@@ -545,7 +550,7 @@ __device__ __forceinline__ void run_phase_warp(const StepArgs& a, const BatchPar
 			int k, item;
 			if (PH == PH_WHEELS) { k = i / per; item = i - k * per; }  // the wheels of a car sit in neighbouring lanes
 			else { item = i / nMine; k = i - item * nMine; }           // same item kind in neighbouring lanes
-			const Ctx cx = make_ctx(a, sP, sSc, sS, a0, warp + k * NW);
+			const Ctx cx = make_ctx<MODE>(a, sP, sSc, sS, a0, warp + k * NW);
 			phase_run(cx, PH, item);
 		}
 	}
@@ -567,6 +572,7 @@ __device__ __forceinline__ void run_phase_warp(const StepArgs& a, const BatchPar
 #endif
 
 // ptxas derives 128 registers from __launch_bounds__(448); the register file holds 144 per thread at this block size
+template <int MODE>
 #if defined(RSB_MAXNREG)
 __global__ void __maxnreg__(RSB_MAXNREG) arena_step_kernel(const StepArgs a) {
 #else
@@ -619,20 +625,20 @@ __global__ void __launch_bounds__(STEP_THREADS, BLOCKS_PER_SM) arena_step_kernel
 				}
 				if (lane == 0) *myq = 0u;  // this warp's detector queue
 				__syncwarp();
-				run_phase_warp<PH_INIT>(a, sP, sSc, sS, a0, nA, warp, lane);
-				run_phase_warp<PH_PRE_BEGIN>(a, sP, sSc, sS, a0, nA, warp, lane);
-				run_phase_warp<PH_WHEELS>(a, sP, sSc, sS, a0, nA, warp, lane);
-				run_phase_warp<PH_CAR_LOGIC>(a, sP, sSc, sS, a0, nA, warp, lane);
-				run_phase_warp<PH_PREDICT>(a, sP, sSc, sS, a0, nA, warp, lane);
-				run_phase_warp<PH_PAIRS>(a, sP, sSc, sS, a0, nA, warp, lane);
-				run_phase_warp<PH_NARROW_STATIC>(a, sP, sSc, sS, a0, nA, warp, lane);
-				run_phase_warp<PH_NARROW_DETECT>(a, sP, sSc, sS, a0, nA, warp, lane);
-				run_phase_warp<PH_NARROW_COMMIT>(a, sP, sSc, sS, a0, nA, warp, lane);
-				run_phase_warp<PH_DYN_SOLVE>(a, sP, sSc, sS, a0, nA, warp, lane);
-				run_phase_warp<PH_FINISH_BODY>(a, sP, sSc, sS, a0, nA, warp, lane);
-				run_phase_warp<PH_CAR_POST>(a, sP, sSc, sS, a0, nA, warp, lane);
-				run_phase_warp<PH_PADS_POST>(a, sP, sSc, sS, a0, nA, warp, lane);
-				run_phase_warp<PH_TAIL>(a, sP, sSc, sS, a0, nA, warp, lane);
+				run_phase_warp<MODE, PH_INIT>(a, sP, sSc, sS, a0, nA, warp, lane);
+				run_phase_warp<MODE, PH_PRE_BEGIN>(a, sP, sSc, sS, a0, nA, warp, lane);
+				run_phase_warp<MODE, PH_WHEELS>(a, sP, sSc, sS, a0, nA, warp, lane);
+				run_phase_warp<MODE, PH_CAR_LOGIC>(a, sP, sSc, sS, a0, nA, warp, lane);
+				run_phase_warp<MODE, PH_PREDICT>(a, sP, sSc, sS, a0, nA, warp, lane);
+				run_phase_warp<MODE, PH_PAIRS>(a, sP, sSc, sS, a0, nA, warp, lane);
+				run_phase_warp<MODE, PH_NARROW_STATIC>(a, sP, sSc, sS, a0, nA, warp, lane);
+				run_phase_warp<MODE, PH_NARROW_DETECT>(a, sP, sSc, sS, a0, nA, warp, lane);
+				run_phase_warp<MODE, PH_NARROW_COMMIT>(a, sP, sSc, sS, a0, nA, warp, lane);
+				run_phase_warp<MODE, PH_DYN_SOLVE>(a, sP, sSc, sS, a0, nA, warp, lane);
+				run_phase_warp<MODE, PH_FINISH_BODY>(a, sP, sSc, sS, a0, nA, warp, lane);
+				run_phase_warp<MODE, PH_CAR_POST>(a, sP, sSc, sS, a0, nA, warp, lane);
+				run_phase_warp<MODE, PH_PADS_POST>(a, sP, sSc, sS, a0, nA, warp, lane);
+				run_phase_warp<MODE, PH_TAIL>(a, sP, sSc, sS, a0, nA, warp, lane);
 				if (a.ballTrace && lane < nMine) {
 					const int ar = warp + lane * NW;
 					ball_to_api(((const ArenaS*)(sS + (size_t)ar * a.lay.stride))->ball, a.ballTrace[(size_t)(t + 1) * a.nArenas + a0 + ar]);
@@ -648,27 +654,27 @@ __global__ void __launch_bounds__(STEP_THREADS, BLOCKS_PER_SM) arena_step_kernel
 				for (int i = tid; i < nA * nCars; i += STEP_THREADS) ((ArenaS*)(sS + (size_t)(i / nCars) * a.lay.stride))->cars[i % nCars].controls = src[i];
 				__syncthreads();
 			}
-			run_phase_block<PH_INIT>(a, sP, sSc, sS, a0, nA, ptid);
+			run_phase_block<MODE, PH_INIT>(a, sP, sSc, sS, a0, nA, ptid);
 #if defined(RSB_EXP_TWICE)
-			run_phase_block<PH_INIT, 15>(a, sP, sSc, sS, a0, nA, ptid);
+			run_phase_block<MODE, PH_INIT, 15>(a, sP, sSc, sS, a0, nA, ptid);
 #endif
-			run_phase_block<PH_PRE_BEGIN>(a, sP, sSc, sS, a0, nA, ptid);
-			run_phase_block<PH_WHEELS>(a, sP, sSc, sS, a0, nA, ptid);
+			run_phase_block<MODE, PH_PRE_BEGIN>(a, sP, sSc, sS, a0, nA, ptid);
+			run_phase_block<MODE, PH_WHEELS>(a, sP, sSc, sS, a0, nA, ptid);
 #if defined(RSB_EXP_TWICE)  // developer experiment: the wheel phase is idempotent; its second run measures the same code WARM in the instruction cache
-			run_phase_block<PH_WHEELS, 14>(a, sP, sSc, sS, a0, nA, ptid);
+			run_phase_block<MODE, PH_WHEELS, 14>(a, sP, sSc, sS, a0, nA, ptid);
 #endif
-			run_phase_block<PH_CAR_LOGIC>(a, sP, sSc, sS, a0, nA, ptid);
-			run_phase_block<PH_PREDICT>(a, sP, sSc, sS, a0, nA, ptid);
+			run_phase_block<MODE, PH_CAR_LOGIC>(a, sP, sSc, sS, a0, nA, ptid);
+			run_phase_block<MODE, PH_PREDICT>(a, sP, sSc, sS, a0, nA, ptid);
 			if (tid == 0) *(unsigned*)(smem + SMEM_P_BYTES + SMEM_SC_BYTES) = 0u;  // detector queue; the next write to it is two barriers away
-			run_phase_block<PH_PAIRS>(a, sP, sSc, sS, a0, nA, ptid);
-			run_phase_block<PH_NARROW_STATIC>(a, sP, sSc, sS, a0, nA, ptid);
-			run_phase_block<PH_NARROW_DETECT>(a, sP, sSc, sS, a0, nA, ptid);
-			run_phase_block<PH_NARROW_COMMIT>(a, sP, sSc, sS, a0, nA, ptid);
-			run_phase_block<PH_DYN_SOLVE>(a, sP, sSc, sS, a0, nA, ptid);
-			run_phase_block<PH_FINISH_BODY>(a, sP, sSc, sS, a0, nA, ptid);
-			run_phase_block<PH_CAR_POST>(a, sP, sSc, sS, a0, nA, ptid);
-			run_phase_block<PH_PADS_POST>(a, sP, sSc, sS, a0, nA, ptid);
-			run_phase_block<PH_TAIL>(a, sP, sSc, sS, a0, nA, ptid);
+			run_phase_block<MODE, PH_PAIRS>(a, sP, sSc, sS, a0, nA, ptid);
+			run_phase_block<MODE, PH_NARROW_STATIC>(a, sP, sSc, sS, a0, nA, ptid);
+			run_phase_block<MODE, PH_NARROW_DETECT>(a, sP, sSc, sS, a0, nA, ptid);
+			run_phase_block<MODE, PH_NARROW_COMMIT>(a, sP, sSc, sS, a0, nA, ptid);
+			run_phase_block<MODE, PH_DYN_SOLVE>(a, sP, sSc, sS, a0, nA, ptid);
+			run_phase_block<MODE, PH_FINISH_BODY>(a, sP, sSc, sS, a0, nA, ptid);
+			run_phase_block<MODE, PH_CAR_POST>(a, sP, sSc, sS, a0, nA, ptid);
+			run_phase_block<MODE, PH_PADS_POST>(a, sP, sSc, sS, a0, nA, ptid);
+			run_phase_block<MODE, PH_TAIL>(a, sP, sSc, sS, a0, nA, ptid);
 			if (a.ballTrace)  // the ball is next written in PH_CAR_LOGIC, several barriers from here
 				for (int i = tid; i < nA; i += STEP_THREADS) {
 					RsbBallState& o = a.ballTrace[(size_t)(t + 1) * a.nArenas + a0 + i];
@@ -708,13 +714,31 @@ __global__ void __launch_bounds__(STEP_THREADS, BLOCKS_PER_SM) arena_step_kernel
 	if (tid == 0 && blockIdx.x < 1024) g_blockCycles[blockIdx.x] = (unsigned long long)(clock64() - _kt0);
 #endif
 }
+// One instantiation per game mode (the product build); -DRSB_ONE_KERNEL (developer A/B builds: one seventh of the compile time)
+// keeps a single kernel that reads the mode at run time.
+typedef void (*StepKernel)(const StepArgs);
+static StepKernel step_kernel_of(int mode) {
+#if defined(RSB_ONE_KERNEL)
+	(void)mode;
+	return arena_step_kernel<-1>;
+#else
+	switch (mode) {
+	case SOCCAR: return arena_step_kernel<SOCCAR>;
+	case HOOPS: return arena_step_kernel<HOOPS>;
+	case HEATSEEKER: return arena_step_kernel<HEATSEEKER>;
+	case SNOWDAY: return arena_step_kernel<SNOWDAY>;
+	case DROPSHOT: return arena_step_kernel<DROPSHOT>;
+	default: return arena_step_kernel<THE_VOID>;
+	}
+#endif
+}
 #else
 // host check build (tests only): the same phases, one thread, state in place
 static void arena_step_host(const StepArgs& a) {
 	const int nCars = a.P->nCars;
 	for (int arena = 0; arena < a.nArenas; arena++) {
 		uint16_t hq[512]; unsigned hnq = 0;
-		Ctx cx; cx.q = hq; cx.nq = &hnq; cx.qcap = DETECT_QUEUE_CAP; cx.arLocal = 0;
+		Ctx cx; cx.q = hq; cx.nq = &hnq; cx.qcap = DETECT_QUEUE_CAP; cx.arLocal = 0; ctx_set_mode(cx, *a.P, a.sc);
 		cx.s = a.S + arena; cx.g = cx.s; cx.w = a.W + arena; cx.epa = a.E; cx.p = a.P; cx.sc = a.sc; cx.ev = a.ev; cx.arena = arena;
 		cx.body = a.H[arena].body; cx.wheels = a.H[arena].wheels; cx.padLocked = a.H[arena].padLocked; cx.misc = a.H[arena].misc;
 		cx.pl = &a.H[arena].pairs; cx.mf = a.H[arena].mf; cx.solv = a.H[arena].solv;
@@ -779,7 +803,7 @@ RSB_GLOBAL void get_misc_kernel(const ArenaS* S, const BatchParams* P, const Sce
 	KERNEL_1D(i, nArenas);
 	if (ticks) ticks[i] = S[i].tickCount;
 	if (errs) errs[i] = S[i].errorFlags;
-	if (scored) { Ctx cx; cx.s = (ArenaS*)&S[i]; cx.w = nullptr; cx.epa = nullptr; cx.body = nullptr; cx.wheels = nullptr; cx.padLocked = nullptr; cx.misc = nullptr; cx.pl = nullptr; cx.mf = nullptr; cx.solv = nullptr; cx.p = P; cx.sc = sc; cx.arena = i; cx.ev.buf = nullptr; scored[i] = is_ball_scored(cx) ? 1 : 0; }
+	if (scored) { Ctx cx; cx.s = (ArenaS*)&S[i]; cx.w = nullptr; cx.epa = nullptr; cx.body = nullptr; cx.wheels = nullptr; cx.padLocked = nullptr; cx.misc = nullptr; cx.pl = nullptr; cx.mf = nullptr; cx.solv = nullptr; cx.p = P; cx.sc = sc; cx.arena = i; cx.ev.buf = nullptr; ctx_set_mode(cx, *P, sc); scored[i] = is_ball_scored(cx) ? 1 : 0; }
 }
 RSB_GLOBAL void get_car_internals_kernel(const ArenaS* S, RsbCarInternal* out, int nArenas, int nCars) {
 	KERNEL_1D(i, nArenas * nCars);
@@ -1162,9 +1186,10 @@ int rsb_batch_create_ex(int device, int game_mode, const RsbArenaConfig* arena_c
 		if ((size_t)prop.sharedMemPerBlockOptin < 227 * 1024) throw std::runtime_error("device offers less than 227 KB of shared memory per block: rocketsim_b200 targets sm_100a");
 		static std::mutex attrMutex; std::lock_guard<std::mutex> lk(attrMutex);
 		cudaFuncAttributes fa;
-		CUDA_OK(cudaFuncGetAttributes(&fa, arena_step_kernel));
+		const StepKernel kern = step_kernel_of(game_mode);
+		CUDA_OK(cudaFuncGetAttributes(&fa, kern));
 		b->smemBudget = SMEM_MAX - fa.sharedSizeBytes;  // dynamic shared memory left beside the kernel's static part
-		CUDA_OK(cudaFuncSetAttribute(arena_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smemBudget));
+		CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smemBudget));
 	}
 #endif
 	BatchParams& P = b->hp;
@@ -1192,7 +1217,7 @@ int rsb_batch_create_ex(int device, int game_mode, const RsbArenaConfig* arena_c
 	}
 	{
 		ArenaS tmpS; memset(&tmpS, 0, sizeof(tmpS));
-		Ctx cx; cx.s = &tmpS; cx.w = nullptr; cx.epa = nullptr; cx.body = nullptr; cx.wheels = nullptr; cx.padLocked = nullptr; cx.misc = nullptr; cx.pl = nullptr; cx.mf = nullptr; cx.solv = nullptr; cx.p = &P; cx.sc = nullptr; cx.arena = 0; cx.ev.buf = nullptr;
+		Ctx cx; cx.s = &tmpS; cx.w = nullptr; cx.epa = nullptr; cx.body = nullptr; cx.wheels = nullptr; cx.padLocked = nullptr; cx.misc = nullptr; cx.pl = nullptr; cx.mf = nullptr; cx.solv = nullptr; cx.p = &P; cx.sc = nullptr; cx.arena = 0; cx.ev.buf = nullptr; ctx_set_mode(cx, P, nullptr);
 		for (int bidx = 0; bidx <= n_cars; bidx++) P.motionDisc[bidx] = body_angular_motion_disc(cx, bidx);
 		P.boundRadius[0] = P.ballIsSphere ? P.ballRadiusBT : (sqrtf(P.ballRadiusBT * P.ballRadiusBT + (K::PUCK_HEIGHT * UU_TO_BT / 2) * (K::PUCK_HEIGHT * UU_TO_BT / 2)) + 0.04f);
 		for (int c = 0; c < n_cars; c++) P.boundRadius[c + 1] = len(P.carCfg[c].hitboxHalf) + 0.04f;
@@ -1231,7 +1256,7 @@ int rsb_batch_create_ex(int device, int game_mode, const RsbArenaConfig* arena_c
 		A.ball.hsCurTargetSpeed = K::HS_INITIAL_TARGET_SPEED;
 		A.dsChargeLevel = 1;  // BallState::DropshotInfo default; every tile starts intact (state 0)
 		for (int p = 0; p < P.nPads; p++) { A.pads[p].isActive = 1; }
-		Ctx cx; cx.s = &A; cx.g = &A; cx.w = &tmpW; cx.epa = nullptr; cx.p = &P; cx.sc = &hsc; cx.arena = a; cx.ev.buf = nullptr;
+		Ctx cx; cx.s = &A; cx.g = &A; cx.w = &tmpW; cx.epa = nullptr; cx.p = &P; cx.sc = &hsc; cx.arena = a; cx.ev.buf = nullptr; ctx_set_mode(cx, P, &hsc);
 		cx.body = tmpH.body; cx.wheels = tmpH.wheels; cx.padLocked = tmpH.padLocked; cx.misc = tmpH.misc; cx.pl = &tmpH.pairs; cx.mf = tmpH.mf; cx.solv = tmpH.solv;
 		for (int c = 0; c < n_cars; c++) {
 			tmpH.body[c + 1].invInertiaLocal = P.carCfg[c].invInertiaLocal;
@@ -1314,7 +1339,7 @@ static void launch_step(RsbBatch* b, int n_ticks, const CtrlS* seq, int nCtrl) {
 	const size_t smem = SMEM_P_BYTES + SMEM_SC_BYTES + SMEM_Q_BYTES + (size_t)a.apb * a.lay.stride;
 	a.chunkNext = b->dChunkNext;
 	CUDA_OK(cudaMemsetAsync(b->dChunkNext, 0, sizeof(int), b->stream));
-	arena_step_kernel<<<grid, STEP_THREADS, smem, b->stream>>>(a);
+	step_kernel_of(P.mode)<<<grid, STEP_THREADS, smem, b->stream>>>(a);
 	CUDA_OK(cudaGetLastError());
 #else
 	arena_step_host(a);
@@ -1430,7 +1455,7 @@ int rsb_set_event_tracker(RsbBatch* b, int enable, const RsbEventTrackerConfig* 
 }
 RSB_GLOBAL void going_in_kernel(ArenaS* S, const BatchParams* P, float maxTime, float extraMargin, uint8_t* in, uint8_t* team, int nArenas) {
 	KERNEL_1D(i, nArenas);
-	Ctx cx; cx.s = &S[i]; cx.w = nullptr; cx.epa = nullptr; cx.body = nullptr; cx.wheels = nullptr; cx.padLocked = nullptr; cx.misc = nullptr; cx.pl = nullptr; cx.mf = nullptr; cx.solv = nullptr; cx.p = P; cx.sc = nullptr; cx.arena = i; cx.ev.buf = nullptr;
+	Ctx cx; cx.s = &S[i]; cx.w = nullptr; cx.epa = nullptr; cx.body = nullptr; cx.wheels = nullptr; cx.padLocked = nullptr; cx.misc = nullptr; cx.pl = nullptr; cx.mf = nullptr; cx.solv = nullptr; cx.p = P; cx.sc = nullptr; cx.arena = i; cx.ev.buf = nullptr; ctx_set_mode(cx, *P, nullptr);
 	int t = 0; bool sup;
 	in[i] = is_ball_probably_going_in(cx, maxTime, extraMargin, t, sup) ? 1 : 0;
 	if (team) team[i] = (uint8_t)t;
@@ -1488,7 +1513,7 @@ RSB_GLOBAL void fresh_world_kernel(ArenaS* S, const BatchParams* P, const Scene*
 	A.tickCount = tickCount;
 	A.worldFresh = 1;
 	A.trkLastBallUpdate = 0; A.trkShotCooldown = 0.f; A.trkBallShot = 0; A.trkScoredLast = 0;
-	Ctx cx; cx.s = &A; cx.w = nullptr; cx.epa = nullptr; cx.body = nullptr; cx.wheels = nullptr; cx.padLocked = nullptr; cx.misc = nullptr; cx.pl = nullptr; cx.mf = nullptr; cx.solv = nullptr; cx.p = P; cx.sc = sc; cx.arena = 0; cx.ev.buf = nullptr;
+	Ctx cx; cx.s = &A; cx.w = nullptr; cx.epa = nullptr; cx.body = nullptr; cx.wheels = nullptr; cx.padLocked = nullptr; cx.misc = nullptr; cx.pl = nullptr; cx.mf = nullptr; cx.solv = nullptr; cx.p = P; cx.sc = sc; cx.arena = 0; cx.ev.buf = nullptr; ctx_set_mode(cx, *P, sc);
 	const int nCars = P->nCars;
 	for (int b = 0; b <= nCars; b++) {
 		V3 mn, mx;

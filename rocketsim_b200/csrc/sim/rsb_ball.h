@@ -57,7 +57,7 @@ RSB_HD Ang round_angle_ue3(Ang ang) {
 RSB_HD void ball_pretick(const Ctx& cx) {
 	BallS& b = cx.s->ball;
 	BodyW& bw = cx.body[0];
-	const int mode = cx.p->mode;
+	const int mode = cx.mode;
 	const float dt = cx.p->dt;
 	if (mode == HEATSEEKER) {
 		V3 pos = b.rb.pos * BT_TO_UU, vel = b.rb.vel * BT_TO_UU;
@@ -107,7 +107,7 @@ RSB_HD void ball_pretick(const Ctx& cx) {
 RSB_HD_NOINLINE void ball_on_hit(Ctx cx, int ci, V3 relPosUU) {
 	BallS& b = cx.s->ball;
 	CarS& c = cx.s->cars[ci];
-	const int mode = cx.p->mode;
+	const int mode = cx.mode;
 	const uint64_t tickCount = cx.s->tickCount;
 	V3 carPos = c.rb.pos * BT_TO_UU, carVel = c.rb.vel * BT_TO_UU;
 	V3 ballPos = b.rb.pos * BT_TO_UU, ballVel = b.rb.vel * BT_TO_UU;
@@ -164,7 +164,7 @@ RSB_HD_NOINLINE void ball_on_hit(Ctx cx, int ci, V3 relPosUU) {
 // Ball::_OnWorldCollision (ball-world contact hook)
 RSB_HD_NOINLINE void ball_on_world_collision(Ctx cx, V3 normal) {
 	BallS& b = cx.s->ball;
-	const int mode = cx.p->mode;
+	const int mode = cx.mode;
 	if (mode == HEATSEEKER) {
 		if (b.hsYTargetDir != 0.f) {
 			V3 pos = b.rb.pos * BT_TO_UU;
@@ -209,7 +209,7 @@ RSB_HD void ball_finish_tick(const Ctx& cx) {
 // Arena::IsBallScored
 RSB_HD bool is_ball_scored(const Ctx& cx) {
 	const BallS& b = cx.s->ball;
-	switch (cx.p->mode) {
+	switch (cx.mode) {
 	case SOCCAR: case HEATSEEKER: case SNOWDAY: {
 		float ballPosY = b.rb.pos.y * BT_TO_UU;
 		return fabsf(ballPosY) > (cx.p->mut.goalBaseThresholdY + cx.p->mut.ballRadius);

@@ -53,7 +53,7 @@ RSB_HD void car_respawn(const Ctx& cx, int ci) {
 	CarS& c = cx.s->cars[ci];
 	const BatchParams& P = *cx.p;
 	int slot = (int)(minstd_next(cx.s->rng) % 4u);  // Math::RandInt(0, 4, -1)
-	K::SpawnPos sp = respawn_slot(P.mode == HOOPS, slot);
+	K::SpawnPos sp = respawn_slot(cx.mode == HOOPS, slot);
 	bool blue = (P.team[ci] == 0);
 	V3 posUU(sp.x, sp.y * (blue ? 1.f : -1.f), K::CAR_RESPAWN_Z);
 	car_reset_state(c, P.mut.carSpawnBoostAmount);

@@ -34,7 +34,7 @@ RSB_HD void static_aabb(const Ctx& cx, int obj, V3& mn, V3& mx) {
 }
 // CF_NO_CONTACT_RESPONSE of a static object: only a broken Dropshot tile has it (Arena::SetDropshotTilesState, Arena.cpp:225-242)
 RSB_HD bool static_no_response(const Ctx& cx, int obj) {
-	if (cx.p->mode != DROPSHOT) return false;
+	if (cx.mode != DROPSHOT) return false;
 	const int t = static_tile_index(*cx.sc, obj - STATIC_BASE);
 	return t >= 0 && (cx.g->tiles[t] & 4u) != 0;
 }
@@ -79,7 +79,7 @@ RSB_HD void compound_aabb(const CarCfgD& cfg, const M3& basis, const V3& origin,
 RSB_HD void body_shape_aabb(const Ctx& cx, int b, const M3& basis, const V3& origin, V3& mn, V3& mx) {
 	const BatchParams& P = *cx.p;
 	if (b == 0) {
-		if (P.ballIsSphere) {
+		if (cx.ballIsSphere) {
 			float margin = P.ballRadiusBT + 0.08f;  // btSphereShape::getAabb (btSphereShape.cpp:52-59)
 			V3 e(margin, margin, margin);
 			mn = origin - e; mx = origin + e;
@@ -240,7 +240,7 @@ RSB_HD float body_angular_motion_disc(const Ctx& cx, int obj) {
 	// btCollisionShape::getAngularMotionDisc (btCollisionShape.cpp:126-158)
 	if (obj >= STATIC_BASE) return kLargeFloat;
 	const BatchParams& P = *cx.p;
-	if (obj == 0 && P.ballIsSphere) return (P.ballRadiusBT + 0.08f) + 0.f;
+	if (obj == 0 && cx.ballIsSphere) return (P.ballRadiusBT + 0.08f) + 0.f;
 	V3 mn, mx;
 	body_shape_aabb(cx, obj, m3identity(), v3zero(), mn, mx);
 	float radius = len(mx - mn) * 0.5f;
@@ -500,7 +500,7 @@ RSB_ACP_ATTR void add_contact_point(const Ctx& cx, int mi, const V3& normalOnB, 
 		}
 	} else if (d0 && m.body0 == 0 && !d1) {
 		ball_on_world_collision(cx, cp.normalB);
-		if (cx.p->mode != SNOWDAY) cp.isSpecial = 1;
+		if (cx.mode != SNOWDAY) cp.isSpecial = 1;
 	}
 	if (triMesh >= 0) adjust_internal_edge(cx, cp, cx.sc->meshes[triMesh], triIndex);
 }
@@ -856,7 +856,7 @@ RSB_HD void collide_static_pairs(const Ctx& cx, int b) {
 	// The sphere ball used to run its closed-form sphere-triangle tests inside the walk, one after the other on the ball's thread --
 	// next to a ramp that thread was the slowest of the whole phase.  It now records its triangles like every other shape and
 	// the tests run one per thread in PH_NARROW_DETECT.
-	const bool inlineBody = RSB_SPHERE_INLINE && (b == 0) && P.ballIsSphere;
+	const bool inlineBody = RSB_SPHERE_INLINE && (b == 0) && cx.ballIsSphere;
 	RSB_SUBPROF_BEGIN();
 	for (int k = 0; k < nPairs; k++) {
 		if (cx.pl->b[k] != b) continue;
@@ -866,9 +866,9 @@ RSB_HD void collide_static_pairs(const Ctx& cx, int b) {
 		const int sk = a - STATIC_BASE;
 		const bool isMesh = sk < sc.nMeshes;
 		const RigidS& rb = rigid_of(cx, b);
-		if (sc.nTiles && static_tile_index(sc, sk) >= 0) continue;  // (tile, ball): a pending record of the arena item (enqueue_dynamic_pairs)
+		if (cx.nTiles && static_tile_index(sc, sk) >= 0) continue;  // (tile, ball): a pending record of the arena item (enqueue_dynamic_pairs)
 		if (inlineBody) {
-			Convex shape = ball_convex(P);
+			Convex shape = ball_convex(cx);
 			Xform xf; xf.basis = rb.basis; xf.origin = rb.pos;
 			int mi = new_manifold(cx, k, 0, a);
 			if (isMesh) convex_vs_mesh<false>(cx, mi, shape, xf, sk, cx.pl->entry[k]);
@@ -876,7 +876,7 @@ RSB_HD void collide_static_pairs(const Ctx& cx, int b) {
 			continue;
 		}
 		Convex shape; Xform xf;
-		if (b == 0) { shape = ball_convex(P); xf.basis = rb.basis; xf.origin = rb.pos; }
+		if (b == 0) { shape = ball_convex(cx); xf.basis = rb.basis; xf.origin = rb.pos; }
 		else {
 			// btCompoundLeafCallback::ProcessChildShape: child AABB vs the other shape's AABB
 			V3 omn, omx;
@@ -900,7 +900,7 @@ RSB_HD void collide_static_pairs(const Ctx& cx, int b) {
 // from before this tick's car hits.  (Sharing the ball-car emit site also keeps the queue-full fallback at one inlined detector.)
 RSB_HD void enqueue_dynamic_pairs(const Ctx& cx) {
 	const BatchParams& P = *cx.p;
-	const bool hasTiles = cx.sc->nTiles != 0;
+	const bool hasTiles = cx.nTiles != 0;
 	for (int k = 0; k < cx.pl->nPairs; k++) {
 		const int a = cx.pl->a[k], b = cx.pl->b[k];
 		const bool tilePair = hasTiles && a >= STATIC_BASE && static_tile_index(*cx.sc, a - STATIC_BASE) >= 0;
@@ -910,7 +910,7 @@ RSB_HD void enqueue_dynamic_pairs(const Ctx& cx) {
 			if (!tilePair) {
 				// (ball, car): swapped compound -> convex-convex(box of the car, ball shape); manifold (car, ball)
 				const RigidS& rball = rigid_of(cx, 0);
-				Convex ball = ball_convex(P); Xform xfb; xfb.basis = rball.basis; xfb.origin = rball.pos;
+				Convex ball = ball_convex(cx); Xform xfb; xfb.basis = rball.basis; xfb.origin = rball.pos;
 				V3 omn, omx;
 				convex_world_aabb(cx, ball, xfb, omn, omx);
 				if (!aabb_overlap(cx.body[b].childMin, cx.body[b].childMax, omn, omx)) continue;
@@ -962,7 +962,7 @@ void detect_tile_ball(Ctx cx, int idx) {
 	Convex hull; hull.kind = SH_HULL; hull.margin = 0.04f; hull.he = v3zero(); hull.pts = td.pts; hull.npts = 6;
 	Xform xfT; xfT.basis = m3identity(); xfT.origin = static_origin(cx, a);
 	const RigidS& rball = rigid_of(cx, b);
-	Convex ball = ball_convex(P); Xform xfb; xfb.basis = rball.basis; xfb.origin = rball.pos;
+	Convex ball = ball_convex(cx); Xform xfb; xfb.basis = rball.basis; xfb.origin = rball.pos;
 	V3 n, pt; float d;
 	const bool hit = convex_convex_detect(cx, cx.mf[k].breakingThresh, hull, xfT, ball, xfb, n, pt, d);
 	if (hit) { rec->normal = n; rec->point = pt; rec->depth = d; }
@@ -977,10 +977,10 @@ RSB_HD void detect_candidate(const Ctx& cx, int idx) {
 	const int a = cx.pl->a[k], b = cx.pl->b[k];
 	V3 n, pt; float d;
 	if (a >= STATIC_BASE) {
-		if (cx.sc->nTiles && static_tile_index(*cx.sc, a - STATIC_BASE) >= 0) { detect_tile_ball(cx, idx); return; }
+		if (cx.nTiles && static_tile_index(*cx.sc, a - STATIC_BASE) >= 0) { detect_tile_ball(cx, idx); return; }
 		// (body b, triangle of an arena mesh)
 		const RigidS& rb = rigid_of(cx, b);
-		if (b == 0 && P.ballIsSphere) {
+		if (b == 0 && cx.ballIsSphere) {
 			// sphere vs triangle in closed form (SphereTriangleDetector, the reference's choice for this shape pair)
 			V3 t[3];
 			mesh_triangle(cx.sc->meshes[rec->mesh], rec->tri, t[0], t[1], t[2]);
@@ -991,7 +991,7 @@ RSB_HD void detect_candidate(const Ctx& cx, int idx) {
 			return;
 		}
 		Convex shape; Xform xf;
-		if (b == 0) { shape = ball_convex(P); xf.basis = rb.basis; xf.origin = rb.pos; }
+		if (b == 0) { shape = ball_convex(cx); xf.basis = rb.basis; xf.origin = rb.pos; }
 		else { shape = car_box(P.carCfg[b - 1]); xf = cx.body[b].childXf; }
 		Convex triShape; triShape.kind = SH_TRI; triShape.margin = 0.f; triShape.he = v3zero(); triShape.pts = nullptr; triShape.npts = 0;
 		mesh_triangle(cx.sc->meshes[rec->mesh], rec->tri, triShape.tri[0], triShape.tri[1], triShape.tri[2]);
@@ -1001,7 +1001,7 @@ RSB_HD void detect_candidate(const Ctx& cx, int idx) {
 		rec->state = hit ? CAND_CONTACT : CAND_NONE;
 	} else if (a == 0) {
 		const RigidS& rball = rigid_of(cx, 0);
-		Convex ball = ball_convex(P); Xform xfb; xfb.basis = rball.basis; xfb.origin = rball.pos;
+		Convex ball = ball_convex(cx); Xform xfb; xfb.basis = rball.basis; xfb.origin = rball.pos;
 		Convex box = car_box(P.carCfg[b - 1]); const Xform xfc = cx.body[b].childXf;
 		const bool hit = convex_convex_detect(cx, cx.mf[k].breakingThresh, box, xfc, ball, xfb, n, pt, d);
 		if (hit) { rec->normal = n; rec->point = pt; rec->depth = d; }
@@ -1028,7 +1028,7 @@ RSB_HD void commit_candidates(const Ctx& cx, int b) {
 	for (int i = 0; i < n; i++) {
 		const CandRec r = cx.w->cand[i];
 		const int k = r.pair;
-		const bool dyn = cx.pl->a[k] < STATIC_BASE || (cx.sc->nTiles && static_tile_index(*cx.sc, cx.pl->a[k] - STATIC_BASE) >= 0);  // + (tile, ball)
+		const bool dyn = cx.pl->a[k] < STATIC_BASE || (cx.nTiles && static_tile_index(*cx.sc, cx.pl->a[k] - STATIC_BASE) >= 0);  // + (tile, ball)
 		if (b < 0 ? !dyn : (dyn || cx.pl->b[k] != b)) continue;
 		if (k != curPair) { if (curPair >= 0) refresh_contact_points(cx, curPair); curPair = k; }
 		if (r.state != CAND_CONTACT) continue;

@@ -245,9 +245,10 @@ RSB_HD_NOINLINE bool ray_convex(Convex shapeB, Xform xfB, V3 from, V3 to, float&
 	return false;
 }
 
-RSB_HD Convex ball_convex(const BatchParams& P) {
+RSB_HD Convex ball_convex(const Ctx& cx) {
+	const BatchParams& P = *cx.p;
 	Convex c;
-	if (P.ballIsSphere) { c.kind = SH_SPHERE; c.margin = P.ballRadiusBT; c.he = v3zero(); c.pts = nullptr; c.npts = 0; }
+	if (cx.ballIsSphere) { c.kind = SH_SPHERE; c.margin = P.ballRadiusBT; c.he = v3zero(); c.pts = nullptr; c.npts = 0; }
 	else { c.kind = SH_HULL; c.margin = 0.04f; c.he = v3zero(); c.pts = P.puckPts; c.npts = PUCK_POINTS; }
 	return c;
 }
@@ -315,7 +316,7 @@ RSB_HD bool cast_vehicle_ray(const Ctx& cx, int self, const V3& from, const V3& 
 			}
 			if (b == 0) {
 				xf.basis = rb.basis; xf.origin = rb.pos;
-				shp = ball_convex(P);
+				shp = ball_convex(cx);
 			} else {
 				const CarCfgD& cfg = P.carCfg[b - 1];
 				xf.basis = rb.basis * m3identity();

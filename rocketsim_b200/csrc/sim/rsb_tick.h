@@ -79,7 +79,7 @@ RSB_HD void phase_run(const Ctx& cx, int phase, int item) {
 	ArenaS& S = *cx.s;
 	const int nCars = P.nCars;
 	const float dt = P.dt;
-	const bool hasArenaStuff = (P.mode != THE_VOID);
+	const bool hasArenaStuff = (cx.mode != THE_VOID);
 	const bool ballOnly = (nCars == 0);
 	switch (phase) {
 	case PH_INIT: init_body_work(cx, item); break;
@@ -120,7 +120,7 @@ RSB_HD void phase_run(const Ctx& cx, int phase, int item) {
 		break;
 	case PH_NARROW_DETECT: detect_candidate(cx, item); break;
 	case PH_NARROW_COMMIT:
-		if (!(RSB_SPHERE_INLINE && item == 0 && P.ballIsSphere)) commit_candidates(cx, item);
+		if (!(RSB_SPHERE_INLINE && item == 0 && cx.ballIsSphere)) commit_candidates(cx, item);
 		break;
 	case PH_DYN_SOLVE: {
 		RSB_SUBPROF_BEGIN();
@@ -157,10 +157,10 @@ RSB_HD void phase_run(const Ctx& cx, int phase, int item) {
 		ball_finish_tick(cx);
 		// Dropshot: the rigid bodies of tiles broken this tick lose their contact response now (Arena.cpp:741-746; a damage on
 		// tick 0 is never synchronised there -- `lastDamageTick &&` -- and therefore not here either)
-		if (P.mode == DROPSHOT && cx.g->dsLastDamageTick && cx.g->dsLastDamageTick == S.tickCount) dropshot_sync_tiles(*cx.g);
+		if (cx.mode == DROPSHOT && cx.g->dsLastDamageTick && cx.g->dsLastDamageTick == S.tickCount) dropshot_sync_tiles(*cx.g);
 		// ---- T6: goal event, tick counter
 		{
-			const bool scored = P.mode != THE_VOID && is_ball_scored(cx);
+			const bool scored = cx.mode != THE_VOID && is_ball_scored(cx);
 			if (scored) {
 				float y = -S.ball.rb.pos.y;
 				push_event(cx, 1u /*RSB_EVENT_GOAL*/, (y < 0.f) ? 0u : 1u, 0u);

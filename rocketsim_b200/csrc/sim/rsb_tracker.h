@@ -23,7 +23,7 @@ RSB_HD bool is_ball_probably_going_in(const Ctx& cx, float maxTime, float extraM
 	const V3 ballPos = cx.s->ball.rb.pos * BT_TO_UU;
 	const V3 ballVel = cx.s->ball.rb.vel * BT_TO_UU;
 	supported = true;
-	const int mode = cx.p->mode;
+	const int mode = cx.mode;
 	if (mode == SOCCAR || mode == SNOWDAY) {
 		if (fabsf(ballVel.y) < kFltEps) return false;
 		float scoreDirSgn = (float)rs_sgn(ballVel.y);

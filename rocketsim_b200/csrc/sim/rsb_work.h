@@ -194,9 +194,16 @@ struct Ctx {
 	const Scene* sc;
 	EventSink ev;
 	int arena;  // global arena index inside the batch
+	// Batch constants that select code paths (game mode, ball shape, Dropshot tiles).  The step kernel is instantiated once per
+	// game mode and writes compile-time constants here (make_ctx): after inlining, every `cx.mode == ...` / `cx.ballIsSphere`
+	// test folds away and the other modes' code (Heatseeker steering, puck hull paths, tile pairs) leaves the instantiation.
+	// Everywhere else (host check build, helper kernels) they are copied from BatchParams / Scene (ctx_set_mode).
+	int mode, ballIsSphere, nTiles;
 	// detector work queue of the executing block (PH_NARROW_DETECT): entries = arLocal * 128 + candidate index
 	uint16_t* q; unsigned* nq; int qcap; int arLocal;
 };
+
+RSB_HD void ctx_set_mode(Ctx& cx, const BatchParams& P, const Scene* sc) { cx.mode = P.mode; cx.ballIsSphere = P.ballIsSphere; cx.nTiles = sc ? sc->nTiles : 0; }
 
 struct SolverView {
 	int* cnt;  // [0] solver bodies, [1] contact rows, [2] friction rows
