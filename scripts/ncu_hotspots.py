@@ -2,7 +2,7 @@
 functions by warp-stall samples.  usage: ncu_hotspots.py REP.ncu-rep LIB.so [kernel-substring]"""
 import csv, os, re, subprocess, sys, tempfile, collections, bisect, glob
 rep, lib = sys.argv[1], sys.argv[2]
-kern = "arena_step_kernel"
+kern = os.environ.get("RSB_HOTSPOT_KERNEL", "arena_step_kernelILi0E")  # the Soccar instantiation (the bench workload); one .text section per game mode
 focus = sys.argv[3] if len(sys.argv) > 3 else None  # only count instructions whose inline chain passes through this function
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tmp = tempfile.mkdtemp()

@@ -1,7 +1,7 @@
 """Developer tool: static SASS size of the tick kernel attributed to source functions (inclusive over the inline
 chain) -- finds what inlining blows the instruction footprint up.  usage: sass_size.py LIB.so [kernel-substring]"""
 import os, re, subprocess, sys, tempfile, collections, glob
-lib = sys.argv[1]; kern = sys.argv[2] if len(sys.argv) > 2 else "arena_step_kernel"
+lib = sys.argv[1]; kern = sys.argv[2] if len(sys.argv) > 2 else "arena_step_kernelILi0E"
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(lib)], cwd=tmp, check=True, capture_output=True)
