@@ -390,8 +390,14 @@ __device__ __forceinline__ Ctx make_ctx(const StepArgs& a, const BatchParams* sP
 //   * body phases: all balls in the first warp(s), cars dealt over the other warps -- the sphere and the box code paths
 //     never share a warp;
 //   * car logic: cars first, dealt evenly over all warps in low lanes; pad and ball items fill the remaining lanes/rounds.
+// i / d for the small numbers of the item maps (i < 65,536): one multiply-high with m = div_magic(d) instead of a 32-bit division
+// (~30 instructions), paid twice per phase and tick by every thread -- 5.6 % of all warp instructions in the round-2 profile.
+struct ItemDiv { unsigned mNA, mPer; };
+__device__ __forceinline__ unsigned div_magic(int d) { return d > 1 ? 0xFFFFFFFFu / (unsigned)d + 1u : 0u; }
+__device__ __forceinline__ int fast_div(int i, int d, unsigned m) { return d > 1 ? (int)__umulhi((unsigned)i, m) : i; }
+
 template <int PH>
-__device__ __forceinline__ bool map_item(int k, int tid, int ptid, int nA, const BatchParams& P, int& ar, int& item) {
+__device__ __forceinline__ bool map_item(int k, int tid, int ptid, int nA, const BatchParams& P, const ItemDiv dv, int& ar, int& item) {
 	constexpr int NW = STEP_THREADS / 32;
 	const int nCars = P.nCars;
 	const int warp = tid >> 5, lane = tid & 31;
@@ -401,7 +407,7 @@ __device__ __forceinline__ bool map_item(int k, int tid, int ptid, int nA, const
 	if (PH == PH_WHEELS && (RSB_MAP & 1)) {
 		const int i = tid + k * STEP_THREADS, per = nCars * 4;
 		if (i >= nA * per) return false;
-		ar = i / per; item = i - ar * per;
+		ar = fast_div(i, per, dv.mPer); item = i - ar * per;
 		return true;
 	}
 	if ((PH == PH_INIT || PH == PH_PREDICT || PH == PH_NARROW_STATIC || PH == PH_FINISH_BODY) && (RSB_MAP & 2)) {
@@ -445,15 +451,15 @@ __device__ __forceinline__ bool map_item(int k, int tid, int ptid, int nA, const
 #endif
 	const int i = (RSB_NARROW_NATURAL ? tid : ptid) + k * STEP_THREADS;
 	if (i >= phase_items(P, PH) * nA) return false;
-	ar = i % nA; item = i / nA;
+	item = fast_div(i, nA, dv.mNA); ar = i - item * nA;
 	return true;
 }
 
 template <int PH>
-__device__ __forceinline__ bool phase_thread_busy(int tid, int ptid, int nA, const BatchParams& P) { int ar, item; return map_item<PH>(0, tid, ptid, nA, P, ar, item); }
+__device__ __forceinline__ bool phase_thread_busy(int tid, int ptid, int nA, const BatchParams& P, const ItemDiv dv) { int ar, item; return map_item<PH>(0, tid, ptid, nA, P, dv, ar, item); }
 
 template <int MODE, int PH, int SLOT = PH>
-__device__ __forceinline__ void run_phase_block(const StepArgs& a, const BatchParams* sP, const Scene* sSc, unsigned char* sS, int a0, int nA, int ptid) {
+__device__ __forceinline__ void run_phase_block(const StepArgs& a, const BatchParams* sP, const Scene* sSc, unsigned char* sS, int a0, int nA, int ptid, const ItemDiv dv) {
 #if defined(RSB_PROFILE)
 	__shared__ unsigned long long s_profMax;
 #endif
@@ -484,20 +490,20 @@ __device__ __forceinline__ void run_phase_block(const StepArgs& a, const BatchPa
 		PHASE_PROF_ITEMS(SLOT, ptid < nq);
 	} else {
 	const int n = phase_items(*sP, PH) * nA;
-	const int nRounds = (n + STEP_THREADS - 1) / STEP_THREADS + 1;
+	const int nRounds = (n + STEP_THREADS - 1) / STEP_THREADS + ((RSB_MAP & 6) ? 1 : 0);  // the grouped developer maps leave holes: one more round
 	for (int k = 0; k < nRounds; k++) {
 		int ar, item;
-		if (!map_item<PH>(k, threadIdx.x, ptid, nA, *sP, ar, item)) continue;
+		if (!map_item<PH>(k, threadIdx.x, ptid, nA, *sP, dv, ar, item)) continue;
 		const Ctx cx = make_ctx<MODE>(a, sP, sSc, sS, a0, ar);
 		phase_run(cx, PH, item);
 	}
-	PHASE_PROF_ITEMS(SLOT, phase_thread_busy<PH>(threadIdx.x, ptid, nA, *sP));
+	PHASE_PROF_ITEMS(SLOT, phase_thread_busy<PH>(threadIdx.x, ptid, nA, *sP, dv));
 	}
 #if defined(RSB_PROFILE)
 	__shared__ unsigned long long s_profMax2;
 	if (PH == PH_NARROW_DETECT || PH == PH_DYN_SOLVE) {
 		EpaScratch* es = a.E + ((size_t)blockIdx.x * STEP_THREADS + threadIdx.x);
-		if (phase_thread_busy<PH>(threadIdx.x, ptid, nA, *sP)) { unsigned long long d = (unsigned long long)(clock64() - _pt0); int c = es->profCalls; atomicMax(&s_profMax2, (d << 20) | (unsigned long long)(c & 0xfffff)); }
+		if (phase_thread_busy<PH>(threadIdx.x, ptid, nA, *sP, dv)) { unsigned long long d = (unsigned long long)(clock64() - _pt0); int c = es->profCalls; atomicMax(&s_profMax2, (d << 20) | (unsigned long long)(c & 0xfffff)); }
 		es->profCalls = 0;
 	}
 #endif
@@ -600,6 +606,7 @@ __global__ void __launch_bounds__(STEP_THREADS, BLOCKS_PER_SM) arena_step_kernel
 	for (int chunk = blockIdx.x; chunk < nChunks;) {
 		const int a0 = chunk * a.apb;
 		const int nA = min(a.apb, a.nArenas - a0);
+		ItemDiv dv; dv.mNA = div_magic(nA); dv.mPer = div_magic(nCars * 4);
 		__syncthreads();
 		// stage the records: persistent prefix from HBM, per-tick scratch zeroed
 		for (int i = tid; i < nA * strideWords; i += STEP_THREADS) {
@@ -654,27 +661,27 @@ __global__ void __launch_bounds__(STEP_THREADS, BLOCKS_PER_SM) arena_step_kernel
 				for (int i = tid; i < nA * nCars; i += STEP_THREADS) ((ArenaS*)(sS + (size_t)(i / nCars) * a.lay.stride))->cars[i % nCars].controls = src[i];
 				__syncthreads();
 			}
-			run_phase_block<MODE, PH_INIT>(a, sP, sSc, sS, a0, nA, ptid);
+			run_phase_block<MODE, PH_INIT>(a, sP, sSc, sS, a0, nA, ptid, dv);
 #if defined(RSB_EXP_TWICE)
-			run_phase_block<MODE, PH_INIT, 15>(a, sP, sSc, sS, a0, nA, ptid);
+			run_phase_block<MODE, PH_INIT, 15>(a, sP, sSc, sS, a0, nA, ptid, dv);
 #endif
-			run_phase_block<MODE, PH_PRE_BEGIN>(a, sP, sSc, sS, a0, nA, ptid);
-			run_phase_block<MODE, PH_WHEELS>(a, sP, sSc, sS, a0, nA, ptid);
+			run_phase_block<MODE, PH_PRE_BEGIN>(a, sP, sSc, sS, a0, nA, ptid, dv);
+			run_phase_block<MODE, PH_WHEELS>(a, sP, sSc, sS, a0, nA, ptid, dv);
 #if defined(RSB_EXP_TWICE)  // developer experiment: the wheel phase is idempotent; its second run measures the same code WARM in the instruction cache
-			run_phase_block<MODE, PH_WHEELS, 14>(a, sP, sSc, sS, a0, nA, ptid);
+			run_phase_block<MODE, PH_WHEELS, 14>(a, sP, sSc, sS, a0, nA, ptid, dv);
 #endif
-			run_phase_block<MODE, PH_CAR_LOGIC>(a, sP, sSc, sS, a0, nA, ptid);
-			run_phase_block<MODE, PH_PREDICT>(a, sP, sSc, sS, a0, nA, ptid);
+			run_phase_block<MODE, PH_CAR_LOGIC>(a, sP, sSc, sS, a0, nA, ptid, dv);
+			run_phase_block<MODE, PH_PREDICT>(a, sP, sSc, sS, a0, nA, ptid, dv);
 			if (tid == 0) *(unsigned*)(smem + SMEM_P_BYTES + SMEM_SC_BYTES) = 0u;  // detector queue; the next write to it is two barriers away
-			run_phase_block<MODE, PH_PAIRS>(a, sP, sSc, sS, a0, nA, ptid);
-			run_phase_block<MODE, PH_NARROW_STATIC>(a, sP, sSc, sS, a0, nA, ptid);
-			run_phase_block<MODE, PH_NARROW_DETECT>(a, sP, sSc, sS, a0, nA, ptid);
-			run_phase_block<MODE, PH_NARROW_COMMIT>(a, sP, sSc, sS, a0, nA, ptid);
-			run_phase_block<MODE, PH_DYN_SOLVE>(a, sP, sSc, sS, a0, nA, ptid);
-			run_phase_block<MODE, PH_FINISH_BODY>(a, sP, sSc, sS, a0, nA, ptid);
-			run_phase_block<MODE, PH_CAR_POST>(a, sP, sSc, sS, a0, nA, ptid);
-			run_phase_block<MODE, PH_PADS_POST>(a, sP, sSc, sS, a0, nA, ptid);
-			run_phase_block<MODE, PH_TAIL>(a, sP, sSc, sS, a0, nA, ptid);
+			run_phase_block<MODE, PH_PAIRS>(a, sP, sSc, sS, a0, nA, ptid, dv);
+			run_phase_block<MODE, PH_NARROW_STATIC>(a, sP, sSc, sS, a0, nA, ptid, dv);
+			run_phase_block<MODE, PH_NARROW_DETECT>(a, sP, sSc, sS, a0, nA, ptid, dv);
+			run_phase_block<MODE, PH_NARROW_COMMIT>(a, sP, sSc, sS, a0, nA, ptid, dv);
+			run_phase_block<MODE, PH_DYN_SOLVE>(a, sP, sSc, sS, a0, nA, ptid, dv);
+			run_phase_block<MODE, PH_FINISH_BODY>(a, sP, sSc, sS, a0, nA, ptid, dv);
+			run_phase_block<MODE, PH_CAR_POST>(a, sP, sSc, sS, a0, nA, ptid, dv);
+			run_phase_block<MODE, PH_PADS_POST>(a, sP, sSc, sS, a0, nA, ptid, dv);
+			run_phase_block<MODE, PH_TAIL>(a, sP, sSc, sS, a0, nA, ptid, dv);
 			if (a.ballTrace)  // the ball is next written in PH_CAR_LOGIC, several barriers from here
 				for (int i = tid; i < nA; i += STEP_THREADS) {
 					RsbBallState& o = a.ballTrace[(size_t)(t + 1) * a.nArenas + a0 + i];
