@@ -171,6 +171,9 @@ int rsb_debug_get_solver_bodies(RsbBatch* b, int arena, float* out, int cap, int
 
 /* Debug probe: the four per-arena scratch ints of the last tick ([0] solver ran, [1] #manifolds solved, [2..3] developer use). */
 int rsb_debug_get_misc(RsbBatch* b, int arena, int* out4);
+/* Test hook: usable capacity of the per-block detector queue (1..512).  Results never depend on it (records that do not fit
+ * are swept up after the queued ones); tests shrink it to exercise that sweep. */
+int rsb_debug_set_detect_queue_cap(RsbBatch* b, int cap);
 
 /* Developer builds (-DRSB_PROFILE) only: per tick phase p: out[p] block wall cycles, out[16+p] busy-thread cycles,
  * out[32+p] busy threads, out[48+p] slowest-thread cycles (each summed over blocks and ticks); zeros otherwise. */

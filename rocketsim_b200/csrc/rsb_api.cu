@@ -127,6 +127,7 @@ struct RsbBatch {
 	ArenaH* dH = nullptr;          // global mirror of the hot per-tick scratch
 	EpaScratch* dE = nullptr;      // EPA working sets, one per thread of the step grid
 	int* dChunkNext = nullptr;     // work counter of a multi-wave launch (chunks beyond the resident grid are fetched dynamically)
+	int detectQueueCap = 0;        // 0 = the full queue; rsb_debug_set_detect_queue_cap (tests shrink it to exercise the overflow sweep)
 	RsbBallState* traceOut = nullptr;  // consumed by the next launch (rsb_predict_ball)
 	RsbBatch* pred = nullptr;      // ball-only sibling batch used by rsb_predict_ball (created on first use)
 	RsbArenaConfig acfg;           // the ArenaConfig the batch was created with (customBoostPads points into acfgPads)
@@ -329,6 +330,7 @@ struct StepArgs {
 	ArenaS* S; ArenaH* H; ArenaW* W; EpaScratch* E; const BatchParams* P; const Scene* sc; EventSink ev;
 	int nArenas, nTicks; const CtrlS* ctrlSeq; int nCtrl; int apb;
 	int* chunkNext;  // device counter (starts at 0): a block that has finished its chunk fetches chunk gridDim.x + counter++
+	int qcap;    // usable entries of the block's detector queue (DETECT_QUEUE_CAP; smaller only through rsb_debug_set_detect_queue_cap)
 	int mirror;  // keep the full debug mirror (ArenaH) up to date: single-tick launches only
 	RsbBallState* ballTrace;  // optional [nTicks + 1][nArenas]: Ball::GetState() after every tick (row t + 1), see rsb_predict_ball
 	ArenaLayout lay;
@@ -371,7 +373,7 @@ __device__ __forceinline__ Ctx make_ctx(const StepArgs& a, const BatchParams* sP
 #if RSB_WARP_SCHED
 	cx.nq = (unsigned*)(smem + SMEM_P_BYTES + SMEM_SC_BYTES + (size_t)(threadIdx.x >> 5) * (16 + WARP_QUEUE_CAP * 2)); cx.q = (uint16_t*)(cx.nq + 4); cx.qcap = WARP_QUEUE_CAP; cx.arLocal = ar;
 #else
-	cx.nq = (unsigned*)(smem + SMEM_P_BYTES + SMEM_SC_BYTES); cx.q = (uint16_t*)(cx.nq + 4); cx.qcap = DETECT_QUEUE_CAP; cx.arLocal = ar;
+	cx.nq = (unsigned*)(smem + SMEM_P_BYTES + SMEM_SC_BYTES); cx.q = (uint16_t*)(cx.nq + 4); cx.qcap = a.qcap; cx.arLocal = ar;
 #endif
 	unsigned char* base = sS + (size_t)ar * a.lay.stride;
 	cx.s = (ArenaS*)base; cx.g = a.S + (a0 + ar); cx.body = (BodyW*)(base + a.lay.bodyOff); cx.wheels = (WheelW*)(base + a.lay.wheelOff);
@@ -471,10 +473,10 @@ __device__ __forceinline__ void run_phase_block(const StepArgs& a, const BatchPa
 		const unsigned* nqp = (const unsigned*)(smem + SMEM_P_BYTES + SMEM_SC_BYTES);
 		const uint16_t* q = (const uint16_t*)(nqp + 4);
 		const int pushed = (int)*nqp;
-		const int nq = min(pushed, DETECT_QUEUE_CAP);
+		const int nq = min(pushed, a.qcap);
 		// pass 0: the queued records.  pass 1 (only after a queue overflow, block-uniform): every record of every resident arena
 		// that is still pending -- the ones that did not fit the queue.  One detector call site for both.
-		const int nPass = pushed > DETECT_QUEUE_CAP ? 2 : 1;
+		const int nPass = pushed > a.qcap ? 2 : 1;
 		for (int pass = 0; pass < nPass; pass++) {
 			const int n = pass == 0 ? nq : nA * MAX_CANDS;
 			for (int i = ptid; i < n; i += STEP_THREADS) {
@@ -745,7 +747,7 @@ static void arena_step_host(const StepArgs& a) {
 	const int nCars = a.P->nCars;
 	for (int arena = 0; arena < a.nArenas; arena++) {
 		uint16_t hq[512]; unsigned hnq = 0;
-		Ctx cx; cx.q = hq; cx.nq = &hnq; cx.qcap = DETECT_QUEUE_CAP; cx.arLocal = 0; ctx_set_mode(cx, *a.P, a.sc);
+		Ctx cx; cx.q = hq; cx.nq = &hnq; cx.qcap = a.qcap; cx.arLocal = 0; ctx_set_mode(cx, *a.P, a.sc);
 		cx.s = a.S + arena; cx.g = cx.s; cx.w = a.W + arena; cx.epa = a.E; cx.p = a.P; cx.sc = a.sc; cx.ev = a.ev; cx.arena = arena;
 		cx.body = a.H[arena].body; cx.wheels = a.H[arena].wheels; cx.padLocked = a.H[arena].padLocked; cx.misc = a.H[arena].misc;
 		cx.pl = &a.H[arena].pairs; cx.mf = a.H[arena].mf; cx.solv = a.H[arena].solv;
@@ -1332,6 +1334,7 @@ static void launch_step(RsbBatch* b, int n_ticks, const CtrlS* seq, int nCtrl) {
 	a.lay = ArenaLayout::make(P.nCars, P.nPads); a.sc = b->dScene; a.ev = sink_of(b);
 	a.nArenas = P.nArenas; a.nTicks = n_ticks; a.ctrlSeq = seq; a.nCtrl = nCtrl; a.apb = 1; a.mirror = (n_ticks == 1) ? 1 : 0;
 	a.ballTrace = b->traceOut; b->traceOut = nullptr;
+	a.qcap = b->detectQueueCap > 0 ? b->detectQueueCap : DETECT_QUEUE_CAP;
 #ifndef RSB_HOSTCHECK
 	// chunk size: fill every SM once if the batch fits (one wave), else the fewest equal waves
 	const int sms = b->numSMs * BLOCKS_PER_SM;  // resident block slots
@@ -1893,6 +1896,15 @@ int rsb_debug_get_misc(RsbBatch* b, int arena, int* out4) {
 	API_BEGIN set_device(b);
 	DebugSnap s = debug_snap(b, arena);
 	for (int i = 0; i < 4; i++) out4[i] = s.h[0].misc[i];
+	API_END
+}
+
+// ---- test hook: usable capacity of the per-block detector queue (1 .. DETECT_QUEUE_CAP).  Results do not depend on it: records
+// that do not fit are picked up by the overflow sweep of PH_NARROW_DETECT; tests shrink it to run that sweep on every tick.
+int rsb_debug_set_detect_queue_cap(RsbBatch* b, int cap) {
+	API_BEGIN
+	if (cap < 1 || cap > DETECT_QUEUE_CAP) throw std::runtime_error("detector queue capacity must be in [1, " + std::to_string(DETECT_QUEUE_CAP) + "]");
+	b->detectQueueCap = cap;
 	API_END
 }
 

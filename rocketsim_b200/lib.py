@@ -29,7 +29,7 @@ EXPORTS = [
     "rsb_get_car_internals", "rsb_set_car_internals", "rsb_get_ball_internals", "rsb_set_ball_internals",
     "rsb_reset_to_random_kickoff", "rsb_scene_counts", "rsb_scene_dump", "rsb_scene_num_meshes", "rsb_scene_cells",
     "rsb_bench_fill_controls_device", "rsb_debug_get_wheels", "rsb_step_with_controls", "rsb_set_auto_reset", "rsb_debug_get_manifolds", "rsb_debug_get_solver_rows", "rsb_debug_profile", "rsb_debug_get_solver_bodies", "rsb_debug_get_misc", "rsb_car_config_preset", "rsb_default_mutator_config", "rsb_set_event_tracker", "rsb_is_ball_probably_going_in", "rsb_predict_ball", "rsb_serialize_arena", "rsb_deserialize_arena", "rsb_clone_arena", "rsb_set_arena_offset", "rsb_batch_create_ex", "rsb_default_arena_config",
-    "rsb_get_dropshot_tiles", "rsb_set_dropshot_tiles",
+    "rsb_get_dropshot_tiles", "rsb_set_dropshot_tiles", "rsb_debug_set_detect_queue_cap",
 ]
 
 
@@ -83,6 +83,8 @@ def _declare(L):
     L.rsb_debug_get_solver_bodies.argtypes = [vp, i32, vp, i32, vp]
     L.rsb_debug_profile.argtypes = [vp, i32]
     L.rsb_debug_get_misc.argtypes = [vp, i32, vp]
+    if hasattr(L, "rsb_debug_set_detect_queue_cap"):
+        L.rsb_debug_set_detect_queue_cap.argtypes = [vp, i32]
     L.rsb_predict_ball.argtypes = [vp, i32, vp]
     L.rsb_clone_arena.argtypes = [vp, u32, u32]
     L.rsb_serialize_arena.argtypes = [vp, u32, vp, C.c_size_t, vp]

@@ -12,7 +12,7 @@ import numpy as np
 import pytest
 
 import parity_util as pu
-from rocketsim_b200 import types as T
+from rocketsim_b200 import lib as lib_mod, types as T
 from rocketsim_b200.arena_batch import ArenaBatch
 
 N_FULL = 4096
@@ -119,3 +119,48 @@ def test_events_and_auto_reset_full_size(cudalib):
     assert int(b.get_error_flags().max()) == 0
     assert np.all(b.get_tick_counts() == 240)
     b.close()
+
+
+def _queue_cap_run(lib, mode, teams, n_arenas, cap, ticks=150):
+    """Cars driven into each other, the ball and the walls (GJK / EPA / box-box records every tick), with the usable capacity of the
+    per-block detector queue set to `cap` (None = the product's 512)."""
+    b = ArenaBatch(mode, n_arenas, teams, seed=5, lib=lib)
+    if cap is not None:
+        lib_mod.check(lib, lib.rsb_debug_set_detect_queue_cap(b.h, cap))
+    b.reset_to_random_kickoff((5 + np.arange(n_arenas)).astype(np.int32))
+    cs = b.get_car_states()
+    n = len(teams)
+    for i in range(n):  # a column of cars heading for the +x wall, the rear ones faster: they run into each other, then into the ramp
+        cs[:, i]["pos"]["x"] = 1800.0 + 270.0 * i; cs[:, i]["pos"]["y"] = (np.arange(n_arenas) % 7) * 9.0 + 25.0 * (i % 2); cs[:, i]["pos"]["z"] = 17.0
+        cs[:, i]["rotMat"]["forward"] = (1, 0, 0, 0); cs[:, i]["rotMat"]["right"] = (0, 1, 0, 0); cs[:, i]["rotMat"]["up"] = (0, 0, 1, 0)
+        cs[:, i]["vel"]["x"] = 2200.0 - 300.0 * i; cs[:, i]["vel"]["y"] = 0.0
+    ai = np.repeat(np.arange(n_arenas), n); ci = np.tile(np.arange(n), n_arenas)
+    b.set_car_states(ai, ci, cs.ravel())
+    bs = b.get_ball_states()
+    bs["pos"]["x"] = 3500.0; bs["pos"]["y"] = 20.0; bs["pos"]["z"] = 120.0; bs["vel"]["x"] = 600.0
+    b.set_ball_states(np.arange(n_arenas), bs)
+    ctrl = np.zeros((ticks, n_arenas, n), T.CarControls); ctrl["throttle"] = 1; ctrl["boost"] = 1
+    b.step_with_controls(ctrl)
+    res = dict(cars=b.get_car_states(), ball=b.get_ball_states(), err=b.get_error_flags(), ev=len(b.get_events(cap=1 << 20)))
+    b.close()
+    return res
+
+
+def _check_queue_overflow(lib, n_arenas):
+    """The detector-queue overflow sweep (run_phase_block<PH_NARROW_DETECT> / arena_tick): with room for ONE record per block, all
+    the others of a tick go through the sweep -- and nothing may change."""
+    for mode, teams in ((T.MODE_SOCCAR, [0, 0, 0, 1, 1, 1]), (T.MODE_SNOWDAY, [0, 0, 1, 1])):
+        full = _queue_cap_run(lib, mode, teams, n_arenas, None)
+        tiny = _queue_cap_run(lib, mode, teams, n_arenas, 1)
+        assert int(full["err"].max()) == 0 and int(tiny["err"].max()) == 0
+        assert full["ev"] > 0, "no bump in the whole run: the scenario produces no car-car records"
+        assert same(full["cars"], tiny["cars"]) and same(full["ball"], tiny["ball"]), f"mode {mode}: results depend on the detector queue capacity"
+
+
+def test_hostcheck_detector_queue_overflow_sweep(hostlib):
+    _check_queue_overflow(hostlib, 3)
+
+
+@pytest.mark.gpu
+def test_cuda_detector_queue_overflow_sweep(cudalib):
+    _check_queue_overflow(cudalib, 300)
