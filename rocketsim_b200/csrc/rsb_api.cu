@@ -1450,7 +1450,7 @@ int rsb_set_arena_offset(RsbBatch* b, uint32_t off) {
 int rsb_set_event_tracker(RsbBatch* b, int enable, const RsbEventTrackerConfig* cfg) {
 	API_BEGIN
 	set_device(b);
-	if (enable && (b->hp.mode == HEATSEEKER || b->hp.mode == THE_VOID))
+	if (enable && (b->hp.mode == HEATSEEKER || b->hp.mode == DROPSHOT || b->hp.mode == THE_VOID))
 		throw std::runtime_error("Arena::IsBallProbablyGoingIn() is not supported for gamemode " + std::to_string(b->hp.mode));  // Arena.cpp:887
 	b->hp.trackerEnabled = enable ? 1 : 0;
 	TrackerCfgD& t = b->hp.tracker;
@@ -1473,7 +1473,7 @@ RSB_GLOBAL void going_in_kernel(ArenaS* S, const BatchParams* P, float maxTime, 
 int rsb_is_ball_probably_going_in(RsbBatch* b, float max_time, float extra_margin, uint8_t* out, uint8_t* goal_team_out) {
 	API_BEGIN
 	set_device(b);
-	if (b->hp.mode == HEATSEEKER || b->hp.mode == THE_VOID)
+	if (b->hp.mode == HEATSEEKER || b->hp.mode == DROPSHOT || b->hp.mode == THE_VOID)  // Arena.cpp:775-889: Soccar, Snowday and Hoops only
 		throw std::runtime_error("Arena::IsBallProbablyGoingIn() is not supported for gamemode " + std::to_string(b->hp.mode));
 	const int n = b->hp.nArenas;
 	b->ensure_scratch((size_t)n * 2);

@@ -59,6 +59,11 @@ def _tile_api(lib):
     assert (d["chargeLevel"] == 1).all() and not d["hasDamaged"].any() and (d["accumulatedHitForce"] == 0).all()
     with pytest.raises(Exception):
         b.set_dropshot_tiles([0], np.full((1, 2, 70), 3, np.uint8))
+    # Arena::IsBallProbablyGoingIn (and with it the GameEventTracker) has no Dropshot case in the reference (Arena.cpp:775-889)
+    with pytest.raises(Exception):
+        b.is_ball_probably_going_in()
+    with pytest.raises(Exception):
+        b.set_event_tracker(True)
     b.close()
     s = pu.ArenaBatch(T.MODE_SOCCAR, 1, [0, 1], lib=lib)
     with pytest.raises(Exception):
